@@ -1,0 +1,73 @@
+"""ctypes binding of ``libfisr_b200.so`` (C ABI in ``include/fisr_b200.h``).
+
+There is no CPU path: if the library is missing, or no sm_100 GPU is present when a context is
+created, the import / constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfisr_b200.so")
+
+FISR_OK = 0
+PREC_F16X3 = 0      # fp16 (hi, lo) split operands, fp32-class result (default)
+PREC_F16 = 1        # single fp16 operands, fast mode
+
+_lib: Optional[C.CDLL] = None
+
+
+class FisrError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Loads the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FisrError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(fisr_b200 has no CPU or PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i, f, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+    sig = {
+        "fisr_create": (i, [i, C.POINTER(vp)]),
+        "fisr_destroy": (None, [vp]),
+        "fisr_last_error": (C.c_char_p, [vp]),
+        "fisr_set_precision": (i, [vp, i]),
+        "fisr_get_precision": (i, [vp]),
+        "fisr_num_params": (i, []),
+        "fisr_param_name": (C.c_char_p, [i]),
+        "fisr_param_shape": (i, [i, C.POINTER(i)]),
+        "fisr_set_param": (i, [vp, C.c_char_p, vp, sz]),
+        "fisr_get_param": (i, [vp, C.c_char_p, vp, sz]),
+        "fisr_forward": (i, [vp, vp, i, i, i, vp, vp, vp, vp]),
+        "fisr_forward_host": (i, [vp, vp, i, i, i, vp, vp, vp]),
+        "fisr_window_device": (i, [vp, vp, vp, vp, i, i, i, i, i, i, vp, vp]),
+        "fisr_window_device_f32": (i, [vp, vp, vp, vp, i, i, i, i, vp, vp]),
+        "fisr_window_host": (i, [vp, vp, vp, vp, i, i, i, i, vp]),
+        "fisr_warp_device": (i, [vp, vp, vp, f, vp, i, i, f, vp]),
+        "fisr_warp_host": (i, [vp, vp, vp, f, vp, i, i, f]),
+        "fisr_conv3x3": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp]),
+        "fisr_debug_conv_output": (i, [vp, C.c_char_p, vp, sz]),
+        "fisr_launch_count": (C.c_longlong, [vp]),
+        "fisr_plan_info": (i, [vp, i, i, i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i), C.POINTER(sz)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)       # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+EXPORTS = [
+    "fisr_create", "fisr_destroy", "fisr_last_error", "fisr_set_precision", "fisr_get_precision", "fisr_num_params",
+    "fisr_param_name", "fisr_param_shape", "fisr_set_param", "fisr_get_param", "fisr_forward", "fisr_forward_host",
+    "fisr_window_device", "fisr_window_device_f32", "fisr_window_host", "fisr_warp_device", "fisr_warp_host",
+    "fisr_conv3x3", "fisr_debug_conv_output", "fisr_launch_count", "fisr_plan_info",
+]

@@ -1,0 +1,399 @@
+// HBM-bound helper kernels around the conv stack: weight packing, input packing (with the reference's
+// "bicubic" = strided subsample), legacy bilinear x2 upsample, 2x2 max-pool, tile pack / unpack for the
+// tiled video path, and the flow warp.  All are one-pass, vectorised, coalesced along the channel axis.
+#include "common.cuh"
+#include "aux_kernels.h"
+
+namespace fisr {
+
+namespace {
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
+}
+__device__ __forceinline__ void unpack8(const uint4& v, __half (&h)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        h[2 * i] = __ushort_as_half(static_cast<unsigned short>(w[i] & 0xFFFF));
+        h[2 * i + 1] = __ushort_as_half(static_cast<unsigned short>(w[i] >> 16));
+    }
+}
+// 8 consecutive channels of a (hi, lo) activation -> fp32
+template <int PLANES>
+__device__ __forceinline__ void load8(const __half* p, size_t plane, float (&f)[8]) {
+    __half h[8], l[8];
+    unpack8(*reinterpret_cast<const uint4*>(p), h);
+    if (PLANES == 2) {
+        unpack8(*reinterpret_cast<const uint4*>(p + plane), l);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = join_f16(h[i], l[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __half2float(h[i]);
+    }
+}
+template <int PLANES>
+__device__ __forceinline__ void store8(__half* p, size_t plane, const float (&f)[8]) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const SplitHalf s0 = split_f32(f[2 * q]), s1 = split_f32(f[2 * q + 1]);
+        hi[q] = pack_h2(s0.hi, s1.hi);
+        lo[q] = pack_h2(s0.lo, s1.lo);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (PLANES == 2) *reinterpret_cast<uint4*>(p + plane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// ---------------------------------------------------------------- weights
+// w: fp32 HWIO [3,3,cin,cout] (ops.py:8) -> [plane][kb][tap][cout_pad][64] fp16, zero padded.
+__global__ void prep_weights_kernel(const float* __restrict__ w, __half* __restrict__ out, int cin, int cout, int KB,
+                                    int cout_pad, int planes) {
+    const size_t per_plane = static_cast<size_t>(KB) * 9 * cout_pad * 64;
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= per_plane) return;
+    const int cl = i & 63;
+    size_t r = i >> 6;
+    const int co = r % cout_pad; r /= cout_pad;
+    const int tap = r % 9;
+    const int kb = r / 9;
+    const int ci = kb * 64 + cl;
+    float v = 0.f;
+    if (ci < cin && co < cout) v = w[(static_cast<size_t>(tap) * cin + ci) * cout + co];
+    const SplitHalf s = split_f32(v);
+    out[i] = s.hi;
+    if (planes == 2) out[per_plane + i] = s.lo;
+}
+
+// ---------------------------------------------------------------- input pack
+// img fp32 NHWC [N,H,W,29] -> level-3 input (full res), level-2 (x[::2, ::2]) and level-1 (x[::4, ::4]) buffers,
+// fp16 (hi, lo), 64 channels each; only channels [0, cin) are written (FISRnet.py:81,112,144).
+template <int PLANES>
+__global__ void pack_input_kernel(const float* __restrict__ img, int N, int H, int W, int cin, __half* l3, size_t p3,
+                                  __half* l2, size_t p2, __half* l1, size_t p1) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t total = static_cast<size_t>(N) * H * W * 32;
+    if (i >= total) return;
+    const int c = i & 31;
+    if (c >= cin) return;
+    const size_t pix = i >> 5;
+    const int x = pix % W;
+    const int y = (pix / W) % H;
+    const int n = pix / (static_cast<size_t>(W) * H);
+    const SplitHalf s = split_f32(img[pix * cin + c]);
+    l3[pix * 64 + c] = s.hi;
+    if (PLANES == 2) l3[p3 + pix * 64 + c] = s.lo;
+    if (((x | y) & 1) == 0) {
+        const size_t q = (static_cast<size_t>(n) * (H / 2) + y / 2) * (W / 2) + x / 2;
+        l2[q * 64 + c] = s.hi;
+        if (PLANES == 2) l2[p2 + q * 64 + c] = s.lo;
+    }
+    if (((x | y) & 3) == 0) {
+        const size_t q = (static_cast<size_t>(n) * (H / 4) + y / 4) * (W / 4) + x / 4;
+        l1[q * 64 + c] = s.hi;
+        if (PLANES == 2) l1[p1 + q * 64 + c] = s.lo;
+    }
+}
+
+// ---------------------------------------------------------------- legacy bilinear x2 (ops.py:69)
+// out[2k] = in[k], out[2k+1] = (in[k] + in[min(k+1, n-1)]) / 2, along H then W (TF-1.13 resize_images).
+template <int PLANES>
+__global__ void upsample2_kernel(const __half* __restrict__ in, size_t pin, __half* __restrict__ out, size_t pout,
+                                 int N, int h, int w, int C) {
+    const int cv = C / 8;
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t total = static_cast<size_t>(N) * (2 * h) * (2 * w) * cv;
+    if (i >= total) return;
+    const int c8 = (i % cv) * 8;
+    size_t r = i / cv;
+    const int X = r % (2 * w); r /= (2 * w);
+    const int Y = r % (2 * h);
+    const int n = r / (2 * h);
+    const int y0 = Y >> 1, x0 = X >> 1;
+    const int y1 = (Y & 1) ? min(y0 + 1, h - 1) : y0;
+    const int x1 = (X & 1) ? min(x0 + 1, w - 1) : x0;
+    const __half* base = in + static_cast<size_t>(n) * h * w * C + c8;
+    float a[8], b[8], c[8], d[8], o[8];
+    load8<PLANES>(base + (static_cast<size_t>(y0) * w + x0) * C, pin, a);
+    load8<PLANES>(base + (static_cast<size_t>(y1) * w + x0) * C, pin, b);
+    load8<PLANES>(base + (static_cast<size_t>(y0) * w + x1) * C, pin, c);
+    load8<PLANES>(base + (static_cast<size_t>(y1) * w + x1) * C, pin, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float v0 = (Y & 1) ? 0.5f * (a[j] + b[j]) : a[j];
+        const float v1 = (Y & 1) ? 0.5f * (c[j] + d[j]) : c[j];
+        o[j] = (X & 1) ? 0.5f * (v0 + v1) : v0;
+    }
+    store8<PLANES>(out + ((static_cast<size_t>(n) * 2 * h + Y) * 2 * w + X) * C + c8, pout, o);
+}
+
+// ---------------------------------------------------------------- 2x2 max pool (ops.py:54)
+// Source may be a channel slice [coff, coff+C) of a wider (virtual-concat) buffer with cs channels.
+template <int PLANES>
+__global__ void maxpool2_kernel(const __half* __restrict__ in, size_t pin, int cs, int coff, __half* __restrict__ out,
+                                size_t pout, int N, int H, int W, int C) {
+    const int cv = C / 8;
+    const int h = H / 2, w = W / 2;
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t total = static_cast<size_t>(N) * h * w * cv;
+    if (i >= total) return;
+    const int c8 = (i % cv) * 8;
+    size_t r = i / cv;
+    const int x = r % w; r /= w;
+    const int y = r % h;
+    const int n = r / h;
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            float f[8];
+            load8<PLANES>(in + ((static_cast<size_t>(n) * H + 2 * y + dy) * W + 2 * x + dx) * cs + coff + c8, pin, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+        }
+    // the maximum is one of the inputs, so re-splitting reproduces its (hi, lo) pair exactly
+    store8<PLANES>(out + ((static_cast<size_t>(n) * h + y) * w + x) * C + c8, pout, m);
+}
+
+// ---------------------------------------------------------------- test / debug converters
+template <int PLANES>
+__global__ void act_from_f32_kernel(const float* __restrict__ src, int C, __half* __restrict__ dst, size_t plane,
+                                    int cs, size_t npix) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= npix * cs) return;
+    const int c = i % cs;
+    const size_t pix = i / cs;
+    const float v = c < C ? src[pix * C + c] : 0.f;
+    const SplitHalf s = split_f32(v);
+    dst[i] = s.hi;
+    if (PLANES == 2) dst[plane + i] = s.lo;
+}
+template <int PLANES>
+__global__ void act_to_f32_kernel(const __half* __restrict__ src, size_t plane, int cs, int coff, float* __restrict__ dst,
+                                  int C, size_t npix) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= npix * C) return;
+    const int c = i % C;
+    const size_t pix = i / C;
+    const size_t s = pix * cs + coff + c;
+    dst[i] = PLANES == 2 ? join_f16(src[s], src[plane + s]) : __half2float(src[s]);
+}
+
+// ---------------------------------------------------------------- tiled video path
+// Builds the network input of T tiles straight from the frame-sized device arrays (FISRnet.py:1008-1024,1035,1044):
+//   frames u8 [h,w,9] -> /255 (256-entry table = the reference's float64 division rounded to fp32), clip [0,1]
+//   flow  f32 [h,w,8] -> /96 /2, clip [-1,1]          warp f32 [h,w,12] (already /255) -> clip [0,1]
+// Tile t covers rows [ylo[t], ylo[t]+th) x cols [xlo[t], xlo[t]+tw) of the (cropped) frame.
+template <int PLANES>
+__global__ void tile_pack_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ flow,
+                                 const float* __restrict__ warp, int fw, TileList tiles, int th, int tw,
+                                 const float* __restrict__ lut255, __half* l3, size_t p3, __half* l2, size_t p2,
+                                 __half* l1, size_t p1) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t total = static_cast<size_t>(tiles.count) * th * tw * 32;
+    if (i >= total) return;
+    const int c = i & 31;
+    if (c >= 29) return;
+    const size_t pix = i >> 5;
+    const int x = pix % tw;
+    const int y = (pix / tw) % th;
+    const int t = pix / (static_cast<size_t>(tw) * th);
+    const size_t src = static_cast<size_t>(tiles.ylo[t] + y) * fw + tiles.xlo[t] + x;
+    float v;
+    if (c < 9) {
+        v = lut255[frames[src * 9 + c]];
+    } else if (c < 17) {
+        v = __fdiv_rn(__fdiv_rn(flow[src * 8 + (c - 9)], 96.f), 2.f);
+        v = fminf(fmaxf(v, -1.f), 1.f);
+    } else {
+        v = fminf(fmaxf(warp[src * 12 + (c - 17)], 0.f), 1.f);
+    }
+    const SplitHalf s = split_f32(v);
+    l3[pix * 64 + c] = s.hi;
+    if (PLANES == 2) l3[p3 + pix * 64 + c] = s.lo;
+    if (((x | y) & 1) == 0) {
+        const size_t q = (static_cast<size_t>(t) * (th / 2) + y / 2) * (tw / 2) + x / 2;
+        l2[q * 64 + c] = s.hi;
+        if (PLANES == 2) l2[p2 + q * 64 + c] = s.lo;
+    }
+    if (((x | y) & 3) == 0) {
+        const size_t q = (static_cast<size_t>(t) * (th / 4) + y / 4) * (tw / 4) + x / 4;
+        l1[q * 64 + c] = s.hi;
+        if (PLANES == 2) l1[p1 + q * 64 + c] = s.lo;
+    }
+}
+
+// pred_l3 of T tiles [T,2th,2tw,9] fp32 -> trim the halo (utils.py:138-159), clip [0,1], uint8(x*255) with the
+// reference's float64 truncation (FISRnet.py:1060-1064), paste into the [OH,OW,9] canvas (FISRnet.py:1056-1057).
+__global__ void tile_unpack_u8_kernel(const float* __restrict__ pred, TileList tiles, int th2, int tw2,
+                                      uint8_t* __restrict__ canvas, int OW, int core_h, int core_w) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t total = static_cast<size_t>(tiles.count) * core_h * core_w * 9;
+    if (i >= total) return;
+    const int c = i % 9;
+    size_t r = i / 9;
+    const int x = r % core_w; r /= core_w;
+    const int y = r % core_h;
+    const int t = r / core_h;
+    const float v = pred[((static_cast<size_t>(t) * th2 + tiles.trim_y[t] + y) * tw2 + tiles.trim_x[t] + x) * 9 + c];
+    const double cl = fmin(fmax(static_cast<double>(v), 0.0), 1.0);
+    canvas[(static_cast<size_t>(tiles.out_y[t] + y) * OW + tiles.out_x[t] + x) * 9 + c] =
+        static_cast<uint8_t>(static_cast<int>(cl * 255.0));
+}
+// same, but keeps fp32 (for parity tests against the oracle's float canvas)
+__global__ void tile_unpack_f32_kernel(const float* __restrict__ pred, TileList tiles, int th2, int tw2,
+                                       float* __restrict__ canvas, int OW, int core_h, int core_w) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t total = static_cast<size_t>(tiles.count) * core_h * core_w * 9;
+    if (i >= total) return;
+    const int c = i % 9;
+    size_t r = i / 9;
+    const int x = r % core_w; r /= core_w;
+    const int y = r % core_h;
+    const int t = r / core_h;
+    canvas[(static_cast<size_t>(tiles.out_y[t] + y) * OW + tiles.out_x[t] + x) * 9 + c] =
+        pred[((static_cast<size_t>(t) * th2 + tiles.trim_y[t] + y) * tw2 + tiles.trim_x[t] + x) * 9 + c];
+}
+
+// ---------------------------------------------------------------- flow warp
+// One frame pair direction of FISR_for_video_Warp_Img (FISR_for_video_warp_img_with_flo.py:112-128):
+//   yuv u8 [h,w,3] --YUV2RGB (:35-45)--> rgb; dst(y,x) = bilinear(rgb, (x,y) + 0.5*flow(y,x)) with OpenCV's
+//   remap arithmetic (cv2.remap INTER_LINEAR, BORDER_REPLICATE, :66): coordinates rounded to 1/32 px
+//   (cvRound = round-half-even of x*32), 4 taps weighted by the fp32 table (1-fy)(1-fx).., index-clamped border;
+//   --RGB2YUV (:48-57)--> float32 0..255 (not rounded).  `scale` multiplies the result (1/255 yields the
+//   network's warp input directly, utils.py:51).
+__device__ __forceinline__ void yuv2rgb(const uint8_t* p, double (&rgb)[3]) {
+    // T = 255 * Tinv, offset = T @ [16,128,128]  (float64 in the reference; evaluated in fp64 here too)
+    const double y = p[0], u = p[1], v = p[2];
+    const double t00 = 255 * 0.00456621, t02 = 255 * 0.00625893, t11 = 255 * -0.00153632, t12 = 255 * -0.00318811,
+                 t21 = 255 * 0.00791071;
+    const double o0 = t00 * 16 + t02 * 128, o1 = t00 * 16 + t11 * 128 + t12 * 128, o2 = t00 * 16 + t21 * 128;
+    const double r = t00 * y + 0.0 * u + t02 * v - o0;
+    const double g = t00 * y + t11 * u + t12 * v - o1;
+    const double b = t00 * y + t21 * u + 0.0 * v - o2;
+    rgb[0] = fmin(fmax(r, 0.0), 255.0);
+    rgb[1] = fmin(fmax(g, 0.0), 255.0);
+    rgb[2] = fmin(fmax(b, 0.0), 255.0);
+}
+
+__global__ void warp_yuv_kernel(const uint8_t* __restrict__ yuv, const float* __restrict__ flow, float flow_scale,
+                                float* __restrict__ out, int h, int w, float out_scale) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const size_t p = static_cast<size_t>(y) * w + x;
+    const float2 f = *reinterpret_cast<const float2*>(flow + p * 2);
+    const float mx = f.x * flow_scale + static_cast<float>(x);      // ..warp_img_with_flo.py:64-65,123
+    const float my = f.y * flow_scale + static_cast<float>(y);
+    const int ix = __float2int_rn(mx * 32.f), iy = __float2int_rn(my * 32.f);
+    const int sx = ix >> 5, sy = iy >> 5;
+    const float fx = static_cast<float>(ix & 31) * (1.f / 32.f), fy = static_cast<float>(iy & 31) * (1.f / 32.f);
+    const int x0 = min(max(sx, 0), w - 1), x1 = min(max(sx + 1, 0), w - 1);
+    const int y0 = min(max(sy, 0), h - 1), y1 = min(max(sy + 1, 0), h - 1);
+    double a[3], b[3], c[3], d[3];
+    yuv2rgb(yuv + (static_cast<size_t>(y0) * w + x0) * 3, a);
+    yuv2rgb(yuv + (static_cast<size_t>(y0) * w + x1) * 3, b);
+    yuv2rgb(yuv + (static_cast<size_t>(y1) * w + x0) * 3, c);
+    yuv2rgb(yuv + (static_cast<size_t>(y1) * w + x1) * 3, d);
+    const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+    double rgb[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        rgb[k] = a[k] * w00 + b[k] * w01 + c[k] * w10 + d[k] * w11;
+    // RGB2YUV, T / 255 and offsets [16,128,128]
+    const double T[3][3] = {{65.481 / 255, 128.553 / 255, 24.966 / 255},
+                            {-37.797 / 255, -74.203 / 255, 112.0 / 255},
+                            {112.0 / 255, -93.786 / 255, -18.214 / 255}};
+    const double off[3] = {16, 128, 128};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double v = T[k][0] * rgb[0] + T[k][1] * rgb[1] + T[k][2] * rgb[2] + off[k];
+        out[p * 3 + k] = static_cast<float>(fmin(fmax(v, 0.0), 255.0)) * out_scale;
+    }
+}
+
+inline unsigned blocks_for(size_t total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
+
+}  // namespace
+
+// ================================================================ host launchers
+void launch_prep_weights(const float* w, __half* out, int cin, int cout, int KB, int cout_pad, int planes,
+                         cudaStream_t st) {
+    const size_t total = static_cast<size_t>(KB) * 9 * cout_pad * 64;
+    prep_weights_kernel<<<blocks_for(total, 256), 256, 0, st>>>(w, out, cin, cout, KB, cout_pad, planes);
+}
+
+void launch_pack_input(const float* img, int N, int H, int W, int cin, ActBuf l3, ActBuf l2, ActBuf l1, int planes,
+                       cudaStream_t st) {
+    const size_t total = static_cast<size_t>(N) * H * W * 32;
+    if (planes == 2)
+        pack_input_kernel<2><<<blocks_for(total, 256), 256, 0, st>>>(img, N, H, W, cin, l3.p, l3.plane, l2.p, l2.plane,
+                                                                     l1.p, l1.plane);
+    else
+        pack_input_kernel<1><<<blocks_for(total, 256), 256, 0, st>>>(img, N, H, W, cin, l3.p, l3.plane, l2.p, l2.plane,
+                                                                     l1.p, l1.plane);
+}
+
+void launch_upsample2(ActBuf in, ActBuf out, int N, int h, int w, int C, int planes, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(N) * 4 * h * w * (C / 8);
+    if (planes == 2)
+        upsample2_kernel<2><<<blocks_for(total, 256), 256, 0, st>>>(in.p, in.plane, out.p, out.plane, N, h, w, C);
+    else
+        upsample2_kernel<1><<<blocks_for(total, 256), 256, 0, st>>>(in.p, in.plane, out.p, out.plane, N, h, w, C);
+}
+
+void launch_maxpool2(ActBuf in, int cs, int coff, ActBuf out, int N, int H, int W, int C, int planes, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
+    if (planes == 2)
+        maxpool2_kernel<2><<<blocks_for(total, 256), 256, 0, st>>>(in.p, in.plane, cs, coff, out.p, out.plane, N, H, W, C);
+    else
+        maxpool2_kernel<1><<<blocks_for(total, 256), 256, 0, st>>>(in.p, in.plane, cs, coff, out.p, out.plane, N, H, W, C);
+}
+
+void launch_act_from_f32(const float* src, int C, ActBuf dst, int cs, size_t npix, int planes, cudaStream_t st) {
+    if (planes == 2)
+        act_from_f32_kernel<2><<<blocks_for(npix * cs, 256), 256, 0, st>>>(src, C, dst.p, dst.plane, cs, npix);
+    else
+        act_from_f32_kernel<1><<<blocks_for(npix * cs, 256), 256, 0, st>>>(src, C, dst.p, dst.plane, cs, npix);
+}
+
+void launch_act_to_f32(ActBuf src, int cs, int coff, float* dst, int C, size_t npix, int planes, cudaStream_t st) {
+    if (planes == 2)
+        act_to_f32_kernel<2><<<blocks_for(npix * C, 256), 256, 0, st>>>(src.p, src.plane, cs, coff, dst, C, npix);
+    else
+        act_to_f32_kernel<1><<<blocks_for(npix * C, 256), 256, 0, st>>>(src.p, src.plane, cs, coff, dst, C, npix);
+}
+
+void launch_tile_pack(const uint8_t* frames, const float* flow, const float* warp, int fw, const TileList& tiles, int th,
+                      int tw, const float* lut255, ActBuf l3, ActBuf l2, ActBuf l1, int planes, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(tiles.count) * th * tw * 32;
+    if (planes == 2)
+        tile_pack_kernel<2><<<blocks_for(total, 256), 256, 0, st>>>(frames, flow, warp, fw, tiles, th, tw, lut255, l3.p,
+                                                                    l3.plane, l2.p, l2.plane, l1.p, l1.plane);
+    else
+        tile_pack_kernel<1><<<blocks_for(total, 256), 256, 0, st>>>(frames, flow, warp, fw, tiles, th, tw, lut255, l3.p,
+                                                                    l3.plane, l2.p, l2.plane, l1.p, l1.plane);
+}
+
+void launch_tile_unpack_u8(const float* pred, const TileList& tiles, int th2, int tw2, uint8_t* canvas, int OW,
+                           int core_h, int core_w, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(tiles.count) * core_h * core_w * 9;
+    tile_unpack_u8_kernel<<<blocks_for(total, 256), 256, 0, st>>>(pred, tiles, th2, tw2, canvas, OW, core_h, core_w);
+}
+void launch_tile_unpack_f32(const float* pred, const TileList& tiles, int th2, int tw2, float* canvas, int OW,
+                            int core_h, int core_w, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(tiles.count) * core_h * core_w * 9;
+    tile_unpack_f32_kernel<<<blocks_for(total, 256), 256, 0, st>>>(pred, tiles, th2, tw2, canvas, OW, core_h, core_w);
+}
+
+void launch_warp_yuv(const uint8_t* yuv, const float* flow, float flow_scale, float* out, int h, int w, float out_scale,
+                     cudaStream_t st) {
+    dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+    warp_yuv_kernel<<<grid, block, 0, st>>>(yuv, flow, flow_scale, out, h, w, out_scale);
+}
+
+}  // namespace fisr

@@ -1,0 +1,24 @@
+// Host-visible launch record of the tcgen05 3x3 conv kernel (conv_umma.cu).
+#pragma once
+#include "common.cuh"
+
+namespace fisr {
+
+// opt-in dynamic shared memory budget per CTA (227 KB minus the kernel's static barriers)
+constexpr int kConvMaxSmem = 231424;
+
+struct ConvLaunch {
+    CUtensorMap tmA_hi, tmA_lo, tmB;
+    ConvArgs args;
+    int NT, chunks, planes;
+    int smem_bytes;
+    double efficiency;      // useful fraction of the MMA rows issued (tile quantisation + halo columns)
+};
+
+// Chooses NT / chunk count / patch pitch for an H x W x n_img conv and fills the geometry fields of L->args.
+bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int num_sms, ConvLaunch* L);
+
+cudaError_t conv3x3_init();
+cudaError_t launch_conv3x3(const ConvLaunch& L, int num_sms, cudaStream_t stream);
+
+}  // namespace fisr

@@ -1,0 +1,901 @@
+// C ABI (include/fisr_b200.h): context, parameter store, forward plan (buffers + TMA descriptors + launch list,
+// replayed as a CUDA graph) for FISRnet.model (FISRnet.py:73-173), the tiled window driver
+// (FISRnet.py:994-1065) and the flow warp.  No torch types; PyTorch only hands in raw device pointers.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/fisr_b200.h"
+#include "aux_kernels.h"
+#include "common.cuh"
+#include "conv_umma.h"
+
+using namespace fisr;
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+constexpr int CH = 64;       // FISRnet.py:74
+constexpr int IN_CH = 29;    // FISRnet.py:287
+
+struct ParamDef {
+    std::string name;        // conv name without /w, /b
+    int cin, cout;
+};
+
+// Creation order of the variables in FISRnet.model (FISRnet.py:78-171; block scopes ops.py:40,49,60,68).
+std::vector<ParamDef> build_inventory() {
+    std::vector<ParamDef> v;
+    auto res_block = [&](const std::string& p, int c) {
+        v.push_back({p + "/conv/0", c, c});
+        v.push_back({p + "/conv/1", c, c});
+    };
+    auto enc = [&](const std::string& p, int c1, int c) {
+        v.push_back({p + "/conv/0", c1, c});
+        res_block(p + "/res_block/0", c);
+        res_block(p + "/res_block/1", c);
+    };
+    auto dec = [&](const std::string& p, int c1, int c) {
+        v.push_back({p + "/resize", c1, c});
+        v.push_back({p + "/conv/0", 2 * c, c});
+        res_block(p + "/res_block/0", c);
+        res_block(p + "/res_block/1", c);
+    };
+    auto head = [&](const std::string& p, int cout) {
+        v.push_back({p + "/conv/0", CH, CH});
+        res_block(p + "/res_block/0", CH);
+        v.push_back({p + "/conv/1", CH, CH * 4});
+        v.push_back({p + "/conv/2", CH, cout});
+    };
+    for (int lvl = 1; lvl <= 3; ++lvl) {
+        const std::string p = "FISRnet/level_" + std::to_string(lvl);
+        enc(p + "/enc/level_0", lvl == 1 ? IN_CH : IN_CH + 9, CH);
+        enc(p + "/enc/level_1", CH, CH * 2);
+        enc(p + "/enc/level_2", CH * 2, CH * 4);
+        v.push_back({p + "/bottleneck/conv/0", CH * 4, CH * 8});
+        res_block(p + "/bottleneck/res_block/0", CH * 8);
+        dec(p + "/dec/level_2", CH * 8, CH * 4);
+        dec(p + "/dec/level_1", CH * 4, CH * 2);
+        dec(p + "/dec/level_0", CH * 2, CH);
+        head(p + "/FI-SR", 6);
+        head(p + "/SR", 3);
+    }
+    return v;
+}
+
+const std::vector<ParamDef>& inventory() {
+    static const std::vector<ParamDef> inv = build_inventory();
+    return inv;
+}
+const std::vector<std::string>& param_names() {
+    static std::vector<std::string> names;
+    if (names.empty())
+        for (const auto& d : inventory()) {
+            names.push_back(d.name + "/w");
+            names.push_back(d.name + "/b");
+        }
+    return names;
+}
+
+struct ConvParam {
+    int cin = 0, cout = 0, KB = 0, cout_pad = 0;
+    float* d_w = nullptr;        // fp32 HWIO master copy
+    float* d_b = nullptr;        // fp32 [cout_pad], zero padded
+    __half* d_wp = nullptr;      // packed (hi, lo) operand planes
+    bool packed = false;
+};
+
+struct DebugTensor {
+    const float* raw = nullptr;
+    int N = 0, H = 0, W = 0, C = 0;
+};
+
+enum OpKind { OP_CONV, OP_UPSAMPLE, OP_POOL };
+struct Op {
+    OpKind kind;
+    ConvLaunch conv;
+    ActBuf in, out;
+    int N, H, W, C, cs, coff;
+};
+
+struct Plan {
+    int N = 0, H = 0, W = 0, planes = 0;
+    std::vector<void*> allocs;
+    size_t bytes = 0;
+    std::vector<Op> ops;
+    ActBuf in_lvl[3];
+    float* pred[3] = {nullptr, nullptr, nullptr};
+    std::map<std::string, DebugTensor> debug;
+    cudaGraphExec_t graph = nullptr;
+    double flops = 0, eff_weighted = 0;
+    ~Plan() {
+        if (graph) cudaGraphExecDestroy(graph);
+        for (void* p : allocs) cudaFree(p);
+    }
+};
+
+}  // namespace
+
+struct fisr_ctx {
+    int device = 0;
+    int num_sms = 148;
+    int planes = 2;
+    bool use_graph = true;
+    cudaStream_t stream = nullptr;
+    EncodeTiledFn encode = nullptr;
+    std::vector<ConvParam> params;
+    std::map<std::string, int> conv_index;
+    std::map<std::string, std::unique_ptr<Plan>> plans;
+    int* d_err = nullptr;
+    float* d_lut255 = nullptr;
+    long long launches = 0;
+    std::string err;
+    // staging for the host entry points
+    void* stage[8] = {nullptr};
+    size_t stage_bytes[8] = {0};
+    Plan* last_plan = nullptr;
+};
+
+namespace {
+
+std::string g_create_error;
+
+int fail(fisr_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                               \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return fail(ctx, FISR_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+struct Guard {   // makes ctx->device current for the duration of a call
+    int prev = -1;
+    explicit Guard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int ensure_stage(fisr_ctx* ctx, int slot, size_t bytes) {
+    if (ctx->stage_bytes[slot] >= bytes) return FISR_OK;
+    if (ctx->stage[slot]) cudaFree(ctx->stage[slot]);
+    ctx->stage[slot] = nullptr;
+    ctx->stage_bytes[slot] = 0;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->stage[slot], bytes));
+    ctx->stage_bytes[slot] = bytes;
+    return FISR_OK;
+}
+
+int check_kernel_error(fisr_ctx* ctx) {
+    int h = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&h, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h != 0) {
+        cudaMemset(ctx->d_err, 0, sizeof(int));
+        return fail(ctx, FISR_E_KERNEL, "conv kernel pipeline time-out, barrier code %d", h);
+    }
+    return FISR_OK;
+}
+
+int ensure_packed(fisr_ctx* ctx, ConvParam& p, cudaStream_t st) {
+    if (p.packed) return FISR_OK;
+    launch_prep_weights(p.d_w, p.d_wp, p.cin, p.cout, p.KB, p.cout_pad, ctx->planes, st);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    p.packed = true;
+    return FISR_OK;
+}
+
+// ---------------------------------------------------------------- plan builder
+struct Builder {
+    fisr_ctx* ctx;
+    Plan* plan;
+    int rc = FISR_OK;
+
+    void* alloc(size_t bytes, bool zero) {
+        void* p = nullptr;
+        if (rc != FISR_OK) return nullptr;
+        bytes = (bytes + 1023) / 1024 * 1024;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            rc = fail(ctx, FISR_E_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            return nullptr;
+        }
+        if (zero) cudaMemsetAsync(p, 0, bytes, ctx->stream);
+        plan->allocs.push_back(p);
+        plan->bytes += bytes;
+        return p;
+    }
+    ActBuf act(int N, int H, int W, int C, bool zero = false) {
+        ActBuf b;
+        const size_t elems = static_cast<size_t>(N) * H * W * C;
+        b.plane = (elems + 511) / 512 * 512;
+        b.p = static_cast<__half*>(alloc(b.plane * plan->planes * sizeof(__half), zero));
+        return b;
+    }
+    float* f32(int N, int H, int W, int C) { return static_cast<float*>(alloc(static_cast<size_t>(N) * H * W * C * 4, false)); }
+
+    bool encode_act(CUtensorMap* tm, const __half* base, int cs, int N, int H, int W, int P, int rows) {
+        cuuint64_t dims[4] = {(cuuint64_t)cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)cs * 2, (cuuint64_t)W * cs * 2, (cuuint64_t)H * W * cs * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)P, (cuuint32_t)rows, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = ctx->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), dims, strides, box, es,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            rc = fail(ctx, FISR_E_CUDA, "cuTensorMapEncodeTiled(act %dx%dx%dx%d box %dx%d) failed: %d", N, H, W, cs, P, rows, (int)r);
+            return false;
+        }
+        return true;
+    }
+    bool encode_w(CUtensorMap* tm, const __half* base, size_t rows, int NT) {
+        cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+        cuuint64_t strides[1] = {128};
+        cuuint32_t box[2] = {64, (cuuint32_t)NT};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = ctx->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, es,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            rc = fail(ctx, FISR_E_CUDA, "cuTensorMapEncodeTiled(weights rows %zu box %d) failed: %d", rows, NT, (int)r);
+            return false;
+        }
+        return true;
+    }
+
+    struct ConvOut {
+        const float* res = nullptr;
+        int res_cs = 0;
+        float* raw = nullptr;
+        int raw_cs = 0, raw_off0 = 0, raw_off1 = 0, raw_split = 0;
+        ActBuf act;
+        int act_cs = 0, act_off0 = 0, act_off1 = 0, act_split = 0;
+        bool relu = true, d2s = false, scalar = false;
+    };
+
+    // One conv launch: input = channels [cin_off, cin_off + KB*64) of `in` (cs channels, N x H x W).
+    void conv(const ConvParam& p, ActBuf in, int in_cs, int cin_off, int N, int H, int W, const ConvOut& o,
+              const std::string& name) {
+        if (rc != FISR_OK) return;
+        Op op{};
+        op.kind = OP_CONV;
+        ConvLaunch& L = op.conv;
+        if (!plan_conv_geometry(H, W, N, p.cout_pad, plan->planes, ctx->num_sms, &L)) {
+            rc = fail(ctx, FISR_E_INVALID, "no tile geometry for conv %s (%dx%d)", name.c_str(), H, W);
+            return;
+        }
+        ConvArgs& a = L.args;
+        a.bias = p.d_b;
+        a.res = o.res; a.res_cs = o.res_cs;
+        a.out_raw = o.raw; a.raw_cs = o.raw_cs; a.raw_off0 = o.raw_off0; a.raw_off1 = o.raw_off1; a.raw_split = o.raw_split;
+        a.out_act = o.act.p; a.act_plane = o.act.plane;
+        a.act_cs = o.act_cs; a.act_off0 = o.act_off0; a.act_off1 = o.act_off1; a.act_split = o.act_split;
+        a.act_relu = o.relu; a.act_d2s = o.d2s; a.scalar_out = o.scalar;
+        a.err = ctx->d_err;
+        a.N = N; a.H = H; a.W = W;
+        a.cin_off = cin_off; a.KB = p.KB; a.cout = p.cout;
+        if (!encode_act(&L.tmA_hi, in.p, in_cs, N, H, W, a.P, a.TH + 2)) return;
+        if (!encode_act(&L.tmA_lo, in.p + (plan->planes == 2 ? in.plane : 0), in_cs, N, H, W, a.P, a.TH + 2)) return;
+        if (!encode_w(&L.tmB, p.d_wp, static_cast<size_t>(plan->planes) * p.KB * 9 * p.cout_pad, L.NT)) return;
+        const double fl = 2.0 * 9 * p.cin * p.cout * static_cast<double>(H) * W * N;
+        plan->flops += fl;
+        plan->eff_weighted += fl * L.efficiency;
+        if (o.raw && !o.scalar) plan->debug[name] = DebugTensor{o.raw, N, H, W, o.raw_cs};
+        plan->ops.push_back(op);
+    }
+    void upsample(ActBuf in, ActBuf out, int N, int h, int w, int C) {
+        Op op{};
+        op.kind = OP_UPSAMPLE; op.in = in; op.out = out; op.N = N; op.H = h; op.W = w; op.C = C;
+        plan->ops.push_back(op);
+    }
+    void pool(ActBuf in, int cs, int coff, ActBuf out, int N, int H, int W, int C) {
+        Op op{};
+        op.kind = OP_POOL; op.in = in; op.out = out; op.N = N; op.H = H; op.W = W; op.C = C; op.cs = cs; op.coff = coff;
+        plan->ops.push_back(op);
+    }
+
+    const ConvParam& P(const std::string& name) {
+        auto it = ctx->conv_index.find(name);
+        if (it == ctx->conv_index.end()) {
+            rc = fail(ctx, FISR_E_INVALID, "unknown conv %s", name.c_str());
+            static ConvParam dummy;
+            return dummy;
+        }
+        return ctx->params[it->second];
+    }
+
+    // res_block (ops.py:39-44) x2 + trailing ReLU, given n0 (raw fp32) and relu(n0) (act): used by enc / dec levels.
+    // Final activation relu(n2) goes to `dst` (channel offset dst_off of a dst_cs-channel buffer).
+    void two_res_blocks(const std::string& p, ActBuf a0, const float* n0, int c, int N, int H, int W, ActBuf dst,
+                        int dst_cs, int dst_off) {
+        ActBuf a1 = act(N, H, W, c), a2 = act(N, H, W, c), a3 = act(N, H, W, c);
+        float* n1 = f32(N, H, W, c);
+        ConvOut o;
+        o = ConvOut{}; o.act = a1; o.act_cs = c;
+        conv(P(p + "/res_block/0/conv/0"), a0, c, 0, N, H, W, o, p + "/res_block/0/conv/0");
+        o = ConvOut{}; o.res = n0; o.res_cs = c; o.raw = n1; o.raw_cs = c; o.act = a2; o.act_cs = c;
+        conv(P(p + "/res_block/0/conv/1"), a1, c, 0, N, H, W, o, p + "/res_block/0/conv/1");
+        o = ConvOut{}; o.act = a3; o.act_cs = c;
+        conv(P(p + "/res_block/1/conv/0"), a2, c, 0, N, H, W, o, p + "/res_block/1/conv/0");
+        o = ConvOut{}; o.res = n1; o.res_cs = c; o.act = dst; o.act_cs = dst_cs; o.act_off1 = dst_off;
+        conv(P(p + "/res_block/1/conv/1"), a3, c, 0, N, H, W, o, p + "/res_block/1/conv/1");
+    }
+
+    // Enc_level_res (ops.py:48-55): skip = relu(...) lands in channels [c, 2c) of the decoder's concat buffer
+    // (virtual tf.concat of ops.py:71); the 2x2 max-pooled copy feeds the next level down.
+    ActBuf enc_level(const std::string& p, ActBuf x, int x_cs, int c, int N, int H, int W, ActBuf cat) {
+        ActBuf a0 = act(N, H, W, c);
+        float* n0 = f32(N, H, W, c);
+        ConvOut o; o.raw = n0; o.raw_cs = c; o.act = a0; o.act_cs = c;
+        conv(P(p + "/conv/0"), x, x_cs, 0, N, H, W, o, p + "/conv/0");
+        two_res_blocks(p, a0, n0, c, N, H, W, cat, 2 * c, c);
+        ActBuf pooled = act(N, H / 2, W / 2, c);
+        pool(cat, 2 * c, c, pooled, N, H, W, c);
+        return pooled;
+    }
+
+    // Dec_level_res (ops.py:67-76): x is [N, H/2, W/2, c1]; cat already holds the skip in channels [c, 2c).
+    ActBuf dec_level(const std::string& p, ActBuf x, int c1, int c, int N, int H, int W, ActBuf cat) {
+        ActBuf up = act(N, H, W, c1);
+        upsample(x, up, N, H / 2, W / 2, c1);
+        ConvOut o; o.act = cat; o.act_cs = 2 * c; o.act_off1 = 0;
+        conv(P(p + "/resize"), up, c1, 0, N, H, W, o, p + "/resize");
+        ActBuf a0 = act(N, H, W, c);
+        float* n0 = f32(N, H, W, c);
+        o = ConvOut{}; o.raw = n0; o.raw_cs = c; o.act = a0; o.act_cs = c;
+        conv(P(p + "/conv/0"), cat, 2 * c, 0, N, H, W, o, p + "/conv/0");
+        ActBuf out = act(N, H, W, c);
+        two_res_blocks(p, a0, n0, c, N, H, W, out, c, 0);
+        return out;
+    }
+
+    // FI-SR / SR head (FISRnet.py:95-106).  pred is [N,2H,2W,9]; next (may be null) is the next level's input buffer.
+    void head(const std::string& p, ActBuf x, int N, int H, int W, int cout, float* pred, ActBuf next) {
+        const int c = CH;
+        ActBuf a0 = act(N, H, W, c), a1 = act(N, H, W, c), a2 = act(N, H, W, c);
+        float* m0 = f32(N, H, W, c);
+        ConvOut o; o.raw = m0; o.raw_cs = c; o.act = a0; o.act_cs = c;
+        conv(P(p + "/conv/0"), x, c, 0, N, H, W, o, p + "/conv/0");
+        o = ConvOut{}; o.act = a1; o.act_cs = c;
+        conv(P(p + "/res_block/0/conv/0"), a0, c, 0, N, H, W, o, p + "/res_block/0/conv/0");
+        o = ConvOut{}; o.res = m0; o.res_cs = c; o.act = a2; o.act_cs = c;
+        conv(P(p + "/res_block/0/conv/1"), a1, c, 0, N, H, W, o, p + "/res_block/0/conv/1");
+        ActBuf shuf = act(N, 2 * H, 2 * W, c);
+        o = ConvOut{}; o.act = shuf; o.act_cs = c; o.d2s = true;       // relu + depth_to_space (FISRnet.py:99,105)
+        conv(P(p + "/conv/1"), a2, c, 0, N, H, W, o, p + "/conv/1");
+        // conv/2: FI-SR's 6 channels go to pred[..., 0:3] and [6:9], SR's 3 to [3:6] (FISRnet.py:107-108);
+        // the same values feed channels 29.. of the next level's input (FISRnet.py:113,144), without ReLU.
+        o = ConvOut{}; o.scalar = true; o.relu = false;
+        o.raw = pred; o.raw_cs = 9;
+        o.act = next; o.act_cs = 64;
+        if (cout == 6) { o.raw_split = 3; o.raw_off0 = 0; o.raw_off1 = 3; o.act_split = 3; o.act_off0 = IN_CH; o.act_off1 = IN_CH + 3; }
+        else           { o.raw_split = 0; o.raw_off1 = 3; o.act_split = 0; o.act_off1 = IN_CH + 3; }
+        conv(P(p + "/conv/2"), shuf, c, 0, N, 2 * H, 2 * W, o, p + "/conv/2");
+    }
+
+    void level(int lvl, ActBuf in, int N, int H, int W, float* pred, ActBuf next) {
+        const std::string p = "FISRnet/level_" + std::to_string(lvl);
+        ActBuf cat0 = act(N, H, W, 2 * CH), cat1 = act(N, H / 2, W / 2, 4 * CH), cat2 = act(N, H / 4, W / 4, 8 * CH);
+        ActBuf n = enc_level(p + "/enc/level_0", in, 64, CH, N, H, W, cat0);
+        n = enc_level(p + "/enc/level_1", n, CH, 2 * CH, N, H / 2, W / 2, cat1);
+        n = enc_level(p + "/enc/level_2", n, 2 * CH, 4 * CH, N, H / 4, W / 4, cat2);
+        {   // Bottleneck_res (ops.py:59-63)
+            const std::string b = p + "/bottleneck";
+            const int c = 8 * CH, h = H / 8, w = W / 8;
+            ActBuf a0 = act(N, h, w, c), a1 = act(N, h, w, c), out = act(N, h, w, c);
+            float* n0 = f32(N, h, w, c);
+            ConvOut o; o.raw = n0; o.raw_cs = c; o.act = a0; o.act_cs = c;
+            conv(P(b + "/conv/0"), n, 4 * CH, 0, N, h, w, o, b + "/conv/0");
+            o = ConvOut{}; o.act = a1; o.act_cs = c;
+            conv(P(b + "/res_block/0/conv/0"), a0, c, 0, N, h, w, o, b + "/res_block/0/conv/0");
+            o = ConvOut{}; o.res = n0; o.res_cs = c; o.act = out; o.act_cs = c;
+            conv(P(b + "/res_block/0/conv/1"), a1, c, 0, N, h, w, o, b + "/res_block/0/conv/1");
+            n = out;
+        }
+        n = dec_level(p + "/dec/level_2", n, 8 * CH, 4 * CH, N, H / 4, W / 4, cat2);
+        n = dec_level(p + "/dec/level_1", n, 4 * CH, 2 * CH, N, H / 2, W / 2, cat1);
+        n = dec_level(p + "/dec/level_0", n, 2 * CH, CH, N, H, W, cat0);
+        head(p + "/FI-SR", n, N, H, W, 6, pred, next);
+        head(p + "/SR", n, N, H, W, 3, pred, next);
+    }
+};
+
+int run_ops(fisr_ctx* ctx, Plan* plan, cudaStream_t st) {
+    for (const Op& op : plan->ops) {
+        switch (op.kind) {
+            case OP_CONV: {
+                cudaError_t e = launch_conv3x3(op.conv, ctx->num_sms, st);
+                if (e != cudaSuccess) return fail(ctx, FISR_E_CUDA, "conv launch failed: %s", cudaGetErrorString(e));
+                break;
+            }
+            case OP_UPSAMPLE: launch_upsample2(op.in, op.out, op.N, op.H, op.W, op.C, plan->planes, st); break;
+            case OP_POOL: launch_maxpool2(op.in, op.cs, op.coff, op.out, op.N, op.H, op.W, op.C, plan->planes, st); break;
+        }
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FISR_OK;
+}
+
+int get_plan(fisr_ctx* ctx, int N, int H, int W, Plan** out) {
+    if (N < 1 || H < 32 || W < 32 || H % 32 || W % 32)
+        return fail(ctx, FISR_E_INVALID, "FISRnet.model needs N >= 1 and H, W multiples of 32 (got %d x %d x %d)", N, H, W);
+    char key[64];
+    snprintf(key, sizeof key, "%d_%d_%d_%d", N, H, W, ctx->planes);
+    auto it = ctx->plans.find(key);
+    if (it != ctx->plans.end()) { *out = it->second.get(); return FISR_OK; }
+
+    for (auto& p : ctx->params) {
+        int rc = ensure_packed(ctx, p, ctx->stream);
+        if (rc != FISR_OK) return rc;
+    }
+    std::unique_ptr<Plan> plan(new Plan());
+    plan->N = N; plan->H = H; plan->W = W; plan->planes = ctx->planes;
+    Builder b{ctx, plan.get()};
+    // level inputs: 64-channel buffers, channels >= 29 (38) stay zero (zero weights there, but 0 * NaN != 0)
+    plan->in_lvl[0] = b.act(N, H / 4, W / 4, 64, true);
+    plan->in_lvl[1] = b.act(N, H / 2, W / 2, 64, true);
+    plan->in_lvl[2] = b.act(N, H, W, 64, true);
+    plan->pred[0] = b.f32(N, H / 2, W / 2, 9);
+    plan->pred[1] = b.f32(N, H, W, 9);
+    plan->pred[2] = b.f32(N, 2 * H, 2 * W, 9);
+    b.level(1, plan->in_lvl[0], N, H / 4, W / 4, plan->pred[0], plan->in_lvl[1]);
+    b.level(2, plan->in_lvl[1], N, H / 2, W / 2, plan->pred[1], plan->in_lvl[2]);
+    b.level(3, plan->in_lvl[2], N, H, W, plan->pred[2], ActBuf{});
+    if (b.rc != FISR_OK) return b.rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+
+    if (ctx->use_graph) {
+        cudaGraph_t g = nullptr;
+        CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = run_ops(ctx, plan.get(), ctx->stream);
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+        if (rc != FISR_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail(ctx, FISR_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&plan->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(ctx, FISR_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    }
+    *out = plan.get();
+    ctx->plans[key] = std::move(plan);
+    return FISR_OK;
+}
+
+// Runs the conv stack of `plan` on stream st (inputs already packed into plan->in_lvl).
+int run_plan(fisr_ctx* ctx, Plan* plan, cudaStream_t st) {
+    ctx->last_plan = plan;
+    ctx->launches += static_cast<long long>(plan->ops.size());
+    if (plan->graph) {
+        // an instantiated graph may be launched into any stream, not only the one it was captured on
+        CUDA_TRY(ctx, cudaGraphLaunch(plan->graph, st));
+        return FISR_OK;
+    }
+    return run_ops(ctx, plan, st);
+}
+
+// Host restatement of utils.get_HW_boundary / trim_patch_boundary (utils.py:118-159) for the whole tile grid.
+struct TileGeom {
+    int h, w, sH, sW;
+    struct T { int ylo, yhi, xlo, xhi, trim_y, trim_x; };
+    std::vector<T> tiles;
+};
+TileGeom tile_geometry(int H, int W, int pH, int pW) {
+    const int pb = 32;
+    TileGeom g;
+    g.h = H - H % (32 * pH);                       // FISRnet.py:1006-1007
+    g.w = W - W % (32 * pW);
+    g.sH = g.h / pH;
+    g.sW = g.w / pW;
+    for (int p = 0; p < pH * pW; ++p) {
+        const int iy = p / pW, ix = p % pW;         // FISRnet.py:1029-1030
+        TileGeom::T t;
+        t.ylo = std::max(iy * g.sH - pb, 0);
+        t.yhi = std::min((iy + 1) * g.sH + pb, g.h);
+        t.xlo = std::max(ix * g.sW - pb, 0);
+        t.xhi = std::min((ix + 1) * g.sW + pb, g.w);
+        t.trim_y = (iy * g.sH < pb) ? 0 : pb * 2;   // utils.py:142-145 (sf = 2)
+        t.trim_x = (ix * g.sW < pb) ? 0 : pb * 2;   // utils.py:150-153
+        g.tiles.push_back(t);
+    }
+    return g;
+}
+
+int window_impl(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, const float* d_warp, int H, int W, int pH,
+                int pW, int tile_first, int tile_count, uint8_t* d_canvas_u8, float* d_canvas_f32, cudaStream_t st) {
+    if (pH < 1 || pW < 1 || H < 32 * pH || W < 32 * pW) return fail(ctx, FISR_E_INVALID, "bad tile grid %dx%d for %dx%d", pH, pW, H, W);
+    if (tile_first < 0 || tile_count < 0 || tile_first + tile_count > pH * pW)
+        return fail(ctx, FISR_E_INVALID, "tile range [%d,+%d) outside the %dx%d grid", tile_first, tile_count, pH, pW);
+    const TileGeom g = tile_geometry(H, W, pH, pW);
+    // group the requested tiles by input size so that each group is one batched forward
+    std::vector<bool> done(pH * pW, false);
+    for (int p = tile_first; p < tile_first + tile_count; ++p) {
+        if (done[p]) continue;
+        const int th = g.tiles[p].yhi - g.tiles[p].ylo, tw = g.tiles[p].xhi - g.tiles[p].xlo;
+        TileList tl{};
+        for (int q = p; q < tile_first + tile_count && tl.count < kMaxTiles; ++q) {
+            if (done[q]) continue;
+            if (g.tiles[q].yhi - g.tiles[q].ylo != th || g.tiles[q].xhi - g.tiles[q].xlo != tw) continue;
+            const int k = tl.count++;
+            tl.ylo[k] = g.tiles[q].ylo; tl.xlo[k] = g.tiles[q].xlo;
+            tl.trim_y[k] = g.tiles[q].trim_y; tl.trim_x[k] = g.tiles[q].trim_x;
+            tl.out_y[k] = (q / pW) * g.sH * 2; tl.out_x[k] = (q % pW) * g.sW * 2;
+            done[q] = true;
+        }
+        Plan* plan = nullptr;
+        int rc = get_plan(ctx, tl.count, th, tw, &plan);
+        if (rc != FISR_OK) return rc;
+        // frames are W wide on the device (uncropped rows); the crop is a view (img[:h, :w], FISRnet.py:1008)
+        launch_tile_pack(d_frames, d_flow, d_warp, W, tl, th, tw, ctx->d_lut255, plan->in_lvl[2], plan->in_lvl[1],
+                         plan->in_lvl[0], plan->planes, st);
+        ctx->launches++;
+        rc = run_plan(ctx, plan, st);
+        if (rc != FISR_OK) return rc;
+        if (d_canvas_u8)
+            launch_tile_unpack_u8(plan->pred[2], tl, 2 * th, 2 * tw, d_canvas_u8, 2 * g.w, 2 * g.sH, 2 * g.sW, st);
+        if (d_canvas_f32)
+            launch_tile_unpack_f32(plan->pred[2], tl, 2 * th, 2 * tw, d_canvas_f32, 2 * g.w, 2 * g.sH, 2 * g.sW, st);
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    return FISR_OK;
+}
+
+}  // namespace
+
+// ================================================================ C ABI
+extern "C" {
+
+int fisr_create(int device, fisr_ctx** out) {
+    if (!out) return fail(nullptr, FISR_E_INVALID, "fisr_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, FISR_E_CUDA, "no CUDA device: %s (fisr_b200 has no CPU path)", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, FISR_E_INVALID, "device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, FISR_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, FISR_E_CUDA, "fisr_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    std::unique_ptr<fisr_ctx> ctx(new fisr_ctx());
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    Guard guard(device);
+    cudaFree(0);
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    if ((e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q)) != cudaSuccess || !fn)
+        return fail(nullptr, FISR_E_CUDA, "cuTensorMapEncodeTiled unavailable: %s", cudaGetErrorString(e));
+    ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    if ((e = conv3x3_init()) != cudaSuccess)
+        return fail(nullptr, FISR_E_CUDA, "conv kernel attribute setup failed: %s", cudaGetErrorString(e));
+    const char* g = getenv("FISR_NO_GRAPH");
+    ctx->use_graph = !(g && g[0] == '1');
+    fisr_ctx* c = ctx.get();
+    CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(nullptr, cudaMalloc(&c->d_err, sizeof(int)));
+    CUDA_TRY(nullptr, cudaMemset(c->d_err, 0, sizeof(int)));
+    {
+        float lut[256];
+        for (int i = 0; i < 256; ++i) lut[i] = static_cast<float>(static_cast<double>(i) / 255.0);   // FISRnet.py:1011
+        CUDA_TRY(nullptr, cudaMalloc(&c->d_lut255, sizeof lut));
+        CUDA_TRY(nullptr, cudaMemcpy(c->d_lut255, lut, sizeof lut, cudaMemcpyHostToDevice));
+    }
+    const auto& inv = inventory();
+    c->params.resize(inv.size());
+    for (size_t i = 0; i < inv.size(); ++i) {
+        ConvParam& p = c->params[i];
+        p.cin = inv[i].cin; p.cout = inv[i].cout;
+        p.KB = (p.cin + 63) / 64;
+        p.cout_pad = p.cout <= 16 ? 16 : (p.cout + 63) / 64 * 64;
+        const size_t wn = static_cast<size_t>(9) * p.cin * p.cout;
+        CUDA_TRY(nullptr, cudaMalloc(&p.d_w, wn * 4));
+        CUDA_TRY(nullptr, cudaMemset(p.d_w, 0, wn * 4));
+        CUDA_TRY(nullptr, cudaMalloc(&p.d_b, p.cout_pad * 4));
+        CUDA_TRY(nullptr, cudaMemset(p.d_b, 0, p.cout_pad * 4));
+        CUDA_TRY(nullptr, cudaMalloc(&p.d_wp, static_cast<size_t>(2) * p.KB * 9 * p.cout_pad * 64 * 2));
+        c->conv_index[inv[i].name] = static_cast<int>(i);
+    }
+    CUDA_TRY(nullptr, cudaDeviceSynchronize());   // legacy-stream memsets above vs. the non-blocking context stream
+    *out = ctx.release();
+    return FISR_OK;
+}
+
+void fisr_destroy(fisr_ctx* ctx) {
+    if (!ctx) return;
+    Guard guard(ctx->device);
+    cudaDeviceSynchronize();
+    ctx->plans.clear();
+    for (auto& p : ctx->params) { cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); }
+    for (void* s : ctx->stage) if (s) cudaFree(s);
+    cudaFree(ctx->d_err);
+    cudaFree(ctx->d_lut255);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* fisr_last_error(const fisr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int fisr_set_precision(fisr_ctx* ctx, int precision) {
+    if (!ctx) return FISR_E_INVALID;
+    if (precision != FISR_PREC_F16X3 && precision != FISR_PREC_F16) return fail(ctx, FISR_E_INVALID, "unknown precision %d", precision);
+    const int planes = precision == FISR_PREC_F16X3 ? 2 : 1;
+    if (planes != ctx->planes) {
+        Guard guard(ctx->device);
+        cudaDeviceSynchronize();
+        ctx->plans.clear();
+        ctx->last_plan = nullptr;
+        ctx->planes = planes;
+        for (auto& p : ctx->params) p.packed = false;
+    }
+    return FISR_OK;
+}
+int fisr_get_precision(const fisr_ctx* ctx) { return ctx && ctx->planes == 1 ? FISR_PREC_F16 : FISR_PREC_F16X3; }
+
+int fisr_num_params(void) { return static_cast<int>(param_names().size()); }
+const char* fisr_param_name(int index) {
+    const auto& n = param_names();
+    return (index >= 0 && index < (int)n.size()) ? n[index].c_str() : nullptr;
+}
+int fisr_param_shape(int index, int dims[4]) {
+    const auto& inv = inventory();
+    if (index < 0 || index >= 2 * (int)inv.size() || !dims) return FISR_E_INVALID;
+    const ParamDef& d = inv[index / 2];
+    if (index % 2 == 0) { dims[0] = 3; dims[1] = 3; dims[2] = d.cin; dims[3] = d.cout; return 4; }
+    dims[0] = d.cout; dims[1] = dims[2] = dims[3] = 1;
+    return 1;
+}
+
+static int split_param_name(fisr_ctx* ctx, const char* name, int* conv, bool* is_w) {
+    if (!name) return fail(ctx, FISR_E_INVALID, "parameter name is NULL");
+    std::string s(name);
+    if (s.size() < 3 || (s.substr(s.size() - 2) != "/w" && s.substr(s.size() - 2) != "/b"))
+        return fail(ctx, FISR_E_INVALID, "parameter name must end in /w or /b: %s", name);
+    auto it = ctx->conv_index.find(s.substr(0, s.size() - 2));
+    if (it == ctx->conv_index.end()) return fail(ctx, FISR_E_INVALID, "unknown parameter %s", name);
+    *conv = it->second;
+    *is_w = s.back() == 'w';
+    return FISR_OK;
+}
+
+int fisr_set_param(fisr_ctx* ctx, const char* name, const float* h_data, size_t count) {
+    if (!ctx || !h_data) return FISR_E_INVALID;
+    int ci; bool is_w;
+    int rc = split_param_name(ctx, name, &ci, &is_w);
+    if (rc != FISR_OK) return rc;
+    Guard guard(ctx->device);
+    ConvParam& p = ctx->params[ci];
+    const size_t expect = is_w ? static_cast<size_t>(9) * p.cin * p.cout : static_cast<size_t>(p.cout);
+    if (count != expect) return fail(ctx, FISR_E_INVALID, "%s has %zu elements, got %zu", name, expect, count);
+    // Copy and re-pack on ONE stream: a pageable cudaMemcpy on the legacy stream may return before its DMA has
+    // landed, and the context stream is non-blocking, so the pack kernel would race with it.
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    CUDA_TRY(ctx, cudaMemcpyAsync(is_w ? p.d_w : p.d_b, h_data, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (is_w) {
+        p.packed = false;
+        // plans hold pointers to the packed planes, which are rewritten in place: re-pack now
+        rc = ensure_packed(ctx, p, ctx->stream);
+        if (rc != FISR_OK) return rc;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return FISR_OK;
+}
+
+int fisr_get_param(fisr_ctx* ctx, const char* name, float* h_data, size_t count) {
+    if (!ctx || !h_data) return FISR_E_INVALID;
+    int ci; bool is_w;
+    int rc = split_param_name(ctx, name, &ci, &is_w);
+    if (rc != FISR_OK) return rc;
+    Guard guard(ctx->device);
+    ConvParam& p = ctx->params[ci];
+    const size_t expect = is_w ? static_cast<size_t>(9) * p.cin * p.cout : static_cast<size_t>(p.cout);
+    if (count != expect) return fail(ctx, FISR_E_INVALID, "%s has %zu elements, got %zu", name, expect, count);
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_data, is_w ? p.d_w : p.d_b, count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return FISR_OK;
+}
+
+int fisr_forward(fisr_ctx* ctx, const float* d_img, int N, int H, int W, float* d_l1, float* d_l2, float* d_l3,
+                 void* stream) {
+    if (!ctx || !d_img) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    Plan* plan = nullptr;
+    int rc = get_plan(ctx, N, H, W, &plan);
+    if (rc != FISR_OK) return rc;
+    launch_pack_input(d_img, N, H, W, IN_CH, plan->in_lvl[2], plan->in_lvl[1], plan->in_lvl[0], plan->planes, st);
+    ctx->launches++;
+    rc = run_plan(ctx, plan, st);
+    if (rc != FISR_OK) return rc;
+    const size_t n1 = static_cast<size_t>(N) * (H / 2) * (W / 2) * 9, n2 = static_cast<size_t>(N) * H * W * 9, n3 = n2 * 4;
+    if (d_l1) CUDA_TRY(ctx, cudaMemcpyAsync(d_l1, plan->pred[0], n1 * 4, cudaMemcpyDeviceToDevice, st));
+    if (d_l2) CUDA_TRY(ctx, cudaMemcpyAsync(d_l2, plan->pred[1], n2 * 4, cudaMemcpyDeviceToDevice, st));
+    if (d_l3) CUDA_TRY(ctx, cudaMemcpyAsync(d_l3, plan->pred[2], n3 * 4, cudaMemcpyDeviceToDevice, st));
+    return FISR_OK;
+}
+
+int fisr_forward_host(fisr_ctx* ctx, const float* h_img, int N, int H, int W, float* h_l1, float* h_l2, float* h_l3) {
+    if (!ctx || !h_img) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    Plan* plan = nullptr;
+    int rc = get_plan(ctx, N, H, W, &plan);
+    if (rc != FISR_OK) return rc;
+    const size_t in_bytes = static_cast<size_t>(N) * H * W * IN_CH * 4;
+    if ((rc = ensure_stage(ctx, 0, in_bytes)) != FISR_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage[0], h_img, in_bytes, cudaMemcpyHostToDevice, st));
+    launch_pack_input(static_cast<const float*>(ctx->stage[0]), N, H, W, IN_CH, plan->in_lvl[2], plan->in_lvl[1],
+                      plan->in_lvl[0], plan->planes, st);
+    ctx->launches++;
+    rc = run_plan(ctx, plan, st);
+    if (rc != FISR_OK) return rc;
+    const size_t n1 = static_cast<size_t>(N) * (H / 2) * (W / 2) * 9, n2 = static_cast<size_t>(N) * H * W * 9, n3 = n2 * 4;
+    if (h_l1) CUDA_TRY(ctx, cudaMemcpyAsync(h_l1, plan->pred[0], n1 * 4, cudaMemcpyDeviceToHost, st));
+    if (h_l2) CUDA_TRY(ctx, cudaMemcpyAsync(h_l2, plan->pred[1], n2 * 4, cudaMemcpyDeviceToHost, st));
+    if (h_l3) CUDA_TRY(ctx, cudaMemcpyAsync(h_l3, plan->pred[2], n3 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return check_kernel_error(ctx);
+}
+
+int fisr_window_device(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, const float* d_warp, int H, int W,
+                       int pH, int pW, int tile_first, int tile_count, uint8_t* d_canvas, void* stream) {
+    if (!ctx || !d_frames || !d_flow || !d_warp || !d_canvas) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return window_impl(ctx, d_frames, d_flow, d_warp, H, W, pH, pW, tile_first, tile_count, d_canvas, nullptr, st);
+}
+
+int fisr_window_device_f32(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, const float* d_warp, int H,
+                           int W, int pH, int pW, float* d_canvas, void* stream) {
+    if (!ctx || !d_frames || !d_flow || !d_warp || !d_canvas) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return window_impl(ctx, d_frames, d_flow, d_warp, H, W, pH, pW, 0, pH * pW, nullptr, d_canvas, st);
+}
+
+int fisr_window_host(fisr_ctx* ctx, const uint8_t* h_frames, const float* h_flow, const float* h_warp, int H, int W,
+                     int pH, int pW, uint8_t* h_canvas) {
+    if (!ctx || !h_frames || !h_flow || !h_warp || !h_canvas) return FISR_E_INVALID;
+    if (pH < 1 || pW < 1) return fail(ctx, FISR_E_INVALID, "bad tile grid");
+    Guard guard(ctx->device);
+    const size_t px = static_cast<size_t>(H) * W;
+    const int h = H - H % (32 * pH), w = W - W % (32 * pW);
+    const size_t out_bytes = static_cast<size_t>(2 * h) * (2 * w) * 9;
+    int rc;
+    if ((rc = ensure_stage(ctx, 1, px * 9)) != FISR_OK) return rc;
+    if ((rc = ensure_stage(ctx, 2, px * 8 * 4)) != FISR_OK) return rc;
+    if ((rc = ensure_stage(ctx, 3, px * 12 * 4)) != FISR_OK) return rc;
+    if ((rc = ensure_stage(ctx, 4, out_bytes)) != FISR_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage[1], h_frames, px * 9, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage[2], h_flow, px * 8 * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage[3], h_warp, px * 12 * 4, cudaMemcpyHostToDevice, st));
+    rc = window_impl(ctx, static_cast<const uint8_t*>(ctx->stage[1]), static_cast<const float*>(ctx->stage[2]),
+                     static_cast<const float*>(ctx->stage[3]), H, W, pH, pW, 0, pH * pW,
+                     static_cast<uint8_t*>(ctx->stage[4]), nullptr, st);
+    if (rc != FISR_OK) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_canvas, ctx->stage[4], out_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return check_kernel_error(ctx);
+}
+
+int fisr_warp_device(fisr_ctx* ctx, const uint8_t* d_yuv, const float* d_flow, float flow_scale, float* d_out, int h,
+                     int w, float out_scale, void* stream) {
+    if (!ctx || !d_yuv || !d_flow || !d_out || h < 1 || w < 1) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    launch_warp_yuv(d_yuv, d_flow, flow_scale, d_out, h, w, out_scale, st);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FISR_OK;
+}
+
+int fisr_warp_host(fisr_ctx* ctx, const uint8_t* h_yuv, const float* h_flow, float flow_scale, float* h_out, int h, int w,
+                   float out_scale) {
+    if (!ctx || !h_yuv || !h_flow || !h_out || h < 1 || w < 1) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    const size_t px = static_cast<size_t>(h) * w;
+    int rc;
+    if ((rc = ensure_stage(ctx, 5, px * 3)) != FISR_OK) return rc;
+    if ((rc = ensure_stage(ctx, 6, px * 2 * 4)) != FISR_OK) return rc;
+    if ((rc = ensure_stage(ctx, 7, px * 3 * 4)) != FISR_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage[5], h_yuv, px * 3, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage[6], h_flow, px * 8, cudaMemcpyHostToDevice, st));
+    launch_warp_yuv(static_cast<const uint8_t*>(ctx->stage[5]), static_cast<const float*>(ctx->stage[6]), flow_scale,
+                    static_cast<float*>(ctx->stage[7]), h, w, out_scale, st);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_out, ctx->stage[7], px * 12, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return FISR_OK;
+}
+
+int fisr_conv3x3(fisr_ctx* ctx, const float* d_x, const float* d_w, const float* d_b, const float* d_res, int N, int H,
+                 int W, int Cin, int Cout, int relu, int d2s, float* d_raw, float* d_act) {
+    if (!ctx || !d_x || !d_w || !d_b || N < 1 || H < 1 || W < 1 || Cin < 1 || Cout < 1) return FISR_E_INVALID;
+    if (Cout > 16 && Cout % 64) return fail(ctx, FISR_E_INVALID, "Cout must be <= 16 or a multiple of 64");
+    if (d2s && Cout != 256) return fail(ctx, FISR_E_INVALID, "depth_to_space epilogue needs Cout = 256");
+    if (Cout <= 16 && d_res) return fail(ctx, FISR_E_INVALID, "narrow outputs take no residual");
+    Guard guard(ctx->device);
+    cudaStream_t st = ctx->stream;
+    Plan tmp;                       // owns the scratch buffers of this call
+    tmp.planes = ctx->planes;
+    Builder b{ctx, &tmp};
+    ConvParam p;
+    p.cin = Cin; p.cout = Cout; p.KB = (Cin + 63) / 64; p.cout_pad = Cout <= 16 ? 16 : Cout;
+    p.d_w = const_cast<float*>(d_w);
+    p.d_b = static_cast<float*>(b.alloc(p.cout_pad * 4, true));
+    p.d_wp = static_cast<__half*>(b.alloc(static_cast<size_t>(2) * p.KB * 9 * p.cout_pad * 64 * 2, false));
+    const int cs = p.KB * 64;
+    ActBuf xin = b.act(N, H, W, cs);
+    const int oc = d2s ? Cout / 4 : Cout, oH = d2s ? 2 * H : H, oW = d2s ? 2 * W : W;
+    const int ocs = Cout <= 16 ? 16 : oc;
+    ActBuf yact = b.act(N, oH, oW, ocs, true);
+    if (b.rc != FISR_OK) return b.rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(p.d_b, d_b, Cout * 4, cudaMemcpyDeviceToDevice, st));
+    launch_prep_weights(p.d_w, p.d_wp, Cin, Cout, p.KB, p.cout_pad, ctx->planes, st);
+    launch_act_from_f32(d_x, Cin, xin, cs, static_cast<size_t>(N) * H * W, ctx->planes, st);
+    Builder::ConvOut o;
+    o.res = d_res; o.res_cs = Cout;
+    o.raw = d_raw; o.raw_cs = Cout;
+    o.act = d_act ? yact : ActBuf{}; o.act_cs = ocs;
+    o.relu = relu != 0; o.d2s = d2s != 0; o.scalar = Cout <= 16;
+    b.conv(p, xin, cs, 0, N, H, W, o, "test");
+    if (b.rc != FISR_OK) return b.rc;
+    int rc = run_ops(ctx, &tmp, st);
+    ctx->launches += 3;
+    if (rc != FISR_OK) return rc;
+    if (d_act) launch_act_to_f32(yact, ocs, 0, d_act, oc, static_cast<size_t>(N) * oH * oW, ctx->planes, st);
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return check_kernel_error(ctx);
+}
+
+int fisr_debug_conv_output(fisr_ctx* ctx, const char* conv_name, float* h_dst, size_t count) {
+    if (!ctx || !conv_name || !h_dst) return FISR_E_INVALID;
+    if (!ctx->last_plan) return fail(ctx, FISR_E_INVALID, "no forward has run yet");
+    Guard guard(ctx->device);
+    auto it = ctx->last_plan->debug.find(conv_name);
+    if (it == ctx->last_plan->debug.end()) return fail(ctx, FISR_E_INVALID, "conv %s keeps no fp32 output", conv_name);
+    const DebugTensor& t = it->second;
+    const size_t n = static_cast<size_t>(t.N) * t.H * t.W * t.C;
+    if (count != n) return fail(ctx, FISR_E_INVALID, "%s has %zu elements, got %zu", conv_name, n, count);
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    CUDA_TRY(ctx, cudaMemcpy(h_dst, t.raw, n * 4, cudaMemcpyDeviceToHost));
+    return FISR_OK;
+}
+
+long long fisr_launch_count(const fisr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int fisr_plan_info(fisr_ctx* ctx, int N, int H, int W, double* flops, double* mma_efficiency, int* num_launches,
+                   size_t* workspace_bytes) {
+    if (!ctx) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    Plan* plan = nullptr;
+    int rc = get_plan(ctx, N, H, W, &plan);
+    if (rc != FISR_OK) return rc;
+    if (flops) *flops = plan->flops;
+    if (mma_efficiency) *mma_efficiency = plan->flops > 0 ? plan->eff_weighted / plan->flops : 0;
+    if (num_launches) *num_launches = static_cast<int>(plan->ops.size());
+    if (workspace_bytes) *workspace_bytes = plan->bytes;
+    return FISR_OK;
+}
+
+}  // extern "C"

@@ -49,12 +49,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as an error flag, never as a hung GPU.
-// Returns false on timeout (caller records it and bails out).
+// Returns false after ~4 s without progress (caller records it and bails out).
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
-    for (uint32_t it = 0; it < (1u << 24); ++it) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const unsigned long long t0 = global_timer_ns();
+    for (uint32_t it = 1;; ++it) {
         if (mbar_try_wait(bar, parity)) return true;
+        if ((it & 255u) == 0 && global_timer_ns() - t0 > 4000000000ull) break;
     }
-    if (err_flag) atomicExch(err_flag, code);
+    if (err_flag) atomicCAS(err_flag, 0, code);
     return false;
 }
 

@@ -1,0 +1,244 @@
+"""Device context of the B200 FISRnet path: owns one ``fisr_ctx`` (C ABI) on one GPU.
+
+PyTorch is used only as the container of device memory and for the current CUDA stream;
+every kernel that runs is in ``libfisr_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FisrError, PREC_F16, PREC_F16X3
+
+_PREC = {"f16x3": PREC_F16X3, "fp32": PREC_F16X3, "f16": PREC_F16, "fast": PREC_F16}
+
+
+def param_inventory() -> "OrderedDict[str, Tuple[int, ...]]":
+    """name -> shape of the 276 tensors ``FISRnet.model`` creates (ops.py:8-9), in creation order."""
+    lib = _lib.load()
+    out: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    dims = (C.c_int * 4)()
+    for k in range(lib.fisr_num_params()):
+        rank = lib.fisr_param_shape(k, dims)
+        out[lib.fisr_param_name(k).decode()] = tuple(dims[j] for j in range(rank))
+    return out
+
+
+class Engine:
+    def __init__(self, device: int = 0, precision: str = "f16x3"):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise FisrError("fisr_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = int(device)
+        h = C.c_void_p()
+        rc = self.lib.fisr_create(self.device, C.byref(h))
+        if rc != 0:
+            raise FisrError(f"fisr_create failed ({rc}): {self.lib.fisr_last_error(None).decode()}")
+        self.h = h
+        # All library work is issued on this side stream, ordered against torch's current stream on entry and
+        # exit (torch's default stream has handle 0, which the C ABI reads as "the context's own stream").
+        self.stream = torch.cuda.Stream(self.device)
+        self.set_precision(precision)
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            raise FisrError(f"{what} failed ({rc}): {self.lib.fisr_last_error(self.h).decode()}")
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.fisr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self) -> int:
+        return self.stream.cuda_stream
+
+    def _enter(self, *tensors) -> None:
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        for t in tensors:
+            if t is not None:
+                t.record_stream(self.stream)
+
+    def _exit(self) -> None:
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+    def _dev(self, t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+        if not (t.is_cuda and t.device.index == self.device and t.dtype == dtype and t.is_contiguous()):
+            raise FisrError(f"expected a contiguous {dtype} tensor on cuda:{self.device}, got {t.dtype} on {t.device}")
+        return t
+
+    def set_precision(self, precision: str) -> None:
+        if precision not in _PREC:
+            raise FisrError(f"unknown precision {precision!r}; use one of {sorted(_PREC)}")
+        self._check(self.lib.fisr_set_precision(self.h, _PREC[precision]), "fisr_set_precision")
+        self.precision = "f16" if _PREC[precision] == PREC_F16 else "f16x3"
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.fisr_launch_count(self.h))
+
+    # ------------------------------------------------------------------ parameters
+    def set_params(self, params: Dict[str, "np.ndarray | torch.Tensor"]) -> None:
+        for name, shape in param_inventory().items():
+            if name not in params:
+                raise FisrError(f"missing parameter {name}")
+            a = params[name]
+            a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            if tuple(a.shape) != shape:
+                raise FisrError(f"{name}: expected shape {shape}, got {tuple(a.shape)}")
+            self._check(self.lib.fisr_set_param(self.h, name.encode(), a.ctypes.data, a.size), f"fisr_set_param({name})")
+
+    def get_params(self) -> "OrderedDict[str, np.ndarray]":
+        out: "OrderedDict[str, np.ndarray]" = OrderedDict()
+        for name, shape in param_inventory().items():
+            a = np.empty(shape, dtype=np.float32)
+            self._check(self.lib.fisr_get_param(self.h, name.encode(), a.ctypes.data, a.size), f"fisr_get_param({name})")
+            out[name] = a
+        return out
+
+    # ------------------------------------------------------------------ FISRnet.model
+    def forward(self, img: torch.Tensor, want=(True, True, True)):
+        """``FISRnet.model`` (FISRnet.py:73-173): img [N,H,W,29] fp32 on the GPU -> (pred_l1, pred_l2, pred_l3)."""
+        img = self._dev(img, torch.float32)
+        n, h, w, c = img.shape
+        if c != 29:
+            raise FisrError(f"FISRnet.model takes 29 input channels, got {c}")
+        outs = [torch.empty((n, h // 2, w // 2, 9), device=img.device) if want[0] else None,
+                torch.empty((n, h, w, 9), device=img.device) if want[1] else None,
+                torch.empty((n, 2 * h, 2 * w, 9), device=img.device) if want[2] else None]
+        ptr = [o.data_ptr() if o is not None else None for o in outs]
+        self._enter(img, *outs)
+        self._check(self.lib.fisr_forward(self.h, img.data_ptr(), n, h, w, ptr[0], ptr[1], ptr[2], self._stream()),
+                    "fisr_forward")
+        self._exit()
+        return tuple(outs)
+
+    def forward_host(self, img: np.ndarray):
+        """Same through host buffers (the ``sess.run(feed_dict)`` of FISRnet.py:1048): numpy in, numpy out."""
+        img = np.ascontiguousarray(img, dtype=np.float32)
+        n, h, w, c = img.shape
+        if c != 29:
+            raise FisrError(f"FISRnet.model takes 29 input channels, got {c}")
+        o1 = np.empty((n, h // 2, w // 2, 9), np.float32)
+        o2 = np.empty((n, h, w, 9), np.float32)
+        o3 = np.empty((n, 2 * h, 2 * w, 9), np.float32)
+        self._check(self.lib.fisr_forward_host(self.h, img.ctypes.data, n, h, w, o1.ctypes.data, o2.ctypes.data,
+                                               o3.ctypes.data), "fisr_forward_host")
+        return o1, o2, o3
+
+    # ------------------------------------------------------------------ tiled window (FISRnet.py:994-1065)
+    @staticmethod
+    def canvas_shape(H: int, W: int, num_patch=(2, 2)) -> Tuple[int, int, int]:
+        h = H - H % (32 * num_patch[0])
+        w = W - W % (32 * num_patch[1])
+        return 2 * h, 2 * w, 9
+
+    def window(self, frames: torch.Tensor, flow: torch.Tensor, warp: torch.Tensor, num_patch=(2, 2),
+               tiles: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One sliding window on device tensors: frames u8 [H,W,9], flow f32 [H,W,8], warp f32 [H,W,12]
+        -> uint8 canvas [2h,2w,9].  ``tiles=(first, count)`` restricts the work to part of the tile grid."""
+        frames = self._dev(frames, torch.uint8)
+        flow = self._dev(flow, torch.float32)
+        warp = self._dev(warp, torch.float32)
+        H, W, _ = frames.shape
+        if out is None:
+            out = torch.zeros(self.canvas_shape(H, W, num_patch), dtype=torch.uint8, device=frames.device)
+        first, count = tiles if tiles is not None else (0, num_patch[0] * num_patch[1])
+        self._enter(frames, flow, warp, out)
+        self._check(self.lib.fisr_window_device(self.h, frames.data_ptr(), flow.data_ptr(), warp.data_ptr(), H, W,
+                                                num_patch[0], num_patch[1], first, count, self._dev(out, torch.uint8).data_ptr(),
+                                                self._stream()), "fisr_window_device")
+        self._exit()
+        return out
+
+    def window_f32(self, frames: torch.Tensor, flow: torch.Tensor, warp: torch.Tensor, num_patch=(2, 2)) -> torch.Tensor:
+        frames = self._dev(frames, torch.uint8)
+        H, W, _ = frames.shape
+        out = torch.zeros(self.canvas_shape(H, W, num_patch), dtype=torch.float32, device=frames.device)
+        self._enter(frames, flow, warp, out)
+        self._check(self.lib.fisr_window_device_f32(self.h, frames.data_ptr(), self._dev(flow, torch.float32).data_ptr(),
+                                                    self._dev(warp, torch.float32).data_ptr(), H, W, num_patch[0],
+                                                    num_patch[1], out.data_ptr(), self._stream()), "fisr_window_device_f32")
+        self._exit()
+        return out
+
+    def window_host(self, frames: np.ndarray, flow: np.ndarray, warp: np.ndarray, num_patch=(2, 2),
+                    out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Host-buffer form of :meth:`window` (H2D + tiles + D2H inside the call)."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        flow = np.ascontiguousarray(flow, dtype=np.float32)
+        warp = np.ascontiguousarray(warp, dtype=np.float32)
+        H, W, _ = frames.shape
+        if flow.shape != (H, W, 8) or warp.shape != (H, W, 12) or frames.shape[2] != 9:
+            raise FisrError(f"window shapes: frames {frames.shape}, flow {flow.shape}, warp {warp.shape}")
+        if out is None:
+            out = np.empty(self.canvas_shape(H, W, num_patch), np.uint8)
+        self._check(self.lib.fisr_window_host(self.h, frames.ctypes.data, flow.ctypes.data, warp.ctypes.data, H, W,
+                                              num_patch[0], num_patch[1], out.ctypes.data), "fisr_window_host")
+        return out
+
+    # ------------------------------------------------------------------ flow warp
+    def warp(self, yuv: torch.Tensor, flow: torch.Tensor, flow_scale: float = 0.5, out_scale: float = 1.0) -> torch.Tensor:
+        """``warp_flow`` with the colour round trip (..warp_img_with_flo.py:61-67,112-128) on device tensors."""
+        yuv = self._dev(yuv, torch.uint8)
+        flow = self._dev(flow, torch.float32)
+        h, w, _ = yuv.shape
+        out = torch.empty((h, w, 3), dtype=torch.float32, device=yuv.device)
+        self._enter(yuv, flow, out)
+        self._check(self.lib.fisr_warp_device(self.h, yuv.data_ptr(), flow.data_ptr(), flow_scale, out.data_ptr(), h, w,
+                                              out_scale, self._stream()), "fisr_warp_device")
+        self._exit()
+        return out
+
+    def warp_host(self, yuv: np.ndarray, flow: np.ndarray, flow_scale: float = 0.5, out_scale: float = 1.0) -> np.ndarray:
+        yuv = np.ascontiguousarray(yuv, dtype=np.uint8)
+        flow = np.ascontiguousarray(flow, dtype=np.float32)
+        h, w, _ = yuv.shape
+        out = np.empty((h, w, 3), np.float32)
+        self._check(self.lib.fisr_warp_host(self.h, yuv.ctypes.data, flow.ctypes.data, flow_scale, out.ctypes.data, h, w,
+                                            out_scale), "fisr_warp_host")
+        return out
+
+    # ------------------------------------------------------------------ test hooks
+    def conv3x3(self, x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, res: Optional[torch.Tensor] = None,
+                relu: bool = True, d2s: bool = False, want_raw: bool = True, want_act: bool = True):
+        x = self._dev(x, torch.float32)
+        w = self._dev(w, torch.float32)
+        b = self._dev(b, torch.float32)
+        n, h, wd, cin = x.shape
+        cout = w.shape[3]
+        raw = torch.empty((n, h, wd, cout), device=x.device) if want_raw else None
+        act = None
+        if want_act:
+            act = torch.empty((n, 2 * h, 2 * wd, cout // 4) if d2s else (n, h, wd, cout), device=x.device)
+        torch.cuda.synchronize(self.device)
+        self._check(self.lib.fisr_conv3x3(self.h, x.data_ptr(), w.data_ptr(), b.data_ptr(),
+                                          self._dev(res, torch.float32).data_ptr() if res is not None else None,
+                                          n, h, wd, cin, cout, int(relu), int(d2s),
+                                          raw.data_ptr() if raw is not None else None,
+                                          act.data_ptr() if act is not None else None), "fisr_conv3x3")
+        return raw, act
+
+    def debug_conv_output(self, conv_name: str, shape) -> np.ndarray:
+        a = np.empty(shape, np.float32)
+        self._check(self.lib.fisr_debug_conv_output(self.h, conv_name.encode(), a.ctypes.data, a.size),
+                    "fisr_debug_conv_output")
+        return a
+
+    def plan_info(self, n: int, h: int, w: int) -> dict:
+        fl, eff, nl, ws = C.c_double(), C.c_double(), C.c_int(), C.c_size_t()
+        self._check(self.lib.fisr_plan_info(self.h, n, h, w, C.byref(fl), C.byref(eff), C.byref(nl), C.byref(ws)),
+                    "fisr_plan_info")
+        return {"flops": fl.value, "mma_row_efficiency": eff.value, "launches": nl.value, "workspace_bytes": ws.value}

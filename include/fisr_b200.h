@@ -1,0 +1,110 @@
+/* fisr_b200 -- C ABI of the B200-native FISRnet hot path.
+ *
+ * The reference (JihyongOh/FISR @ 34d9305) is pure Python on TensorFlow 1.13 and has no FFI of its own; the
+ * operator surface that `main.py` drives is the Python class `FISRnet` (FISRnet.py:14-17).  This library is what a
+ * ctypes binding underneath that class calls (fisr_b200/_lib.py; INTEGRATION.md shows the stub).  Each entry point
+ * names the reference code it stands in for.
+ *
+ * Conventions: every function returns 0 on success or a negative FISR_E_* code; fisr_last_error() gives the text.
+ * No exceptions cross the boundary.  Pointers named d_* are CUDA device pointers on the context's device, h_* are
+ * host pointers (pinned memory makes the host entry points faster but is not required).  The caller owns every
+ * buffer it passes; the context owns its workspace.  A context is bound to one GPU and is not thread-safe (the
+ * reference drives one tf.Session from one Python thread, main.py:137-139).  All tensors are NHWC, float32 unless
+ * the name says u8.
+ */
+#ifndef FISR_B200_H
+#define FISR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fisr_ctx fisr_ctx;
+
+enum {
+    FISR_OK = 0,
+    FISR_E_INVALID = -1,    /* bad argument (shape not a multiple of 32, unknown parameter name, ...) */
+    FISR_E_CUDA = -2,       /* CUDA runtime / driver error */
+    FISR_E_KERNEL = -3,     /* a kernel reported a pipeline time-out through its error flag */
+    FISR_E_NOMEM = -4
+};
+
+/* Arithmetic of the conv stack (DESIGN.md "Numerics").  The reference computes in fp32 (cuDNN on Pascal). */
+enum {
+    FISR_PREC_F16X3 = 0,    /* fp16 (hi,lo) split operands, 3 tcgen05 MMAs per K-slice, fp32 accumulate: fp32-class */
+    FISR_PREC_F16 = 1       /* single fp16 operands, 1 MMA per K-slice: fast mode, ~7e-4 max-abs on the cascade   */
+};
+
+/* ---- lifetime --------------------------------------------------------------------------------------------- */
+/* Stands in for `tf.Session(...)` + `FISRnet(sess, args)` (main.py:137-143, FISRnet.py:17). */
+int fisr_create(int device, fisr_ctx** out);
+void fisr_destroy(fisr_ctx* ctx);
+/* Text of the last error on this context (ctx may be NULL for a failed fisr_create). Never NULL. */
+const char* fisr_last_error(const fisr_ctx* ctx);
+int fisr_set_precision(fisr_ctx* ctx, int precision);
+int fisr_get_precision(const fisr_ctx* ctx);
+
+/* ---- parameters: the 138 (w, b) pairs created by tf.get_variable in ops.py:8-9 under scope "FISRnet/" ---- */
+/* Names are the TF variable names without the ":0" suffix, e.g. "FISRnet/level_1/enc/level_0/conv/0/w";
+ * w is HWIO [3,3,Cin,Cout], b is [Cout]; creation order of FISRnet.py:78-171. */
+int fisr_num_params(void);
+const char* fisr_param_name(int index);
+int fisr_param_shape(int index, int dims[4]);               /* returns rank (4 for w, 1 for b) */
+int fisr_set_param(fisr_ctx* ctx, const char* name, const float* h_data, size_t count);   /* saver.restore, FISRnet.py:1109 */
+int fisr_get_param(fisr_ctx* ctx, const char* name, float* h_data, size_t count);         /* saver.save,    FISRnet.py:1098 */
+
+/* ---- FISRnet.model (FISRnet.py:73-173) -------------------------------------------------------------------- */
+/* img [N,H,W,29] -> pred_l1 [N,H/2,W/2,9], pred_l2 [N,H,W,9], pred_l3 [N,2H,2W,9]; H, W multiples of 32.
+ * Output pointers may be NULL to skip that copy.  `stream` is a cudaStream_t (NULL = the context's stream);
+ * the call is asynchronous with respect to the host on that stream. */
+int fisr_forward(fisr_ctx* ctx, const float* d_img, int N, int H, int W, float* d_pred_l1, float* d_pred_l2,
+                 float* d_pred_l3, void* stream);
+/* Same through host buffers: the `sess.run(test_Pred, feed_dict=...)` of FISRnet.py:1048 (H2D, forward, D2H, sync). */
+int fisr_forward_host(fisr_ctx* ctx, const float* h_img, int N, int H, int W, float* h_pred_l1, float* h_pred_l2,
+                      float* h_pred_l3);
+
+/* ---- one sliding window of FISR_for_video / test (FISRnet.py:994-1065, 798-883) ---------------------------- */
+/* frames u8 [H,W,9] (3 consecutive YUV frames), flow f32 [H,W,8] in LR pixels, warp f32 [H,W,12] already /255
+ * (utils.py:51).  Crops to h = H - H % (32*pH), w likewise (:1006-1007), normalises and clips (:1011-1021), runs the
+ * pH x pW tile grid with the 32-pixel halo (utils.py:118-159), trims, pastes, clips to [0,1] and writes
+ * uint8(x*255) into canvas u8 [2h,2w,9] (:1060-1064).  Only tiles [tile_first, tile_first+tile_count) of the
+ * row-major grid are computed and pasted, so ranks of a multi-GPU job can shard one window; pass 0, pH*pW for all. */
+int fisr_window_device(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, const float* d_warp, int H, int W,
+                       int pH, int pW, int tile_first, int tile_count, uint8_t* d_canvas, void* stream);
+int fisr_window_host(fisr_ctx* ctx, const uint8_t* h_frames, const float* h_flow, const float* h_warp, int H, int W,
+                     int pH, int pW, uint8_t* h_canvas);
+/* float canvas [2h,2w,9] before clipping (what FISRnet.py:1057 accumulates), for parity tests */
+int fisr_window_device_f32(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, const float* d_warp, int H,
+                           int W, int pH, int pW, float* d_canvas, void* stream);
+
+/* ---- flow warp (FISR_tfoptflow/FISR_for_video_warp_img_with_flo.py:61-67,112-128) -------------------------- */
+/* yuv u8 [h,w,3] --YUV2RGB--> cv2.remap(INTER_LINEAR, BORDER_REPLICATE) at (x,y) + flow_scale*flow --RGB2YUV-->
+ * out f32 [h,w,3] = value * out_scale (the reference stores 0..255, i.e. out_scale 1; 1/255 feeds the network). */
+int fisr_warp_device(fisr_ctx* ctx, const uint8_t* d_yuv, const float* d_flow, float flow_scale, float* d_out, int h,
+                     int w, float out_scale, void* stream);
+int fisr_warp_host(fisr_ctx* ctx, const uint8_t* h_yuv, const float* h_flow, float flow_scale, float* h_out, int h,
+                   int w, float out_scale);
+
+/* ---- introspection / test hooks ---------------------------------------------------------------------------- */
+/* Single 3x3 SAME conv through the production kernel (ops.py:7-11 plus the fused epilogue):
+ * y = conv(x, w) + b (+ res); raw = y; act = relu ? max(y,0) : y, optionally depth_to_space(2) (FISRnet.py:99).
+ * x [N,H,W,Cin], w HWIO, res / raw [N,H,W,Cout], act [N,H,W,Cout] or [N,2H,2W,Cout/4]; device pointers, any may be
+ * NULL except x, w, b.  Synchronous. */
+int fisr_conv3x3(fisr_ctx* ctx, const float* d_x, const float* d_w, const float* d_b, const float* d_res, int N, int H,
+                 int W, int Cin, int Cout, int relu, int d2s, float* d_raw, float* d_act);
+/* After a forward: copies the pre-activation output of the named conv (e.g. ".../enc/level_0/conv/0") as
+ * float32 NHWC to host, when the plan materialises it; returns FISR_E_INVALID otherwise. */
+int fisr_debug_conv_output(fisr_ctx* ctx, const char* conv_name, float* h_dst, size_t count);
+/* Kernel launches issued by this context since creation (the `gpu_launches` evidence bench.py reports). */
+long long fisr_launch_count(const fisr_ctx* ctx);
+/* Conv FLOPs (2*9*Cin*Cout*h*w*N) and mean MMA row efficiency of the plan for (N,H,W). */
+int fisr_plan_info(fisr_ctx* ctx, int N, int H, int W, double* flops, double* mma_efficiency, int* num_launches,
+                   size_t* workspace_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FISR_B200_H */
