@@ -190,7 +190,7 @@ __global__ void act_to_f32_kernel(const __half* __restrict__ src, size_t plane, 
 // Tile t covers rows [ylo[t], ylo[t]+th) x cols [xlo[t], xlo[t]+tw) of the (cropped) frame.
 template <int PLANES>
 __global__ void tile_pack_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ flow,
-                                 const float* __restrict__ warp, int fw, TileList tiles, int th, int tw,
+                                 const float* __restrict__ warp, int fh, int fw, TileList tiles, int th, int tw,
                                  const float* __restrict__ lut255, __half* l3, size_t p3, __half* l2, size_t p2,
                                  __half* l1, size_t p1) {
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
@@ -202,7 +202,7 @@ __global__ void tile_pack_kernel(const uint8_t* __restrict__ frames, const float
     const int x = pix % tw;
     const int y = (pix / tw) % th;
     const int t = pix / (static_cast<size_t>(tw) * th);
-    const size_t src = static_cast<size_t>(tiles.ylo[t] + y) * fw + tiles.xlo[t] + x;
+    const size_t src = (static_cast<size_t>(tiles.win[t]) * fh + tiles.ylo[t] + y) * fw + tiles.xlo[t] + x;
     float v;
     if (c < 9) {
         v = lut255[frames[src * 9 + c]];
@@ -230,7 +230,7 @@ __global__ void tile_pack_kernel(const uint8_t* __restrict__ frames, const float
 // pred_l3 of T tiles [T,2th,2tw,9] fp32 -> trim the halo (utils.py:138-159), clip [0,1], uint8(x*255) with the
 // reference's float64 truncation (FISRnet.py:1060-1064), paste into the [OH,OW,9] canvas (FISRnet.py:1056-1057).
 __global__ void tile_unpack_u8_kernel(const float* __restrict__ pred, TileList tiles, int th2, int tw2,
-                                      uint8_t* __restrict__ canvas, int OW, int core_h, int core_w) {
+                                      uint8_t* __restrict__ canvas, int OH, int OW, int core_h, int core_w) {
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     const size_t total = static_cast<size_t>(tiles.count) * core_h * core_w * 9;
     if (i >= total) return;
@@ -241,12 +241,12 @@ __global__ void tile_unpack_u8_kernel(const float* __restrict__ pred, TileList t
     const int t = r / core_h;
     const float v = pred[((static_cast<size_t>(t) * th2 + tiles.trim_y[t] + y) * tw2 + tiles.trim_x[t] + x) * 9 + c];
     const double cl = fmin(fmax(static_cast<double>(v), 0.0), 1.0);
-    canvas[(static_cast<size_t>(tiles.out_y[t] + y) * OW + tiles.out_x[t] + x) * 9 + c] =
+    canvas[((static_cast<size_t>(tiles.out_img[t]) * OH + tiles.out_y[t] + y) * OW + tiles.out_x[t] + x) * 9 + c] =
         static_cast<uint8_t>(static_cast<int>(cl * 255.0));
 }
 // same, but keeps fp32 (for parity tests against the oracle's float canvas)
 __global__ void tile_unpack_f32_kernel(const float* __restrict__ pred, TileList tiles, int th2, int tw2,
-                                       float* __restrict__ canvas, int OW, int core_h, int core_w) {
+                                       float* __restrict__ canvas, int OH, int OW, int core_h, int core_w) {
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     const size_t total = static_cast<size_t>(tiles.count) * core_h * core_w * 9;
     if (i >= total) return;
@@ -255,7 +255,7 @@ __global__ void tile_unpack_f32_kernel(const float* __restrict__ pred, TileList 
     const int x = r % core_w; r /= core_w;
     const int y = r % core_h;
     const int t = r / core_h;
-    canvas[(static_cast<size_t>(tiles.out_y[t] + y) * OW + tiles.out_x[t] + x) * 9 + c] =
+    canvas[((static_cast<size_t>(tiles.out_img[t]) * OH + tiles.out_y[t] + y) * OW + tiles.out_x[t] + x) * 9 + c] =
         pred[((static_cast<size_t>(t) * th2 + tiles.trim_y[t] + y) * tw2 + tiles.trim_x[t] + x) * 9 + c];
 }
 
@@ -368,26 +368,26 @@ void launch_act_to_f32(ActBuf src, int cs, int coff, float* dst, int C, size_t n
         act_to_f32_kernel<1><<<blocks_for(npix * C, 256), 256, 0, st>>>(src.p, src.plane, cs, coff, dst, C, npix);
 }
 
-void launch_tile_pack(const uint8_t* frames, const float* flow, const float* warp, int fw, const TileList& tiles, int th,
-                      int tw, const float* lut255, ActBuf l3, ActBuf l2, ActBuf l1, int planes, cudaStream_t st) {
+void launch_tile_pack(const uint8_t* frames, const float* flow, const float* warp, int fh, int fw, const TileList& tiles,
+                      int th, int tw, const float* lut255, ActBuf l3, ActBuf l2, ActBuf l1, int planes, cudaStream_t st) {
     const size_t total = static_cast<size_t>(tiles.count) * th * tw * 32;
     if (planes == 2)
-        tile_pack_kernel<2><<<blocks_for(total, 256), 256, 0, st>>>(frames, flow, warp, fw, tiles, th, tw, lut255, l3.p,
+        tile_pack_kernel<2><<<blocks_for(total, 256), 256, 0, st>>>(frames, flow, warp, fh, fw, tiles, th, tw, lut255, l3.p,
                                                                     l3.plane, l2.p, l2.plane, l1.p, l1.plane);
     else
-        tile_pack_kernel<1><<<blocks_for(total, 256), 256, 0, st>>>(frames, flow, warp, fw, tiles, th, tw, lut255, l3.p,
+        tile_pack_kernel<1><<<blocks_for(total, 256), 256, 0, st>>>(frames, flow, warp, fh, fw, tiles, th, tw, lut255, l3.p,
                                                                     l3.plane, l2.p, l2.plane, l1.p, l1.plane);
 }
 
-void launch_tile_unpack_u8(const float* pred, const TileList& tiles, int th2, int tw2, uint8_t* canvas, int OW,
+void launch_tile_unpack_u8(const float* pred, const TileList& tiles, int th2, int tw2, uint8_t* canvas, int OH, int OW,
                            int core_h, int core_w, cudaStream_t st) {
     const size_t total = static_cast<size_t>(tiles.count) * core_h * core_w * 9;
-    tile_unpack_u8_kernel<<<blocks_for(total, 256), 256, 0, st>>>(pred, tiles, th2, tw2, canvas, OW, core_h, core_w);
+    tile_unpack_u8_kernel<<<blocks_for(total, 256), 256, 0, st>>>(pred, tiles, th2, tw2, canvas, OH, OW, core_h, core_w);
 }
-void launch_tile_unpack_f32(const float* pred, const TileList& tiles, int th2, int tw2, float* canvas, int OW,
+void launch_tile_unpack_f32(const float* pred, const TileList& tiles, int th2, int tw2, float* canvas, int OH, int OW,
                             int core_h, int core_w, cudaStream_t st) {
     const size_t total = static_cast<size_t>(tiles.count) * core_h * core_w * 9;
-    tile_unpack_f32_kernel<<<blocks_for(total, 256), 256, 0, st>>>(pred, tiles, th2, tw2, canvas, OW, core_h, core_w);
+    tile_unpack_f32_kernel<<<blocks_for(total, 256), 256, 0, st>>>(pred, tiles, th2, tw2, canvas, OH, OW, core_h, core_w);
 }
 
 void launch_warp_yuv(const uint8_t* yuv, const float* flow, float flow_scale, float* out, int h, int w, float out_scale,

@@ -14,9 +14,11 @@ constexpr int kMaxTiles = 32;
 // Geometry of the tiles one batched forward covers (utils.py:118-159 restated on the host, see fisr_api.cu).
 struct TileList {
     int count;
+    int win[kMaxTiles];                        // which window (frame triple) of the batch the tile reads
     int ylo[kMaxTiles], xlo[kMaxTiles];        // input window origin inside the cropped frame
     int trim_y[kMaxTiles], trim_x[kMaxTiles];  // halo rows / cols to drop from the x2 output
-    int out_y[kMaxTiles], out_x[kMaxTiles];    // paste origin inside the x2 canvas
+    int out_img[kMaxTiles];                    // destination image (window canvas, or unit slot)
+    int out_y[kMaxTiles], out_x[kMaxTiles];    // paste origin inside the destination image
 };
 
 void launch_prep_weights(const float* w, __half* out, int cin, int cout, int KB, int cout_pad, int planes, cudaStream_t st);
@@ -25,12 +27,13 @@ void launch_upsample2(ActBuf in, ActBuf out, int N, int h, int w, int C, int pla
 void launch_maxpool2(ActBuf in, int cs, int coff, ActBuf out, int N, int H, int W, int C, int planes, cudaStream_t st);
 void launch_act_from_f32(const float* src, int C, ActBuf dst, int cs, size_t npix, int planes, cudaStream_t st);
 void launch_act_to_f32(ActBuf src, int cs, int coff, float* dst, int C, size_t npix, int planes, cudaStream_t st);
-void launch_tile_pack(const uint8_t* frames, const float* flow, const float* warp, int fw, const TileList& tiles, int th,
-                      int tw, const float* lut255, ActBuf l3, ActBuf l2, ActBuf l1, int planes, cudaStream_t st);
-void launch_tile_unpack_u8(const float* pred, const TileList& tiles, int th2, int tw2, uint8_t* canvas, int OW, int core_h,
-                           int core_w, cudaStream_t st);
-void launch_tile_unpack_f32(const float* pred, const TileList& tiles, int th2, int tw2, float* canvas, int OW, int core_h,
-                            int core_w, cudaStream_t st);
+void launch_tile_pack(const uint8_t* frames, const float* flow, const float* warp, int fh, int fw, const TileList& tiles,
+                      int th, int tw, const float* lut255, ActBuf l3, ActBuf l2, ActBuf l1, int planes, cudaStream_t st);
+// canvas: images of OH x OW x 9, tile t lands in image out_img[t] at (out_y[t], out_x[t])
+void launch_tile_unpack_u8(const float* pred, const TileList& tiles, int th2, int tw2, uint8_t* canvas, int OH, int OW,
+                           int core_h, int core_w, cudaStream_t st);
+void launch_tile_unpack_f32(const float* pred, const TileList& tiles, int th2, int tw2, float* canvas, int OH, int OW,
+                            int core_h, int core_w, cudaStream_t st);
 void launch_warp_yuv(const uint8_t* yuv, const float* flow, float flow_scale, float* out, int h, int w, float out_scale,
                      cudaStream_t st);
 

@@ -105,6 +105,9 @@ struct Op {
     ConvLaunch conv;
     ActBuf in, out;
     int N, H, W, C, cs, coff;
+    double flops;            // algorithmic conv FLOPs (0 for pool / upsample)
+    double bytes;            // algorithmic HBM bytes of the launch
+    char name[96];
 };
 
 struct Plan {
@@ -297,17 +300,28 @@ struct Builder {
         const double fl = 2.0 * 9 * p.cin * p.cout * static_cast<double>(H) * W * N;
         plan->flops += fl;
         plan->eff_weighted += fl * L.efficiency;
+        op.flops = fl;
+        {   // algorithmic HBM bytes: input + weights once, every output / residual once
+            const double px = static_cast<double>(N) * H * W, eb = 2.0 * plan->planes;
+            op.bytes = px * p.KB * 64 * eb + 9.0 * p.KB * 64 * p.cout_pad * eb + (o.res ? px * p.cout * 4 : 0) +
+                       (o.raw ? px * (o.scalar ? p.cout : p.cout) * 4 : 0) + (o.act.p ? px * p.cout * eb : 0);
+        }
+        snprintf(op.name, sizeof op.name, "%s", name.c_str());
         if (o.raw && !o.scalar) plan->debug[name] = DebugTensor{o.raw, N, H, W, o.raw_cs};
         plan->ops.push_back(op);
     }
     void upsample(ActBuf in, ActBuf out, int N, int h, int w, int C) {
         Op op{};
         op.kind = OP_UPSAMPLE; op.in = in; op.out = out; op.N = N; op.H = h; op.W = w; op.C = C;
+        op.bytes = static_cast<double>(N) * h * w * C * 2.0 * plan->planes * 5;
+        snprintf(op.name, sizeof op.name, "upsample2 %dx%dx%d", h, w, C);
         plan->ops.push_back(op);
     }
     void pool(ActBuf in, int cs, int coff, ActBuf out, int N, int H, int W, int C) {
         Op op{};
         op.kind = OP_POOL; op.in = in; op.out = out; op.N = N; op.H = H; op.W = W; op.C = C; op.cs = cs; op.coff = coff;
+        op.bytes = static_cast<double>(N) * H * W * C * 2.0 * plan->planes * 1.25;
+        snprintf(op.name, sizeof op.name, "maxpool2 %dx%dx%d", H, W, C);
         plan->ops.push_back(op);
     }
 
@@ -417,8 +431,10 @@ struct Builder {
     }
 };
 
-int run_ops(fisr_ctx* ctx, Plan* plan, cudaStream_t st) {
+int run_ops(fisr_ctx* ctx, Plan* plan, cudaStream_t st, std::vector<cudaEvent_t>* marks = nullptr) {
+    size_t idx = 0;
     for (const Op& op : plan->ops) {
+        if (marks) cudaEventRecord((*marks)[idx++], st);
         switch (op.kind) {
             case OP_CONV: {
                 cudaError_t e = launch_conv3x3(op.conv, ctx->num_sms, st);
@@ -429,6 +445,7 @@ int run_ops(fisr_ctx* ctx, Plan* plan, cudaStream_t st) {
             case OP_POOL: launch_maxpool2(op.in, op.cs, op.coff, op.out, op.N, op.H, op.W, op.C, plan->planes, st); break;
         }
     }
+    if (marks) cudaEventRecord((*marks)[idx], st);
     CUDA_TRY(ctx, cudaGetLastError());
     return FISR_OK;
 }
@@ -516,44 +533,67 @@ TileGeom tile_geometry(int H, int W, int pH, int pW) {
     return g;
 }
 
-int window_impl(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, const float* d_warp, int H, int W, int pH,
-                int pW, int tile_first, int tile_count, uint8_t* d_canvas_u8, float* d_canvas_f32, cudaStream_t st) {
-    if (pH < 1 || pW < 1 || H < 32 * pH || W < 32 * pW) return fail(ctx, FISR_E_INVALID, "bad tile grid %dx%d for %dx%d", pH, pW, H, W);
-    if (tile_first < 0 || tile_count < 0 || tile_first + tile_count > pH * pW)
-        return fail(ctx, FISR_E_INVALID, "tile range [%d,+%d) outside the %dx%d grid", tile_first, tile_count, pH, pW);
+// Runs a list of (window, tile) units: unit id = window * (pH*pW) + tile.  Units with equal tile size are batched
+// into one forward.  layout 0: canvas is [B, 2h, 2w, 9], every tile pasted at its place in its window's frame
+// (FISRnet.py:1056-1057); layout 1: canvas is [n_units, 2sH, 2sW, 9], unit i of the list in slot i (the send buffer
+// of the multi-GPU all-gather).
+int units_impl(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, const float* d_warp, int B, int H, int W,
+               int pH, int pW, const int* units, int n_units, int layout, uint8_t* d_canvas_u8, float* d_canvas_f32,
+               cudaStream_t st) {
+    if (B < 1 || pH < 1 || pW < 1 || H < 32 * pH || W < 32 * pW)
+        return fail(ctx, FISR_E_INVALID, "bad window batch %d or tile grid %dx%d for %dx%d", B, pH, pW, H, W);
+    if (n_units < 0 || (n_units > 0 && !units)) return fail(ctx, FISR_E_INVALID, "bad unit list");
+    const int T = pH * pW;
+    for (int i = 0; i < n_units; ++i)
+        if (units[i] < 0 || units[i] >= B * T) return fail(ctx, FISR_E_INVALID, "unit %d outside %d windows x %d tiles", units[i], B, T);
     const TileGeom g = tile_geometry(H, W, pH, pW);
-    // group the requested tiles by input size so that each group is one batched forward
-    std::vector<bool> done(pH * pW, false);
-    for (int p = tile_first; p < tile_first + tile_count; ++p) {
-        if (done[p]) continue;
-        const int th = g.tiles[p].yhi - g.tiles[p].ylo, tw = g.tiles[p].xhi - g.tiles[p].xlo;
+    const int OH = layout == 0 ? 2 * g.h : 2 * g.sH, OW = layout == 0 ? 2 * g.w : 2 * g.sW;
+    std::vector<bool> done(n_units, false);
+    for (int i = 0; i < n_units; ++i) {
+        if (done[i]) continue;
+        const TileGeom::T& ti = g.tiles[units[i] % T];
+        const int th = ti.yhi - ti.ylo, tw = ti.xhi - ti.xlo;
         TileList tl{};
-        for (int q = p; q < tile_first + tile_count && tl.count < kMaxTiles; ++q) {
-            if (done[q]) continue;
-            if (g.tiles[q].yhi - g.tiles[q].ylo != th || g.tiles[q].xhi - g.tiles[q].xlo != tw) continue;
+        for (int j = i; j < n_units && tl.count < kMaxTiles; ++j) {
+            if (done[j]) continue;
+            const int q = units[j] % T;
+            const TileGeom::T& tj = g.tiles[q];
+            if (tj.yhi - tj.ylo != th || tj.xhi - tj.xlo != tw) continue;
             const int k = tl.count++;
-            tl.ylo[k] = g.tiles[q].ylo; tl.xlo[k] = g.tiles[q].xlo;
-            tl.trim_y[k] = g.tiles[q].trim_y; tl.trim_x[k] = g.tiles[q].trim_x;
-            tl.out_y[k] = (q / pW) * g.sH * 2; tl.out_x[k] = (q % pW) * g.sW * 2;
-            done[q] = true;
+            tl.win[k] = units[j] / T;
+            tl.ylo[k] = tj.ylo; tl.xlo[k] = tj.xlo;
+            tl.trim_y[k] = tj.trim_y; tl.trim_x[k] = tj.trim_x;
+            if (layout == 0) { tl.out_img[k] = units[j] / T; tl.out_y[k] = (q / pW) * g.sH * 2; tl.out_x[k] = (q % pW) * g.sW * 2; }
+            else             { tl.out_img[k] = j; tl.out_y[k] = 0; tl.out_x[k] = 0; }
+            done[j] = true;
         }
         Plan* plan = nullptr;
         int rc = get_plan(ctx, tl.count, th, tw, &plan);
         if (rc != FISR_OK) return rc;
-        // frames are W wide on the device (uncropped rows); the crop is a view (img[:h, :w], FISRnet.py:1008)
-        launch_tile_pack(d_frames, d_flow, d_warp, W, tl, th, tw, ctx->d_lut255, plan->in_lvl[2], plan->in_lvl[1],
+        // frames are H x W on the device (uncropped); the crop is a view (img[:h, :w], FISRnet.py:1008)
+        launch_tile_pack(d_frames, d_flow, d_warp, H, W, tl, th, tw, ctx->d_lut255, plan->in_lvl[2], plan->in_lvl[1],
                          plan->in_lvl[0], plan->planes, st);
         ctx->launches++;
         rc = run_plan(ctx, plan, st);
         if (rc != FISR_OK) return rc;
         if (d_canvas_u8)
-            launch_tile_unpack_u8(plan->pred[2], tl, 2 * th, 2 * tw, d_canvas_u8, 2 * g.w, 2 * g.sH, 2 * g.sW, st);
+            launch_tile_unpack_u8(plan->pred[2], tl, 2 * th, 2 * tw, d_canvas_u8, OH, OW, 2 * g.sH, 2 * g.sW, st);
         if (d_canvas_f32)
-            launch_tile_unpack_f32(plan->pred[2], tl, 2 * th, 2 * tw, d_canvas_f32, 2 * g.w, 2 * g.sH, 2 * g.sW, st);
+            launch_tile_unpack_f32(plan->pred[2], tl, 2 * th, 2 * tw, d_canvas_f32, OH, OW, 2 * g.sH, 2 * g.sW, st);
         ctx->launches++;
         CUDA_TRY(ctx, cudaGetLastError());
     }
     return FISR_OK;
+}
+
+int window_impl(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, const float* d_warp, int H, int W, int pH,
+                int pW, int tile_first, int tile_count, uint8_t* d_canvas_u8, float* d_canvas_f32, cudaStream_t st) {
+    if (pH < 1 || pW < 1) return fail(ctx, FISR_E_INVALID, "bad tile grid %dx%d", pH, pW);
+    if (tile_first < 0 || tile_count < 0 || tile_first + tile_count > pH * pW)
+        return fail(ctx, FISR_E_INVALID, "tile range [%d,+%d) outside the %dx%d grid", tile_first, tile_count, pH, pW);
+    std::vector<int> units(tile_count);
+    for (int i = 0; i < tile_count; ++i) units[i] = tile_first + i;
+    return units_impl(ctx, d_frames, d_flow, d_warp, 1, H, W, pH, pW, units.data(), tile_count, 0, d_canvas_u8, d_canvas_f32, st);
 }
 
 }  // namespace
@@ -762,6 +802,15 @@ int fisr_window_device(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_fl
     return window_impl(ctx, d_frames, d_flow, d_warp, H, W, pH, pW, tile_first, tile_count, d_canvas, nullptr, st);
 }
 
+int fisr_units_device(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, const float* d_warp, int B, int H, int W,
+                      int pH, int pW, const int* h_units, int n_units, int layout, uint8_t* d_out, void* stream) {
+    if (!ctx || !d_frames || !d_flow || !d_warp || !d_out) return FISR_E_INVALID;
+    if (layout != 0 && layout != 1) return fail(ctx, FISR_E_INVALID, "layout must be 0 (frames) or 1 (unit-major)");
+    Guard guard(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return units_impl(ctx, d_frames, d_flow, d_warp, B, H, W, pH, pW, h_units, n_units, layout, d_out, nullptr, st);
+}
+
 int fisr_window_device_f32(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, const float* d_warp, int H,
                            int W, int pH, int pW, float* d_canvas, void* stream) {
     if (!ctx || !d_frames || !d_flow || !d_warp || !d_canvas) return FISR_E_INVALID;
@@ -880,6 +929,44 @@ int fisr_debug_conv_output(fisr_ctx* ctx, const char* conv_name, float* h_dst, s
     CUDA_TRY(ctx, cudaDeviceSynchronize());
     CUDA_TRY(ctx, cudaMemcpy(h_dst, t.raw, n * 4, cudaMemcpyDeviceToHost));
     return FISR_OK;
+}
+
+int fisr_profile_ops(fisr_ctx* ctx, int N, int H, int W, int reps, int max_ops, float* ms, double* flops, double* bytes,
+                     int* kinds, char* names, int name_stride) {
+    if (!ctx || reps < 1) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    Plan* plan = nullptr;
+    int rc = get_plan(ctx, N, H, W, &plan);
+    if (rc != FISR_OK) return rc;
+    const int n = static_cast<int>(plan->ops.size());
+    if (!ms) return n;
+    if (max_ops < n) return fail(ctx, FISR_E_INVALID, "plan has %d ops, buffers hold %d", n, max_ops);
+    std::vector<cudaEvent_t> marks(n + 1);
+    for (auto& e : marks) CUDA_TRY(ctx, cudaEventCreate(&e));
+    for (int i = 0; i < n; ++i) ms[i] = 0.f;
+    rc = run_ops(ctx, plan, ctx->stream);                       // warm-up
+    for (int r = 0; r < reps && rc == FISR_OK; ++r) {
+        rc = run_ops(ctx, plan, ctx->stream, &marks);
+        ctx->launches += n;
+        if (rc != FISR_OK) break;
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < n; ++i) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, marks[i], marks[i + 1]);
+            ms[i] += t / reps;
+        }
+    }
+    for (auto& e : marks) cudaEventDestroy(e);
+    if (rc != FISR_OK) return rc;
+    for (int i = 0; i < n; ++i) {
+        const Op& op = plan->ops[i];
+        if (flops) flops[i] = op.flops;
+        if (bytes) bytes[i] = op.bytes;
+        if (kinds) kinds[i] = static_cast<int>(op.kind) * 1000 + (op.kind == OP_CONV ? op.conv.NT * 1 + op.conv.chunks * 0 : 0);
+        if (names && name_stride > 0) snprintf(names + static_cast<size_t>(i) * name_stride, name_stride, "%s", op.name);
+    }
+    rc = check_kernel_error(ctx);
+    return rc == FISR_OK ? n : rc;
 }
 
 long long fisr_launch_count(const fisr_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -163,6 +163,27 @@ class Engine:
         self._exit()
         return out
 
+    def units(self, frames: torch.Tensor, flow: torch.Tensor, warp: torch.Tensor, units, num_patch=(2, 2),
+              layout: str = "units", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Batched (window, tile) units: frames u8 [B,H,W,9], flow [B,H,W,8], warp [B,H,W,12]; unit id =
+        window * tiles_per_window + tile.  layout "frames" -> [B,2h,2w,9]; "units" -> [len(units),2h/pH,2w/pW,9]."""
+        frames = self._dev(frames, torch.uint8)
+        flow = self._dev(flow, torch.float32)
+        warp = self._dev(warp, torch.float32)
+        B, H, W, _ = frames.shape
+        oh, ow, _ = self.canvas_shape(H, W, num_patch)
+        units = [int(u) for u in units]
+        if out is None:
+            shape = (B, oh, ow, 9) if layout == "frames" else (len(units), oh // num_patch[0], ow // num_patch[1], 9)
+            out = torch.zeros(shape, dtype=torch.uint8, device=frames.device)
+        arr = (C.c_int * max(1, len(units)))(*units)
+        self._enter(frames, flow, warp, out)
+        self._check(self.lib.fisr_units_device(self.h, frames.data_ptr(), flow.data_ptr(), warp.data_ptr(), B, H, W,
+                                               num_patch[0], num_patch[1], arr, len(units), 0 if layout == "frames" else 1,
+                                               self._dev(out, torch.uint8).data_ptr(), self._stream()), "fisr_units_device")
+        self._exit()
+        return out
+
     def window_f32(self, frames: torch.Tensor, flow: torch.Tensor, warp: torch.Tensor, num_patch=(2, 2)) -> torch.Tensor:
         frames = self._dev(frames, torch.uint8)
         H, W, _ = frames.shape
@@ -236,6 +257,28 @@ class Engine:
         self._check(self.lib.fisr_debug_conv_output(self.h, conv_name.encode(), a.ctypes.data, a.size),
                     "fisr_debug_conv_output")
         return a
+
+    def profile_ops(self, n: int, h: int, w: int, reps: int = 3):
+        """Per-launch device time of the (n,h,w) plan: list of dicts {name, kind, ms, flops, bytes}."""
+        torch.cuda.synchronize(self.device)
+        cnt = self.lib.fisr_profile_ops(self.h, n, h, w, 1, 0, None, None, None, None, None, 0)
+        if cnt < 0:
+            self._check(cnt, "fisr_profile_ops")
+        ms = (C.c_float * cnt)()
+        fl = (C.c_double * cnt)()
+        by = (C.c_double * cnt)()
+        kd = (C.c_int * cnt)()
+        names = C.create_string_buffer(cnt * 96)
+        rc = self.lib.fisr_profile_ops(self.h, n, h, w, reps, cnt, ms, fl, by, kd, names, 96)
+        if rc < 0:
+            self._check(rc, "fisr_profile_ops")
+        out = []
+        for k in range(cnt):
+            nm = names.raw[k * 96:(k + 1) * 96].split(b"\0", 1)[0].decode()
+            kind = "conv" if kd[k] < 1000 else ("upsample" if kd[k] < 2000 else "pool")
+            out.append({"name": nm, "kind": kind, "nt": kd[k] % 1000, "ms": float(ms[k]), "flops": float(fl[k]),
+                        "bytes": float(by[k])})
+        return out
 
     def plan_info(self, n: int, h: int, w: int) -> dict:
         fl, eff, nl, ws = C.c_double(), C.c_double(), C.c_int(), C.c_size_t()

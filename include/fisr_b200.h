@@ -74,6 +74,13 @@ int fisr_forward_host(fisr_ctx* ctx, const float* h_img, int N, int H, int W, fl
  * row-major grid are computed and pasted, so ranks of a multi-GPU job can shard one window; pass 0, pH*pW for all. */
 int fisr_window_device(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, const float* d_warp, int H, int W,
                        int pH, int pW, int tile_first, int tile_count, uint8_t* d_canvas, void* stream);
+/* Batched form over B windows: frames u8 [B,H,W,9], flow [B,H,W,8], warp [B,H,W,12].  A unit is one (window, tile)
+ * pair, id = window * (pH*pW) + tile; h_units lists the units this call computes (the shard of this rank).  Units of
+ * equal tile size run as ONE batched forward.  layout 0: d_out is [B,2h,2w,9], tiles pasted into their frames;
+ * layout 1: d_out is [n_units, 2h/pH, 2w/pW, 9], unit i of the list in slot i -- the contiguous send buffer of the
+ * one all-gather the multi-GPU path needs (the loops of FISRnet.py:994,1028 carry no dependence). */
+int fisr_units_device(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, const float* d_warp, int B, int H, int W,
+                      int pH, int pW, const int* h_units, int n_units, int layout, uint8_t* d_out, void* stream);
 int fisr_window_host(fisr_ctx* ctx, const uint8_t* h_frames, const float* h_flow, const float* h_warp, int H, int W,
                      int pH, int pW, uint8_t* h_canvas);
 /* float canvas [2h,2w,9] before clipping (what FISRnet.py:1057 accumulates), for parity tests */
@@ -98,6 +105,12 @@ int fisr_conv3x3(fisr_ctx* ctx, const float* d_x, const float* d_w, const float*
 /* After a forward: copies the pre-activation output of the named conv (e.g. ".../enc/level_0/conv/0") as
  * float32 NHWC to host, when the plan materialises it; returns FISR_E_INVALID otherwise. */
 int fisr_debug_conv_output(fisr_ctx* ctx, const char* conv_name, float* h_dst, size_t count);
+/* Per-launch device times of the plan for (N,H,W): runs it `reps` times op by op with CUDA events between launches
+ * (no graph) and returns the op count; with ms == NULL only returns the count.  flops / bytes are the algorithmic
+ * figures of each launch (2*9*Cin*Cout*h*w*N; operands + outputs once), kinds[i] = 0 conv (+ its N tile), 1000
+ * upsample, 2000 max-pool; names is max_ops strings of name_stride bytes.  Feeds bench.py's roofline block. */
+int fisr_profile_ops(fisr_ctx* ctx, int N, int H, int W, int reps, int max_ops, float* ms, double* flops, double* bytes,
+                     int* kinds, char* names, int name_stride);
 /* Kernel launches issued by this context since creation (the `gpu_launches` evidence bench.py reports). */
 long long fisr_launch_count(const fisr_ctx* ctx);
 /* Conv FLOPs (2*9*Cin*Cout*h*w*N) and mean MMA row efficiency of the plan for (N,H,W). */
