@@ -8,9 +8,7 @@ namespace fisr {
 
 namespace {
 
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-    return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
-}
+
 __device__ __forceinline__ void unpack8(const uint4& v, __half (&h)[8]) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -37,11 +35,7 @@ template <int PLANES>
 __device__ __forceinline__ void store8(__half* p, size_t plane, const float (&f)[8]) {
     uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const SplitHalf s0 = split_f32(f[2 * q]), s1 = split_f32(f[2 * q + 1]);
-        hi[q] = pack_h2(s0.hi, s1.hi);
-        lo[q] = pack_h2(s0.lo, s1.lo);
-    }
+    for (int q = 0; q < 4; ++q) split2_f32(f[2 * q], f[2 * q + 1], hi[q], lo[q]);
     *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     if (PLANES == 2) *reinterpret_cast<uint4*>(p + plane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }

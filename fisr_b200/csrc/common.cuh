@@ -24,6 +24,15 @@ __device__ __forceinline__ SplitHalf split_f32(float x) {
     s.lo = __float2half_rn(x - __half2float(s.hi));
     return s;
 }
+// Packed split of two values: cvt.rn.f16x2.f32 (F2FP, full-rate ALU) instead of scalar F2F conversions, which run
+// on the quarter-rate XU pipe and were the measured bottleneck of the conv epilogue (ncu: pipe_xu at 109 %).
+__device__ __forceinline__ void split2_f32(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 b = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - b.x, x1 - b.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ float join_f16(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
 
 // Everything the 3x3 conv kernel needs besides the tensor maps (see conv_umma.cu).
@@ -38,6 +47,7 @@ struct ConvArgs {
     int cin_off, KB;          // first input channel in the source buffer, number of 64-channel K blocks
     int cout, NB;             // true output channels, number of N blocks (cout_pad = NB * NT)
     int P, TH, TW;            // patch pitch (= TW + 2), output rows / cols per tile
+    int inv_p;                // ceil(2^20 / P): q / P == (q * inv_p) >> 20 for q < 2^20 / P
     int tiles_x, tiles_y, num_tiles;
     int raw_cs, raw_off0, raw_off1, raw_split;   // fp32 output channel stride / channel map
     int act_cs, act_off0, act_off1, act_split;   // fp16 output channel stride / channel map

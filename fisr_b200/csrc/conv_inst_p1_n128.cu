@@ -1,0 +1,8 @@
+// Instantiation unit of the tcgen05 conv kernel: PLANES = 1, N tile = 128 (see conv_umma_kernel.cuh).
+#include "conv_umma_kernel.cuh"
+
+namespace fisr {
+namespace convk {
+FISR_CONV_FAMILY(128, 1, FISR_FOR_EPI)
+}  // namespace convk
+}  // namespace fisr

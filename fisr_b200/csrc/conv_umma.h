@@ -5,12 +5,13 @@
 namespace fisr {
 
 // opt-in dynamic shared memory budget per CTA (227 KB minus the kernel's static barriers)
-constexpr int kConvMaxSmem = 231424;
+constexpr int kConvMaxSmem = 230400;
 
 struct ConvLaunch {
     CUtensorMap tmA_hi, tmA_lo, tmB;
     ConvArgs args;
     int NT, chunks, planes;
+    int epi;                // epilogue variant: 1 residual in, 2 fp32 out, 4 depth-to-space (convk::EPI_*)
     int smem_bytes;
     double efficiency;      // useful fraction of the MMA rows issued (tile quantisation + halo columns)
 };

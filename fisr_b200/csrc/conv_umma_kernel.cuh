@@ -1,0 +1,462 @@
+// 3x3 stride-1 SAME convolution (+bias, +residual, ReLU, depth-to-space, virtual concat) as a
+// persistent, warp-specialised tcgen05 implicit GEMM for sm_100a.  Device template; instantiated per
+// (planes, N tile) in conv_inst_*.cu, dispatched from conv_umma.cu.
+//
+// Replaces the reference's `Conv2d` (ops.py:7-11) together with the element-wise ops the reference
+// runs around it: `relu` (ops.py:17-18), the residual add of `res_block` (ops.py:43),
+// `tf.depth_to_space` (FISRnet.py:99,105), `tf.concat` (ops.py:71, FISRnet.py:108,113,144).
+//
+// Data layout in HBM
+//   activations : NHWC fp16, channel count padded to a multiple of 64, as a (hi, lo) plane pair
+//                 (x = hi + lo, see common.cuh) -- 4 B / element like the fp32 the reference stores.
+//   weights     : [plane][kb][tap][cout_pad][64] fp16 (K-major rows of 128 B), hi/lo planes.
+//   residual / pre-activation outputs : NHWC fp32.
+//
+// One CTA tile = TH x TW output pixels x NT output channels.  Per 64-channel K block the producer
+// TMA-loads ONE halo'd input patch (TH+2) x (TW+2) x 64ch (4-D box, out-of-bounds = SAME zero padding)
+// into 128B-swizzled shared memory with pixel pitch P = TW+2.  GEMM row m of the tile is patch position
+// m (row-major with pitch P), so the A operand of tap (ky,kx) is the same patch read through a UMMA
+// descriptor whose start address is advanced by (ky*P+kx) rows of 128 B: no im2col re-read, every
+// activation byte crosses L2->SMEM once per tile (plus halo).  Rows with (m % P) >= TW are computed
+// and discarded.  Weights stream per tap through a ring of slots.
+//
+// STACK (split mode, NT <= 64): the weight slot of a tap holds [B_hi; B_lo] as one 2*NT-row operand, so
+//   D[:, 0:NT] = A_hi * B_hi + A_lo * B_hi        D[:, NT:2NT] = A_hi * B_lo
+// take 2 MMAs (N = 2NT, then N = NT) instead of 3 and A_hi is fetched from shared memory once for both
+// products: an N = 64 MMA needs 48 cycles of shared-memory operand reads for 32 cycles of math (ncu:
+// pipe_tc 80 % busy at 50 % tensor math), so the narrow layers are bound by exactly that traffic.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 =
+// epilogue (TMEM -> registers -> smem transpose -> bias/residual/ReLU/split -> coalesced HBM stores).
+// Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.  The epilogue
+// is CUDA-core work on every output element; 8 warps (two per TMEM lane quarter) keep the four schedulers
+// issuing while the tensor core runs.
+#pragma once
+#include "common.cuh"
+#include "conv_umma.h"
+#include "sm100_ptx.cuh"
+
+namespace fisr {
+namespace convk {
+
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kMaxBSlots = 12;
+constexpr int kMaxAStages = 2;
+constexpr int kStageBytesPerWarp = 32 * 64;   // [32 px][16 ch] fp32, 16-B groups XOR-swizzled (conflict-free both ways)
+
+// epilogue variants (template flags)
+enum { EPI_RES = 1, EPI_RAW = 2, EPI_D2S = 4 };
+
+// error codes written to ConvArgs::err on a barrier timeout
+enum { ERR_A_EMPTY = 11, ERR_B_EMPTY = 12, ERR_A_FULL = 21, ERR_B_FULL = 22, ERR_ACC_EMPTY = 23, ERR_ACC_FULL = 31 };
+
+struct TileCoord {
+    int n, y0, x0, nb;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile) {
+    TileCoord t;
+    t.nb = tile % a.NB;
+    int s = tile / a.NB;
+    const int tx = s % a.tiles_x;
+    s /= a.tiles_x;
+    const int ty = s % a.tiles_y;
+    t.n = s / a.tiles_y;
+    t.y0 = ty * a.TH;
+    t.x0 = tx * a.TW;
+    return t;
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+// Narrow head outputs (Cout = 6 / 3, FISRnet.py:100,106): thread = pixel, channel-mapped scalar stores into the
+// 9-channel pred tensor and into channels 29.. of the next level's input (FISRnet.py:107-108,113,144).
+template <int PLANES>
+__device__ __forceinline__ void epilogue_scalar16(const ConvArgs& a, const float* __restrict__ sBias, const uint32_t (&v)[16],
+                                                  int pix) {
+#pragma unroll
+    for (int ch = 0; ch < 16; ++ch) {
+        if (ch < a.cout) {
+            const float f = __uint_as_float(v[ch]) + sBias[ch];
+            if (a.out_raw) a.out_raw[static_cast<size_t>(pix) * a.raw_cs + ch + (ch < a.raw_split ? a.raw_off0 : a.raw_off1)] = f;
+            if (a.out_act) {
+                const SplitHalf s = split_f32(a.act_relu ? fmaxf(f, 0.f) : f);
+                __half* d = a.out_act + static_cast<size_t>(pix) * a.act_cs + ch + (ch < a.act_split ? a.act_off0 : a.act_off1);
+                d[0] = s.hi;
+                if (PLANES == 2) d[a.act_plane] = s.lo;
+            }
+        }
+    }
+}
+
+template <int NT, int CHUNKS, int PLANES, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvArgs a) {
+    constexpr bool STACK = (PLANES == 2) && (NT <= 64);
+    constexpr int DCOLS = STACK ? 2 * NT : NT;                  // accumulator columns per 128-row chunk
+    constexpr int ACC_COLS = CHUNKS * DCOLS;                    // fp32 columns of one accumulator stage
+    constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
+    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns must be a power of two <= 512");
+    constexpr int PLANE_BYTES = NT * 128;                       // one weight plane of one tap
+    constexpr int B_SLOT_BYTES = STACK ? 2 * PLANE_BYTES : PLANE_BYTES;
+    constexpr int SLOTS_PER_TAP = STACK ? 1 : PLANES;
+    constexpr bool NARROW = NT < 32;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t a_stage_bytes = PLANES * a.a_plane_bytes;
+    const uint32_t sA = smem_u32(smem);
+    const uint32_t sB = sA + a.a_stages * a_stage_bytes;
+    float* sBias = reinterpret_cast<float*>(smem + a.a_stages * a_stage_bytes + a.b_slots * B_SLOT_BYTES);
+    const uint32_t sBias32 = sB + a.b_slots * B_SLOT_BYTES;
+    const uint32_t sStage32 = sBias32 + 2048;      // kEpiWarps x [32 px][16 ch] fp32 transpose buffers
+
+    __shared__ __align__(8) uint64_t bars[2 * kMaxAStages + 2 * kMaxBSlots + 4];
+    __shared__ uint32_t tmem_slot;
+    const uint32_t bar0 = smem_u32(bars);
+    auto a_full = [&](int s) { return bar0 + 8u * s; };
+    auto a_empty = [&](int s) { return bar0 + 8u * (kMaxAStages + s); };
+    auto b_full = [&](int s) { return bar0 + 8u * (2 * kMaxAStages + s); };
+    auto b_empty = [&](int s) { return bar0 + 8u * (2 * kMaxAStages + kMaxBSlots + s); };
+    auto acc_full = [&](int s) { return bar0 + 8u * (2 * kMaxAStages + 2 * kMaxBSlots + s); };
+    auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kMaxAStages + 2 * kMaxBSlots + 2 + s); };
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // broadcast: lets ptxas treat the role branches as warp-uniform
+
+    if (tid == 0) {
+        for (int s = 0; s < a.a_stages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < a.b_slots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), kEpiWarps); }
+        fence_mbar_init();
+        tma_prefetch_desc(&tmA_hi);
+        if (PLANES == 2) tma_prefetch_desc(&tmA_lo);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
+    for (int i = tid; i < a.NB * NT; i += kThreads) sBias[i] = a.bias[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    const int box_bytes = (a.TH + 2) * a.P * 128;
+    const int cout_pad = a.NB * NT;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (elect_one()) {
+            uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+            bool ok = true;
+            // A patches are prefetched one (tile, kb) item ahead of the weight stream.
+            int pf_tile = blockIdx.x, pf_kb = 0;
+            auto issue_a = [&]() -> bool {
+                if (pf_tile >= a.num_tiles) return true;
+                if (!mbar_wait(a_empty(as), aph ^ 1, a.err, ERR_A_EMPTY)) return false;
+                const TileCoord t = decode_tile(a, pf_tile);
+                mbar_expect_tx(a_full(as), PLANES * box_bytes);
+                const uint32_t dst = sA + as * a_stage_bytes;
+                tma_load_4d(dst, &tmA_hi, a_full(as), a.cin_off + pf_kb * 64, t.x0 - 1, t.y0 - 1, t.n);
+                if (PLANES == 2)
+                    tma_load_4d(dst + a.a_plane_bytes, &tmA_lo, a_full(as), a.cin_off + pf_kb * 64, t.x0 - 1, t.y0 - 1, t.n);
+                if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1; }
+                if (++pf_kb == a.KB) { pf_kb = 0; pf_tile += gridDim.x; }
+                return true;
+            };
+            ok = issue_a();
+            for (int tile = blockIdx.x; tile < a.num_tiles && ok; tile += gridDim.x) {
+                const int nb = tile % a.NB;
+                for (int kb = 0; kb < a.KB && ok; ++kb) {
+                    for (int tap = 0; tap < 9 && ok; ++tap) {
+                        if (tap == 2 && a.a_stages > 1) ok = issue_a();
+                        for (int sl = 0; sl < SLOTS_PER_TAP && ok; ++sl) {
+                            ok = mbar_wait(b_empty(bs), bph ^ 1, a.err, ERR_B_EMPTY);
+                            if (!ok) break;
+                            mbar_expect_tx(b_full(bs), B_SLOT_BYTES);
+                            const uint32_t dst = sB + bs * B_SLOT_BYTES;
+                            if (STACK) {
+                                tma_load_2d(dst, &tmB, b_full(bs), 0, ((0 * a.KB + kb) * 9 + tap) * cout_pad + nb * NT);
+                                tma_load_2d(dst + PLANE_BYTES, &tmB, b_full(bs), 0, ((1 * a.KB + kb) * 9 + tap) * cout_pad + nb * NT);
+                            } else {
+                                tma_load_2d(dst, &tmB, b_full(bs), 0, ((sl * a.KB + kb) * 9 + tap) * cout_pad + nb * NT);
+                            }
+                            if (++bs == (uint32_t)a.b_slots) { bs = 0; bph ^= 1; }
+                        }
+                    }
+                    if (a.a_stages == 1 && ok) ok = issue_a();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        // The whole warp walks the pipeline convergently (waits, stage counters and descriptor words stay in
+        // uniform registers); only the tcgen05 instructions are predicated on one elected lane.
+        constexpr uint32_t idesc = umma_idesc_f16(128, NT);
+        constexpr uint32_t idesc2 = umma_idesc_f16(128, STACK ? 2 * NT : NT);
+        const bool lead = elect_one();
+        uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < a.num_tiles && ok; tile += gridDim.x) {
+            ok = __all_sync(0xffffffffu, mbar_wait(acc_empty(cs), cph ^ 1, a.err, ERR_ACC_EMPTY));
+            if (!ok) break;
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + cs * ACC_COLS;
+            for (int kb = 0; kb < a.KB && ok; ++kb) {
+                ok = __all_sync(0xffffffffu, mbar_wait(a_full(as), aph, a.err, ERR_A_FULL));
+                if (!ok) break;
+                const uint32_t a_hi0 = umma_desc_lo(sA + as * a_stage_bytes);
+                const uint32_t a_lo0 = umma_desc_lo(sA + as * a_stage_bytes + a.a_plane_bytes);
+                uint32_t first = kb == 0 ? 0u : 1u;          // accumulate flag of the very first MMA of the tile
+#pragma unroll 1
+                for (int ky = 0; ky < 3 && ok; ++ky) {
+#pragma unroll 1
+                    for (int kx = 0; kx < 3 && ok; ++kx) {
+                        const uint32_t a_off = static_cast<uint32_t>(ky * a.P + kx) * 8u;      // rows of 128 B, >> 4
+                        const uint32_t ah = a_hi0 + a_off, al = a_lo0 + a_off;
+                        ok = __all_sync(0xffffffffu, mbar_wait(b_full(bs), bph, a.err, ERR_B_FULL));
+                        if (!ok) break;
+                        tc_fence_after();
+                        {
+                            const uint32_t b0 = umma_desc_lo(sB + bs * B_SLOT_BYTES);
+                            if (lead) {
+#pragma unroll
+                                for (int c = 0; c < CHUNKS; ++c) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        // A_hi * [B_hi (; B_lo)]
+                                        umma_f16_lohi(d_tmem + c * DCOLS, ah + c * 1024 + k * 2, b0 + k * 2, kUmmaDescHiSw128,
+                                                      idesc2, k == 0 ? first : 1u);
+                                        if (PLANES == 2)   // A_lo * B_hi
+                                            umma_f16_lohi(d_tmem + c * DCOLS, al + c * 1024 + k * 2, b0 + k * 2,
+                                                          kUmmaDescHiSw128, idesc, 1u);
+                                    }
+                                }
+                                umma_commit(b_empty(bs));
+                            }
+                            first = 1u;
+                            if (++bs == (uint32_t)a.b_slots) { bs = 0; bph ^= 1; }
+                        }
+                        if (PLANES == 2 && !STACK) {   // separate lo weight plane: A_hi * B_lo
+                            ok = __all_sync(0xffffffffu, mbar_wait(b_full(bs), bph, a.err, ERR_B_FULL));
+                            if (!ok) break;
+                            tc_fence_after();
+                            const uint32_t b0 = umma_desc_lo(sB + bs * B_SLOT_BYTES);
+                            if (lead) {
+#pragma unroll
+                                for (int c = 0; c < CHUNKS; ++c) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        umma_f16_lohi(d_tmem + c * DCOLS, ah + c * 1024 + k * 2, b0 + k * 2, kUmmaDescHiSw128,
+                                                      idesc, 1u);
+                                }
+                                umma_commit(b_empty(bs));
+                            }
+                            if (++bs == (uint32_t)a.b_slots) { bs = 0; bph ^= 1; }
+                        }
+                    }
+                }
+                if (lead && ok) umma_commit(a_empty(as));
+                if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1; }
+            }
+            if (lead && ok) umma_commit(acc_full(cs));
+            if (++cs == 2) { cs = 0; cph ^= 1; }
+        }
+    } else {
+        // ============================== epilogue ==============================
+        const int ew = warp - 2;             // 0..7
+        const int q4 = warp & 3;             // TMEM lane quarter this warp may read
+        const int grp = ew >> 2;             // the two warps of a quarter split the chunks (or the channel range)
+        uint32_t cs = 0, cph = 0;
+        bool ok = true;
+        // this warp's share of the tile: chunk my_c, channel range [c_begin, c_end)
+        constexpr int CSPAN = NARROW ? NT : (CHUNKS == 2 ? NT : NT / 2);
+        const int my_c = CHUNKS == 2 ? grp : 0;
+        const int c_begin = (NARROW || CHUNKS == 2) ? 0 : grp * CSPAN;
+        const bool idle = NARROW && CHUNKS == 1 && grp == 1;
+        const uint32_t stg = sStage32 + ew * kStageBytesPerWarp;
+        const float relu_floor = a.act_relu ? 0.f : -INFINITY;
+        // Transpose staging: element (row r, 16-B group j) lives at group r*4 + (j ^ ((r >> 1) & 3)).
+        //   write: lane = row, group j      -> the 8 lanes of a phase hit 8 different bank groups
+        //   read : lane -> row (lane >> 2) + 8*i, group lane & 3 -> 2 rows x 4 groups per phase, again all different
+        const uint32_t wr_base = stg + lane * 64, wr_sw = (lane >> 1) & 3;
+        const uint32_t rd_row = lane >> 2, rd_grp = lane & 3;
+
+        for (int tile = blockIdx.x; tile < a.num_tiles && ok; tile += gridDim.x) {
+            const TileCoord t = decode_tile(a, tile);
+            const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + cs * ACC_COLS + my_c * DCOLS;
+            if constexpr (NARROW) {
+                ok = __all_sync(0xffffffffu, mbar_wait(acc_full(cs), cph, a.err, ERR_ACC_FULL));
+                if (!ok) break;
+                tc_fence_after();
+                if (!idle) {
+                    const int q = my_c * 128 + q4 * 32 + lane;
+                    const int ty = (q * a.inv_p) >> 20, tx = q - ty * a.P;
+                    const int y = t.y0 + ty, x = t.x0 + tx;
+                    const bool valid = (tx < a.TW) && (ty < a.TH) && (y < a.H) && (x < a.W);
+                    uint32_t v[16];
+                    tmem_ld_32x16(tacc, v);
+                    if (STACK) {
+                        uint32_t v2[16];
+                        tmem_ld_32x16(tacc + NT, v2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+                    } else {
+                        tmem_ld_wait();
+                    }
+                    if (valid) epilogue_scalar16<PLANES>(a, sBias, v, (t.n * a.H + y) * a.W + x);
+                }
+            } else {
+                // After the transpose lane l serves pixels (l >> 2) + 8*i of this warp's 32-pixel group, channels
+                // 4*(l & 3) .. +3 of each 16-channel step: 4 lanes cover 64 contiguous bytes of fp32 per pixel.
+                const int cg_lane = t.nb * NT + c_begin + 4 * rd_grp;
+                uint32_t o_res[4], o_raw[4], o_act[4];
+                uint32_t vmask = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int q = my_c * 128 + q4 * 32 + 8 * i + rd_row;
+                    const int ty = (q * a.inv_p) >> 20, tx = q - ty * a.P;
+                    const int y = t.y0 + ty, x = t.x0 + tx;
+                    const bool valid = (tx < a.TW) && (ty < a.TH) && (y < a.H) && (x < a.W);
+                    vmask |= (valid ? 1u : 0u) << i;
+                    const uint32_t pix = valid ? static_cast<uint32_t>((t.n * a.H + y) * a.W + x) : 0u;
+                    if (EPI & EPI_RES) o_res[i] = pix * a.res_cs + cg_lane;
+                    if (EPI & EPI_RAW) o_raw[i] = pix * a.raw_cs + a.raw_off1 + cg_lane;
+                    if (EPI & EPI_D2S) o_act[i] = valid ? static_cast<uint32_t>((t.n * 2 * a.H + 2 * y) * (2 * a.W) + 2 * x) * a.act_cs : 0u;
+                    else o_act[i] = pix * a.act_cs + a.act_off1 + cg_lane;
+                }
+                constexpr int ITERS = CSPAN / 16;
+                // residual loads run one step ahead so that their DRAM latency is never exposed
+                float4 rr[4];
+                if (EPI & EPI_RES) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if ((vmask >> i) & 1) rr[i] = __ldg(reinterpret_cast<const float4*>(a.res + o_res[i]));
+                    }
+                }
+                ok = __all_sync(0xffffffffu, mbar_wait(acc_full(cs), cph, a.err, ERR_ACC_FULL));
+                if (!ok) break;
+                tc_fence_after();
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it) {
+                    const int c0 = it * 16;
+                    float4 rn[4];
+                    if ((EPI & EPI_RES) && it + 1 < ITERS) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            rn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if ((vmask >> i) & 1) rn[i] = __ldg(reinterpret_cast<const float4*>(a.res + o_res[i] + c0 + 16));
+                        }
+                    }
+                    const float4 b4 = lds128(sBias32 + (cg_lane + c0) * 4);
+                    uint32_t v[16];
+                    tmem_ld_32x16(tacc + c_begin + c0, v);
+                    if (STACK) {
+                        uint32_t v2[16];
+                        tmem_ld_32x16(tacc + NT + c_begin + c0, v2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+                    } else {
+                        tmem_ld_wait();
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        sts128(wr_base + ((j ^ wr_sw) << 4), __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t r = rd_row + 8 * i;
+                        const float4 val = lds128(stg + r * 64 + ((rd_grp ^ ((r >> 1) & 3)) << 4));
+                        if ((vmask >> i) & 1) {
+                            float f0 = val.x + b4.x, f1 = val.y + b4.y, f2 = val.z + b4.z, f3 = val.w + b4.w;
+                            if (EPI & EPI_RES) { f0 += rr[i].x; f1 += rr[i].y; f2 += rr[i].z; f3 += rr[i].w; }
+                            if (EPI & EPI_RAW) *reinterpret_cast<float4*>(a.out_raw + o_raw[i] + c0) = make_float4(f0, f1, f2, f3);
+                            f0 = fmaxf(f0, relu_floor); f1 = fmaxf(f1, relu_floor);
+                            f2 = fmaxf(f2, relu_floor); f3 = fmaxf(f3, relu_floor);
+                            uint32_t h01, l01, h23, l23;
+                            split2_f32(f0, f1, h01, l01);
+                            split2_f32(f2, f3, h23, l23);
+                            __half* d;
+                            if (EPI & EPI_D2S) {   // tf.depth_to_space(x, 2): out[n,2y+i,2x+j,c] = in[n,y,x,(2i+j)*64+c]
+                                const int cg = cg_lane + c0, g = cg >> 6;
+                                d = a.out_act + o_act[i] + static_cast<uint32_t>(((g >> 1) * (2 * a.W) + (g & 1)) * a.act_cs + (cg & 63));
+                            } else {
+                                d = a.out_act + o_act[i] + c0;
+                            }
+                            *reinterpret_cast<uint2*>(d) = make_uint2(h01, h23);
+                            if (PLANES == 2) *reinterpret_cast<uint2*>(d + a.act_plane) = make_uint2(l01, l23);
+                        }
+                    }
+                    __syncwarp();
+                    if ((EPI & EPI_RES) && it + 1 < ITERS) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) rr[i] = rn[i];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(cs));
+            if (++cs == 2) { cs = 0; cph ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int NT, int CHUNKS, int PLANES, int EPI>
+cudaError_t init_inst() {
+    return cudaFuncSetAttribute(conv3x3_umma_kernel<NT, CHUNKS, PLANES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kConvMaxSmem);
+}
+
+template <int NT, int CHUNKS, int PLANES, int EPI>
+cudaError_t launch_inst(const ConvLaunch& L, int num_sms, cudaStream_t stream) {
+    const int grid = L.args.num_tiles < num_sms ? L.args.num_tiles : num_sms;
+    conv3x3_umma_kernel<NT, CHUNKS, PLANES, EPI><<<grid, kThreads, L.smem_bytes, stream>>>(L.tmA_hi, L.tmA_lo, L.tmB, L.args);
+    return cudaGetLastError();
+}
+
+// One translation unit per (PLANES, NT) instantiates these (conv_inst_*.cu).
+template <int NT, int PLANES>
+cudaError_t init_family();
+template <int NT, int PLANES>
+cudaError_t launch_family(const ConvLaunch& L, int num_sms, cudaStream_t stream);
+
+#define FISR_CONV_FAMILY(NT_, PL_, LIST)                                                                    \
+    template <>                                                                                             \
+    cudaError_t init_family<NT_, PL_>() {                                                                   \
+        cudaError_t e = cudaSuccess;                                                                        \
+        LIST(FISR_INIT_ONE, NT_, PL_)                                                                       \
+        return e;                                                                                           \
+    }                                                                                                       \
+    template <>                                                                                             \
+    cudaError_t launch_family<NT_, PL_>(const ConvLaunch& L, int num_sms, cudaStream_t stream) {            \
+        LIST(FISR_LAUNCH_ONE, NT_, PL_)                                                                     \
+        return cudaErrorInvalidValue;                                                                       \
+    }
+#define FISR_INIT_ONE(NT_, PL_, CH_, EPI_) if (e == cudaSuccess) e = init_inst<NT_, CH_, PL_, (EPI_)>();
+#define FISR_LAUNCH_ONE(NT_, PL_, CH_, EPI_) \
+    if (L.chunks == CH_ && L.epi == (EPI_)) return launch_inst<NT_, CH_, PL_, (EPI_)>(L, num_sms, stream);
+// epilogue variants the network uses: act | act+raw | act+res | act+raw+res | act+d2s
+#define FISR_FOR_EPI(M, NT_, PL_)                                                                           \
+    M(NT_, PL_, 1, 0) M(NT_, PL_, 2, 0) M(NT_, PL_, 1, EPI_RAW) M(NT_, PL_, 2, EPI_RAW)                      \
+    M(NT_, PL_, 1, EPI_RES) M(NT_, PL_, 2, EPI_RES) M(NT_, PL_, 1, EPI_RES | EPI_RAW) M(NT_, PL_, 2, EPI_RES | EPI_RAW) \
+    M(NT_, PL_, 1, EPI_D2S) M(NT_, PL_, 2, EPI_D2S)
+#define FISR_FOR_EPI_NARROW(M, NT_, PL_) M(NT_, PL_, 1, 0) M(NT_, PL_, 2, 0)
+
+}  // namespace convk
+}  // namespace fisr

@@ -293,6 +293,13 @@ struct Builder {
         a.act_relu = o.relu; a.act_d2s = o.d2s; a.scalar_out = o.scalar;
         a.err = ctx->d_err;
         a.N = N; a.H = H; a.W = W;
+        L.epi = o.scalar ? 0 : ((o.res ? 1 : 0) | (o.raw ? 2 : 0) | (o.d2s ? 4 : 0));
+        if (!o.scalar && !o.act.p) { rc = fail(ctx, FISR_E_INVALID, "conv %s: the wide epilogue always writes an activation", name.c_str()); return; }
+        {   // the epilogue indexes with 32-bit element offsets
+            const double px = static_cast<double>(N) * H * W * (o.d2s ? 4 : 1);
+            const int cs_max = std::max(std::max(o.raw_cs, o.res_cs), o.act_cs);
+            if (px * cs_max >= 4294967296.0) { rc = fail(ctx, FISR_E_INVALID, "conv %s: %d x %d x %d x %d exceeds 32-bit offsets; split the batch", name.c_str(), N, H, W, cs_max); return; }
+        }
         a.cin_off = cin_off; a.KB = p.KB; a.cout = p.cout;
         if (!encode_act(&L.tmA_hi, in.p, in_cs, N, H, W, a.P, a.TH + 2)) return;
         if (!encode_act(&L.tmA_lo, in.p + (plan->planes == 2 ? in.plane : 0), in_cs, N, H, W, a.P, a.TH + 2)) return;
@@ -883,6 +890,7 @@ int fisr_conv3x3(fisr_ctx* ctx, const float* d_x, const float* d_w, const float*
     if (Cout > 16 && Cout % 64) return fail(ctx, FISR_E_INVALID, "Cout must be <= 16 or a multiple of 64");
     if (d2s && Cout != 256) return fail(ctx, FISR_E_INVALID, "depth_to_space epilogue needs Cout = 256");
     if (Cout <= 16 && d_res) return fail(ctx, FISR_E_INVALID, "narrow outputs take no residual");
+    if (d2s && (d_raw || d_res)) return fail(ctx, FISR_E_INVALID, "the depth_to_space epilogue has neither residual input nor fp32 output");
     Guard guard(ctx->device);
     cudaStream_t st = ctx->stream;
     Plan tmp;                       // owns the scratch buffers of this call
@@ -905,7 +913,7 @@ int fisr_conv3x3(fisr_ctx* ctx, const float* d_x, const float* d_w, const float*
     Builder::ConvOut o;
     o.res = d_res; o.res_cs = Cout;
     o.raw = d_raw; o.raw_cs = Cout;
-    o.act = d_act ? yact : ActBuf{}; o.act_cs = ocs;
+    o.act = (d_act || Cout > 16) ? yact : ActBuf{}; o.act_cs = ocs;
     o.relu = relu != 0; o.d2s = d2s != 0; o.scalar = Cout <= 16;
     b.conv(p, xin, cs, 0, N, H, W, o, "test");
     if (b.rc != FISR_OK) return b.rc;

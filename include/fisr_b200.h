@@ -99,7 +99,7 @@ int fisr_warp_host(fisr_ctx* ctx, const uint8_t* h_yuv, const float* h_flow, flo
 /* Single 3x3 SAME conv through the production kernel (ops.py:7-11 plus the fused epilogue):
  * y = conv(x, w) + b (+ res); raw = y; act = relu ? max(y,0) : y, optionally depth_to_space(2) (FISRnet.py:99).
  * x [N,H,W,Cin], w HWIO, res / raw [N,H,W,Cout], act [N,H,W,Cout] or [N,2H,2W,Cout/4]; device pointers, any may be
- * NULL except x, w, b.  Synchronous. */
+ * NULL except x, w, b (d2s excludes res and raw: the network never combines them).  Synchronous. */
 int fisr_conv3x3(fisr_ctx* ctx, const float* d_x, const float* d_w, const float* d_b, const float* d_res, int N, int H,
                  int W, int Cin, int Cout, int relu, int d2s, float* d_raw, float* d_act);
 /* After a forward: copies the pre-activation output of the named conv (e.g. ".../enc/level_0/conv/0") as

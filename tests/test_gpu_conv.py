@@ -64,7 +64,7 @@ def test_conv_depth_to_space_epilogue(engine):
     x, w, b, _ = _case(2, 24, 40, 64, 256, seed=7, res=False)
     y = torch.relu(_ref(x, w, b, None))
     exp = O.to_nhwc(O.depth_to_space2(O.to_nchw(y)))
-    _, act = engine.conv3x3(x.cuda(), w.cuda(), b.cuda(), None, relu=True, d2s=True)
+    _, act = engine.conv3x3(x.cuda(), w.cuda(), b.cuda(), None, relu=True, d2s=True, want_raw=False)
     assert tuple(act.shape) == (2, 48, 80, 64)
     assert (act.cpu().double() - exp).abs().max() < 2e-5 * float(y.abs().max())
 

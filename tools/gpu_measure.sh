@@ -8,6 +8,6 @@ timeout 300 python tools/profile_layers.py 8 192 192 f16x3 > gpurun_out/layers_c
 timeout 300 python tools/profile_layers.py 4 544 992 f16 > gpurun_out/layers_f16.txt 2>&1; head -2 gpurun_out/layers_f16.txt
 if [ "$1" != "nonCU" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches.csv python tools/ncu_target.py 4 544 992 > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv3x3_umma -s 170 -c 3 -o gpurun_out/prof_conv -f python tools/ncu_target.py 4 544 992 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv3x3_umma -s 232 -c 4 -o gpurun_out/prof_conv -f python tools/ncu_target.py 4 544 992 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 fi
 ls -la gpurun_out
