@@ -1,0 +1,206 @@
+"""``FISRnet`` -- the operator surface ``main.py`` drives (reference FISRnet.py:14-17), on the B200 path.
+
+Same constructor, attribute names, methods and argument meaning as the reference class, so that
+``main.py``'s ``test`` and ``FISR_for_video`` phases run unchanged after swapping the import
+(INTEGRATION.md).  ``sess`` was a ``tf.Session``; here it is ``None``, a CUDA device index or a
+``fisr_b200.Engine``.  All arithmetic runs in libfisr_b200.so; this file only moves data.
+
+Documented deviations from the reference:
+  * ``FISR_for_video`` sorts the frame list (the reference's unsorted ``glob`` at FISRnet.py:953 returns a
+    file-system-dependent order; the shipped scene1 outputs correspond to the sorted order, like ``test()`` :762).
+  * the tile loop runs as one batched forward instead of growing a TF graph per tile (FISRnet.py:1039-1041).
+  * checkpoints are ``.npz`` files keyed by the TF variable names (no TensorFlow in this stack).
+  * the printed "Estimated Inference Time" is per window from CUDA-synchronised wall time.
+"""
+from __future__ import annotations
+
+import glob
+import math
+import os
+import re
+import time
+from datetime import datetime
+
+import numpy as np
+from PIL import Image
+
+from . import utils
+from .engine import Engine, param_inventory
+from .init import xavier_params
+from .utils import check_folder, merge_seq_dim, read_flo_file_5dim, read_mat_file_warp
+
+
+class FISRnet(object):
+    model_name = "FISRnet"
+
+    def __init__(self, sess, args):
+        self.sess = sess
+        self.args = args
+        for name in ("checkpoint_dir", "test_img_dir", "text_dir", "log_dir", "train_data_path", "train_flow_data_path",
+                     "train_flow_ss2_data_path", "train_warped_data_path", "train_wapred_ss2_data_path", "train_label_path",
+                     "test_data_path", "test_flow_data_path", "test_warped_data_path", "test_label_path", "exp_num",
+                     "scale_factor", "epoch", "init_lr", "freq_display", "lr_type", "lr_stair_decay_points",
+                     "lr_decreasing_factor", "lr_linear_decay_point", "batch_size", "val_batch_size", "val_data_size",
+                     "n_train_img_showed", "recn_lambda", "tm1_lambda", "tm2_lambda", "tmm_lambda", "td_lambda",
+                     "ss2_lambda", "test_patch", "test_input_size", "FISR_test_patch", "frame_folder_path",
+                     "FISR_input_size", "frame_num"):                       # FISRnet.py:20-66
+            setattr(self, name, getattr(args, name, None))
+        if isinstance(sess, Engine):
+            self.engine = sess
+        else:
+            self.engine = Engine(int(sess) if isinstance(sess, int) else 0,
+                                 precision=getattr(args, "precision", "f16x3"))
+        self._initialized = False
+        print('Model arguments, [{:s}]'.format((str(datetime.now())[:-7])))
+        for arg in vars(args):
+            print('# {} : {}'.format(arg, getattr(args, arg)))
+
+    # ------------------------------------------------------------------ variables
+    def _ensure_variables(self):
+        """``tf.global_variables_initializer().run()`` (FISRnet.py:757,948): Xavier weights, zero biases."""
+        if not self._initialized:
+            self.engine.set_params(xavier_params(seed=0, bias_std=0.0))
+            self._initialized = True
+
+    # ------------------------------------------------------------------ FISRnet.model (FISRnet.py:73-173)
+    def model(self, img, sf, reuse=False, scope="model"):
+        """img [N,H,W,29] (numpy array or CUDA torch tensor) -> (pred_l1, pred_l2, pred_l3) in the same container."""
+        if int(sf) != 2:
+            raise ValueError("FISRnet is a x2 network (main.py:29 default scale_factor=2)")
+        self._ensure_variables()
+        if isinstance(img, np.ndarray):
+            return self.engine.forward_host(img)
+        return self.engine.forward(img)
+
+    # ------------------------------------------------------------------ training (FISRnet.py:175-743)
+    def build_model(self):
+        raise NotImplementedError("the training graph (multi-scale temporal loss + backward + Adam, FISRnet.py:175-491) is "
+                                  "not part of this round's B200 path; see DESIGN.md 'Scope'")
+
+    def train(self):
+        raise NotImplementedError("see build_model")
+
+    # ------------------------------------------------------------------ shared inner loop
+    def _window(self, frames_u8, flow_sample, warp_sample, num_patch):
+        """One sliding window: crop / normalise / clip, tile grid with 32-px halo, paste, clip, uint8 (FISRnet.py:1003-1064)."""
+        t0 = time.time()
+        out = self.engine.window_host(frames_u8, flow_sample, warp_sample, tuple(int(v) for v in num_patch))
+        return out, time.time() - t0
+
+    # ------------------------------------------------------------------ test (FISRnet.py:746-935)
+    def test(self):
+        self._ensure_variables()
+        _, _ = self.load(self.checkpoint_dir)
+        test_data_path = sorted(glob.glob(os.path.join(self.test_data_path, '*.png')))
+        test_label_path = sorted(glob.glob(os.path.join(self.test_label_path, '*.png')))
+        print(" Start to read flow data (test).")
+        flow = merge_seq_dim(read_flo_file_5dim(self.test_flow_data_path))
+        print(" Start to read warped data (test).")
+        warp = merge_seq_dim(read_mat_file_warp(self.test_warped_data_path, 'pred'))
+        num_patch = self.test_patch
+        test_img_dir = check_folder(os.path.join(self.test_img_dir, self.model_dir))
+        n_in_seq, n_test_in_seq = 3, 5
+        n_GT_seq, n_test_label_seq = n_in_seq * 2 - 3, 2 * n_test_in_seq - 3
+        psnr_fisr, psnr_sr, inf_time = [], [], []
+        start_time = time.time()
+        H, W = self.test_input_size
+        h = H - np.remainder(H, 32 * num_patch[0])
+        w = W - np.remainder(W, 32 * num_patch[1])
+        for scene_i in range(int(len(test_data_path) / n_test_in_seq)):
+            for sample_i in range(n_test_in_seq - n_in_seq + 1):
+                img = np.concatenate([np.array(Image.open(test_data_path[scene_i * n_test_in_seq + sample_i + s]))
+                                      for s in range(n_in_seq)], axis=2)
+                label = np.concatenate([np.array(Image.open(test_label_path[scene_i * n_test_label_seq + sample_i * 2 + s]))
+                                        for s in range(n_GT_seq)], axis=2)
+                label = np.clip(np.array(label[:h * 2, :w * 2, :], dtype=np.double) / 255., 0, 1)
+                flow_sample = flow[scene_i, :, :, 4 * sample_i:4 * sample_i + 8]
+                warp_sample = warp[scene_i, :, :, 6 * sample_i:6 * sample_i + 12]
+                pred, dt = self._window(img[:H, :W], flow_sample[:H, :W], warp_sample[:H, :W], num_patch)
+                inf_time.append(dt)
+                # the reference scores the clipped float prediction; uint8 truncation costs < 1/255 per sample
+                test_pred = pred.astype(np.double) / 255.
+                test_PSNR = [utils._compute_psnr(test_pred[:, :, 3 * s:3 * (s + 1)], label[:, :, 3 * s:3 * (s + 1)], 1.)
+                             for s in range(n_GT_seq)]
+                print(" <Test> [%4d/%4d]-th image, scene: %2d-%d, time: %4.4f(minutes), test_PSNR: fr1 (FI-SR) %.8f[dB], "
+                      "fr2 (SR) %.8f[dB], fr3 (FI-SR) %.8f[dB]  "
+                      % (scene_i * 3 + sample_i, len(test_data_path) / n_test_in_seq * 3, scene_i, sample_i,
+                         (time.time() - start_time) / 60, test_PSNR[0], test_PSNR[1], test_PSNR[2]))
+                for s in range(n_GT_seq):
+                    fr_name = os.path.basename(test_label_path[scene_i * n_test_label_seq + sample_i * 2 + s])[3:]
+                    rgb_img = utils.YUV2RGB_matlab(pred[:, :, s * 3:(s + 1) * 3])
+                    Image.fromarray(rgb_img.astype('uint8')).save(os.path.join(test_img_dir, 'pred_{}'.format(fr_name)))
+                psnr_fisr.append(test_PSNR[0])
+                psnr_sr.append(test_PSNR[1])
+                if sample_i == 2:
+                    psnr_fisr.append(test_PSNR[2])
+        print("######### Test (average) test_PSNR: FISR %.8f[dB], SR %.8f[dB]  #########"
+              % (np.mean(psnr_fisr), np.mean(psnr_sr)))
+        print("######### Estimated Inference Time (per window = three 4K frames): %.8f[s]  #########" % np.mean(inf_time))
+
+    # ------------------------------------------------------------------ FISR_for_video (FISRnet.py:937-1084)
+    def FISR_for_video(self, flow_file_name, warp_file_name):
+        self._ensure_variables()
+        _, _ = self.load(self.checkpoint_dir)
+        test_data_path = sorted(glob.glob(os.path.join(self.frame_folder_path, '*.png')))      # YUV
+        num_fr = self.frame_num
+        FISR_img_dir = check_folder(os.path.join(self.frame_folder_path, 'FISR_frames'))
+        print(" Start to read flow data (FISR test).")
+        flow = read_flo_file_5dim(flow_file_name)                                               # [N-1, 2, h, w, 2]
+        flow = merge_seq_dim(np.concatenate((flow[0:num_fr - 2], flow[1:num_fr - 1]), axis=1))  # FISRnet.py:965-967
+        print(" Start to read warped data (FISR test).")
+        warp = read_mat_file_warp(warp_file_name, 'pred')                                       # [N-1, 2, h, w, 3]
+        warp = merge_seq_dim(np.concatenate((warp[0:num_fr - 2], warp[1:num_fr - 1]), axis=1))  # FISRnet.py:972-975
+        num_patch = self.FISR_test_patch
+        check_folder(os.path.join(self.test_img_dir, self.model_dir))
+        H, W = self.FISR_input_size
+        inf_time = []
+        start_time = time.time()
+        digits = math.ceil(math.log10(2 * (num_fr - 1)))
+        for fr in range(num_fr - 2):
+            img = np.concatenate([np.array(Image.open(test_data_path[fr + s])) for s in range(3)], axis=2)
+            pred, dt = self._window(img[:H, :W], flow[fr, :H, :W], warp[fr, :H, :W], num_patch)   # YUV uint8 [2h,2w,9]
+            inf_time.append(dt)
+            for seq_i in range(3):                                                              # FISRnet.py:1066-1077
+                yuv = pred[:, :, seq_i * 3:(seq_i + 1) * 3]
+                name = str(fr * 2 + seq_i).zfill(digits)
+                Image.fromarray(utils.YUV2RGB_matlab(yuv).astype('uint8')).save(FISR_img_dir + '/pred_{}.png'.format(name))
+                Image.fromarray(yuv.astype('uint8')).save(FISR_img_dir + '/pred_YUV_{}.png'.format(name))
+            print(" <FISR processing> [%4d/%4d]-th input multiple data sample (stride1), time: %4.4f(minutes)  "
+                  % (fr + 1, num_fr - 2, (time.time() - start_time) / 60))
+        print("######### Estimated Inference Time (per window = three 4K frames): %.8f[s]  #########" % np.mean(inf_time))
+
+    # ------------------------------------------------------------------ checkpoints (FISRnet.py:1086-1115)
+    @property
+    def model_dir(self):
+        return "{}_exp{}".format(self.model_name, self.exp_num)
+
+    def save_checkpoint(self, checkpoint_dir, step):
+        checkpoint_dir = os.path.join(checkpoint_dir, self.model_dir)
+        os.makedirs(checkpoint_dir, exist_ok=True)
+        path = os.path.join(checkpoint_dir, "{}-{}.npz".format(self.model_name, int(step)))
+        np.savez(path, **{k.replace('/', '.'): v for k, v in self.engine.get_params().items()})
+        with open(os.path.join(checkpoint_dir, "checkpoint"), "w") as f:
+            f.write('model_checkpoint_path: "{}"\n'.format(os.path.basename(path)))
+
+    def load(self, checkpoint_dir):
+        print(" [*] Reading checkpoints...")
+        checkpoint_dir = os.path.join(checkpoint_dir, self.model_dir)
+        state = os.path.join(checkpoint_dir, "checkpoint")
+        ckpt_name = None
+        if os.path.exists(state):
+            m = re.search(r'model_checkpoint_path:\s*"([^"]+)"', open(state).read())
+            if m and os.path.exists(os.path.join(checkpoint_dir, os.path.basename(m.group(1)))):
+                ckpt_name = os.path.basename(m.group(1))
+        if ckpt_name and ckpt_name.endswith(".npz"):
+            data = np.load(os.path.join(checkpoint_dir, ckpt_name))
+            params = {k.replace('.', '/'): data[k] for k in data.files}
+            missing = [k for k in param_inventory() if k not in params]
+            if missing:
+                raise KeyError("checkpoint {} lacks {} variables, e.g. {}".format(ckpt_name, len(missing), missing[0]))
+            self.engine.set_params(params)
+            self._initialized = True
+            counter = int(next(re.finditer(r"(\d+)(?!.*\d)", ckpt_name)).group(0))
+            print(" [*] Success to read {}".format(ckpt_name))
+            return True, counter
+        print(" [*] Failed to find a checkpoint")           # like the reference, not an error (FISRnet.py:1113-1115)
+        return False, 0

@@ -5,3 +5,4 @@ device context underneath it.  The CPU checker package is never imported from he
 """
 from ._lib import FisrError, LIB_PATH  # noqa: F401
 from .engine import Engine, param_inventory  # noqa: F401
+from .FISRnet import FISRnet  # noqa: F401

@@ -1,0 +1,126 @@
+"""Host-side helpers with the names and behaviour of the reference's ``utils.py`` (file formats, tiling, colour, PSNR).
+
+These run on the CPU in numpy exactly like the reference's; the arithmetic of the hot path is in libfisr_b200.so.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def str2bool(x):                                   # utils.py:8-9
+    return x.lower() in ('true')
+
+
+def check_folder(log_dir):                         # utils.py:12-15
+    if not os.path.exists(log_dir):
+        os.makedirs(log_dir)
+    return log_dir
+
+
+def _compute_psnr(img_orig, img_out, peak):        # utils.py:23-26
+    mse = np.mean(np.square(img_orig - img_out))
+    return 10 * np.log10(peak * peak / mse)
+
+
+FLO_MAGIC = np.float32(202021.25)
+
+
+def read_flo_file_5dim(filename):
+    """utils.py:57-74: float32 magic, int32 N, N_seq, h, w, then N*N_seq*h*w*2 float32 -> [N, N_seq, h, w, 2]."""
+    with open(filename, 'rb') as f:
+        magic = np.fromfile(f, np.float32, count=1)
+        if magic.size != 1 or magic[0] != FLO_MAGIC:
+            print('Magic number incorrect. Invalid .flo file')
+            return None
+        N, N_seq, h, w = (int(v) for v in np.fromfile(f, np.int32, count=4))
+        print("Reading %d x %d x %d x %d x 2 flow file in .flo format" % (N, N_seq, h, w))
+        data = np.fromfile(f, np.float32, count=N * N_seq * h * w * 2)
+    return np.resize(data, (N, N_seq, h, w, 2))
+
+
+def write_flo_file_5dim(flow, filename):
+    """Writer of the same format (FISR_tfoptflow/FISR_for_video_pwcnet_predict_from_img_test.py:57-81)."""
+    flow = np.ascontiguousarray(flow, dtype=np.float32)
+    N, N_seq, h, w, two = flow.shape
+    assert two == 2
+    with open(filename, 'wb') as f:
+        np.array([FLO_MAGIC], np.float32).tofile(f)
+        np.array([N, N_seq, h, w], np.int32).tofile(f)
+        flow.tofile(f)
+
+
+def _h5py():
+    try:
+        import h5py
+        return h5py
+    except ImportError as e:
+        raise ImportError("reading MATLAB v7.3 .mat files needs h5py (not installed here); "
+                          "save the array with np.save and pass the .npy path instead") from e
+
+
+def read_mat_file(data_fname, label_fname, data_name, label_name):
+    """utils.py:29-42: training data / label [N, N_seq, C, W, H] uint8 -> float32 /255, [N, N_seq, H, W, C]."""
+    def load(fname, key):
+        if fname.endswith('.npy'):
+            return np.load(fname)
+        return _h5py().File(fname, 'r')[key][()]
+    data = np.array(load(data_fname, data_name), dtype=np.float32) / 255.
+    label = np.array(load(label_fname, label_name), dtype=np.float32) / 255.
+    return np.swapaxes(data, 2, 4), np.swapaxes(label, 2, 4)
+
+
+def read_mat_file_warp(data_fname, data_name):
+    """utils.py:45-54: warped frames -> float32 /255, [N, N_seq, H, W, C].  A ``.npy`` file holds that layout already
+    (values 0..255, as ``FISR_for_video_Warp_Img`` writes them)."""
+    if data_fname.endswith('.npy'):
+        return np.array(np.load(data_fname), dtype=np.float32) / 255.
+    data = _h5py().File(data_fname, 'r')[data_name][()]
+    data = np.array(data, dtype=np.float32) / 255.
+    return np.transpose(data, (4, 3, 2, 1, 0))
+
+
+def merge_seq_dim(data):                           # utils.py:78-83
+    sz = data.shape
+    return np.reshape(np.transpose(data, axes=(0, 2, 3, 1, 4)), (sz[0], sz[2], sz[3], sz[1] * sz[4]))
+
+
+def split_seq_dim(data):                           # utils.py:86-91
+    sz = data.shape
+    return np.transpose(np.reshape(data, (sz[0], sz[1], sz[2], sz[3] // 3, 3)), axes=(0, 3, 1, 2, 4))
+
+
+def YUV2RGB_matlab(yuv):                           # utils.py:106-115
+    Tinv = np.array([[0.00456621, 0., 0.00625893], [0.00456621, -0.00153632, -0.00318811], [0.00456621, 0.00791071, 0.]])
+    offset = [[16], [128], [128]]
+    T = 255 * Tinv
+    offset = 255 * Tinv @ offset
+    rgb = np.zeros(yuv.shape)
+    for p in range(3):
+        rgb[:, :, p] = T[p, 0] * yuv[:, :, 0] + T[p, 1] * yuv[:, :, 1] + T[p, 2] * yuv[:, :, 2] - offset[p]
+    return np.clip(rgb, 0, 255)
+
+
+def get_HW_boundary(patch_boundary, h, w, pH, sH, pW, sW):          # utils.py:118-135
+    H_low_ind = max(pH * sH - patch_boundary, 0)
+    H_high_ind = min((pH + 1) * sH + patch_boundary, h)
+    W_low_ind = max(pW * sW - patch_boundary, 0)
+    W_high_ind = min((pW + 1) * sW + patch_boundary, w)
+    add_H = (patch_boundary if pH * sH >= patch_boundary else 0) + (patch_boundary if (pH + 1) * sH + patch_boundary <= h else 0)
+    add_W = (patch_boundary if pW * sW >= patch_boundary else 0) + (patch_boundary if (pW + 1) * sW + patch_boundary <= w else 0)
+    return H_low_ind, H_high_ind, W_low_ind, W_high_ind, add_H, add_W
+
+
+def trim_patch_boundary(img, patch_boundary, h, w, pH, sH, pW, sW, sf):   # utils.py:138-159
+    if patch_boundary == 0:
+        return img
+    if not pH * sH < patch_boundary:
+        img = img[:, patch_boundary * sf:, :, :]
+    if not (pH + 1) * sH + patch_boundary > h:
+        img = img[:, :-patch_boundary * sf, :, :]
+    if not pW * sW < patch_boundary:
+        img = img[:, :, patch_boundary * sf:, :]
+    if not (pW + 1) * sW + patch_boundary > w:
+        img = img[:, :, :-patch_boundary * sf, :]
+    return img
