@@ -156,10 +156,16 @@ class FISRnet(object):
         inf_time = []
         start_time = time.time()
         digits = math.ceil(math.log10(2 * (num_fr - 1)))
-        for fr in range(num_fr - 2):
-            img = np.concatenate([np.array(Image.open(test_data_path[fr + s])) for s in range(3)], axis=2)
-            pred, dt = self._window(img[:H, :W], flow[fr, :H, :W], warp[fr, :H, :W], num_patch)   # YUV uint8 [2h,2w,9]
-            inf_time.append(dt)
+        def windows():
+            for fr in range(num_fr - 2):
+                img = np.concatenate([np.array(Image.open(test_data_path[fr + s])) for s in range(3)], axis=2)
+                yield img[:H, :W], flow[fr, :H, :W], warp[fr, :H, :W]
+
+        # two windows in flight: the copies of window k+1 overlap the kernels of window k (fisr_window_submit / _wait)
+        t_prev = time.time()
+        for fr, pred in enumerate(self.engine.video_windows(windows(), tuple(int(v) for v in num_patch))):   # YUV uint8 [2h,2w,9]
+            inf_time.append(time.time() - t_prev)
+            t_prev = time.time()
             for seq_i in range(3):                                                              # FISRnet.py:1066-1077
                 yuv = pred[:, :, seq_i * 3:(seq_i + 1) * 3]
                 name = str(fr * 2 + seq_i).zfill(digits)

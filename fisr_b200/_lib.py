@@ -51,6 +51,8 @@ def load() -> C.CDLL:
         "fisr_units_device": (i, [vp, vp, vp, vp, i, i, i, i, i, C.POINTER(i), i, i, vp, vp]),
         "fisr_window_device_f32": (i, [vp, vp, vp, vp, i, i, i, i, vp, vp]),
         "fisr_window_host": (i, [vp, vp, vp, vp, i, i, i, i, vp]),
+        "fisr_window_submit": (i, [vp, i, vp, vp, vp, i, i, i, i, vp]),
+        "fisr_window_wait": (i, [vp, i]),
         "fisr_warp_device": (i, [vp, vp, vp, f, vp, i, i, f, vp]),
         "fisr_warp_host": (i, [vp, vp, vp, f, vp, i, i, f]),
         "fisr_conv3x3": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp]),
@@ -71,6 +73,6 @@ def load() -> C.CDLL:
 EXPORTS = [
     "fisr_create", "fisr_destroy", "fisr_last_error", "fisr_set_precision", "fisr_get_precision", "fisr_num_params",
     "fisr_param_name", "fisr_param_shape", "fisr_set_param", "fisr_get_param", "fisr_forward", "fisr_forward_host",
-    "fisr_window_device", "fisr_units_device", "fisr_window_device_f32", "fisr_window_host", "fisr_warp_device", "fisr_warp_host",
+    "fisr_window_device", "fisr_units_device", "fisr_window_device_f32", "fisr_window_host", "fisr_window_submit", "fisr_window_wait", "fisr_warp_device", "fisr_warp_host",
     "fisr_conv3x3", "fisr_debug_conv_output", "fisr_profile_ops", "fisr_launch_count", "fisr_plan_info",
 ]

@@ -187,37 +187,39 @@ __global__ void tile_pack_kernel(const uint8_t* __restrict__ frames, const float
                                  const float* __restrict__ warp, int fh, int fw, TileList tiles, int th, int tw,
                                  const float* __restrict__ lut255, __half* l3, size_t p3, __half* l2, size_t p2,
                                  __half* l1, size_t p1) {
+    // thread = (pixel, group of 8 channels); 4 groups write channels 0..31 (29..31 = 0) as 16-byte vectors
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-    const size_t total = static_cast<size_t>(tiles.count) * th * tw * 32;
+    const size_t total = static_cast<size_t>(tiles.count) * th * tw * 4;
     if (i >= total) return;
-    const int c = i & 31;
-    if (c >= 29) return;
-    const size_t pix = i >> 5;
+    const int g = i & 3;
+    const size_t pix = i >> 2;
     const int x = pix % tw;
     const int y = (pix / tw) % th;
     const int t = pix / (static_cast<size_t>(tw) * th);
     const size_t src = (static_cast<size_t>(tiles.win[t]) * fh + tiles.ylo[t] + y) * fw + tiles.xlo[t] + x;
-    float v;
-    if (c < 9) {
-        v = lut255[frames[src * 9 + c]];
-    } else if (c < 17) {
-        v = __fdiv_rn(__fdiv_rn(flow[src * 8 + (c - 9)], 96.f), 2.f);
-        v = fminf(fmaxf(v, -1.f), 1.f);
-    } else {
-        v = fminf(fmaxf(warp[src * 12 + (c - 17)], 0.f), 1.f);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        float f = 0.f;
+        if (c < 9) {
+            f = lut255[frames[src * 9 + c]];
+        } else if (c < 17) {
+            f = __fdiv_rn(__fdiv_rn(flow[src * 8 + (c - 9)], 96.f), 2.f);
+            f = fminf(fmaxf(f, -1.f), 1.f);
+        } else if (c < 29) {
+            f = fminf(fmaxf(warp[src * 12 + (c - 17)], 0.f), 1.f);
+        }
+        v[j] = f;
     }
-    const SplitHalf s = split_f32(v);
-    l3[pix * 64 + c] = s.hi;
-    if (PLANES == 2) l3[p3 + pix * 64 + c] = s.lo;
+    store8<PLANES>(l3 + pix * 64 + g * 8, p3, v);
     if (((x | y) & 1) == 0) {
         const size_t q = (static_cast<size_t>(t) * (th / 2) + y / 2) * (tw / 2) + x / 2;
-        l2[q * 64 + c] = s.hi;
-        if (PLANES == 2) l2[p2 + q * 64 + c] = s.lo;
+        store8<PLANES>(l2 + q * 64 + g * 8, p2, v);
     }
     if (((x | y) & 3) == 0) {
         const size_t q = (static_cast<size_t>(t) * (th / 4) + y / 4) * (tw / 4) + x / 4;
-        l1[q * 64 + c] = s.hi;
-        if (PLANES == 2) l1[p1 + q * 64 + c] = s.lo;
+        store8<PLANES>(l1 + q * 64 + g * 8, p1, v);
     }
 }
 
@@ -225,6 +227,34 @@ __global__ void tile_pack_kernel(const uint8_t* __restrict__ frames, const float
 // reference's float64 truncation (FISRnet.py:1060-1064), paste into the [OH,OW,9] canvas (FISRnet.py:1056-1057).
 __global__ void tile_unpack_u8_kernel(const float* __restrict__ pred, TileList tiles, int th2, int tw2,
                                       uint8_t* __restrict__ canvas, int OH, int OW, int core_h, int core_w) {
+    // thread = 4 consecutive pixels of one row: 9 float4 loads, 9 packed 32-bit stores (all offsets are multiples of 4 px)
+    const int qw = core_w / 4;
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t total = static_cast<size_t>(tiles.count) * core_h * qw;
+    if (i >= total) return;
+    const int x = (i % qw) * 4;
+    size_t r = i / qw;
+    const int y = r % core_h;
+    const int t = r / core_h;
+    const float4* src = reinterpret_cast<const float4*>(
+        pred + ((static_cast<size_t>(t) * th2 + tiles.trim_y[t] + y) * tw2 + tiles.trim_x[t] + x) * 9);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(
+        canvas + ((static_cast<size_t>(tiles.out_img[t]) * OH + tiles.out_y[t] + y) * OW + tiles.out_x[t] + x) * 9);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        const float4 v = __ldg(src + j);
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        uint32_t w = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double cl = fmin(fmax(static_cast<double>(f[k]), 0.0), 1.0);
+            w |= static_cast<uint32_t>(static_cast<int>(cl * 255.0)) << (8 * k);
+        }
+        dst[j] = w;
+    }
+}
+__global__ void tile_unpack_u8_scalar_kernel(const float* __restrict__ pred, TileList tiles, int th2, int tw2,
+                                             uint8_t* __restrict__ canvas, int OH, int OW, int core_h, int core_w) {
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     const size_t total = static_cast<size_t>(tiles.count) * core_h * core_w * 9;
     if (i >= total) return;
@@ -364,7 +394,7 @@ void launch_act_to_f32(ActBuf src, int cs, int coff, float* dst, int C, size_t n
 
 void launch_tile_pack(const uint8_t* frames, const float* flow, const float* warp, int fh, int fw, const TileList& tiles,
                       int th, int tw, const float* lut255, ActBuf l3, ActBuf l2, ActBuf l1, int planes, cudaStream_t st) {
-    const size_t total = static_cast<size_t>(tiles.count) * th * tw * 32;
+    const size_t total = static_cast<size_t>(tiles.count) * th * tw * 4;
     if (planes == 2)
         tile_pack_kernel<2><<<blocks_for(total, 256), 256, 0, st>>>(frames, flow, warp, fh, fw, tiles, th, tw, lut255, l3.p,
                                                                     l3.plane, l2.p, l2.plane, l1.p, l1.plane);
@@ -375,8 +405,16 @@ void launch_tile_pack(const uint8_t* frames, const float* flow, const float* war
 
 void launch_tile_unpack_u8(const float* pred, const TileList& tiles, int th2, int tw2, uint8_t* canvas, int OH, int OW,
                            int core_h, int core_w, cudaStream_t st) {
-    const size_t total = static_cast<size_t>(tiles.count) * core_h * core_w * 9;
-    tile_unpack_u8_kernel<<<blocks_for(total, 256), 256, 0, st>>>(pred, tiles, th2, tw2, canvas, OH, OW, core_h, core_w);
+    // vector path needs every row segment to start on a 4-pixel boundary (36-byte groups are then 4-byte aligned)
+    bool vec = (core_w % 4 == 0) && (tw2 % 4 == 0) && (OW % 4 == 0);
+    for (int t = 0; t < tiles.count; ++t) vec = vec && (tiles.trim_x[t] % 4 == 0) && (tiles.out_x[t] % 4 == 0);
+    if (vec) {
+        const size_t total = static_cast<size_t>(tiles.count) * core_h * (core_w / 4);
+        tile_unpack_u8_kernel<<<blocks_for(total, 256), 256, 0, st>>>(pred, tiles, th2, tw2, canvas, OH, OW, core_h, core_w);
+    } else {
+        const size_t total = static_cast<size_t>(tiles.count) * core_h * core_w * 9;
+        tile_unpack_u8_scalar_kernel<<<blocks_for(total, 256), 256, 0, st>>>(pred, tiles, th2, tw2, canvas, OH, OW, core_h, core_w);
+    }
 }
 void launch_tile_unpack_f32(const float* pred, const TileList& tiles, int th2, int tw2, float* canvas, int OH, int OW,
                             int core_h, int core_w, cudaStream_t st) {

@@ -146,6 +146,17 @@ struct fisr_ctx {
     void* stage[8] = {nullptr};
     size_t stage_bytes[8] = {0};
     Plan* last_plan = nullptr;
+    // pipelined host path (fisr_window_submit / fisr_window_wait): copies run on their own streams
+    struct HostSlot {
+        void* in[3] = {nullptr, nullptr, nullptr};
+        size_t in_bytes[3] = {0, 0, 0};
+        void* out = nullptr;
+        size_t out_bytes = 0;
+        cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+        int* h_err = nullptr;        // pinned copy of the kernel error flag, filled behind the canvas copy
+        bool busy = false, used = false;
+    } slots[2];
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
 };
 
 namespace {
@@ -672,6 +683,16 @@ void fisr_destroy(fisr_ctx* ctx) {
     ctx->plans.clear();
     for (auto& p : ctx->params) { cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); }
     for (void* s : ctx->stage) if (s) cudaFree(s);
+    for (auto& sl : ctx->slots) {
+        for (void* b : sl.in) if (b) cudaFree(b);
+        if (sl.out) cudaFree(sl.out);
+        if (sl.h_err) cudaFreeHost(sl.h_err);
+        if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
+        if (sl.compute_done) cudaEventDestroy(sl.compute_done);
+        if (sl.d2h_done) cudaEventDestroy(sl.d2h_done);
+    }
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     cudaFree(ctx->d_err);
     cudaFree(ctx->d_lut255);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -850,6 +871,88 @@ int fisr_window_host(fisr_ctx* ctx, const uint8_t* h_frames, const float* h_flow
     CUDA_TRY(ctx, cudaMemcpyAsync(h_canvas, ctx->stage[4], out_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return check_kernel_error(ctx);
+}
+
+static int slot_reserve(fisr_ctx* ctx, void** buf, size_t* have, size_t need) {
+    if (*have >= need) return FISR_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr; *have = 0;
+    CUDA_TRY(ctx, cudaMalloc(buf, need));
+    *have = need;
+    return FISR_OK;
+}
+
+int fisr_window_submit(fisr_ctx* ctx, int slot, const uint8_t* h_frames, const float* h_flow, const float* h_warp, int H,
+                       int W, int pH, int pW, uint8_t* h_canvas) {
+    if (!ctx || !h_frames || !h_flow || !h_warp || !h_canvas) return FISR_E_INVALID;
+    if (slot < 0 || slot > 1) return fail(ctx, FISR_E_INVALID, "slot must be 0 or 1");
+    if (pH < 1 || pW < 1 || H < 32 * pH || W < 32 * pW) return fail(ctx, FISR_E_INVALID, "bad tile grid %dx%d for %dx%d", pH, pW, H, W);
+    Guard guard(ctx->device);
+    fisr_ctx::HostSlot& sl = ctx->slots[slot];
+    if (sl.busy) return fail(ctx, FISR_E_INVALID, "slot %d is still in flight: call fisr_window_wait first", slot);
+    if (!ctx->h2d_stream) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    }
+    if (!sl.h2d_done) {
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl.d2h_done, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaMallocHost(reinterpret_cast<void**>(&sl.h_err), sizeof(int)));
+    }
+    const size_t px = static_cast<size_t>(H) * W;
+    const int h = H - H % (32 * pH), w = W - W % (32 * pW);
+    const size_t out_bytes = static_cast<size_t>(2 * h) * (2 * w) * 9;
+    const size_t need[3] = {px * 9, px * 8 * 4, px * 12 * 4};
+    const void* src[3] = {h_frames, h_flow, h_warp};
+    int rc;
+    for (int i = 0; i < 3; ++i)
+        if ((rc = slot_reserve(ctx, &sl.in[i], &sl.in_bytes[i], need[i])) != FISR_OK) return rc;
+    if ((rc = slot_reserve(ctx, &sl.out, &sl.out_bytes, out_bytes)) != FISR_OK) return rc;
+    // the plan must exist before anything is enqueued (plan creation synchronises)
+    {
+        const TileGeom g = tile_geometry(H, W, pH, pW);
+        Plan* plan = nullptr;
+        for (const auto& t : g.tiles) {
+            int cnt = 0;
+            for (const auto& u : g.tiles) cnt += (u.yhi - u.ylo == t.yhi - t.ylo && u.xhi - u.xlo == t.xhi - t.xlo) ? 1 : 0;
+            if ((rc = get_plan(ctx, std::min(cnt, kMaxTiles), t.yhi - t.ylo, t.xhi - t.xlo, &plan)) != FISR_OK) return rc;
+        }
+    }
+    // H2D: the staging inputs of this slot are free once the previous compute that read them has finished
+    if (sl.used) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->h2d_stream, sl.compute_done, 0));
+    for (int i = 0; i < 3; ++i) CUDA_TRY(ctx, cudaMemcpyAsync(sl.in[i], src[i], need[i], cudaMemcpyHostToDevice, ctx->h2d_stream));
+    CUDA_TRY(ctx, cudaEventRecord(sl.h2d_done, ctx->h2d_stream));
+    // compute (the context stream serialises windows: they share the plan's activation workspace)
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, sl.h2d_done, 0));
+    rc = window_impl(ctx, static_cast<const uint8_t*>(sl.in[0]), static_cast<const float*>(sl.in[1]),
+                     static_cast<const float*>(sl.in[2]), H, W, pH, pW, 0, pH * pW, static_cast<uint8_t*>(sl.out), nullptr,
+                     ctx->stream);
+    if (rc != FISR_OK) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(sl.compute_done, ctx->stream));
+    // D2H
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->d2h_stream, sl.compute_done, 0));
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_canvas, sl.out, out_bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(sl.h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    CUDA_TRY(ctx, cudaEventRecord(sl.d2h_done, ctx->d2h_stream));
+    sl.busy = true;
+    sl.used = true;
+    return FISR_OK;
+}
+
+int fisr_window_wait(fisr_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot > 1) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    fisr_ctx::HostSlot& sl = ctx->slots[slot];
+    if (!sl.busy) return fail(ctx, FISR_E_INVALID, "slot %d has nothing in flight", slot);
+    CUDA_TRY(ctx, cudaEventSynchronize(sl.d2h_done));
+    sl.busy = false;
+    if (*sl.h_err != 0) {
+        const int code = *sl.h_err;
+        cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream);
+        return fail(ctx, FISR_E_KERNEL, "conv kernel pipeline time-out, barrier code %d", code);
+    }
+    return FISR_OK;
 }
 
 int fisr_warp_device(fisr_ctx* ctx, const uint8_t* d_yuv, const float* d_flow, float flow_scale, float* d_out, int h,

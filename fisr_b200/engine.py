@@ -210,6 +210,38 @@ class Engine:
                                               num_patch[0], num_patch[1], out.ctypes.data), "fisr_window_host")
         return out
 
+    def window_submit(self, slot: int, frames: np.ndarray, flow: np.ndarray, warp: np.ndarray, num_patch=(2, 2),
+                      out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Pipelined :meth:`window_host`: enqueue one window on slot 0/1 and return; :meth:`window_wait` delivers ``out``.
+        Arrays must be C-contiguous uint8 / float32 (ideally pinned) and are kept alive until the wait."""
+        for a, dt in ((frames, np.uint8), (flow, np.float32), (warp, np.float32)):
+            if a.dtype != dt or not a.flags.c_contiguous:
+                raise FisrError("window_submit needs C-contiguous uint8 frames and float32 flow / warp")
+        H, W, _ = frames.shape
+        if out is None:
+            out = np.empty(self.canvas_shape(H, W, num_patch), np.uint8)
+        self._check(self.lib.fisr_window_submit(self.h, slot, frames.ctypes.data, flow.ctypes.data, warp.ctypes.data, H, W,
+                                                num_patch[0], num_patch[1], out.ctypes.data), "fisr_window_submit")
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[slot] = (frames, flow, warp, out)
+        return out
+
+    def window_wait(self, slot: int) -> np.ndarray:
+        self._check(self.lib.fisr_window_wait(self.h, slot), "fisr_window_wait")
+        return self._inflight.pop(slot)[3]
+
+    def video_windows(self, windows, num_patch=(2, 2)):
+        """Generator over uint8 canvases for an iterable of (frames, flow, warp) host windows, two windows in flight."""
+        pending = []
+        for k, (fr, fl, wp) in enumerate(windows):
+            self.window_submit(k & 1, np.ascontiguousarray(fr, np.uint8), np.ascontiguousarray(fl, np.float32),
+                               np.ascontiguousarray(wp, np.float32), num_patch)
+            pending.append(k & 1)
+            if len(pending) == 2:
+                yield self.window_wait(pending.pop(0))
+        while pending:
+            yield self.window_wait(pending.pop(0))
+
     # ------------------------------------------------------------------ flow warp
     def warp(self, yuv: torch.Tensor, flow: torch.Tensor, flow_scale: float = 0.5, out_scale: float = 1.0) -> torch.Tensor:
         """``warp_flow`` with the colour round trip (..warp_img_with_flo.py:61-67,112-128) on device tensors."""

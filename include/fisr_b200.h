@@ -83,6 +83,13 @@ int fisr_units_device(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flo
                       int pH, int pW, const int* h_units, int n_units, int layout, uint8_t* d_out, void* stream);
 int fisr_window_host(fisr_ctx* ctx, const uint8_t* h_frames, const float* h_flow, const float* h_warp, int H, int W,
                      int pH, int pW, uint8_t* h_canvas);
+/* Pipelined form of fisr_window_host for clips: submit() enqueues H2D (copy stream), the tiles (context stream) and
+ * D2H (copy stream) for one window and returns at once; wait() blocks until that window's canvas is in h_canvas.
+ * Two slots (0, 1): submitting window k+1 before waiting for window k overlaps its copies with window k's kernels.
+ * Host buffers must stay valid (and should be pinned) until wait() returns. */
+int fisr_window_submit(fisr_ctx* ctx, int slot, const uint8_t* h_frames, const float* h_flow, const float* h_warp, int H,
+                       int W, int pH, int pW, uint8_t* h_canvas);
+int fisr_window_wait(fisr_ctx* ctx, int slot);
 /* float canvas [2h,2w,9] before clipping (what FISRnet.py:1057 accumulates), for parity tests */
 int fisr_window_device_f32(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, const float* d_warp, int H,
                            int W, int pH, int pW, float* d_canvas, void* stream);

@@ -90,3 +90,20 @@ def test_warp_matches_cv2(engine):
     assert np.abs(got1 - ref[1]).max() < 2e-3
     scaled = engine.warp_host(g[1], f12, 0.5, 1.0 / 255.0)
     assert np.abs(scaled - ref[0] / 255.0).max() < 1e-5
+
+
+def test_pipelined_host_path_equals_sync(engine):
+    """fisr_window_submit / fisr_window_wait (two windows in flight) deliver exactly what fisr_window_host does."""
+    engine.set_precision("f16x3")
+    engine.set_params(O.init_params(11))
+    wins = [_window_inputs(200, 330, seed=s) for s in (1, 2, 3)]
+    ref = [engine.window_host(*w, (2, 2)) for w in wins]
+    got = list(engine.video_windows(iter(wins), (2, 2)))
+    assert len(got) == 3
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+    import fisr_b200
+    engine.window_submit(0, *[np.ascontiguousarray(a) for a in wins[0]], (2, 2))
+    with pytest.raises(fisr_b200.FisrError):
+        engine.window_submit(0, *[np.ascontiguousarray(a) for a in wins[0]], (2, 2))     # slot busy
+    engine.window_wait(0)
