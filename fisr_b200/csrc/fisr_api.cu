@@ -15,6 +15,7 @@
 #include "aux_kernels.h"
 #include "common.cuh"
 #include "conv_umma.h"
+#include "train_kernels.h"
 
 using namespace fisr;
 
@@ -92,6 +93,7 @@ struct ConvParam {
     float* d_b = nullptr;        // fp32 [cout_pad], zero padded
     __half* d_wp = nullptr;      // packed (hi, lo) operand planes
     bool packed = false;
+    float *m_w = nullptr, *v_w = nullptr, *m_b = nullptr, *v_b = nullptr;   // Adam slots (allocated on first use)
 };
 
 struct DebugTensor {
@@ -157,6 +159,8 @@ struct fisr_ctx {
         bool busy = false, used = false;
     } slots[2];
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    long long adam_t = 0;        // Adam step counter (global_step of FISRnet.py:232,491)
+    float* d_scalars = nullptr;  // 11 loss scalars
 };
 
 namespace {
@@ -681,7 +685,8 @@ void fisr_destroy(fisr_ctx* ctx) {
     Guard guard(ctx->device);
     cudaDeviceSynchronize();
     ctx->plans.clear();
-    for (auto& p : ctx->params) { cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); }
+    for (auto& p : ctx->params) { cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); cudaFree(p.m_w); cudaFree(p.v_w); cudaFree(p.m_b); cudaFree(p.v_b); }
+    cudaFree(ctx->d_scalars);
     for (void* s : ctx->stage) if (s) cudaFree(s);
     for (auto& sl : ctx->slots) {
         for (void* b : sl.in) if (b) cudaFree(b);
@@ -1078,6 +1083,113 @@ int fisr_profile_ops(fisr_ctx* ctx, int N, int H, int W, int reps, int max_ops, 
     }
     rc = check_kernel_error(ctx);
     return rc == FISR_OK ? n : rc;
+}
+
+// ---------------------------------------------------------------- training-side entry points (forward half)
+int fisr_groups2ovlp(fisr_ctx* ctx, const float* d_pred, int B, int H, int W, float* d_out, void* stream) {
+    if (!ctx || !d_pred || !d_out || B < 1 || H < 1 || W < 1) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    launch_groups2ovlp(d_pred, d_out, B, H, W, st);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FISR_OK;
+}
+
+static int loss_impl(fisr_ctx* ctx, const float* const pred[3], const float* d_label, int B, int h, int w,
+                     const float* lambdas, float* h_out, cudaStream_t st) {
+    LossScales sc;
+    const size_t ws = temporal_loss_workspace(B, h, w, &sc);
+    int rc = ensure_stage(ctx, 5, ws);
+    if (rc != FISR_OK) return rc;
+    if (!ctx->d_scalars) CUDA_TRY(ctx, cudaMalloc(&ctx->d_scalars, 11 * sizeof(float)));
+    LossLambdas lam{1.f, 1.f, 0.1f, 1.f, 0.1f, 1.f};                 // main.py:80-85
+    if (lambdas) lam = LossLambdas{lambdas[0], lambdas[1], lambdas[2], lambdas[3], lambdas[4], lambdas[5]};
+    launch_temporal_loss(pred, d_label, B, h, w, lam, static_cast<double*>(ctx->stage[5]), ctx->d_scalars, st);
+    ctx->launches += 4;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_out, ctx->d_scalars, 11 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return FISR_OK;
+}
+
+int fisr_temporal_loss(fisr_ctx* ctx, const float* d_pred_l1, const float* d_pred_l2, const float* d_pred_l3,
+                       const float* d_label, int B, int h, int w, const float* lambdas, float* h_out, void* stream) {
+    if (!ctx || !d_pred_l1 || !d_pred_l2 || !d_pred_l3 || !d_label || !h_out || B < 1 || h < 4 || w < 4 || h % 4 || w % 4)
+        return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    const float* pred[3] = {d_pred_l1, d_pred_l2, d_pred_l3};
+    return loss_impl(ctx, pred, d_label, B, h, w, lambdas, h_out, st);
+}
+
+int fisr_train_forward(fisr_ctx* ctx, const float* d_data, const float* d_flow, const float* d_flow_ss2, const float* d_warp,
+                       const float* d_warp_ss2, const float* d_label, int B, int h, int w, const float* lambdas, float* h_out,
+                       void* stream) {
+    if (!ctx || !d_data || !d_flow || !d_flow_ss2 || !d_warp || !d_warp_ss2 || !d_label || !h_out || B < 1) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    Plan* plan = nullptr;
+    int rc = get_plan(ctx, 4 * B, h, w, &plan);                       // the 4 weight-shared passes as one batch
+    if (rc != FISR_OK) return rc;
+    const size_t in_bytes = static_cast<size_t>(4) * B * h * w * IN_CH * 4;
+    if ((rc = ensure_stage(ctx, 0, in_bytes)) != FISR_OK) return rc;
+    launch_assemble_passes(d_data, d_flow, d_flow_ss2, d_warp, d_warp_ss2, static_cast<float*>(ctx->stage[0]), B, h, w, st);
+    launch_pack_input(static_cast<const float*>(ctx->stage[0]), 4 * B, h, w, IN_CH, plan->in_lvl[2], plan->in_lvl[1],
+                      plan->in_lvl[0], plan->planes, st);
+    ctx->launches += 2;
+    rc = run_plan(ctx, plan, st);
+    if (rc != FISR_OK) return rc;
+    const float* pred[3] = {plan->pred[0], plan->pred[1], plan->pred[2]};
+    rc = loss_impl(ctx, pred, d_label, B, h, w, lambdas, h_out, st);
+    if (rc != FISR_OK) return rc;
+    return check_kernel_error(ctx);
+}
+
+int fisr_adam_step(fisr_ctx* ctx, const float* const* d_grads, int n_grads, float lr, float beta1, float beta2, float eps) {
+    if (!ctx || !d_grads) return FISR_E_INVALID;
+    if (n_grads != 2 * static_cast<int>(ctx->params.size()))
+        return fail(ctx, FISR_E_INVALID, "expected %d gradient tensors (creation order, w then b), got %d", 2 * (int)ctx->params.size(), n_grads);
+    Guard guard(ctx->device);
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    const long long t = ++ctx->adam_t;
+    const float lr_t = static_cast<float>(lr * std::sqrt(1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(t))) /
+                                          (1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(t))));
+    for (size_t i = 0; i < ctx->params.size(); ++i) {
+        ConvParam& p = ctx->params[i];
+        const size_t wn = static_cast<size_t>(9) * p.cin * p.cout, bn = p.cout;
+        if (!p.m_w) {
+            CUDA_TRY(ctx, cudaMalloc(&p.m_w, wn * 4)); CUDA_TRY(ctx, cudaMalloc(&p.v_w, wn * 4));
+            CUDA_TRY(ctx, cudaMalloc(&p.m_b, bn * 4)); CUDA_TRY(ctx, cudaMalloc(&p.v_b, bn * 4));
+            CUDA_TRY(ctx, cudaMemsetAsync(p.m_w, 0, wn * 4, st)); CUDA_TRY(ctx, cudaMemsetAsync(p.v_w, 0, wn * 4, st));
+            CUDA_TRY(ctx, cudaMemsetAsync(p.m_b, 0, bn * 4, st)); CUDA_TRY(ctx, cudaMemsetAsync(p.v_b, 0, bn * 4, st));
+        }
+        if (!d_grads[2 * i] || !d_grads[2 * i + 1]) return fail(ctx, FISR_E_INVALID, "gradient %zu is NULL", i);
+        launch_adam_tf1(p.d_w, d_grads[2 * i], p.m_w, p.v_w, wn, lr_t, beta1, beta2, eps, st);
+        launch_adam_tf1(p.d_b, d_grads[2 * i + 1], p.m_b, p.v_b, bn, lr_t, beta1, beta2, eps, st);
+        p.packed = false;
+        int rc = ensure_packed(ctx, p, st);          // operand planes follow the fp32 master copy
+        if (rc != FISR_OK) return rc;
+        ctx->launches += 2;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return FISR_OK;
+}
+
+long long fisr_adam_steps(const fisr_ctx* ctx) { return ctx ? ctx->adam_t : 0; }
+
+int fisr_adam_reset(fisr_ctx* ctx, long long step) {
+    if (!ctx || step < 0) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    for (auto& p : ctx->params) {
+        cudaFree(p.m_w); cudaFree(p.v_w); cudaFree(p.m_b); cudaFree(p.v_b);
+        p.m_w = p.v_w = p.m_b = p.v_b = nullptr;
+    }
+    ctx->adam_t = step;
+    return FISR_OK;
 }
 
 long long fisr_launch_count(const fisr_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -1,0 +1,228 @@
+// Training-side kernels that do not need the backward pass: window assembly of the four weight-shared passes,
+// Groups2Ovlp, the multi-scale temporal loss (forward values) + train PSNR, and the TF-1.13 Adam update.
+// All are HBM-bound single-pass kernels; reductions are two-stage with a fixed summation order (deterministic).
+#include "common.cuh"
+#include "train_kernels.h"
+
+namespace fisr {
+
+namespace {
+
+inline unsigned blocks_for(size_t total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
+
+// ---------------------------------------------------------------- window assembly (FISRnet.py:281-306, 392-399)
+// out [4B,h,w,29]: pass p < 3 = stride-1 window p (frames ch [3p,3p+9), flows [4p,4p+8), warps [6p,6p+12));
+// pass 3 = stride 2 (frames 0,2,4 + flow_ss2 + warp_ss2).
+__global__ void assemble_passes_kernel(const float* __restrict__ data, const float* __restrict__ flow,
+                                       const float* __restrict__ flow2, const float* __restrict__ warp,
+                                       const float* __restrict__ warp2, float* __restrict__ out, int B, size_t hw) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t total = static_cast<size_t>(4) * B * hw * 29;
+    if (i >= total) return;
+    const int c = i % 29;
+    const size_t pix = i / 29;                 // over [4B, h, w]
+    const size_t q = pix % (static_cast<size_t>(B) * hw);
+    const int pass = pix / (static_cast<size_t>(B) * hw);
+    float v;
+    if (pass < 3) {
+        if (c < 9) v = data[q * 15 + 3 * pass + c];
+        else if (c < 17) v = flow[q * 16 + 4 * pass + (c - 9)];
+        else v = warp[q * 24 + 6 * pass + (c - 17)];
+    } else {
+        if (c < 9) v = data[q * 15 + (c / 3) * 6 + c % 3];
+        else if (c < 17) v = flow2[q * 8 + (c - 9)];
+        else v = warp2[q * 12 + (c - 17)];
+    }
+    out[i] = v;
+}
+
+// ---------------------------------------------------------------- Groups2Ovlp (ops.py:119-144)
+// pred [3B,H,W,9] (window-major) -> out [B,7,H,W,3] = [f0, f1, (f2+f3)/2, f4, (f5+f6)/2, f7, f8]
+__global__ void groups2ovlp_kernel(const float* __restrict__ pred, float* __restrict__ out, int B, size_t hw) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t total = static_cast<size_t>(B) * 7 * hw * 3;
+    if (i >= total) return;
+    const int c = i % 3;
+    size_t r = i / 3;
+    const size_t p = r % hw; r /= hw;
+    const int f = r % 7;
+    const int b = r / 7;
+    auto P = [&](int k) { return pred[((static_cast<size_t>(k / 3) * B + b) * hw + p) * 9 + 3 * (k % 3) + c]; };
+    float v;
+    switch (f) {
+        case 0: v = P(0); break;
+        case 1: v = P(1); break;
+        case 2: v = (P(2) + P(3)) / 2; break;
+        case 3: v = P(4); break;
+        case 4: v = (P(5) + P(6)) / 2; break;
+        case 5: v = P(7); break;
+        default: v = P(8); break;
+    }
+    out[i] = v;
+}
+
+// ---------------------------------------------------------------- temporal loss (FISRnet.py:312-486)
+// One scale: pred [4B,hs,ws,9] (pass-major), label [B,2h,2w,21] sampled with stride st ("bicubic" = subsample, :263-264).
+// Per pixel the 7 squared-error sums + the 7 per-frame sums of (O - GT)^2 for the PSNR; block partials
+// partial[(b * nblk + blk) * 14 + k].
+constexpr int kLossTerms = 14;
+__global__ void temporal_loss_kernel(const float* __restrict__ pred, const float* __restrict__ label, int B, int hs, int ws,
+                                     int st, int LH, int LW, double* __restrict__ partial) {
+    const int b = blockIdx.y;
+    const size_t hw = static_cast<size_t>(hs) * ws;
+    const size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    float acc[kLossTerms];
+#pragma unroll
+    for (int k = 0; k < kLossTerms; ++k) acc[k] = 0.f;
+    if (p < hw) {
+        const int y = p / ws, x = p % ws;
+        const float* lab = label + ((static_cast<size_t>(b) * LH + static_cast<size_t>(y) * st) * LW + static_cast<size_t>(x) * st) * 21;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float P[9], S[3], G[7], O[7];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) P[k] = pred[((static_cast<size_t>(k / 3) * B + b) * hw + p) * 9 + 3 * (k % 3) + c];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) S[k] = pred[((static_cast<size_t>(3) * B + b) * hw + p) * 9 + 3 * k + c];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) G[k] = lab[3 * k + c];
+            O[0] = P[0]; O[1] = P[1]; O[2] = (P[2] + P[3]) / 2; O[3] = P[4]; O[4] = (P[5] + P[6]) / 2; O[5] = P[7]; O[6] = P[8];
+            float d;
+#pragma unroll
+            for (int w = 0; w < 3; ++w)
+#pragma unroll
+                for (int f = 0; f < 3; ++f) { d = P[3 * w + f] - G[2 * w + f]; acc[0] += d * d; }             // recn  :315-328
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                d = P[3 * i + 2] - P[3 * i + 3]; acc[1] += d * d;                                             // tm    :331-341
+                d = (P[3 * i + 2] + P[3 * i + 3]) / 2 - G[2 * (i + 1)]; acc[2] += d * d;                       // tmm   :344-357
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { d = (O[i + 1] - O[i]) - (G[i + 1] - G[i]); acc[3] += d * d; }         // td    :360-385
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+                d = S[f] - G[2 * f + 1]; acc[4] += d * d;                                                     // recn2 :426-428
+                d = S[f] - O[2 * f + 1]; acc[6] += d * d;                                                     // tm2   :462-477
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { d = (S[i + 1] - S[i]) - (G[2 * i + 3] - G[2 * i + 1]); acc[5] += d * d; }   // td2 :431-459
+#pragma unroll
+            for (int f = 0; f < 7; ++f) { d = O[f] - G[f]; acc[7 + f] += d * d; }                               // PSNR  :485
+        }
+    }
+    __shared__ double red[kLossTerms][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < kLossTerms; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[k][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kLossTerms) {
+        double v = 0;
+        for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) v += red[threadIdx.x][w];
+        partial[(static_cast<size_t>(b) * gridDim.x + blockIdx.x) * kLossTerms + threadIdx.x] = v;
+    }
+}
+
+// Fixed-order reduction of the block partials of the three scales and the 11 scalars of FISRnet.py:651-657.
+__global__ void loss_finalize_kernel(const double* __restrict__ partial, LossScales sc, int B, LossLambdas lam,
+                                     float* __restrict__ out) {
+    __shared__ double sums[3][7];
+    __shared__ double psnr_sum;
+    const int t = threadIdx.x;
+    if (t < 21) {                     // 7 terms x 3 scales: summed over images and blocks
+        const int s = t / 7, k = t % 7;
+        double v = 0;
+        const double* p = partial + sc.offset[s];
+        for (size_t i = 0; i < static_cast<size_t>(B) * sc.nblk[s]; ++i) v += p[i * kLossTerms + k];
+        sums[s][k] = v;
+    }
+    if (t == 31) {                    // train PSNR on the finest scale: per (image, frame) MSE -> dB -> mean
+        double acc = 0;
+        const double* p = partial + sc.offset[2];
+        const double n = static_cast<double>(sc.hw[2]) * 3;
+        for (int b = 0; b < B; ++b)
+            for (int f = 0; f < 7; ++f) {
+                double v = 0;
+                for (int i = 0; i < sc.nblk[2]; ++i) v += p[(static_cast<size_t>(b) * sc.nblk[2] + i) * kLossTerms + 7 + f];
+                acc += 10.0 * log10(1.0 / (v / n));
+            }
+        psnr_sum = acc / (7.0 * B);
+    }
+    __syncthreads();
+    if (t == 0) {
+        const double wgt[3] = {4.0, 2.0, 1.0};                      // l1, l2, l3  (FISRnet.py:326-328)
+        double term[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int s = 0; s < 3; ++s) {
+            const double n1 = static_cast<double>(B) * sc.hw[s] * 3;      // elements of one [B,1,h,w,3] slice
+            const double cnt[7] = {3 * n1, n1, n1, n1, 3 * n1, n1, 3 * n1};
+            for (int k = 0; k < 7; ++k) term[k] += wgt[s] * sums[s][k] / cnt[k];
+        }
+        const double s1 = lam.recn * term[0] + lam.tm1 * term[1] + lam.tmm * term[2] + lam.td * term[3];
+        const double s2 = lam.recn * term[4] + lam.td * term[5] + lam.tm2 * term[6];
+        out[0] = term[0]; out[1] = term[1]; out[2] = term[2]; out[3] = term[3]; out[4] = s1;
+        out[5] = term[4]; out[6] = term[5]; out[7] = term[6]; out[8] = s2;
+        out[9] = s1 + lam.ss2 * s2;
+        out[10] = psnr_sum;
+    }
+}
+
+// ---------------------------------------------------------------- Adam, TF-1.13 formula (FISRnet.py:489-491)
+__global__ void adam_tf1_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, size_t n, float lr_t, float beta1, float beta2, float eps) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i];
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    theta[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+
+}  // namespace
+
+void launch_assemble_passes(const float* data, const float* flow, const float* flow2, const float* warp, const float* warp2,
+                            float* out, int B, int h, int w, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(4) * B * h * w * 29;
+    assemble_passes_kernel<<<blocks_for(total, 256), 256, 0, st>>>(data, flow, flow2, warp, warp2, out, B, static_cast<size_t>(h) * w);
+}
+
+void launch_groups2ovlp(const float* pred, float* out, int B, int H, int W, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(B) * 7 * H * W * 3;
+    groups2ovlp_kernel<<<blocks_for(total, 256), 256, 0, st>>>(pred, out, B, static_cast<size_t>(H) * W);
+}
+
+size_t temporal_loss_workspace(int B, int h, int w, LossScales* sc) {
+    size_t off = 0;
+    for (int s = 0; s < 3; ++s) {
+        const int hs = h / 2 << s, ws = w / 2 << s;           // pred_l1 is [h/2, w/2], pred_l3 [2h, 2w]
+        sc->hw[s] = static_cast<long long>(hs) * ws;
+        sc->nblk[s] = static_cast<int>((sc->hw[s] + 255) / 256);
+        sc->offset[s] = off;
+        off += static_cast<size_t>(B) * sc->nblk[s] * kLossTerms;
+    }
+    return off * sizeof(double);
+}
+
+void launch_temporal_loss(const float* const pred[3], const float* label, int B, int h, int w, const LossLambdas& lam,
+                          double* workspace, float* d_out, cudaStream_t st) {
+    LossScales sc;
+    temporal_loss_workspace(B, h, w, &sc);
+    for (int s = 0; s < 3; ++s) {
+        const int hs = h / 2 << s, ws = w / 2 << s;
+        dim3 grid(sc.nblk[s], B);
+        temporal_loss_kernel<<<grid, 256, 0, st>>>(pred[s], label, B, hs, ws, 4 >> s, 2 * h, 2 * w, workspace + sc.offset[s]);
+    }
+    loss_finalize_kernel<<<1, 32, 0, st>>>(workspace, sc, B, lam, d_out);
+}
+
+void launch_adam_tf1(float* theta, const float* g, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,
+                     float eps, cudaStream_t st) {
+    adam_tf1_kernel<<<blocks_for(n, 256), 256, 0, st>>>(theta, g, m, v, n, lr_t, beta1, beta2, eps);
+}
+
+}  // namespace fisr

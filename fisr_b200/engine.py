@@ -264,6 +264,64 @@ class Engine:
                                             out_scale), "fisr_warp_host")
         return out
 
+    # ------------------------------------------------------------------ training-side forward half
+    LOSS_NAMES = ("recnLoss", "tmLoss", "tmmLoss", "tdLoss", "totalLoss_s1", "recnLoss_ss2", "tdLoss_ss2", "tmLoss_ss2",
+                  "totalLoss_ss2", "total_loss", "train_PSNR")
+
+    @staticmethod
+    def _lambdas(lambdas):
+        if lambdas is None:
+            return None
+        vals = [float(lambdas[k]) for k in ("recn", "tm1", "tm2", "tmm", "td", "ss2")]
+        return (C.c_float * 6)(*vals)
+
+    def groups2ovlp(self, pred: torch.Tensor) -> torch.Tensor:
+        """``Groups2Ovlp`` (ops.py:119-144): pred [3B,H,W,9] of windows 0,1,2 -> [B,7,H,W,3]."""
+        pred = self._dev(pred, torch.float32)
+        n, H, W, _ = pred.shape
+        out = torch.empty((n // 3, 7, H, W, 3), device=pred.device)
+        self._enter(pred, out)
+        self._check(self.lib.fisr_groups2ovlp(self.h, pred.data_ptr(), n // 3, H, W, out.data_ptr(), self._stream()),
+                    "fisr_groups2ovlp")
+        self._exit()
+        return out
+
+    def temporal_loss(self, preds, label: torch.Tensor, lambdas=None) -> dict:
+        """The 11 scalars of FISRnet.py:651-657 from the three outputs of the 4B-batch forward and label [B,2h,2w,21]."""
+        p = [self._dev(t, torch.float32) for t in preds]
+        label = self._dev(label, torch.float32)
+        B, H2, W2, _ = label.shape
+        out = (C.c_float * 11)()
+        self._enter(*p, label)
+        self._check(self.lib.fisr_temporal_loss(self.h, p[0].data_ptr(), p[1].data_ptr(), p[2].data_ptr(), label.data_ptr(),
+                                                B, H2 // 2, W2 // 2, self._lambdas(lambdas), out, self._stream()),
+                    "fisr_temporal_loss")
+        self._exit()
+        return dict(zip(self.LOSS_NAMES, (float(v) for v in out)))
+
+    def train_forward(self, data, flow, flow_ss2, warp, warp_ss2, label, lambdas=None) -> dict:
+        """Forward half of one training step (FISRnet.py:281-486): 4 weight-shared passes as one batch + loss scalars."""
+        ts = [self._dev(t, torch.float32) for t in (data, flow, flow_ss2, warp, warp_ss2, label)]
+        B, h, w, _ = ts[0].shape
+        out = (C.c_float * 11)()
+        self._enter(*ts)
+        self._check(self.lib.fisr_train_forward(self.h, *[t.data_ptr() for t in ts], B, h, w, self._lambdas(lambdas), out,
+                                                self._stream()), "fisr_train_forward")
+        self._exit()
+        return dict(zip(self.LOSS_NAMES, (float(v) for v in out)))
+
+    def adam_step(self, grads: Dict[str, torch.Tensor], lr: float, beta1=0.9, beta2=0.999, eps=1e-8) -> int:
+        """``tf.train.AdamOptimizer(lr)`` update (TF-1.13 formula) from device gradients keyed by variable name."""
+        names = list(param_inventory())
+        keep = [self._dev(grads[n].contiguous(), torch.float32) for n in names]
+        arr = (C.c_void_p * len(keep))(*[t.data_ptr() for t in keep])
+        torch.cuda.synchronize(self.device)
+        self._check(self.lib.fisr_adam_step(self.h, arr, len(keep), lr, beta1, beta2, eps), "fisr_adam_step")
+        return int(self.lib.fisr_adam_steps(self.h))
+
+    def adam_reset(self, step: int = 0) -> None:
+        self._check(self.lib.fisr_adam_reset(self.h, step), "fisr_adam_reset")
+
     # ------------------------------------------------------------------ test hooks
     def conv3x3(self, x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, res: Optional[torch.Tensor] = None,
                 relu: bool = True, d2s: bool = False, want_raw: bool = True, want_act: bool = True):

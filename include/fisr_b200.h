@@ -102,6 +102,29 @@ int fisr_warp_device(fisr_ctx* ctx, const uint8_t* d_yuv, const float* d_flow, f
 int fisr_warp_host(fisr_ctx* ctx, const uint8_t* h_yuv, const float* h_flow, float flow_scale, float* h_out, int h,
                    int w, float out_scale);
 
+/* ---- training-side forward half (the backward pass is not part of this revision) ---------------------------- */
+/* Groups2Ovlp (ops.py:119-144): d_pred [3B,H,W,9] = pred of windows 0,1,2 (window-major) -> d_out [B,7,H,W,3]. */
+int fisr_groups2ovlp(fisr_ctx* ctx, const float* d_pred, int B, int H, int W, float* d_out, void* stream);
+/* Multi-scale temporal loss + train PSNR (FISRnet.py:312-486).  d_pred_l* are the three outputs of FISRnet.model on the
+ * 4B-batch [window 0 | window 1 | window 2 | stride 2] (pass-major) of an LR size h x w; d_label [B,2h,2w,21].
+ * lambdas = {recn, tm1, tm2, tmm, td, ss2} (NULL = main.py:80-85 defaults).  h_out[11] = recnLoss, tmLoss, tmmLoss, tdLoss,
+ * totalLoss_s1, recnLoss_ss2, tdLoss_ss2, tmLoss_ss2, totalLoss_ss2, total_loss, train_PSNR (FISRnet.py:651-657).
+ * Synchronous (reads the scalars back). */
+int fisr_temporal_loss(fisr_ctx* ctx, const float* d_pred_l1, const float* d_pred_l2, const float* d_pred_l3,
+                       const float* d_label, int B, int h, int w, const float* lambdas, float* h_out, void* stream);
+/* The forward half of `sess.run([optim, ...])` (FISRnet.py:651): assembles the four weight-shared passes from
+ * data [B,h,w,15], flow [..,16], flow_ss2 [..,8], warp [..,24], warp_ss2 [..,12] (FISRnet.py:281-306,392-399), runs them as
+ * ONE batched forward and evaluates the loss scalars. */
+int fisr_train_forward(fisr_ctx* ctx, const float* d_data, const float* d_flow, const float* d_flow_ss2, const float* d_warp,
+                       const float* d_warp_ss2, const float* d_label, int B, int h, int w, const float* lambdas, float* h_out,
+                       void* stream);
+/* tf.train.AdamOptimizer(lr) update (FISRnet.py:489-491, TF-1.13 formula: lr_t = lr*sqrt(1-b2^t)/(1-b1^t),
+ * theta -= lr_t*m/(sqrt(v)+eps)) of all 276 tensors from device gradients listed in creation order (w, b, w, b, ...);
+ * keeps m, v and the step counter in the context and re-packs the operand planes.  TF defaults: 0.9, 0.999, 1e-8. */
+int fisr_adam_step(fisr_ctx* ctx, const float* const* d_grads, int n_grads, float lr, float beta1, float beta2, float eps);
+long long fisr_adam_steps(const fisr_ctx* ctx);
+int fisr_adam_reset(fisr_ctx* ctx, long long step);
+
 /* ---- introspection / test hooks ---------------------------------------------------------------------------- */
 /* Single 3x3 SAME conv through the production kernel (ops.py:7-11 plus the fused epilogue):
  * y = conv(x, w) + b (+ res); raw = y; act = relu ? max(y,0) : y, optionally depth_to_space(2) (FISRnet.py:99).
