@@ -3,42 +3,12 @@
 // tiled video path, and the flow warp.  All are one-pass, vectorised, coalesced along the channel axis.
 #include "common.cuh"
 #include "aux_kernels.h"
+#include "act_io.cuh"
 
 namespace fisr {
 
 namespace {
 
-
-__device__ __forceinline__ void unpack8(const uint4& v, __half (&h)[8]) {
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        h[2 * i] = __ushort_as_half(static_cast<unsigned short>(w[i] & 0xFFFF));
-        h[2 * i + 1] = __ushort_as_half(static_cast<unsigned short>(w[i] >> 16));
-    }
-}
-// 8 consecutive channels of a (hi, lo) activation -> fp32
-template <int PLANES>
-__device__ __forceinline__ void load8(const __half* p, size_t plane, float (&f)[8]) {
-    __half h[8], l[8];
-    unpack8(*reinterpret_cast<const uint4*>(p), h);
-    if (PLANES == 2) {
-        unpack8(*reinterpret_cast<const uint4*>(p + plane), l);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = join_f16(h[i], l[i]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = __half2float(h[i]);
-    }
-}
-template <int PLANES>
-__device__ __forceinline__ void store8(__half* p, size_t plane, const float (&f)[8]) {
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) split2_f32(f[2 * q], f[2 * q + 1], hi[q], lo[q]);
-    *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    if (PLANES == 2) *reinterpret_cast<uint4*>(p + plane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-}
 
 // ---------------------------------------------------------------- weights
 // w: fp32 HWIO [3,3,cin,cout] (ops.py:8) -> [plane][kb][tap][cout_pad][64] fp16, zero padded.

@@ -3,6 +3,6 @@
 
 namespace fisr {
 namespace convk {
-FISR_CONV_FAMILY(64, 2, FISR_FOR_EPI)
+FISR_CONV_FAMILY(64, 2, FISR_FOR_EPI_TRAIN64)
 }  // namespace convk
 }  // namespace fisr

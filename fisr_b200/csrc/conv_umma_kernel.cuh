@@ -46,7 +46,9 @@ constexpr int kMaxAStages = 2;
 constexpr int kStageBytesPerWarp = 32 * 64;   // [32 px][16 ch] fp32, 16-B groups XOR-swizzled (conflict-free both ways)
 
 // epilogue variants (template flags)
-enum { EPI_RES = 1, EPI_RAW = 2, EPI_D2S = 4 };
+// backward (dgrad) variants: EPI_MASK multiplies the accumulator by [mask > 0] (the ReLU gradient, read from the hi plane
+// of the forward activation) before the residual is added; EPI_S2D stores space-to-depth (adjoint of EPI_D2S).
+enum { EPI_RES = 1, EPI_RAW = 2, EPI_D2S = 4, EPI_MASK = 8, EPI_S2D = 16 };
 
 // error codes written to ConvArgs::err on a barrier timeout
 enum { ERR_A_EMPTY = 11, ERR_B_EMPTY = 12, ERR_A_FULL = 21, ERR_B_FULL = 22, ERR_ACC_EMPTY = 23, ERR_ACC_FULL = 31 };
@@ -318,7 +320,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 // After the transpose lane l serves pixels (l >> 2) + 8*i of this warp's 32-pixel group, channels
                 // 4*(l & 3) .. +3 of each 16-channel step: 4 lanes cover 64 contiguous bytes of fp32 per pixel.
                 const int cg_lane = t.nb * NT + c_begin + 4 * rd_grp;
-                uint32_t o_res[4], o_raw[4], o_act[4];
+                uint32_t o_res[4], o_raw[4], o_act[4], o_msk[4];
                 uint32_t vmask = 0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -330,7 +332,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                     const uint32_t pix = valid ? static_cast<uint32_t>((t.n * a.H + y) * a.W + x) : 0u;
                     if (EPI & EPI_RES) o_res[i] = pix * a.res_cs + cg_lane;
                     if (EPI & EPI_RAW) o_raw[i] = pix * a.raw_cs + a.raw_off1 + cg_lane;
+                    if (EPI & EPI_MASK) o_msk[i] = pix * a.mask_cs + a.mask_off + cg_lane;
                     if (EPI & EPI_D2S) o_act[i] = valid ? static_cast<uint32_t>((t.n * 2 * a.H + 2 * y) * (2 * a.W) + 2 * x) * a.act_cs : 0u;
+                    else if (EPI & EPI_S2D)   // out[n, y/2, x/2, ((y&1)*2 + (x&1))*64 + c] = in[n, y, x, c]
+                        o_act[i] = valid ? static_cast<uint32_t>((t.n * (a.H >> 1) + (y >> 1)) * (a.W >> 1) + (x >> 1)) * a.act_cs +
+                                               static_cast<uint32_t>(((y & 1) * 2 + (x & 1)) * 64) + cg_lane : 0u;
                     else o_act[i] = pix * a.act_cs + a.act_off1 + cg_lane;
                 }
                 constexpr int ITERS = CSPAN / 16;
@@ -357,6 +363,14 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                             if ((vmask >> i) & 1) rn[i] = __ldg(reinterpret_cast<const float4*>(a.res + o_res[i] + c0 + 16));
                         }
                     }
+                    uint2 mk[4];
+                    if (EPI & EPI_MASK) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            mk[i] = make_uint2(0u, 0u);
+                            if ((vmask >> i) & 1) mk[i] = __ldg(reinterpret_cast<const uint2*>(a.mask + o_msk[i] + c0));
+                        }
+                    }
                     const float4 b4 = lds128(sBias32 + (cg_lane + c0) * 4);
                     uint32_t v[16];
                     tmem_ld_32x16(tacc + c_begin + c0, v);
@@ -380,6 +394,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                         const float4 val = lds128(stg + r * 64 + ((rd_grp ^ ((r >> 1) & 3)) << 4));
                         if ((vmask >> i) & 1) {
                             float f0 = val.x + b4.x, f1 = val.y + b4.y, f2 = val.z + b4.z, f3 = val.w + b4.w;
+                            if (EPI & EPI_MASK) {   // fp16 bit patterns 0x0001..0x7FFF are the positive values (post-ReLU: never negative)
+                                if ((mk[i].x & 0x7FFFu) == 0u) f0 = 0.f;
+                                if ((mk[i].x & 0x7FFF0000u) == 0u) f1 = 0.f;
+                                if ((mk[i].y & 0x7FFFu) == 0u) f2 = 0.f;
+                                if ((mk[i].y & 0x7FFF0000u) == 0u) f3 = 0.f;
+                            }
                             if (EPI & EPI_RES) { f0 += rr[i].x; f1 += rr[i].y; f2 += rr[i].z; f3 += rr[i].w; }
                             if (EPI & EPI_RAW) *reinterpret_cast<float4*>(a.out_raw + o_raw[i] + c0) = make_float4(f0, f1, f2, f3);
                             f0 = fmaxf(f0, relu_floor); f1 = fmaxf(f1, relu_floor);
@@ -457,6 +477,14 @@ cudaError_t launch_family(const ConvLaunch& L, int num_sms, cudaStream_t stream)
     M(NT_, PL_, 1, EPI_RES) M(NT_, PL_, 2, EPI_RES) M(NT_, PL_, 1, EPI_RES | EPI_RAW) M(NT_, PL_, 2, EPI_RES | EPI_RAW) \
     M(NT_, PL_, 1, EPI_D2S) M(NT_, PL_, 2, EPI_D2S)
 #define FISR_FOR_EPI_NARROW(M, NT_, PL_) M(NT_, PL_, 1, 0) M(NT_, PL_, 2, 0)
+// dgrad variants (training, split mode only): mask | mask+res | mask+res+raw | mask+raw (| mask+s2d for the 64-wide tile)
+#define FISR_FOR_EPI_BWD(M, NT_, PL_)                                                                       \
+    M(NT_, PL_, 1, EPI_MASK) M(NT_, PL_, 2, EPI_MASK) M(NT_, PL_, 1, EPI_MASK | EPI_RES) M(NT_, PL_, 2, EPI_MASK | EPI_RES) \
+    M(NT_, PL_, 1, EPI_MASK | EPI_RES | EPI_RAW) M(NT_, PL_, 2, EPI_MASK | EPI_RES | EPI_RAW)               \
+    M(NT_, PL_, 1, EPI_MASK | EPI_RAW) M(NT_, PL_, 2, EPI_MASK | EPI_RAW)
+#define FISR_FOR_EPI_TRAIN(M, NT_, PL_) FISR_FOR_EPI(M, NT_, PL_) FISR_FOR_EPI_BWD(M, NT_, PL_)
+#define FISR_FOR_EPI_TRAIN64(M, NT_, PL_) \
+    FISR_FOR_EPI_TRAIN(M, NT_, PL_) M(NT_, PL_, 1, EPI_MASK | EPI_S2D) M(NT_, PL_, 2, EPI_MASK | EPI_S2D)
 
 }  // namespace convk
 }  // namespace fisr

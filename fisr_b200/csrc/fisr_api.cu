@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "conv_umma.h"
 #include "train_kernels.h"
+#include "wgrad_umma.h"
 
 using namespace fisr;
 
@@ -648,6 +649,8 @@ int fisr_create(int device, fisr_ctx** out) {
     ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
     if ((e = conv3x3_init()) != cudaSuccess)
         return fail(nullptr, FISR_E_CUDA, "conv kernel attribute setup failed: %s", cudaGetErrorString(e));
+    if ((e = wgrad3x3_init()) != cudaSuccess)
+        return fail(nullptr, FISR_E_CUDA, "wgrad kernel attribute setup failed: %s", cudaGetErrorString(e));
     const char* g = getenv("FISR_NO_GRAPH");
     ctx->use_graph = !(g && g[0] == '1');
     fisr_ctx* c = ctx.get();
@@ -1029,6 +1032,40 @@ int fisr_conv3x3(fisr_ctx* ctx, const float* d_x, const float* d_w, const float*
     ctx->launches += 3;
     if (rc != FISR_OK) return rc;
     if (d_act) launch_act_to_f32(yact, ocs, 0, d_act, oc, static_cast<size_t>(N) * oH * oW, ctx->planes, st);
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return check_kernel_error(ctx);
+}
+
+int fisr_wgrad3x3(fisr_ctx* ctx, const float* d_x, const float* d_dy, int N, int H, int W, int Cin, int Cout, float scale,
+                  float* d_gw, float* d_gb) {
+    if (!ctx || !d_x || !d_dy || !d_gw || N < 1 || H < 1 || W < 1 || Cin < 1 || Cout < 1) return FISR_E_INVALID;
+    if (ctx->planes != 2) return fail(ctx, FISR_E_INVALID, "the backward kernels need precision f16x3");
+    Guard guard(ctx->device);
+    cudaStream_t st = ctx->stream;
+    Plan tmp;
+    tmp.planes = 2;
+    Builder b{ctx, &tmp};
+    const int CB = (Cin + 63) / 64, OB = (Cout + 63) / 64;
+    ActBuf xin = b.act(N, H, W, CB * 64), dy = b.act(N, H, W, OB * 64);
+    WgradLaunch L{};
+    plan_wgrad(N, H, W, CB, OB, ctx->num_sms, &L);
+    if (const char* e = getenv("FISR_WGRAD_VARIANT")) L.args.variant = atoi(e);
+    float* partial = static_cast<float*>(b.alloc(L.partial_floats * 4, false));
+    const size_t npix = static_cast<size_t>(N) * H * W;
+    float* bws = static_cast<float*>(b.alloc(bias_grad_workspace(npix, Cout), false));
+    if (b.rc != FISR_OK) return b.rc;
+    launch_act_from_f32(d_x, Cin, xin, CB * 64, npix, 2, st);
+    launch_act_from_f32(d_dy, Cout, dy, OB * 64, npix, 2, st);
+    L.args.partial = partial; L.args.err = ctx->d_err; L.args.x_coff = 0; L.args.dy_coff = 0;
+    if (!b.encode_act(&L.tmX_hi, xin.p, CB * 64, N, H, W, kWgTW + 2, kWgTH + 2)) return b.rc;
+    if (!b.encode_act(&L.tmX_lo, xin.p + xin.plane, CB * 64, N, H, W, kWgTW + 2, kWgTH + 2)) return b.rc;
+    if (!b.encode_act(&L.tmD_hi, dy.p, OB * 64, N, H, W, kWgTW, kWgTH)) return b.rc;
+    if (!b.encode_act(&L.tmD_lo, dy.p + dy.plane, OB * 64, N, H, W, kWgTW, kWgTH)) return b.rc;
+    CUDA_TRY(ctx, launch_wgrad3x3(L, st));
+    launch_wgrad_reduce(partial, 2 * L.args.S, L.args.cin_pad, L.args.cout_pad, Cin, Cout, scale, d_gw, st);
+    if (d_gb) launch_bias_grad(dy.p, dy.plane, OB * 64, 0, npix, Cout, scale, bws, d_gb, st);
+    ctx->launches += 6;
+    CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return check_kernel_error(ctx);
 }

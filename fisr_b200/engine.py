@@ -342,6 +342,20 @@ class Engine:
                                           act.data_ptr() if act is not None else None), "fisr_conv3x3")
         return raw, act
 
+    def wgrad3x3(self, x: torch.Tensor, dy: torch.Tensor, scale: float = 1.0, want_bias: bool = True):
+        """Weight / bias gradient of one 3x3 SAME conv (production wgrad kernel): x [N,H,W,Cin], dy [N,H,W,Cout]
+        -> (gw HWIO [3,3,Cin,Cout], gb [Cout])."""
+        x = self._dev(x, torch.float32)
+        dy = self._dev(dy, torch.float32)
+        n, h, wd, cin = x.shape
+        cout = dy.shape[3]
+        gw = torch.empty((3, 3, cin, cout), device=x.device)
+        gb = torch.empty((cout,), device=x.device) if want_bias else None
+        torch.cuda.synchronize(self.device)
+        self._check(self.lib.fisr_wgrad3x3(self.h, x.data_ptr(), dy.data_ptr(), n, h, wd, cin, cout, scale, gw.data_ptr(),
+                                           gb.data_ptr() if gb is not None else None), "fisr_wgrad3x3")
+        return gw, gb
+
     def debug_conv_output(self, conv_name: str, shape) -> np.ndarray:
         a = np.empty(shape, np.float32)
         self._check(self.lib.fisr_debug_conv_output(self.h, conv_name.encode(), a.ctypes.data, a.size),

@@ -132,6 +132,11 @@ int fisr_adam_reset(fisr_ctx* ctx, long long step);
  * NULL except x, w, b (d2s excludes res and raw: the network never combines them).  Synchronous. */
 int fisr_conv3x3(fisr_ctx* ctx, const float* d_x, const float* d_w, const float* d_b, const float* d_res, int N, int H,
                  int W, int Cin, int Cout, int relu, int d2s, float* d_raw, float* d_act);
+/* Weight / bias gradient of one 3x3 SAME conv through the production wgrad kernel (the backward-filter op TF derives
+ * for ops.py:10): gw[ky,kx,ci,co] = scale * sum_p x[p+(ky-1,kx-1),ci] * dy[p,co], gb[co] = scale * sum_p dy[p,co].
+ * x [N,H,W,Cin], dy [N,H,W,Cout], gw HWIO [3,3,Cin,Cout], gb [Cout] (may be NULL); device pointers.  Synchronous. */
+int fisr_wgrad3x3(fisr_ctx* ctx, const float* d_x, const float* d_dy, int N, int H, int W, int Cin, int Cout, float scale,
+                  float* d_gw, float* d_gb);
 /* After a forward: copies the pre-activation output of the named conv (e.g. ".../enc/level_0/conv/0") as
  * float32 NHWC to host, when the plan materialises it; returns FISR_E_INVALID otherwise. */
 int fisr_debug_conv_output(fisr_ctx* ctx, const char* conv_name, float* h_dst, size_t count);
