@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -95,6 +96,26 @@ struct ConvParam {
     __half* d_wp = nullptr;      // packed (hi, lo) operand planes
     bool packed = false;
     float *m_w = nullptr, *v_w = nullptr, *m_b = nullptr, *v_b = nullptr;   // Adam slots (allocated on first use)
+    // training: operand planes of the transposed / rotated filter (dgrad) and the gradients of the last backward
+    int cin_pad = 0, OBk = 0;    // Cin rounded up to 64 (dgrad N extent), 64-channel blocks of Cout (dgrad K blocks)
+    __half* d_wpT = nullptr;
+    bool packedT = false;
+    float *g_w = nullptr, *g_b = nullptr;
+};
+
+// Buffers of one forward level that the backward pass reads again (activations = ReLU masks and wgrad operands).
+struct ResRec { ActBuf a1, a2, a3; };            // two_res_blocks: relu(conv0(a0)), relu(n1), relu(conv0(a2))
+struct EncRec { std::string p; ActBuf x; int x_cs = 0; int c = 0, H = 0, W = 0; ActBuf a0, cat, pooled; ResRec rb; };
+struct BottRec { std::string p; ActBuf x, a0, a1, out; int H = 0, W = 0; };
+struct DecRec { std::string p; ActBuf x_in, up, cat, a0, out; ResRec rb; int c1 = 0, c = 0, H = 0, W = 0; };
+struct HeadRec { std::string p; ActBuf x, a0, a1, a2, shuf; int cout = 0; };
+struct LevelRec { int lvl = 0, N = 0, H = 0, W = 0; ActBuf in; EncRec enc[3]; BottRec bott; DecRec dec[3]; HeadRec head[2]; };
+
+struct BwdOp {
+    std::function<int(cudaStream_t)> run;
+    std::string name;
+    double flops = 0;
+    int launches = 1;
 };
 
 struct DebugTensor {
@@ -123,6 +144,17 @@ struct Plan {
     std::map<std::string, DebugTensor> debug;
     cudaGraphExec_t graph = nullptr;
     double flops = 0, eff_weighted = 0;
+    // training (built on demand by ensure_backward)
+    LevelRec rec[3];
+    std::vector<BwdOp> bwd;
+    bool has_bwd = false;
+    int B = 0;                       // training batch (N = 4B passes)
+    float loss_scale = 1.f;
+    ActBuf gp[3];                    // dy operand of the conv/2 heads per level
+    LossLambdas lam{1.f, 1.f, 0.1f, 1.f, 0.1f, 1.f};
+    const float* label = nullptr;    // set per call
+    float* wg_partial = nullptr;     // split-K slots of the wgrad kernel (sized for the largest layer)
+    float* bias_ws = nullptr;
     ~Plan() {
         if (graph) cudaGraphExecDestroy(graph);
         for (void* p : allocs) cudaFree(p);
@@ -162,6 +194,9 @@ struct fisr_ctx {
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     long long adam_t = 0;        // Adam step counter (global_step of FISRnet.py:232,491)
     float* d_scalars = nullptr;  // 11 loss scalars
+    float* d_zero_bias = nullptr;   // 512 zeros: the dgrad launches of the conv kernel add no bias
+    unsigned* d_gmax = nullptr;     // max |gradient| bits of the last backward (overflow check of the loss scale)
+    float loss_scale_override = 0.f;
 };
 
 namespace {
@@ -287,51 +322,69 @@ struct Builder {
         ActBuf act;
         int act_cs = 0, act_off0 = 0, act_off1 = 0, act_split = 0;
         bool relu = true, d2s = false, scalar = false;
+        ActBuf mask;              // dgrad: ReLU gate (hi plane of a forward activation), mask_cs channels per pixel
+        int mask_cs = 0, mask_off = 0;
+        bool s2d = false;         // dgrad of conv/2: store space-to-depth into a 256-channel buffer
     };
+    // Operand view of a parameter: forward (w) or data-gradient (rotated transpose) planes.
+    struct WView {
+        const __half* wp;
+        int KB, cout_pad, cout, cin;
+        const float* bias;
+    };
+    WView fwd_view(const ConvParam& p) const { return WView{p.d_wp, p.KB, p.cout_pad, p.cout, p.cin, p.d_b}; }
+    WView bwd_view(const ConvParam& p) const { return WView{p.d_wpT, p.OBk, p.cin_pad, p.cin, p.cout, ctx->d_zero_bias}; }
 
     // One conv launch: input = channels [cin_off, cin_off + KB*64) of `in` (cs channels, N x H x W).
     void conv(const ConvParam& p, ActBuf in, int in_cs, int cin_off, int N, int H, int W, const ConvOut& o,
               const std::string& name) {
-        if (rc != FISR_OK) return;
         Op op{};
+        if (!make_conv(fwd_view(p), in, in_cs, cin_off, N, H, W, o, name, &op)) return;
+        if (o.raw && !o.scalar) plan->debug[name] = DebugTensor{o.raw, N, H, W, o.raw_cs};
+        plan->flops += op.flops;
+        plan->eff_weighted += op.flops * op.conv.efficiency;
+        plan->ops.push_back(op);
+    }
+    bool make_conv(const WView& p, ActBuf in, int in_cs, int cin_off, int N, int H, int W, const ConvOut& o,
+                   const std::string& name, Op* out) {
+        if (rc != FISR_OK) return false;
+        Op& op = *out;
         op.kind = OP_CONV;
         ConvLaunch& L = op.conv;
         if (!plan_conv_geometry(H, W, N, p.cout_pad, plan->planes, ctx->num_sms, &L)) {
             rc = fail(ctx, FISR_E_INVALID, "no tile geometry for conv %s (%dx%d)", name.c_str(), H, W);
-            return;
+            return false;
         }
         ConvArgs& a = L.args;
-        a.bias = p.d_b;
+        a.bias = p.bias;
         a.res = o.res; a.res_cs = o.res_cs;
         a.out_raw = o.raw; a.raw_cs = o.raw_cs; a.raw_off0 = o.raw_off0; a.raw_off1 = o.raw_off1; a.raw_split = o.raw_split;
         a.out_act = o.act.p; a.act_plane = o.act.plane;
         a.act_cs = o.act_cs; a.act_off0 = o.act_off0; a.act_off1 = o.act_off1; a.act_split = o.act_split;
         a.act_relu = o.relu; a.act_d2s = o.d2s; a.scalar_out = o.scalar;
+        a.mask = o.mask.p; a.mask_cs = o.mask_cs; a.mask_off = o.mask_off;
         a.err = ctx->d_err;
         a.N = N; a.H = H; a.W = W;
-        L.epi = o.scalar ? 0 : ((o.res ? 1 : 0) | (o.raw ? 2 : 0) | (o.d2s ? 4 : 0));
-        if (!o.scalar && !o.act.p) { rc = fail(ctx, FISR_E_INVALID, "conv %s: the wide epilogue always writes an activation", name.c_str()); return; }
+        L.epi = o.scalar ? 0 : ((o.res ? 1 : 0) | (o.raw ? 2 : 0) | (o.d2s ? 4 : 0) | (o.mask.p ? 8 : 0) | (o.s2d ? 16 : 0));
+        if (!o.scalar && !o.act.p) { rc = fail(ctx, FISR_E_INVALID, "conv %s: the wide epilogue always writes an activation", name.c_str()); return false; }
+        if (o.s2d && (p.cout_pad != 64 || (H & 1) || (W & 1))) { rc = fail(ctx, FISR_E_INVALID, "conv %s: space-to-depth needs 64 output channels and even H, W", name.c_str()); return false; }
         {   // the epilogue indexes with 32-bit element offsets
             const double px = static_cast<double>(N) * H * W * (o.d2s ? 4 : 1);
-            const int cs_max = std::max(std::max(o.raw_cs, o.res_cs), o.act_cs);
-            if (px * cs_max >= 4294967296.0) { rc = fail(ctx, FISR_E_INVALID, "conv %s: %d x %d x %d x %d exceeds 32-bit offsets; split the batch", name.c_str(), N, H, W, cs_max); return; }
+            const int cs_max = std::max(std::max(std::max(o.raw_cs, o.res_cs), o.act_cs), o.mask_cs);
+            if (px * cs_max >= 4294967296.0) { rc = fail(ctx, FISR_E_INVALID, "conv %s: %d x %d x %d x %d exceeds 32-bit offsets; split the batch", name.c_str(), N, H, W, cs_max); return false; }
         }
         a.cin_off = cin_off; a.KB = p.KB; a.cout = p.cout;
-        if (!encode_act(&L.tmA_hi, in.p, in_cs, N, H, W, a.P, a.TH + 2)) return;
-        if (!encode_act(&L.tmA_lo, in.p + (plan->planes == 2 ? in.plane : 0), in_cs, N, H, W, a.P, a.TH + 2)) return;
-        if (!encode_w(&L.tmB, p.d_wp, static_cast<size_t>(plan->planes) * p.KB * 9 * p.cout_pad, L.NT)) return;
-        const double fl = 2.0 * 9 * p.cin * p.cout * static_cast<double>(H) * W * N;
-        plan->flops += fl;
-        plan->eff_weighted += fl * L.efficiency;
-        op.flops = fl;
+        if (!encode_act(&L.tmA_hi, in.p, in_cs, N, H, W, a.P, a.TH + 2)) return false;
+        if (!encode_act(&L.tmA_lo, in.p + (plan->planes == 2 ? in.plane : 0), in_cs, N, H, W, a.P, a.TH + 2)) return false;
+        if (!encode_w(&L.tmB, p.wp, static_cast<size_t>(plan->planes) * p.KB * 9 * p.cout_pad, L.NT)) return false;
+        op.flops = 2.0 * 9 * p.cin * p.cout * static_cast<double>(H) * W * N;
         {   // algorithmic HBM bytes: input + weights once, every output / residual once
             const double px = static_cast<double>(N) * H * W, eb = 2.0 * plan->planes;
             op.bytes = px * p.KB * 64 * eb + 9.0 * p.KB * 64 * p.cout_pad * eb + (o.res ? px * p.cout * 4 : 0) +
-                       (o.raw ? px * (o.scalar ? p.cout : p.cout) * 4 : 0) + (o.act.p ? px * p.cout * eb : 0);
+                       (o.raw ? px * p.cout * 4 : 0) + (o.act.p ? px * p.cout * eb : 0) + (o.mask.p ? px * p.cout * 2 : 0);
         }
         snprintf(op.name, sizeof op.name, "%s", name.c_str());
-        if (o.raw && !o.scalar) plan->debug[name] = DebugTensor{o.raw, N, H, W, o.raw_cs};
-        plan->ops.push_back(op);
+        return true;
     }
     void upsample(ActBuf in, ActBuf out, int N, int h, int w, int C) {
         Op op{};
@@ -360,8 +413,8 @@ struct Builder {
 
     // res_block (ops.py:39-44) x2 + trailing ReLU, given n0 (raw fp32) and relu(n0) (act): used by enc / dec levels.
     // Final activation relu(n2) goes to `dst` (channel offset dst_off of a dst_cs-channel buffer).
-    void two_res_blocks(const std::string& p, ActBuf a0, const float* n0, int c, int N, int H, int W, ActBuf dst,
-                        int dst_cs, int dst_off) {
+    ResRec two_res_blocks(const std::string& p, ActBuf a0, const float* n0, int c, int N, int H, int W, ActBuf dst,
+                          int dst_cs, int dst_off) {
         ActBuf a1 = act(N, H, W, c), a2 = act(N, H, W, c), a3 = act(N, H, W, c);
         float* n1 = f32(N, H, W, c);
         ConvOut o;
@@ -373,23 +426,25 @@ struct Builder {
         conv(P(p + "/res_block/1/conv/0"), a2, c, 0, N, H, W, o, p + "/res_block/1/conv/0");
         o = ConvOut{}; o.res = n1; o.res_cs = c; o.act = dst; o.act_cs = dst_cs; o.act_off1 = dst_off;
         conv(P(p + "/res_block/1/conv/1"), a3, c, 0, N, H, W, o, p + "/res_block/1/conv/1");
+        return ResRec{a1, a2, a3};
     }
 
     // Enc_level_res (ops.py:48-55): skip = relu(...) lands in channels [c, 2c) of the decoder's concat buffer
     // (virtual tf.concat of ops.py:71); the 2x2 max-pooled copy feeds the next level down.
-    ActBuf enc_level(const std::string& p, ActBuf x, int x_cs, int c, int N, int H, int W, ActBuf cat) {
+    ActBuf enc_level(const std::string& p, ActBuf x, int x_cs, int c, int N, int H, int W, ActBuf cat, EncRec* rec) {
         ActBuf a0 = act(N, H, W, c);
         float* n0 = f32(N, H, W, c);
         ConvOut o; o.raw = n0; o.raw_cs = c; o.act = a0; o.act_cs = c;
         conv(P(p + "/conv/0"), x, x_cs, 0, N, H, W, o, p + "/conv/0");
-        two_res_blocks(p, a0, n0, c, N, H, W, cat, 2 * c, c);
+        const ResRec rb = two_res_blocks(p, a0, n0, c, N, H, W, cat, 2 * c, c);
         ActBuf pooled = act(N, H / 2, W / 2, c);
         pool(cat, 2 * c, c, pooled, N, H, W, c);
+        *rec = EncRec{p, x, x_cs, c, H, W, a0, cat, pooled, rb};
         return pooled;
     }
 
     // Dec_level_res (ops.py:67-76): x is [N, H/2, W/2, c1]; cat already holds the skip in channels [c, 2c).
-    ActBuf dec_level(const std::string& p, ActBuf x, int c1, int c, int N, int H, int W, ActBuf cat) {
+    ActBuf dec_level(const std::string& p, ActBuf x, int c1, int c, int N, int H, int W, ActBuf cat, DecRec* rec) {
         ActBuf up = act(N, H, W, c1);
         upsample(x, up, N, H / 2, W / 2, c1);
         ConvOut o; o.act = cat; o.act_cs = 2 * c; o.act_off1 = 0;
@@ -399,12 +454,13 @@ struct Builder {
         o = ConvOut{}; o.raw = n0; o.raw_cs = c; o.act = a0; o.act_cs = c;
         conv(P(p + "/conv/0"), cat, 2 * c, 0, N, H, W, o, p + "/conv/0");
         ActBuf out = act(N, H, W, c);
-        two_res_blocks(p, a0, n0, c, N, H, W, out, c, 0);
+        const ResRec rb = two_res_blocks(p, a0, n0, c, N, H, W, out, c, 0);
+        *rec = DecRec{p, x, up, cat, a0, out, rb, c1, c, H, W};
         return out;
     }
 
     // FI-SR / SR head (FISRnet.py:95-106).  pred is [N,2H,2W,9]; next (may be null) is the next level's input buffer.
-    void head(const std::string& p, ActBuf x, int N, int H, int W, int cout, float* pred, ActBuf next) {
+    void head(const std::string& p, ActBuf x, int N, int H, int W, int cout, float* pred, ActBuf next, HeadRec* rec) {
         const int c = CH;
         ActBuf a0 = act(N, H, W, c), a1 = act(N, H, W, c), a2 = act(N, H, W, c);
         float* m0 = f32(N, H, W, c);
@@ -425,14 +481,17 @@ struct Builder {
         if (cout == 6) { o.raw_split = 3; o.raw_off0 = 0; o.raw_off1 = 3; o.act_split = 3; o.act_off0 = IN_CH; o.act_off1 = IN_CH + 3; }
         else           { o.raw_split = 0; o.raw_off1 = 3; o.act_split = 0; o.act_off1 = IN_CH + 3; }
         conv(P(p + "/conv/2"), shuf, c, 0, N, 2 * H, 2 * W, o, p + "/conv/2");
+        *rec = HeadRec{p, x, a0, a1, a2, shuf, cout};
     }
 
     void level(int lvl, ActBuf in, int N, int H, int W, float* pred, ActBuf next) {
         const std::string p = "FISRnet/level_" + std::to_string(lvl);
+        LevelRec& R = plan->rec[lvl - 1];
+        R.lvl = lvl; R.N = N; R.H = H; R.W = W; R.in = in;
         ActBuf cat0 = act(N, H, W, 2 * CH), cat1 = act(N, H / 2, W / 2, 4 * CH), cat2 = act(N, H / 4, W / 4, 8 * CH);
-        ActBuf n = enc_level(p + "/enc/level_0", in, 64, CH, N, H, W, cat0);
-        n = enc_level(p + "/enc/level_1", n, CH, 2 * CH, N, H / 2, W / 2, cat1);
-        n = enc_level(p + "/enc/level_2", n, 2 * CH, 4 * CH, N, H / 4, W / 4, cat2);
+        ActBuf n = enc_level(p + "/enc/level_0", in, 64, CH, N, H, W, cat0, &R.enc[0]);
+        n = enc_level(p + "/enc/level_1", n, CH, 2 * CH, N, H / 2, W / 2, cat1, &R.enc[1]);
+        n = enc_level(p + "/enc/level_2", n, 2 * CH, 4 * CH, N, H / 4, W / 4, cat2, &R.enc[2]);
         {   // Bottleneck_res (ops.py:59-63)
             const std::string b = p + "/bottleneck";
             const int c = 8 * CH, h = H / 8, w = W / 8;
@@ -444,13 +503,231 @@ struct Builder {
             conv(P(b + "/res_block/0/conv/0"), a0, c, 0, N, h, w, o, b + "/res_block/0/conv/0");
             o = ConvOut{}; o.res = n0; o.res_cs = c; o.act = out; o.act_cs = c;
             conv(P(b + "/res_block/0/conv/1"), a1, c, 0, N, h, w, o, b + "/res_block/0/conv/1");
+            R.bott = BottRec{b, n, a0, a1, out, h, w};
             n = out;
         }
-        n = dec_level(p + "/dec/level_2", n, 8 * CH, 4 * CH, N, H / 4, W / 4, cat2);
-        n = dec_level(p + "/dec/level_1", n, 4 * CH, 2 * CH, N, H / 2, W / 2, cat1);
-        n = dec_level(p + "/dec/level_0", n, 2 * CH, CH, N, H, W, cat0);
-        head(p + "/FI-SR", n, N, H, W, 6, pred, next);
-        head(p + "/SR", n, N, H, W, 3, pred, next);
+        n = dec_level(p + "/dec/level_2", n, 8 * CH, 4 * CH, N, H / 4, W / 4, cat2, &R.dec[2]);
+        n = dec_level(p + "/dec/level_1", n, 4 * CH, 2 * CH, N, H / 2, W / 2, cat1, &R.dec[1]);
+        n = dec_level(p + "/dec/level_0", n, 2 * CH, CH, N, H, W, cat0, &R.dec[0]);
+        head(p + "/FI-SR", n, N, H, W, 6, pred, next, &R.head[0]);
+        head(p + "/SR", n, N, H, W, 3, pred, next, &R.head[1]);
+    }
+    // ================================================================ backward (see "Backward pass" in DESIGN.md)
+    size_t max_partial = 0, max_bias_ws = 0;
+
+    ConvParam* PP(const std::string& name) {
+        auto it = ctx->conv_index.find(name);
+        if (it == ctx->conv_index.end()) { rc = fail(ctx, FISR_E_INVALID, "unknown conv %s", name.c_str()); return nullptr; }
+        return &ctx->params[it->second];
+    }
+
+    // Data gradient of conv `name`: dx = conv3x3(dy, rot180(w)^T) through the forward kernel with the transposed operand
+    // planes, gated by [mask > 0] and accumulated onto `res` in the epilogue (EPI_MASK / EPI_RES / EPI_S2D).
+    void dconv(const std::string& name, ActBuf gin, int gin_cs, int gin_off, int N, int H, int W, ConvOut o) {
+        ConvParam* p = PP(name);
+        if (!p) return;
+        o.relu = false;
+        Op op{};
+        if (!make_conv(bwd_view(*p), gin, gin_cs, gin_off, N, H, W, o, name + " [dgrad]", &op)) return;
+        fisr_ctx* c = ctx;
+        BwdOp b;
+        b.name = op.name; b.flops = op.flops;
+        b.run = [c, op](cudaStream_t st) -> int {
+            const cudaError_t e = launch_conv3x3(op.conv, c->num_sms, st);
+            return e == cudaSuccess ? FISR_OK : fail(c, FISR_E_CUDA, "dgrad launch failed: %s", cudaGetErrorString(e));
+        };
+        plan->bwd.push_back(std::move(b));
+    }
+
+    // Weight + bias gradient of conv `name` from its forward input x and the gradient dy of its output.
+    void wgrad(const std::string& name, ActBuf x, int x_cs, int x_off, ActBuf dy, int dy_cs, int dy_off, int N, int H, int W) {
+        ConvParam* p = PP(name);
+        if (!p || rc != FISR_OK) return;
+        WgradLaunch L{};
+        plan_wgrad(N, H, W, p->KB, p->OBk, ctx->num_sms, &L);
+        L.args.err = ctx->d_err; L.args.x_coff = x_off; L.args.dy_coff = dy_off;
+        if (!encode_act(&L.tmX_hi, x.p, x_cs, N, H, W, kWgTW + 2, kWgTH + 2)) return;
+        if (!encode_act(&L.tmX_lo, x.p + x.plane, x_cs, N, H, W, kWgTW + 2, kWgTH + 2)) return;
+        if (!encode_act(&L.tmD_hi, dy.p, dy_cs, N, H, W, kWgTW, kWgTH)) return;
+        if (!encode_act(&L.tmD_lo, dy.p + dy.plane, dy_cs, N, H, W, kWgTW, kWgTH)) return;
+        const size_t npix = static_cast<size_t>(N) * H * W;
+        max_partial = std::max(max_partial, L.partial_floats);
+        max_bias_ws = std::max(max_bias_ws, bias_grad_workspace(npix, p->cout));
+        fisr_ctx* c = ctx;
+        Plan* pl = plan;
+        BwdOp b;
+        b.name = name + " [wgrad]";
+        b.flops = 2.0 * 9 * p->cin * p->cout * static_cast<double>(npix);
+        b.launches = 4;
+        b.run = [c, pl, L, p, dy, dy_cs, dy_off, npix](cudaStream_t st) -> int {
+            WgradLaunch l = L;
+            l.args.partial = pl->wg_partial;
+            const cudaError_t e = launch_wgrad3x3(l, st);
+            if (e != cudaSuccess) return fail(c, FISR_E_CUDA, "wgrad launch failed: %s", cudaGetErrorString(e));
+            const float inv = 1.f / pl->loss_scale;
+            launch_wgrad_reduce(pl->wg_partial, 2 * l.args.S, l.args.cin_pad, l.args.cout_pad, p->cin, p->cout, inv, p->g_w, st);
+            launch_bias_grad(dy.p, dy.plane, dy_cs, dy_off, npix, p->cout, inv, pl->bias_ws, p->g_b, st);
+            return FISR_OK;
+        };
+        plan->bwd.push_back(std::move(b));
+    }
+
+    void push_simple(const std::string& name, std::function<void(cudaStream_t)> fn) {
+        BwdOp b;
+        b.name = name;
+        b.run = [fn](cudaStream_t st) -> int { fn(st); return FISR_OK; };
+        plan->bwd.push_back(std::move(b));
+    }
+
+    // Backward of two res_blocks (ops.py:39-44 twice): given G(n2) planes g2 + fp32 r2, returns G(n0).
+    //   n1 = n0 + conv1(relu(conv0(relu(n0)))),  n2 = n1 + conv1'(relu(conv0'(relu(n1))));  a0 = relu(n0), rb = {a1, a2, a3}
+    ActBuf two_res_blocks_bwd(const std::string& p, ActBuf a0, const ResRec& rb, ActBuf g2, const float* r2, int c, int N, int H, int W) {
+        ConvOut o;
+        wgrad(p + "/res_block/1/conv/1", rb.a3, c, 0, g2, c, 0, N, H, W);
+        ActBuf gc = act(N, H, W, c);
+        o = ConvOut{}; o.act = gc; o.act_cs = c; o.mask = rb.a3; o.mask_cs = c;
+        dconv(p + "/res_block/1/conv/1", g2, c, 0, N, H, W, o);
+        wgrad(p + "/res_block/1/conv/0", rb.a2, c, 0, gc, c, 0, N, H, W);
+        ActBuf g1 = act(N, H, W, c);
+        float* r1 = f32(N, H, W, c);
+        o = ConvOut{}; o.act = g1; o.act_cs = c; o.raw = r1; o.raw_cs = c; o.mask = rb.a2; o.mask_cs = c; o.res = r2; o.res_cs = c;
+        dconv(p + "/res_block/1/conv/0", gc, c, 0, N, H, W, o);
+        wgrad(p + "/res_block/0/conv/1", rb.a1, c, 0, g1, c, 0, N, H, W);
+        ActBuf gc0 = act(N, H, W, c);
+        o = ConvOut{}; o.act = gc0; o.act_cs = c; o.mask = rb.a1; o.mask_cs = c;
+        dconv(p + "/res_block/0/conv/1", g1, c, 0, N, H, W, o);
+        wgrad(p + "/res_block/0/conv/0", a0, c, 0, gc0, c, 0, N, H, W);
+        ActBuf g0 = act(N, H, W, c);
+        o = ConvOut{}; o.act = g0; o.act_cs = c; o.mask = a0; o.mask_cs = c; o.res = r1; o.res_cs = c;
+        dconv(p + "/res_block/0/conv/0", gc0, c, 0, N, H, W, o);
+        return g0;
+    }
+
+    // Backward of one level (FISRnet.py:84-108 and the same blocks of levels 2, 3).  gp = dy operand of the two conv/2
+    // heads [N,2H,2W,128]; returns G(level input) [N,H,W,64] when want_input_grad (levels 2, 3: channels 29..37 carry the
+    // gradient into the previous level's prediction).
+    ActBuf level_bwd(const LevelRec& R, ActBuf gp, bool want_input_grad) {
+        const int N = R.N, H = R.H, W = R.W, c = CH;
+        ConvOut o;
+        // ---- heads: out = conv2(d2s(relu(conv1(relu(m1))))), m1 = m0 + rb(m0), m0 = conv0(x)
+        float* r_n = f32(N, H, W, c);
+        ActBuf g_n = act(N, H, W, c);
+        for (int hd = 0; hd < 2; ++hd) {
+            const HeadRec& Hd = R.head[hd];
+            const int off = hd == 0 ? 0 : 64;      // gp has 128 channels: FI-SR's dy in [0,6), SR's in [64,67)
+            wgrad(Hd.p + "/conv/2", Hd.shuf, c, 0, gp, 2 * c, off, N, 2 * H, 2 * W);
+            ActBuf g_c2 = act(N, H, W, 4 * c);
+            o = ConvOut{}; o.act = g_c2; o.act_cs = 4 * c; o.mask = Hd.shuf; o.mask_cs = c; o.s2d = true;
+            dconv(Hd.p + "/conv/2", gp, 2 * c, off, N, 2 * H, 2 * W, o);
+            wgrad(Hd.p + "/conv/1", Hd.a2, c, 0, g_c2, 4 * c, 0, N, H, W);
+            float* r_m1 = f32(N, H, W, c);
+            ActBuf g_m1 = act(N, H, W, c);
+            o = ConvOut{}; o.act = g_m1; o.act_cs = c; o.raw = r_m1; o.raw_cs = c; o.mask = Hd.a2; o.mask_cs = c;
+            dconv(Hd.p + "/conv/1", g_c2, 4 * c, 0, N, H, W, o);
+            wgrad(Hd.p + "/res_block/0/conv/1", Hd.a1, c, 0, g_m1, c, 0, N, H, W);
+            ActBuf g_c0 = act(N, H, W, c);
+            o = ConvOut{}; o.act = g_c0; o.act_cs = c; o.mask = Hd.a1; o.mask_cs = c;
+            dconv(Hd.p + "/res_block/0/conv/1", g_m1, c, 0, N, H, W, o);
+            wgrad(Hd.p + "/res_block/0/conv/0", Hd.a0, c, 0, g_c0, c, 0, N, H, W);
+            ActBuf g_m0 = act(N, H, W, c);
+            o = ConvOut{}; o.act = g_m0; o.act_cs = c; o.mask = Hd.a0; o.mask_cs = c; o.res = r_m1; o.res_cs = c;
+            dconv(Hd.p + "/res_block/0/conv/0", g_c0, c, 0, N, H, W, o);
+            wgrad(Hd.p + "/conv/0", Hd.x, c, 0, g_m0, c, 0, N, H, W);
+            // both heads read the decoder output x = relu(n2): the second launch adds the first one's result in place
+            o = ConvOut{}; o.act = g_n; o.act_cs = c; o.raw = r_n; o.raw_cs = c; o.mask = Hd.x; o.mask_cs = c;
+            if (hd == 1) { o.res = r_n; o.res_cs = c; }
+            dconv(Hd.p + "/conv/0", g_m0, c, 0, N, H, W, o);
+        }
+        // ---- decoder levels 0, 1, 2 (ops.py:67-76)
+        ActBuf g_out = g_n;
+        const float* r_out = r_n;
+        ActBuf g_cat[3];
+        for (int k = 0; k < 3; ++k) {
+            const DecRec& D = R.dec[k];
+            const int h = D.H, w = D.W, cc = D.c, c1 = D.c1;
+            ActBuf g0 = two_res_blocks_bwd(D.p, D.a0, D.rb, g_out, r_out, cc, N, h, w);
+            wgrad(D.p + "/conv/0", D.cat, 2 * cc, 0, g0, cc, 0, N, h, w);
+            g_cat[k] = act(N, h, w, 2 * cc);
+            o = ConvOut{}; o.act = g_cat[k]; o.act_cs = 2 * cc; o.mask = D.cat; o.mask_cs = 2 * cc;
+            dconv(D.p + "/conv/0", g0, cc, 0, N, h, w, o);
+            wgrad(D.p + "/resize", D.up, c1, 0, g_cat[k], 2 * cc, 0, N, h, w);
+            ActBuf g_up = act(N, h, w, c1);
+            o = ConvOut{}; o.act = g_up; o.act_cs = c1;
+            dconv(D.p + "/resize", g_cat[k], 2 * cc, 0, N, h, w, o);
+            ActBuf g_x = act(N, h / 2, w / 2, c1);
+            float* r_x = f32(N, h / 2, w / 2, c1);
+            {
+                const ActBuf xin = D.x_in;
+                push_simple("upsample2 backward " + std::to_string(h / 2) + "x" + std::to_string(w / 2) + "x" + std::to_string(c1),
+                            [=](cudaStream_t st) { launch_upsample_bwd(g_up, xin, g_x, r_x, N, h / 2, w / 2, c1, st); });
+            }
+            g_out = g_x;
+            r_out = r_x;
+        }
+        // ---- bottleneck (ops.py:59-63): out = relu(n1), n1 = n0 + conv1(relu(conv0(relu(n0)))), n0 = conv0(pooled)
+        ActBuf g_pool;
+        {
+            const BottRec& Bt = R.bott;
+            const int h = Bt.H, w = Bt.W, cc = 8 * c;
+            wgrad(Bt.p + "/res_block/0/conv/1", Bt.a1, cc, 0, g_out, cc, 0, N, h, w);
+            ActBuf gc = act(N, h, w, cc);
+            o = ConvOut{}; o.act = gc; o.act_cs = cc; o.mask = Bt.a1; o.mask_cs = cc;
+            dconv(Bt.p + "/res_block/0/conv/1", g_out, cc, 0, N, h, w, o);
+            wgrad(Bt.p + "/res_block/0/conv/0", Bt.a0, cc, 0, gc, cc, 0, N, h, w);
+            ActBuf g0 = act(N, h, w, cc);
+            o = ConvOut{}; o.act = g0; o.act_cs = cc; o.mask = Bt.a0; o.mask_cs = cc; o.res = r_out; o.res_cs = cc;
+            dconv(Bt.p + "/res_block/0/conv/0", gc, cc, 0, N, h, w, o);
+            wgrad(Bt.p + "/conv/0", Bt.x, 4 * c, 0, g0, cc, 0, N, h, w);
+            g_pool = act(N, h, w, 4 * c);
+            o = ConvOut{}; o.act = g_pool; o.act_cs = 4 * c;
+            dconv(Bt.p + "/conv/0", g0, cc, 0, N, h, w, o);
+        }
+        // ---- encoder levels 2, 1, 0 (ops.py:48-55)
+        ActBuf g_in{};
+        for (int k = 2; k >= 0; --k) {
+            const EncRec& E = R.enc[k];
+            const int h = E.H, w = E.W, cc = E.c;
+            ActBuf g2 = act(N, h, w, cc);
+            float* r2 = f32(N, h, w, cc);
+            {
+                const ActBuf skip = E.cat, gc = g_cat[k], gpl = g_pool;
+                push_simple("maxpool2 backward " + std::to_string(h) + "x" + std::to_string(w) + "x" + std::to_string(cc),
+                            [=](cudaStream_t st) { launch_pool_bwd(skip, gc, 2 * cc, cc, gpl, g2, r2, N, h, w, cc, st); });
+            }
+            ActBuf g0 = two_res_blocks_bwd(E.p, E.a0, E.rb, g2, r2, cc, N, h, w);
+            wgrad(E.p + "/conv/0", E.x, E.x_cs, 0, g0, cc, 0, N, h, w);
+            if (k > 0) {
+                g_pool = act(N, h, w, cc / 2);
+                o = ConvOut{}; o.act = g_pool; o.act_cs = cc / 2;
+                dconv(E.p + "/conv/0", g0, cc, 0, N, h, w, o);
+            } else if (want_input_grad) {
+                g_in = act(N, h, w, 64);
+                o = ConvOut{}; o.act = g_in; o.act_cs = 64;
+                dconv(E.p + "/conv/0", g0, cc, 0, N, h, w, o);
+            }
+        }
+        return g_in;
+    }
+
+    // Whole backward of one training step (4B passes batched as N): loss gradient per scale, level 3 -> 1.
+    void backward(int B) {
+        Plan* pl = plan;
+        for (int l = 0; l < 3; ++l) pl->gp[l] = act(pl->N, 2 * pl->rec[l].H, 2 * pl->rec[l].W, 128, true);
+        ActBuf g_next{};
+        for (int l = 2; l >= 0; --l) {
+            const LevelRec& R = pl->rec[l];
+            const int hs = 2 * R.H, ws = 2 * R.W, stride = 4 >> l;
+            const float wgt = static_cast<float>(4 >> l);
+            const float* pred = pl->pred[l];
+            const ActBuf extra = g_next, gp = pl->gp[l];
+            const int LH = 2 * pl->H, LW = 2 * pl->W;
+            push_simple("loss gradient level " + std::to_string(l + 1), [=](cudaStream_t st) {
+                launch_loss_grad(pred, pl->label, extra, B, hs, ws, stride, LH, LW, wgt, pl->lam, pl->loss_scale, gp, st);
+            });
+            g_next = level_bwd(R, gp, l > 0);
+        }
+        pl->wg_partial = static_cast<float*>(alloc(max_partial * sizeof(float), false));
+        pl->bias_ws = static_cast<float*>(alloc(max_bias_ws, false));
     }
 };
 
@@ -619,6 +896,85 @@ int window_impl(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, con
     return units_impl(ctx, d_frames, d_flow, d_warp, 1, H, W, pH, pW, units.data(), tile_count, 0, d_canvas_u8, d_canvas_f32, st);
 }
 
+
+// ---------------------------------------------------------------- training plumbing
+int ensure_train_params(fisr_ctx* ctx, cudaStream_t st) {
+    for (auto& p : ctx->params) {
+        if (!p.d_wpT) {
+            CUDA_TRY(ctx, cudaMalloc(&p.d_wpT, static_cast<size_t>(2) * p.OBk * 9 * p.cin_pad * 64 * sizeof(__half)));
+            CUDA_TRY(ctx, cudaMalloc(&p.g_w, static_cast<size_t>(9) * p.cin * p.cout * 4));
+            CUDA_TRY(ctx, cudaMalloc(&p.g_b, static_cast<size_t>(p.cout) * 4));
+            p.packedT = false;
+        }
+        if (!p.packedT) {
+            launch_prep_weights_dgrad(p.d_w, p.d_wpT, p.cin, p.cout, p.OBk, p.cin_pad, st);
+            ctx->launches++;
+            p.packedT = true;
+        }
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FISR_OK;
+}
+
+int ensure_backward(fisr_ctx* ctx, Plan* plan, int B) {
+    if (plan->has_bwd) return FISR_OK;
+    if (plan->planes != 2) return fail(ctx, FISR_E_INVALID, "training needs precision f16x3 (split operands)");
+    Builder b{ctx, plan};
+    b.backward(B);
+    if (b.rc != FISR_OK) return b.rc;
+    plan->B = B;
+    // Loss scale: a power of two near the element count of one finest-scale frame stack, so that d loss / d pred is
+    // O(1) in the fp16 (hi, lo) gradient planes; divided out again by the wgrad / bias-grad reductions.
+    const double n1 = static_cast<double>(B) * (2.0 * plan->H) * (2.0 * plan->W) * 3.0;
+    plan->loss_scale = ctx->loss_scale_override > 0.f ? ctx->loss_scale_override : std::exp2(std::floor(std::log2(n1)));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    plan->has_bwd = true;
+    return FISR_OK;
+}
+
+int run_backward(fisr_ctx* ctx, Plan* plan, cudaStream_t st) {
+    static const bool debug_sync = getenv("FISR_DEBUG_SYNC") && getenv("FISR_DEBUG_SYNC")[0] == '1';
+    for (const BwdOp& op : plan->bwd) {
+        const int rc = op.run(st);
+        if (rc != FISR_OK) return rc;
+        ctx->launches += op.launches;
+        if (debug_sync) {     // bring-up aid: attribute an asynchronous fault to the op that caused it
+            const cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return fail(ctx, FISR_E_CUDA, "backward op '%s' failed: %s", op.name.c_str(), cudaGetErrorString(e));
+        }
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FISR_OK;
+}
+
+int adam_impl(fisr_ctx* ctx, const std::vector<const float*>& grads, float lr, float beta1, float beta2, float eps) {
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    const long long t = ++ctx->adam_t;
+    const float lr_t = static_cast<float>(lr * std::sqrt(1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(t))) /
+                                          (1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(t))));
+    for (size_t i = 0; i < ctx->params.size(); ++i) {
+        ConvParam& p = ctx->params[i];
+        const size_t wn = static_cast<size_t>(9) * p.cin * p.cout, bn = p.cout;
+        if (!p.m_w) {
+            CUDA_TRY(ctx, cudaMalloc(&p.m_w, wn * 4)); CUDA_TRY(ctx, cudaMalloc(&p.v_w, wn * 4));
+            CUDA_TRY(ctx, cudaMalloc(&p.m_b, bn * 4)); CUDA_TRY(ctx, cudaMalloc(&p.v_b, bn * 4));
+            CUDA_TRY(ctx, cudaMemsetAsync(p.m_w, 0, wn * 4, st)); CUDA_TRY(ctx, cudaMemsetAsync(p.v_w, 0, wn * 4, st));
+            CUDA_TRY(ctx, cudaMemsetAsync(p.m_b, 0, bn * 4, st)); CUDA_TRY(ctx, cudaMemsetAsync(p.v_b, 0, bn * 4, st));
+        }
+        launch_adam_tf1(p.d_w, grads[2 * i], p.m_w, p.v_w, wn, lr_t, beta1, beta2, eps, st);
+        launch_adam_tf1(p.d_b, grads[2 * i + 1], p.m_b, p.v_b, bn, lr_t, beta1, beta2, eps, st);
+        p.packed = false;
+        p.packedT = false;
+        int rc = ensure_packed(ctx, p, st);          // operand planes follow the fp32 master copy
+        if (rc != FISR_OK) return rc;
+        ctx->launches += 2;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return FISR_OK;
+}
+
 }  // namespace
 
 // ================================================================ C ABI
@@ -663,6 +1019,9 @@ int fisr_create(int device, fisr_ctx** out) {
         CUDA_TRY(nullptr, cudaMalloc(&c->d_lut255, sizeof lut));
         CUDA_TRY(nullptr, cudaMemcpy(c->d_lut255, lut, sizeof lut, cudaMemcpyHostToDevice));
     }
+    CUDA_TRY(nullptr, cudaMalloc(&c->d_zero_bias, 512 * sizeof(float)));
+    CUDA_TRY(nullptr, cudaMemset(c->d_zero_bias, 0, 512 * sizeof(float)));
+    CUDA_TRY(nullptr, cudaMalloc(&c->d_gmax, sizeof(unsigned)));
     const auto& inv = inventory();
     c->params.resize(inv.size());
     for (size_t i = 0; i < inv.size(); ++i) {
@@ -670,6 +1029,8 @@ int fisr_create(int device, fisr_ctx** out) {
         p.cin = inv[i].cin; p.cout = inv[i].cout;
         p.KB = (p.cin + 63) / 64;
         p.cout_pad = p.cout <= 16 ? 16 : (p.cout + 63) / 64 * 64;
+        p.cin_pad = p.KB * 64;
+        p.OBk = (p.cout + 63) / 64;
         const size_t wn = static_cast<size_t>(9) * p.cin * p.cout;
         CUDA_TRY(nullptr, cudaMalloc(&p.d_w, wn * 4));
         CUDA_TRY(nullptr, cudaMemset(p.d_w, 0, wn * 4));
@@ -688,8 +1049,13 @@ void fisr_destroy(fisr_ctx* ctx) {
     Guard guard(ctx->device);
     cudaDeviceSynchronize();
     ctx->plans.clear();
-    for (auto& p : ctx->params) { cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); cudaFree(p.m_w); cudaFree(p.v_w); cudaFree(p.m_b); cudaFree(p.v_b); }
+    for (auto& p : ctx->params) {
+        cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); cudaFree(p.m_w); cudaFree(p.v_w); cudaFree(p.m_b); cudaFree(p.v_b);
+        cudaFree(p.d_wpT); cudaFree(p.g_w); cudaFree(p.g_b);
+    }
     cudaFree(ctx->d_scalars);
+    cudaFree(ctx->d_zero_bias);
+    cudaFree(ctx->d_gmax);
     for (void* s : ctx->stage) if (s) cudaFree(s);
     for (auto& sl : ctx->slots) {
         for (void* b : sl.in) if (b) cudaFree(b);
@@ -766,6 +1132,7 @@ int fisr_set_param(fisr_ctx* ctx, const char* name, const float* h_data, size_t 
     CUDA_TRY(ctx, cudaMemcpyAsync(is_w ? p.d_w : p.d_b, h_data, count * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (is_w) {
         p.packed = false;
+        p.packedT = false;
         // plans hold pointers to the packed planes, which are rewritten in place: re-pack now
         rc = ensure_packed(ctx, p, ctx->stream);
         if (rc != FISR_OK) return rc;
@@ -1036,6 +1403,49 @@ int fisr_conv3x3(fisr_ctx* ctx, const float* d_x, const float* d_w, const float*
     return check_kernel_error(ctx);
 }
 
+int fisr_dgrad3x3(fisr_ctx* ctx, const float* d_dy, const float* d_w, const float* d_mask, const float* d_res, int N, int H,
+                  int W, int Cin, int Cout, int s2d, float* d_raw, float* d_act) {
+    if (!ctx || !d_dy || !d_w || N < 1 || H < 1 || W < 1 || Cin < 1 || Cout < 1) return FISR_E_INVALID;
+    if (ctx->planes != 2) return fail(ctx, FISR_E_INVALID, "the backward kernels need precision f16x3");
+    if (s2d && (Cin != 64 || !d_mask || d_raw || d_res)) return fail(ctx, FISR_E_INVALID, "space-to-depth dgrad: Cin = 64, gated, act output only");
+    Guard guard(ctx->device);
+    cudaStream_t st = ctx->stream;
+    Plan tmp;
+    tmp.planes = 2;
+    Builder b{ctx, &tmp};
+    ConvParam p;
+    p.cin = Cin; p.cout = Cout; p.KB = (Cin + 63) / 64; p.cin_pad = p.KB * 64; p.OBk = (Cout + 63) / 64;
+    p.d_wpT = static_cast<__half*>(b.alloc(static_cast<size_t>(2) * p.OBk * 9 * p.cin_pad * 64 * 2, false));
+    const size_t npix = static_cast<size_t>(N) * H * W;
+    ActBuf gin = b.act(N, H, W, p.OBk * 64), mask = b.act(N, H, W, p.cin_pad);
+    const int oH = s2d ? H / 2 : H, oW = s2d ? W / 2 : W, ocs = s2d ? 4 * p.cin_pad : p.cin_pad;
+    ActBuf yact = b.act(N, oH, oW, ocs, true);
+    float* raw = d_raw ? b.f32(N, H, W, p.cin_pad) : nullptr;
+    float* res = d_res ? b.f32(N, H, W, p.cin_pad) : nullptr;
+    if (b.rc != FISR_OK) return b.rc;
+    launch_prep_weights_dgrad(d_w, p.d_wpT, Cin, Cout, p.OBk, p.cin_pad, st);
+    launch_act_from_f32(d_dy, Cout, gin, p.OBk * 64, npix, 2, st);
+    if (d_mask) launch_act_from_f32(d_mask, Cin, mask, p.cin_pad, npix, 2, st);
+    if (d_res) {
+        CUDA_TRY(ctx, cudaMemsetAsync(res, 0, npix * p.cin_pad * 4, st));
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(res, p.cin_pad * 4, d_res, Cin * 4, Cin * 4, npix, cudaMemcpyDeviceToDevice, st));
+    }
+    Builder::ConvOut o;
+    o.relu = false;
+    o.act = yact; o.act_cs = ocs; o.s2d = s2d != 0;
+    o.raw = raw; o.raw_cs = p.cin_pad;
+    o.res = res; o.res_cs = p.cin_pad;
+    if (d_mask) { o.mask = mask; o.mask_cs = p.cin_pad; }
+    Op op{};
+    if (!b.make_conv(b.bwd_view(p), gin, p.OBk * 64, 0, N, H, W, o, "test dgrad", &op)) return b.rc;
+    CUDA_TRY(ctx, launch_conv3x3(op.conv, ctx->num_sms, st));
+    ctx->launches += 4;
+    if (d_act) launch_act_to_f32(yact, ocs, 0, d_act, s2d ? 4 * Cin : Cin, static_cast<size_t>(N) * oH * oW, 2, st);
+    if (d_raw) CUDA_TRY(ctx, cudaMemcpy2DAsync(d_raw, Cin * 4, raw, p.cin_pad * 4, Cin * 4, npix, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return check_kernel_error(ctx);
+}
+
 int fisr_wgrad3x3(fisr_ctx* ctx, const float* d_x, const float* d_dy, int N, int H, int W, int Cin, int Cout, float scale,
                   float* d_gw, float* d_gb) {
     if (!ctx || !d_x || !d_dy || !d_gw || N < 1 || H < 1 || W < 1 || Cin < 1 || Cout < 1) return FISR_E_INVALID;
@@ -1188,31 +1598,10 @@ int fisr_adam_step(fisr_ctx* ctx, const float* const* d_grads, int n_grads, floa
     if (n_grads != 2 * static_cast<int>(ctx->params.size()))
         return fail(ctx, FISR_E_INVALID, "expected %d gradient tensors (creation order, w then b), got %d", 2 * (int)ctx->params.size(), n_grads);
     Guard guard(ctx->device);
-    cudaStream_t st = ctx->stream;
-    CUDA_TRY(ctx, cudaDeviceSynchronize());
-    const long long t = ++ctx->adam_t;
-    const float lr_t = static_cast<float>(lr * std::sqrt(1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(t))) /
-                                          (1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(t))));
-    for (size_t i = 0; i < ctx->params.size(); ++i) {
-        ConvParam& p = ctx->params[i];
-        const size_t wn = static_cast<size_t>(9) * p.cin * p.cout, bn = p.cout;
-        if (!p.m_w) {
-            CUDA_TRY(ctx, cudaMalloc(&p.m_w, wn * 4)); CUDA_TRY(ctx, cudaMalloc(&p.v_w, wn * 4));
-            CUDA_TRY(ctx, cudaMalloc(&p.m_b, bn * 4)); CUDA_TRY(ctx, cudaMalloc(&p.v_b, bn * 4));
-            CUDA_TRY(ctx, cudaMemsetAsync(p.m_w, 0, wn * 4, st)); CUDA_TRY(ctx, cudaMemsetAsync(p.v_w, 0, wn * 4, st));
-            CUDA_TRY(ctx, cudaMemsetAsync(p.m_b, 0, bn * 4, st)); CUDA_TRY(ctx, cudaMemsetAsync(p.v_b, 0, bn * 4, st));
-        }
-        if (!d_grads[2 * i] || !d_grads[2 * i + 1]) return fail(ctx, FISR_E_INVALID, "gradient %zu is NULL", i);
-        launch_adam_tf1(p.d_w, d_grads[2 * i], p.m_w, p.v_w, wn, lr_t, beta1, beta2, eps, st);
-        launch_adam_tf1(p.d_b, d_grads[2 * i + 1], p.m_b, p.v_b, bn, lr_t, beta1, beta2, eps, st);
-        p.packed = false;
-        int rc = ensure_packed(ctx, p, st);          // operand planes follow the fp32 master copy
-        if (rc != FISR_OK) return rc;
-        ctx->launches += 2;
-    }
-    CUDA_TRY(ctx, cudaGetLastError());
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    return FISR_OK;
+    std::vector<const float*> g(d_grads, d_grads + n_grads);
+    for (int i = 0; i < n_grads; ++i)
+        if (!g[i]) return fail(ctx, FISR_E_INVALID, "gradient %d is NULL", i);
+    return adam_impl(ctx, g, lr, beta1, beta2, eps);
 }
 
 long long fisr_adam_steps(const fisr_ctx* ctx) { return ctx ? ctx->adam_t : 0; }
@@ -1227,6 +1616,142 @@ int fisr_adam_reset(fisr_ctx* ctx, long long step) {
     }
     ctx->adam_t = step;
     return FISR_OK;
+}
+
+// ---------------------------------------------------------------- training step (forward + loss + backward [+ Adam])
+static int train_backward_impl(fisr_ctx* ctx, const float* d_data, const float* d_flow, const float* d_flow_ss2,
+                               const float* d_warp, const float* d_warp_ss2, const float* d_label, int B, int h, int w,
+                               const float* lambdas, float* h_out, cudaStream_t st) {
+    Plan* plan = nullptr;
+    int rc = get_plan(ctx, 4 * B, h, w, &plan);
+    if (rc != FISR_OK) return rc;
+    if ((rc = ensure_train_params(ctx, ctx->stream)) != FISR_OK) return rc;
+    if ((rc = ensure_backward(ctx, plan, B)) != FISR_OK) return rc;
+    if (st != ctx->stream) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));     // operand packing above
+    const size_t in_bytes = static_cast<size_t>(4) * B * h * w * IN_CH * 4;
+    if ((rc = ensure_stage(ctx, 0, in_bytes)) != FISR_OK) return rc;
+    launch_assemble_passes(d_data, d_flow, d_flow_ss2, d_warp, d_warp_ss2, static_cast<float*>(ctx->stage[0]), B, h, w, st);
+    launch_pack_input(static_cast<const float*>(ctx->stage[0]), 4 * B, h, w, IN_CH, plan->in_lvl[2], plan->in_lvl[1],
+                      plan->in_lvl[0], plan->planes, st);
+    ctx->launches += 2;
+    if ((rc = run_plan(ctx, plan, st)) != FISR_OK) return rc;
+    plan->label = d_label;
+    plan->lam = LossLambdas{1.f, 1.f, 0.1f, 1.f, 0.1f, 1.f};
+    if (lambdas) plan->lam = LossLambdas{lambdas[0], lambdas[1], lambdas[2], lambdas[3], lambdas[4], lambdas[5]};
+    if ((rc = run_backward(ctx, plan, st)) != FISR_OK) return rc;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_gmax, 0, sizeof(unsigned), st));
+    for (auto& p : ctx->params) launch_grad_absmax(p.g_w, static_cast<size_t>(9) * p.cin * p.cout, ctx->d_gmax, st);
+    ctx->launches += static_cast<long long>(ctx->params.size());
+    const float* pred[3] = {plan->pred[0], plan->pred[1], plan->pred[2]};
+    float scalars[11];
+    if ((rc = loss_impl(ctx, pred, d_label, B, h, w, lambdas, scalars, st)) != FISR_OK) return rc;    // synchronises
+    if (h_out) memcpy(h_out, scalars, sizeof scalars);
+    unsigned gmax = 0;
+    CUDA_TRY(ctx, cudaMemcpy(&gmax, ctx->d_gmax, sizeof gmax, cudaMemcpyDeviceToHost));
+    if (gmax >= 0x7F800000u)
+        return fail(ctx, FISR_E_KERNEL, "non-finite gradient (loss scale %g overflowed the fp16 gradient planes): lower it with fisr_set_loss_scale", plan->loss_scale);
+    return check_kernel_error(ctx);
+}
+
+int fisr_train_backward(fisr_ctx* ctx, const float* d_data, const float* d_flow, const float* d_flow_ss2, const float* d_warp,
+                        const float* d_warp_ss2, const float* d_label, int B, int h, int w, const float* lambdas, float* h_out,
+                        void* stream) {
+    if (!ctx || !d_data || !d_flow || !d_flow_ss2 || !d_warp || !d_warp_ss2 || !d_label || B < 1) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return train_backward_impl(ctx, d_data, d_flow, d_flow_ss2, d_warp, d_warp_ss2, d_label, B, h, w, lambdas, h_out, st);
+}
+
+int fisr_adam_apply(fisr_ctx* ctx, float lr, float beta1, float beta2, float eps) {
+    if (!ctx) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    std::vector<const float*> g;
+    for (auto& p : ctx->params) {
+        if (!p.g_w) return fail(ctx, FISR_E_INVALID, "no gradients yet: call fisr_train_backward first");
+        g.push_back(p.g_w);
+        g.push_back(p.g_b);
+    }
+    return adam_impl(ctx, g, lr, beta1, beta2, eps);
+}
+
+int fisr_train_step(fisr_ctx* ctx, const float* d_data, const float* d_flow, const float* d_flow_ss2, const float* d_warp,
+                    const float* d_warp_ss2, const float* d_label, int B, int h, int w, const float* lambdas, float lr,
+                    float* h_out, void* stream) {
+    int rc = fisr_train_backward(ctx, d_data, d_flow, d_flow_ss2, d_warp, d_warp_ss2, d_label, B, h, w, lambdas, h_out, stream);
+    if (rc != FISR_OK) return rc;
+    return fisr_adam_apply(ctx, lr, 0.9f, 0.999f, 1e-8f);
+}
+
+int fisr_get_grad(fisr_ctx* ctx, const char* name, float* h_data, size_t count) {
+    if (!ctx || !h_data) return FISR_E_INVALID;
+    int ci; bool is_w;
+    int rc = split_param_name(ctx, name, &ci, &is_w);
+    if (rc != FISR_OK) return rc;
+    Guard guard(ctx->device);
+    ConvParam& p = ctx->params[ci];
+    if (!p.g_w) return fail(ctx, FISR_E_INVALID, "no gradients yet: call fisr_train_backward first");
+    const size_t expect = is_w ? static_cast<size_t>(9) * p.cin * p.cout : static_cast<size_t>(p.cout);
+    if (count != expect) return fail(ctx, FISR_E_INVALID, "%s has %zu elements, got %zu", name, expect, count);
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    CUDA_TRY(ctx, cudaMemcpy(h_data, is_w ? p.g_w : p.g_b, count * 4, cudaMemcpyDeviceToHost));
+    return FISR_OK;
+}
+
+int fisr_set_loss_scale(fisr_ctx* ctx, float scale) {
+    if (!ctx || !(scale >= 0.f)) return FISR_E_INVALID;
+    ctx->loss_scale_override = scale;
+    for (auto& kv : ctx->plans)
+        if (kv.second->has_bwd && scale > 0.f) kv.second->loss_scale = scale;
+    return FISR_OK;
+}
+
+float fisr_get_loss_scale(fisr_ctx* ctx, int B, int h, int w) {
+    if (!ctx) return 0.f;
+    if (ctx->loss_scale_override > 0.f) return ctx->loss_scale_override;
+    return std::exp2(std::floor(std::log2(static_cast<double>(B) * (2.0 * h) * (2.0 * w) * 3.0)));
+}
+
+int fisr_profile_train(fisr_ctx* ctx, int B, int h, int w, int reps, int max_ops, float* ms, double* flops, char* names,
+                       int name_stride) {
+    if (!ctx || reps < 1 || B < 1) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    Plan* plan = nullptr;
+    int rc = get_plan(ctx, 4 * B, h, w, &plan);
+    if (rc != FISR_OK) return rc;
+    if ((rc = ensure_train_params(ctx, ctx->stream)) != FISR_OK) return rc;
+    if ((rc = ensure_backward(ctx, plan, B)) != FISR_OK) return rc;
+    const int n = static_cast<int>(plan->bwd.size());
+    if (!ms) return n;
+    if (max_ops < n) return fail(ctx, FISR_E_INVALID, "backward has %d ops, buffers hold %d", n, max_ops);
+    if (!plan->label) return fail(ctx, FISR_E_INVALID, "run fisr_train_backward once before profiling (it binds the label)");
+    std::vector<cudaEvent_t> marks(n + 1);
+    for (auto& e : marks) CUDA_TRY(ctx, cudaEventCreate(&e));
+    for (int i = 0; i < n; ++i) ms[i] = 0.f;
+    cudaStream_t st = ctx->stream;
+    for (int r = 0; r < reps + 1 && rc == FISR_OK; ++r) {          // first pass = warm-up
+        for (int i = 0; i < n && rc == FISR_OK; ++i) {
+            cudaEventRecord(marks[i], st);
+            rc = plan->bwd[i].run(st);
+            ctx->launches += plan->bwd[i].launches;
+        }
+        cudaEventRecord(marks[n], st);
+        if (rc != FISR_OK) break;
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        if (r == 0) continue;
+        for (int i = 0; i < n; ++i) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, marks[i], marks[i + 1]);
+            ms[i] += t / reps;
+        }
+    }
+    for (auto& e : marks) cudaEventDestroy(e);
+    if (rc != FISR_OK) return rc;
+    for (int i = 0; i < n; ++i) {
+        if (flops) flops[i] = plan->bwd[i].flops;
+        if (names && name_stride > 0) snprintf(names + static_cast<size_t>(i) * name_stride, name_stride, "%s", plan->bwd[i].name.c_str());
+    }
+    rc = check_kernel_error(ctx);
+    return rc == FISR_OK ? n : rc;
 }
 
 long long fisr_launch_count(const fisr_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -2,6 +2,7 @@
 // Groups2Ovlp, the multi-scale temporal loss (forward values) + train PSNR, and the TF-1.13 Adam update.
 // All are HBM-bound single-pass kernels; reductions are two-stage with a fixed summation order (deterministic).
 #include "common.cuh"
+#include "act_io.cuh"
 #include "train_kernels.h"
 
 namespace fisr {
@@ -170,6 +171,203 @@ __global__ void loss_finalize_kernel(const double* __restrict__ partial, LossSca
     }
 }
 
+
+// ---------------------------------------------------------------- d total_loss / d pred (FISRnet.py:312-484, autodiff of)
+// One scale.  Thread = (image b, pixel p): the 36 derivatives wrt the 9 window frames P and the 3 stride-2 frames S,
+// times the loss scale, plus the gradient that reached this prediction through the next level's input channels
+// 29..37 (FISRnet.py:113,144: pred feeds the next level un-detached).  Written as the (hi, lo) dy operand of the two
+// conv/2 heads: channel j of pred lands in channel perm(j) of a 128-channel buffer, [0,6) = FI-SR's outputs
+// (pred 0,1,2,6,7,8), [64,67) = SR's (pred 3,4,5)  (FISRnet.py:107-108); each head's K block starts 128-B aligned.
+struct LossGradCoef { float c[7]; };   // 2 * scale * weight / count of recn, tm, tmm, td, recn2, td2, tm2
+__global__ void loss_grad_kernel(const float* __restrict__ pred, const float* __restrict__ label, const __half* __restrict__ extra,
+                                 size_t extra_plane, int B, int hs, int ws, int st, int LH, int LW, LossGradCoef k,
+                                 __half* __restrict__ out, size_t out_plane) {
+    const int b = blockIdx.y;
+    const size_t hw = static_cast<size_t>(hs) * ws;
+    const size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (p >= hw) return;
+    const int y = p / ws, x = p % ws;
+    const float* lab = label + ((static_cast<size_t>(b) * LH + static_cast<size_t>(y) * st) * LW + static_cast<size_t>(x) * st) * 21;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float P[9], S[3], G[7], O[7], dP[9], dS[3], dO[7];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) P[q] = pred[((static_cast<size_t>(q / 3) * B + b) * hw + p) * 9 + 3 * (q % 3) + c];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) S[q] = pred[((static_cast<size_t>(3) * B + b) * hw + p) * 9 + 3 * q + c];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) { G[q] = lab[3 * q + c]; dO[q] = 0.f; }
+        O[0] = P[0]; O[1] = P[1]; O[2] = (P[2] + P[3]) / 2; O[3] = P[4]; O[4] = (P[5] + P[6]) / 2; O[5] = P[7]; O[6] = P[8];
+#pragma unroll
+        for (int w = 0; w < 3; ++w)
+#pragma unroll
+            for (int f = 0; f < 3; ++f) dP[3 * w + f] = k.c[0] * (P[3 * w + f] - G[2 * w + f]);                 // recn
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float d1 = k.c[1] * (P[3 * i + 2] - P[3 * i + 3]);                                             // tm
+            const float d2 = 0.5f * k.c[2] * ((P[3 * i + 2] + P[3 * i + 3]) / 2 - G[2 * (i + 1)]);                // tmm
+            dP[3 * i + 2] += d1 + d2;
+            dP[3 * i + 3] += d2 - d1;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {                                                                            // td
+            const float d = k.c[3] * ((O[i + 1] - O[i]) - (G[i + 1] - G[i]));
+            dO[i + 1] += d; dO[i] -= d;
+        }
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            const float d = k.c[6] * (S[f] - O[2 * f + 1]);                                                      // tm2
+            dS[f] = k.c[4] * (S[f] - G[2 * f + 1]) + d;                                                          // recn2
+            dO[2 * f + 1] -= d;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {                                                                            // td2
+            const float d = k.c[5] * ((S[i + 1] - S[i]) - (G[2 * i + 3] - G[2 * i + 1]));
+            dS[i + 1] += d; dS[i] -= d;
+        }
+        dP[0] += dO[0]; dP[1] += dO[1]; dP[2] += 0.5f * dO[2]; dP[3] += 0.5f * dO[2]; dP[4] += dO[3];             // Groups2Ovlp
+        dP[5] += 0.5f * dO[4]; dP[6] += 0.5f * dO[4]; dP[7] += dO[5]; dP[8] += dO[6];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+            const int pass = q < 9 ? q / 3 : 3, f = q < 9 ? q % 3 : q - 9;
+            const int j = 3 * f + c;                                    // pred channel
+            const size_t img = (static_cast<size_t>(pass) * B + b) * hw + p;
+            float g = q < 9 ? dP[q] : dS[q - 9];
+            if (extra) g += join_f16(extra[img * 64 + 29 + j], extra[extra_plane + img * 64 + 29 + j]);
+            const int ch = j < 3 ? j : (j < 6 ? 64 + (j - 3) : j - 3);
+            const SplitHalf sh = split_f32(g);
+            out[img * 128 + ch] = sh.hi;
+            out[out_plane + img * 128 + ch] = sh.lo;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- max-pool backward + skip add (ops.py:54, autodiff of)
+// skip = channels [coff, coff+C) of the concat buffer (post-ReLU); g_cat = gradient that arrived through the concat
+// (same indexing, already gated by [skip > 0]); g_pool = gradient wrt the pooled map.  Each 2x2 window routes g_pool to
+// its first maximum (TF's MaxPoolGrad order); windows whose maximum is 0 route nothing (the ReLU before the pool).
+__global__ void pool_bwd_kernel(const __half* __restrict__ skip, size_t pskip, const __half* __restrict__ gcat, size_t pgcat, int cs,
+                                int coff, const __half* __restrict__ gpool, size_t pgpool, __half* __restrict__ gout, size_t pgout,
+                                float* __restrict__ rout, int N, int H, int W, int C) {
+    const int cv = C / 8, h = H / 2, w = W / 2;
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t total = static_cast<size_t>(N) * h * w * cv;
+    if (i >= total) return;
+    const int c8 = (i % cv) * 8;
+    size_t r = i / cv;
+    const int x = r % w; r /= w;
+    const int y = r % h;
+    const int n = r / h;
+    float gp[8], v[4][8];
+    load8<2>(gpool + ((static_cast<size_t>(n) * h + y) * w + x) * C + c8, pgpool, gp);
+    int arg[8];
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { m[j] = 0.f; arg[j] = -1; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const size_t pix = (static_cast<size_t>(n) * H + 2 * y + (k >> 1)) * W + 2 * x + (k & 1);
+        load8<2>(skip + pix * cs + coff + c8, pskip, v[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (v[k][j] > m[j]) { m[j] = v[k][j]; arg[j] = k; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const size_t pix = (static_cast<size_t>(n) * H + 2 * y + (k >> 1)) * W + 2 * x + (k & 1);
+        float g[8];
+        load8<2>(gcat + pix * cs + coff + c8, pgcat, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (arg[j] == k) g[j] += gp[j];
+        store8<2>(gout + pix * C + c8, pgout, g);
+        float4* ro = reinterpret_cast<float4*>(rout + pix * C + c8);
+        ro[0] = make_float4(g[0], g[1], g[2], g[3]);
+        ro[1] = make_float4(g[4], g[5], g[6], g[7]);
+    }
+}
+
+// ---------------------------------------------------------------- legacy bilinear x2 backward (ops.py:69, autodiff of)
+// Adjoint of out[2k] = in[k], out[2k+1] = (in[k] + in[min(k+1, n-1)]) / 2 along H then W, gated by [x > 0] of the
+// (post-ReLU) tensor that was upsampled.
+__global__ void upsample_bwd_kernel(const __half* __restrict__ gup, size_t pgup, const __half* __restrict__ xin, size_t pxin,
+                                    __half* __restrict__ gout, size_t pgout, float* __restrict__ rout, int N, int h, int w, int C) {
+    const int cv = C / 8;
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t total = static_cast<size_t>(N) * h * w * cv;
+    if (i >= total) return;
+    const int c8 = (i % cv) * 8;
+    size_t r = i / cv;
+    const int x = r % w; r /= w;
+    const int y = r % h;
+    const int n = r / h;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const float wy[3] = {y >= 1 ? 0.5f : 0.f, 1.f, y == h - 1 ? 1.f : 0.5f};
+    const float wx[3] = {x >= 1 ? 0.5f : 0.f, 1.f, x == w - 1 ? 1.f : 0.5f};
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+        if (wy[dy] == 0.f) continue;
+        const int Y = 2 * y + dy - 1;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            if (wx[dx] == 0.f) continue;
+            const int X = 2 * x + dx - 1;
+            float g[8];
+            load8<2>(gup + ((static_cast<size_t>(n) * 2 * h + Y) * 2 * w + X) * C + c8, pgup, g);
+            const float wgt = wy[dy] * wx[dx];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += wgt * g[j];
+        }
+    }
+    const size_t pix = (static_cast<size_t>(n) * h + y) * w + x;
+    float xv[8];
+    load8<2>(xin + pix * C + c8, pxin, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (!(xv[j] > 0.f)) acc[j] = 0.f;
+    store8<2>(gout + pix * C + c8, pgout, acc);
+    if (rout) {
+        float4* ro = reinterpret_cast<float4*>(rout + pix * C + c8);
+        ro[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        ro[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+}
+
+// ---------------------------------------------------------------- dgrad weights
+// w fp32 HWIO [3,3,cin,cout] -> operand planes of the transposed, 180-degree rotated filter: the data gradient of a
+// SAME 3x3 conv is the SAME 3x3 conv of dy with w'[ky,kx,co,ci] = w[2-ky,2-kx,ci,co].
+// Layout [plane][kb over cout][tap][cin_pad][64] like the forward operand.
+__global__ void prep_weights_dgrad_kernel(const float* __restrict__ w, __half* __restrict__ out, int cin, int cout, int KBo,
+                                          int cin_pad) {
+    const size_t per_plane = static_cast<size_t>(KBo) * 9 * cin_pad * 64;
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= per_plane) return;
+    const int cl = i & 63;
+    size_t r = i >> 6;
+    const int ci = r % cin_pad; r /= cin_pad;
+    const int tap = r % 9;
+    const int kb = r / 9;
+    const int co = kb * 64 + cl;
+    float v = 0.f;
+    if (ci < cin && co < cout) v = w[(static_cast<size_t>(8 - tap) * cin + ci) * cout + co];
+    const SplitHalf s = split_f32(v);
+    out[i] = s.hi;
+    out[per_plane + i] = s.lo;
+}
+
+// max |g| over a gradient tensor, as the raw bits of a non-negative float (atomicMax on ints orders them); NaN / Inf
+// give bits >= 0x7F800000, which is how an overflowed loss scale is detected.
+__global__ void grad_absmax_kernel(const float* __restrict__ g, size_t n, unsigned* __restrict__ out) {
+    unsigned m = 0;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        m = max(m, __float_as_uint(g[i]) & 0x7FFFFFFFu);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
 // ---------------------------------------------------------------- Adam, TF-1.13 formula (FISRnet.py:489-491)
 __global__ void adam_tf1_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ m,
                                 float* __restrict__ v, size_t n, float lr_t, float beta1, float beta2, float eps) {
@@ -218,6 +416,46 @@ void launch_temporal_loss(const float* const pred[3], const float* label, int B,
         temporal_loss_kernel<<<grid, 256, 0, st>>>(pred[s], label, B, hs, ws, 4 >> s, 2 * h, 2 * w, workspace + sc.offset[s]);
     }
     loss_finalize_kernel<<<1, 32, 0, st>>>(workspace, sc, B, lam, d_out);
+}
+
+void launch_loss_grad(const float* pred, const float* label, ActBuf extra, int B, int hs, int ws, int st, int LH, int LW,
+                      float wgt, const LossLambdas& lam, float scale, ActBuf out, cudaStream_t stm) {
+    const double n1 = static_cast<double>(B) * hs * ws * 3;
+    const double f = 2.0 * scale * wgt;
+    LossGradCoef k;
+    k.c[0] = static_cast<float>(f * lam.recn / (3 * n1));
+    k.c[1] = static_cast<float>(f * lam.tm1 / n1);
+    k.c[2] = static_cast<float>(f * lam.tmm / n1);
+    k.c[3] = static_cast<float>(f * lam.td / n1);
+    k.c[4] = static_cast<float>(f * lam.ss2 * lam.recn / (3 * n1));
+    k.c[5] = static_cast<float>(f * lam.ss2 * lam.td / n1);
+    k.c[6] = static_cast<float>(f * lam.ss2 * lam.tm2 / (3 * n1));
+    dim3 grid(blocks_for(static_cast<size_t>(hs) * ws, 128), B);
+    loss_grad_kernel<<<grid, 128, 0, stm>>>(pred, label, extra.p, extra.plane, B, hs, ws, st, LH, LW, k, out.p, out.plane);
+}
+
+void launch_pool_bwd(ActBuf skip, ActBuf gcat, int cs, int coff, ActBuf gpool, ActBuf gout, float* rout, int N, int H, int W,
+                     int C, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
+    pool_bwd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(skip.p, skip.plane, gcat.p, gcat.plane, cs, coff, gpool.p, gpool.plane,
+                                                          gout.p, gout.plane, rout, N, H, W, C);
+}
+
+void launch_upsample_bwd(ActBuf gup, ActBuf xin, ActBuf gout, float* rout, int N, int h, int w, int C, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(N) * h * w * (C / 8);
+    upsample_bwd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(gup.p, gup.plane, xin.p, xin.plane, gout.p, gout.plane, rout, N, h,
+                                                              w, C);
+}
+
+void launch_prep_weights_dgrad(const float* w, __half* out, int cin, int cout, int KBo, int cin_pad, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(KBo) * 9 * cin_pad * 64;
+    prep_weights_dgrad_kernel<<<blocks_for(total, 256), 256, 0, st>>>(w, out, cin, cout, KBo, cin_pad);
+}
+
+void launch_grad_absmax(const float* g, size_t n, unsigned* out, cudaStream_t st) {
+    unsigned blocks = blocks_for(n, 256);
+    if (blocks > 592) blocks = 592;
+    grad_absmax_kernel<<<blocks, 256, 0, st>>>(g, n, out);
 }
 
 void launch_adam_tf1(float* theta, const float* g, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,

@@ -310,6 +310,63 @@ class Engine:
         self._exit()
         return dict(zip(self.LOSS_NAMES, (float(v) for v in out)))
 
+    def train_backward(self, data, flow, flow_ss2, warp, warp_ss2, label, lambdas=None) -> dict:
+        """Forward + loss + backward of one step (FISRnet.py:281-491 up to the gradients): returns the 11 scalars;
+        the gradients stay in the context (:meth:`get_grads`, :meth:`adam_apply`)."""
+        ts = [self._dev(t, torch.float32) for t in (data, flow, flow_ss2, warp, warp_ss2, label)]
+        B, h, w, _ = ts[0].shape
+        out = (C.c_float * 11)()
+        self._enter(*ts)
+        self._check(self.lib.fisr_train_backward(self.h, *[t.data_ptr() for t in ts], B, h, w, self._lambdas(lambdas), out,
+                                                 self._stream()), "fisr_train_backward")
+        self._exit()
+        return dict(zip(self.LOSS_NAMES, (float(v) for v in out)))
+
+    def train_step(self, data, flow, flow_ss2, warp, warp_ss2, label, lr: float, lambdas=None) -> dict:
+        """One ``sess.run([self.optim, ...])`` (FISRnet.py:651): forward, loss, backward, TF-1.13 Adam update."""
+        ts = [self._dev(t, torch.float32) for t in (data, flow, flow_ss2, warp, warp_ss2, label)]
+        B, h, w, _ = ts[0].shape
+        out = (C.c_float * 11)()
+        self._enter(*ts)
+        self._check(self.lib.fisr_train_step(self.h, *[t.data_ptr() for t in ts], B, h, w, self._lambdas(lambdas), lr, out,
+                                             self._stream()), "fisr_train_step")
+        self._exit()
+        return dict(zip(self.LOSS_NAMES, (float(v) for v in out)))
+
+    def get_grads(self) -> "OrderedDict[str, np.ndarray]":
+        out: "OrderedDict[str, np.ndarray]" = OrderedDict()
+        for name, shape in param_inventory().items():
+            a = np.empty(shape, dtype=np.float32)
+            self._check(self.lib.fisr_get_grad(self.h, name.encode(), a.ctypes.data, a.size), f"fisr_get_grad({name})")
+            out[name] = a
+        return out
+
+    def adam_apply(self, lr: float, beta1=0.9, beta2=0.999, eps=1e-8) -> int:
+        self._check(self.lib.fisr_adam_apply(self.h, lr, beta1, beta2, eps), "fisr_adam_apply")
+        return int(self.lib.fisr_adam_steps(self.h))
+
+    def set_loss_scale(self, scale: float) -> None:
+        self._check(self.lib.fisr_set_loss_scale(self.h, float(scale)), "fisr_set_loss_scale")
+
+    def profile_train(self, B: int, h: int, w: int, reps: int = 2):
+        """Per-op device time of the backward pass (after one :meth:`train_backward` at that shape)."""
+        torch.cuda.synchronize(self.device)
+        cnt = self.lib.fisr_profile_train(self.h, B, h, w, 1, 0, None, None, None, 0)
+        if cnt < 0:
+            self._check(cnt, "fisr_profile_train")
+        ms = (C.c_float * cnt)()
+        fl = (C.c_double * cnt)()
+        names = C.create_string_buffer(cnt * 128)
+        rc = self.lib.fisr_profile_train(self.h, B, h, w, reps, cnt, ms, fl, names, 128)
+        if rc < 0:
+            self._check(rc, "fisr_profile_train")
+        out = []
+        for k in range(cnt):
+            nm = names.raw[k * 128:(k + 1) * 128].split(b"\0", 1)[0].decode()
+            kind = "dgrad" if nm.endswith("[dgrad]") else ("wgrad" if nm.endswith("[wgrad]") else "aux")
+            out.append({"name": nm, "kind": kind, "ms": float(ms[k]), "flops": float(fl[k])})
+        return out
+
     def adam_step(self, grads: Dict[str, torch.Tensor], lr: float, beta1=0.9, beta2=0.999, eps=1e-8) -> int:
         """``tf.train.AdamOptimizer(lr)`` update (TF-1.13 formula) from device gradients keyed by variable name."""
         names = list(param_inventory())
@@ -340,6 +397,24 @@ class Engine:
                                           n, h, wd, cin, cout, int(relu), int(d2s),
                                           raw.data_ptr() if raw is not None else None,
                                           act.data_ptr() if act is not None else None), "fisr_conv3x3")
+        return raw, act
+
+    def dgrad3x3(self, dy: torch.Tensor, w: torch.Tensor, mask: Optional[torch.Tensor] = None,
+                 res: Optional[torch.Tensor] = None, s2d: bool = False, want_raw: bool = True):
+        """Data gradient of one 3x3 SAME conv (production kernel on rotated-transposed planes):
+        dx = conv3x3(dy, rot180(w)^T) * [mask > 0] + res; dy [N,H,W,Cout], w HWIO forward filter -> (raw, act)."""
+        dy = self._dev(dy, torch.float32)
+        w = self._dev(w, torch.float32)
+        n, h, wd, cout = dy.shape
+        cin = w.shape[2]
+        raw = torch.empty((n, h, wd, cin), device=dy.device) if (want_raw and not s2d) else None
+        act = torch.empty((n, h // 2, wd // 2, 4 * cin) if s2d else (n, h, wd, cin), device=dy.device)
+        torch.cuda.synchronize(self.device)
+        self._check(self.lib.fisr_dgrad3x3(self.h, dy.data_ptr(), w.data_ptr(),
+                                           self._dev(mask, torch.float32).data_ptr() if mask is not None else None,
+                                           self._dev(res, torch.float32).data_ptr() if res is not None else None,
+                                           n, h, wd, cin, cout, int(s2d), raw.data_ptr() if raw is not None else None,
+                                           act.data_ptr()), "fisr_dgrad3x3")
         return raw, act
 
     def wgrad3x3(self, x: torch.Tensor, dy: torch.Tensor, scale: float = 1.0, want_bias: bool = True):

@@ -102,7 +102,7 @@ int fisr_warp_device(fisr_ctx* ctx, const uint8_t* d_yuv, const float* d_flow, f
 int fisr_warp_host(fisr_ctx* ctx, const uint8_t* h_yuv, const float* h_flow, float flow_scale, float* h_out, int h,
                    int w, float out_scale);
 
-/* ---- training-side forward half (the backward pass is not part of this revision) ---------------------------- */
+/* ---- training step: `sess.run([self.optim, ...])` of FISRnet.py:651 -------------------------------------------- */
 /* Groups2Ovlp (ops.py:119-144): d_pred [3B,H,W,9] = pred of windows 0,1,2 (window-major) -> d_out [B,7,H,W,3]. */
 int fisr_groups2ovlp(fisr_ctx* ctx, const float* d_pred, int B, int H, int W, float* d_out, void* stream);
 /* Multi-scale temporal loss + train PSNR (FISRnet.py:312-486).  d_pred_l* are the three outputs of FISRnet.model on the
@@ -122,6 +122,26 @@ int fisr_train_forward(fisr_ctx* ctx, const float* d_data, const float* d_flow, 
  * theta -= lr_t*m/(sqrt(v)+eps)) of all 276 tensors from device gradients listed in creation order (w, b, w, b, ...);
  * keeps m, v and the step counter in the context and re-packs the operand planes.  TF defaults: 0.9, 0.999, 1e-8. */
 int fisr_adam_step(fisr_ctx* ctx, const float* const* d_grads, int n_grads, float lr, float beta1, float beta2, float eps);
+/* Forward + loss + backward of one step: d total_loss / d (every w, b) by hand-written dgrad (the forward tcgen05 kernel
+ * on rotated-transposed operand planes, ReLU gate / residual / space-to-depth fused in the epilogue) and wgrad kernels,
+ * what `AdamOptimizer.minimize` derives from the graph of FISRnet.py:281-484.  Gradients stay in the context
+ * (fisr_get_grad, fisr_adam_apply); h_out[11] as fisr_temporal_loss.  Needs FISR_PREC_F16X3.  Synchronous. */
+int fisr_train_backward(fisr_ctx* ctx, const float* d_data, const float* d_flow, const float* d_flow_ss2, const float* d_warp,
+                        const float* d_warp_ss2, const float* d_label, int B, int h, int w, const float* lambdas, float* h_out,
+                        void* stream);
+/* Gradient of the last fisr_train_backward for one variable (same names / shapes as fisr_get_param). */
+int fisr_get_grad(fisr_ctx* ctx, const char* name, float* h_data, size_t count);
+/* Adam update (same formula as fisr_adam_step) from the context's own gradients. */
+int fisr_adam_apply(fisr_ctx* ctx, float lr, float beta1, float beta2, float eps);
+/* fisr_train_backward + fisr_adam_apply(lr, 0.9, 0.999, 1e-8): one `sess.run(optim)` (FISRnet.py:489-491, 651). */
+int fisr_train_step(fisr_ctx* ctx, const float* d_data, const float* d_flow, const float* d_flow_ss2, const float* d_warp,
+                    const float* d_warp_ss2, const float* d_label, int B, int h, int w, const float* lambdas, float lr,
+                    float* h_out, void* stream);
+/* Gradients travel through the network as fp16 (hi, lo) planes multiplied by a power-of-two loss scale (default:
+ * 2^floor(log2(B*2h*2w*3)), divided out by the weight-gradient reduction).  0 restores the default; a non-finite gradient
+ * makes fisr_train_backward return FISR_E_KERNEL. */
+int fisr_set_loss_scale(fisr_ctx* ctx, float scale);
+float fisr_get_loss_scale(fisr_ctx* ctx, int B, int h, int w);
 long long fisr_adam_steps(const fisr_ctx* ctx);
 int fisr_adam_reset(fisr_ctx* ctx, long long step);
 
@@ -132,6 +152,11 @@ int fisr_adam_reset(fisr_ctx* ctx, long long step);
  * NULL except x, w, b (d2s excludes res and raw: the network never combines them).  Synchronous. */
 int fisr_conv3x3(fisr_ctx* ctx, const float* d_x, const float* d_w, const float* d_b, const float* d_res, int N, int H,
                  int W, int Cin, int Cout, int relu, int d2s, float* d_raw, float* d_act);
+/* Data gradient of one 3x3 SAME conv through the production kernel: dx = conv3x3(dy, rot180(w)^T) * [mask > 0] + res.
+ * dy [N,H,W,Cout], w HWIO [3,3,Cin,Cout] (the FORWARD filter), mask / res / raw / act [N,H,W,Cin]; with s2d the act
+ * output is space_to_depth(2): [N,H/2,W/2,4*Cin] (adjoint of the depth_to_space epilogue).  Synchronous. */
+int fisr_dgrad3x3(fisr_ctx* ctx, const float* d_dy, const float* d_w, const float* d_mask, const float* d_res, int N, int H,
+                  int W, int Cin, int Cout, int s2d, float* d_raw, float* d_act);
 /* Weight / bias gradient of one 3x3 SAME conv through the production wgrad kernel (the backward-filter op TF derives
  * for ops.py:10): gw[ky,kx,ci,co] = scale * sum_p x[p+(ky-1,kx-1),ci] * dy[p,co], gb[co] = scale * sum_p dy[p,co].
  * x [N,H,W,Cin], dy [N,H,W,Cout], gw HWIO [3,3,Cin,Cout], gb [Cout] (may be NULL); device pointers.  Synchronous. */
@@ -146,6 +171,10 @@ int fisr_debug_conv_output(fisr_ctx* ctx, const char* conv_name, float* h_dst, s
  * upsample, 2000 max-pool; names is max_ops strings of name_stride bytes.  Feeds bench.py's roofline block. */
 int fisr_profile_ops(fisr_ctx* ctx, int N, int H, int W, int reps, int max_ops, float* ms, double* flops, double* bytes,
                      int* kinds, char* names, int name_stride);
+/* Per-op device times of the backward pass for batch B (4B passes) at LR size h x w, like fisr_profile_ops; call
+ * fisr_train_backward once first.  Names end in [dgrad] / [wgrad]. */
+int fisr_profile_train(fisr_ctx* ctx, int B, int h, int w, int reps, int max_ops, float* ms, double* flops, char* names,
+                       int name_stride);
 /* Kernel launches issued by this context since creation (the `gpu_launches` evidence bench.py reports). */
 long long fisr_launch_count(const fisr_ctx* ctx);
 /* Conv FLOPs (2*9*Cin*Cout*h*w*N) and mean MMA row efficiency of the plan for (N,H,W). */
