@@ -68,6 +68,7 @@ def load() -> C.CDLL:
         "fisr_train_step": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, C.POINTER(f), f, C.POINTER(f), vp]),
         "fisr_set_loss_scale": (i, [vp, f]),
         "fisr_get_loss_scale": (f, [vp, i, i, i]),
+        "fisr_set_wgrad_exact": (i, [vp, i]),
         "fisr_dgrad3x3": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, vp]),
         "fisr_profile_train": (i, [vp, i, i, i, i, i, C.POINTER(f), C.POINTER(C.c_double), C.c_char_p, i]),
         "fisr_wgrad3x3": (i, [vp, vp, vp, i, i, i, i, i, f, vp, vp]),
@@ -90,6 +91,6 @@ EXPORTS = [
     "fisr_param_name", "fisr_param_shape", "fisr_set_param", "fisr_get_param", "fisr_forward", "fisr_forward_host",
     "fisr_window_device", "fisr_units_device", "fisr_window_device_f32", "fisr_window_host", "fisr_window_submit", "fisr_window_wait", "fisr_warp_device", "fisr_warp_host",
     "fisr_groups2ovlp", "fisr_temporal_loss", "fisr_train_forward", "fisr_adam_step", "fisr_adam_steps", "fisr_adam_reset",
-    "fisr_train_backward", "fisr_get_grad", "fisr_adam_apply", "fisr_train_step", "fisr_set_loss_scale", "fisr_get_loss_scale",
+    "fisr_train_backward", "fisr_get_grad", "fisr_adam_apply", "fisr_train_step", "fisr_set_loss_scale", "fisr_get_loss_scale", "fisr_set_wgrad_exact",
     "fisr_dgrad3x3", "fisr_profile_train", "fisr_conv3x3", "fisr_wgrad3x3", "fisr_debug_conv_output", "fisr_profile_ops", "fisr_launch_count", "fisr_plan_info",
 ]

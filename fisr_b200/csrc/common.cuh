@@ -45,6 +45,7 @@ struct ConvArgs {
     int* err;                 // device error flag (0 = ok)
     int N, H, W;              // output (= input) geometry
     int cin_off, KB;          // first input channel in the source buffer, number of 64-channel K blocks
+    int ksteps_last;          // 16-channel K slices of the last block that hold real input channels (1..4)
     int cout, NB;             // true output channels, number of N blocks (cout_pad = NB * NT)
     int P, TH, TW;            // patch pitch (= TW + 2), output rows / cols per tile
     int inv_p;                // ceil(2^20 / P): q / P == (q * inv_p) >> 20 for q < 2^20 / P

@@ -217,6 +217,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 const uint32_t a_hi0 = umma_desc_lo(sA + as * a_stage_bytes);
                 const uint32_t a_lo0 = umma_desc_lo(sA + as * a_stage_bytes + a.a_plane_bytes);
                 uint32_t first = kb == 0 ? 0u : 1u;          // accumulate flag of the very first MMA of the tile
+                const int ksteps = kb == a.KB - 1 ? a.ksteps_last : 4;   // 16-channel K slices that hold real channels
 #pragma unroll 1
                 for (int ky = 0; ky < 3 && ok; ++ky) {
 #pragma unroll 1
@@ -233,6 +234,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                                 for (int c = 0; c < CHUNKS; ++c) {
 #pragma unroll
                                     for (int k = 0; k < 4; ++k) {
+                                        if (k >= ksteps) break;
                                         // A_hi * [B_hi (; B_lo)]
                                         umma_f16_lohi(d_tmem + c * DCOLS, ah + c * 1024 + k * 2, b0 + k * 2, kUmmaDescHiSw128,
                                                       idesc2, k == 0 ? first : 1u);
@@ -255,9 +257,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 #pragma unroll
                                 for (int c = 0; c < CHUNKS; ++c) {
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k)
+                                    for (int k = 0; k < 4; ++k) {
+                                        if (k >= ksteps) break;
                                         umma_f16_lohi(d_tmem + c * DCOLS, ah + c * 1024 + k * 2, b0 + k * 2, kUmmaDescHiSw128,
                                                       idesc, 1u);
+                                    }
                                 }
                                 umma_commit(b_empty(bs));
                             }

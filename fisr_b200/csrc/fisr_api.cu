@@ -153,8 +153,7 @@ struct Plan {
     ActBuf gp[3];                    // dy operand of the conv/2 heads per level
     LossLambdas lam{1.f, 1.f, 0.1f, 1.f, 0.1f, 1.f};
     const float* label = nullptr;    // set per call
-    float* wg_partial = nullptr;     // split-K slots of the wgrad kernel (sized for the largest layer)
-    float* bias_ws = nullptr;
+    float* wg_partial = nullptr;     // split-K slots of the wgrad kernel (weights + bias, sized for the largest layer)
     ~Plan() {
         if (graph) cudaGraphExecDestroy(graph);
         for (void* p : allocs) cudaFree(p);
@@ -197,6 +196,7 @@ struct fisr_ctx {
     float* d_zero_bias = nullptr;   // 512 zeros: the dgrad launches of the conv kernel add no bias
     unsigned* d_gmax = nullptr;     // max |gradient| bits of the last backward (overflow check of the loss scale)
     float loss_scale_override = 0.f;
+    bool wgrad_exact = false;       // multiply by x's lo plane in every wgrad launch (fisr_set_wgrad_exact)
 };
 
 namespace {
@@ -374,6 +374,8 @@ struct Builder {
             if (px * cs_max >= 4294967296.0) { rc = fail(ctx, FISR_E_INVALID, "conv %s: %d x %d x %d x %d exceeds 32-bit offsets; split the batch", name.c_str(), N, H, W, cs_max); return false; }
         }
         a.cin_off = cin_off; a.KB = p.KB; a.cout = p.cout;
+        a.ksteps_last = (p.cin - (p.KB - 1) * 64 + 15) / 16;       // padded input channels beyond this are zeros: skip their MMAs
+        if (a.ksteps_last < 1 || a.ksteps_last > 4) a.ksteps_last = 4;
         if (!encode_act(&L.tmA_hi, in.p, in_cs, N, H, W, a.P, a.TH + 2)) return false;
         if (!encode_act(&L.tmA_lo, in.p + (plan->planes == 2 ? in.plane : 0), in_cs, N, H, W, a.P, a.TH + 2)) return false;
         if (!encode_w(&L.tmB, p.wp, static_cast<size_t>(plan->planes) * p.KB * 9 * p.cout_pad, L.NT)) return false;
@@ -513,7 +515,7 @@ struct Builder {
         head(p + "/SR", n, N, H, W, 3, pred, next, &R.head[1]);
     }
     // ================================================================ backward (see "Backward pass" in DESIGN.md)
-    size_t max_partial = 0, max_bias_ws = 0;
+    size_t max_partial = 0;
 
     ConvParam* PP(const std::string& name) {
         auto it = ctx->conv_index.find(name);
@@ -544,7 +546,7 @@ struct Builder {
         ConvParam* p = PP(name);
         if (!p || rc != FISR_OK) return;
         WgradLaunch L{};
-        plan_wgrad(N, H, W, p->KB, p->OBk, ctx->num_sms, &L);
+        plan_wgrad(N, H, W, p->KB, p->OBk, ctx->num_sms, ctx->wgrad_exact, &L);
         L.args.err = ctx->d_err; L.args.x_coff = x_off; L.args.dy_coff = dy_off;
         if (!encode_act(&L.tmX_hi, x.p, x_cs, N, H, W, kWgTW + 2, kWgTH + 2)) return;
         if (!encode_act(&L.tmX_lo, x.p + x.plane, x_cs, N, H, W, kWgTW + 2, kWgTH + 2)) return;
@@ -552,21 +554,19 @@ struct Builder {
         if (!encode_act(&L.tmD_lo, dy.p + dy.plane, dy_cs, N, H, W, kWgTW, kWgTH)) return;
         const size_t npix = static_cast<size_t>(N) * H * W;
         max_partial = std::max(max_partial, L.partial_floats);
-        max_bias_ws = std::max(max_bias_ws, bias_grad_workspace(npix, p->cout));
         fisr_ctx* c = ctx;
         Plan* pl = plan;
         BwdOp b;
         b.name = name + " [wgrad]";
         b.flops = 2.0 * 9 * p->cin * p->cout * static_cast<double>(npix);
-        b.launches = 4;
-        b.run = [c, pl, L, p, dy, dy_cs, dy_off, npix](cudaStream_t st) -> int {
+        b.launches = 2;
+        b.run = [c, pl, L, p](cudaStream_t st) -> int {
             WgradLaunch l = L;
             l.args.partial = pl->wg_partial;
+            l.args.bias_partial = pl->wg_partial + l.bias_offset;
             const cudaError_t e = launch_wgrad3x3(l, st);
             if (e != cudaSuccess) return fail(c, FISR_E_CUDA, "wgrad launch failed: %s", cudaGetErrorString(e));
-            const float inv = 1.f / pl->loss_scale;
-            launch_wgrad_reduce(pl->wg_partial, 2 * l.args.S, l.args.cin_pad, l.args.cout_pad, p->cin, p->cout, inv, p->g_w, st);
-            launch_bias_grad(dy.p, dy.plane, dy_cs, dy_off, npix, p->cout, inv, pl->bias_ws, p->g_b, st);
+            launch_wgrad_reduce(l, pl->wg_partial, p->cin, p->cout, 1.f / pl->loss_scale, p->g_w, p->g_b, st);
             return FISR_OK;
         };
         plan->bwd.push_back(std::move(b));
@@ -727,7 +727,6 @@ struct Builder {
             g_next = level_bwd(R, gp, l > 0);
         }
         pl->wg_partial = static_cast<float*>(alloc(max_partial * sizeof(float), false));
-        pl->bias_ws = static_cast<float*>(alloc(max_bias_ws, false));
     }
 };
 
@@ -1458,23 +1457,22 @@ int fisr_wgrad3x3(fisr_ctx* ctx, const float* d_x, const float* d_dy, int N, int
     const int CB = (Cin + 63) / 64, OB = (Cout + 63) / 64;
     ActBuf xin = b.act(N, H, W, CB * 64), dy = b.act(N, H, W, OB * 64);
     WgradLaunch L{};
-    plan_wgrad(N, H, W, CB, OB, ctx->num_sms, &L);
+    plan_wgrad(N, H, W, CB, OB, ctx->num_sms, ctx->wgrad_exact, &L);
     if (const char* e = getenv("FISR_WGRAD_VARIANT")) L.args.variant = atoi(e);
     float* partial = static_cast<float*>(b.alloc(L.partial_floats * 4, false));
     const size_t npix = static_cast<size_t>(N) * H * W;
-    float* bws = static_cast<float*>(b.alloc(bias_grad_workspace(npix, Cout), false));
     if (b.rc != FISR_OK) return b.rc;
     launch_act_from_f32(d_x, Cin, xin, CB * 64, npix, 2, st);
     launch_act_from_f32(d_dy, Cout, dy, OB * 64, npix, 2, st);
-    L.args.partial = partial; L.args.err = ctx->d_err; L.args.x_coff = 0; L.args.dy_coff = 0;
+    L.args.partial = partial; L.args.bias_partial = d_gb ? partial + L.bias_offset : nullptr;
+    L.args.err = ctx->d_err; L.args.x_coff = 0; L.args.dy_coff = 0;
     if (!b.encode_act(&L.tmX_hi, xin.p, CB * 64, N, H, W, kWgTW + 2, kWgTH + 2)) return b.rc;
     if (!b.encode_act(&L.tmX_lo, xin.p + xin.plane, CB * 64, N, H, W, kWgTW + 2, kWgTH + 2)) return b.rc;
     if (!b.encode_act(&L.tmD_hi, dy.p, OB * 64, N, H, W, kWgTW, kWgTH)) return b.rc;
     if (!b.encode_act(&L.tmD_lo, dy.p + dy.plane, OB * 64, N, H, W, kWgTW, kWgTH)) return b.rc;
     CUDA_TRY(ctx, launch_wgrad3x3(L, st));
-    launch_wgrad_reduce(partial, 2 * L.args.S, L.args.cin_pad, L.args.cout_pad, Cin, Cout, scale, d_gw, st);
-    if (d_gb) launch_bias_grad(dy.p, dy.plane, OB * 64, 0, npix, Cout, scale, bws, d_gb, st);
-    ctx->launches += 6;
+    launch_wgrad_reduce(L, partial, Cin, Cout, scale, d_gw, d_gb, st);
+    ctx->launches += 4;
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return check_kernel_error(ctx);
@@ -1702,6 +1700,18 @@ int fisr_set_loss_scale(fisr_ctx* ctx, float scale) {
     ctx->loss_scale_override = scale;
     for (auto& kv : ctx->plans)
         if (kv.second->has_bwd && scale > 0.f) kv.second->loss_scale = scale;
+    return FISR_OK;
+}
+
+int fisr_set_wgrad_exact(fisr_ctx* ctx, int exact) {
+    if (!ctx) return FISR_E_INVALID;
+    if ((exact != 0) != ctx->wgrad_exact) {
+        Guard guard(ctx->device);
+        cudaDeviceSynchronize();
+        ctx->plans.clear();               // backward launch lists bake the choice in
+        ctx->last_plan = nullptr;
+        ctx->wgrad_exact = exact != 0;
+    }
     return FISR_OK;
 }
 

@@ -129,32 +129,37 @@ __global__ void temporal_loss_kernel(const float* __restrict__ pred, const float
 }
 
 // Fixed-order reduction of the block partials of the three scales and the 11 scalars of FISRnet.py:651-657.
+// One block of 32 warps; warp tasks: 21 (scale, term) sums over images and blocks, then B x 7 per-(image, frame) sums
+// for the PSNR.  Lane-strided partial sums + a shuffle tree: the summation order is fixed (deterministic).
 __global__ void loss_finalize_kernel(const double* __restrict__ partial, LossScales sc, int B, LossLambdas lam,
                                      float* __restrict__ out) {
     __shared__ double sums[3][7];
-    __shared__ double psnr_sum;
-    const int t = threadIdx.x;
-    if (t < 21) {                     // 7 terms x 3 scales: summed over images and blocks
-        const int s = t / 7, k = t % 7;
+    __shared__ double psnr_db[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    double db_acc = 0;
+    for (int task = warp; task < 21 + 7 * B; task += nwarp) {
         double v = 0;
-        const double* p = partial + sc.offset[s];
-        for (size_t i = 0; i < static_cast<size_t>(B) * sc.nblk[s]; ++i) v += p[i * kLossTerms + k];
-        sums[s][k] = v;
+        if (task < 21) {                  // 7 terms x 3 scales: summed over images and blocks
+            const int s = task / 7, k = task % 7;
+            const double* p = partial + sc.offset[s];
+            const size_t n = static_cast<size_t>(B) * sc.nblk[s];
+            for (size_t i = lane; i < n; i += 32) v += p[i * kLossTerms + k];
+        } else {                          // train PSNR on the finest scale: per (image, frame) squared error
+            const int b = (task - 21) / 7, f = (task - 21) % 7;
+            const double* p = partial + sc.offset[2] + static_cast<size_t>(b) * sc.nblk[2] * kLossTerms + 7 + f;
+            for (int i = lane; i < sc.nblk[2]; i += 32) v += p[static_cast<size_t>(i) * kLossTerms];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (task < 21) { if (lane == 0) sums[task / 7][task % 7] = v; }
+        else db_acc += 10.0 * log10(1.0 / (v / (static_cast<double>(sc.hw[2]) * 3)));      // MSE -> dB (tf.image.psnr, max_val 1)
     }
-    if (t == 31) {                    // train PSNR on the finest scale: per (image, frame) MSE -> dB -> mean
-        double acc = 0;
-        const double* p = partial + sc.offset[2];
-        const double n = static_cast<double>(sc.hw[2]) * 3;
-        for (int b = 0; b < B; ++b)
-            for (int f = 0; f < 7; ++f) {
-                double v = 0;
-                for (int i = 0; i < sc.nblk[2]; ++i) v += p[(static_cast<size_t>(b) * sc.nblk[2] + i) * kLossTerms + 7 + f];
-                acc += 10.0 * log10(1.0 / (v / n));
-            }
-        psnr_sum = acc / (7.0 * B);
-    }
+    if (lane == 0) psnr_db[warp] = db_acc;
     __syncthreads();
-    if (t == 0) {
+    if (threadIdx.x == 0) {
+        double psnr_sum = 0;
+        for (int w = 0; w < nwarp; ++w) psnr_sum += psnr_db[w];
+        psnr_sum /= 7.0 * B;
         const double wgt[3] = {4.0, 2.0, 1.0};                      // l1, l2, l3  (FISRnet.py:326-328)
         double term[7] = {0, 0, 0, 0, 0, 0, 0};
         for (int s = 0; s < 3; ++s) {
@@ -170,7 +175,6 @@ __global__ void loss_finalize_kernel(const double* __restrict__ partial, LossSca
         out[10] = psnr_sum;
     }
 }
-
 
 // ---------------------------------------------------------------- d total_loss / d pred (FISRnet.py:312-484, autodiff of)
 // One scale.  Thread = (image b, pixel p): the 36 derivatives wrt the 9 window frames P and the 3 stride-2 frames S,
@@ -188,6 +192,7 @@ __global__ void loss_grad_kernel(const float* __restrict__ pred, const float* __
     if (p >= hw) return;
     const int y = p / ws, x = p % ws;
     const float* lab = label + ((static_cast<size_t>(b) * LH + static_cast<size_t>(y) * st) * LW + static_cast<size_t>(x) * st) * 21;
+    float gr[12][3];                   // d loss / d (frame q, colour c), q = 9 window frames then 3 stride-2 frames
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float P[9], S[3], G[7], O[7], dP[9], dS[3], dO[7];
@@ -228,17 +233,27 @@ __global__ void loss_grad_kernel(const float* __restrict__ pred, const float* __
         dP[0] += dO[0]; dP[1] += dO[1]; dP[2] += 0.5f * dO[2]; dP[3] += 0.5f * dO[2]; dP[4] += dO[3];             // Groups2Ovlp
         dP[5] += 0.5f * dO[4]; dP[6] += 0.5f * dO[4]; dP[7] += dO[5]; dP[8] += dO[6];
 #pragma unroll
-        for (int q = 0; q < 12; ++q) {
-            const int pass = q < 9 ? q / 3 : 3, f = q < 9 ? q % 3 : q - 9;
-            const int j = 3 * f + c;                                    // pred channel
-            const size_t img = (static_cast<size_t>(pass) * B + b) * hw + p;
-            float g = q < 9 ? dP[q] : dS[q - 9];
-            if (extra) g += join_f16(extra[img * 64 + 29 + j], extra[extra_plane + img * 64 + 29 + j]);
-            const int ch = j < 3 ? j : (j < 6 ? 64 + (j - 3) : j - 3);
-            const SplitHalf sh = split_f32(g);
-            out[img * 128 + ch] = sh.hi;
-            out[out_plane + img * 128 + ch] = sh.lo;
+        for (int q = 0; q < 12; ++q) gr[q][c] = q < 9 ? dP[q] : dS[q - 9];
+    }
+    // one image (pass, b) at a time: pred channels j = 3f + c -> FI-SR's dy in channels 0..5 (pred 0,1,2,6,7,8; one
+    // 16-byte store per plane), SR's in channels 64..66 (pred 3,4,5; one 8-byte store per plane)
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+        const size_t img = (static_cast<size_t>(pass) * B + b) * hw + p;
+        float g[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) g[j] = gr[pass * 3 + j / 3][j % 3];
+        if (extra) {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) g[j] += join_f16(extra[img * 64 + 29 + j], extra[extra_plane + img * 64 + 29 + j]);
         }
+        const float fi[8] = {g[0], g[1], g[2], g[6], g[7], g[8], 0.f, 0.f};
+        store8<2>(out + img * 128, out_plane, fi);
+        uint32_t h01, l01, h23, l23;
+        split2_f32(g[3], g[4], h01, l01);
+        split2_f32(g[5], 0.f, h23, l23);
+        *reinterpret_cast<uint2*>(out + img * 128 + 64) = make_uint2(h01, h23);
+        *reinterpret_cast<uint2*>(out + out_plane + img * 128 + 64) = make_uint2(l01, l23);
     }
 }
 
@@ -415,7 +430,7 @@ void launch_temporal_loss(const float* const pred[3], const float* label, int B,
         dim3 grid(sc.nblk[s], B);
         temporal_loss_kernel<<<grid, 256, 0, st>>>(pred[s], label, B, hs, ws, 4 >> s, 2 * h, 2 * w, workspace + sc.offset[s]);
     }
-    loss_finalize_kernel<<<1, 32, 0, st>>>(workspace, sc, B, lam, d_out);
+    loss_finalize_kernel<<<1, 1024, 0, st>>>(workspace, sc, B, lam, d_out);
 }
 
 void launch_loss_grad(const float* pred, const float* label, ActBuf extra, int B, int hs, int ws, int st, int LH, int LW,

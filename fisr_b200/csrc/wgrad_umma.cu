@@ -11,7 +11,8 @@
 //
 // Split operands: A = [dy_hi ; dy_lo] stacked along M (two 64-channel chunks, LBO = plane distance), B = x_hi,
 // then B = x_lo, all into the same accumulator: lanes 0-63 hold dy_hi * x, lanes 64-127 hold dy_lo * x, and the
-// reduction kernel adds the halves -- the full (hi+lo)*(hi+lo) product with two M=128 MMAs per K slice.
+// reduction kernel adds the halves -- the full (hi+lo)*(hi+lo) product with two M=128 MMAs per K slice.  Layers with
+// many pixels skip the x_lo MMA (and never load that plane): see plan_wgrad.
 //
 // TMEM: 64 fp32 columns per tap, so a CTA owns taps 0-4 or 5-8 of one (Cout block, Cin block) pair and a share of
 // the pixel tiles (split-K); partial sums go to a slot buffer that `wgrad_reduce_kernel` folds in a fixed order
@@ -30,6 +31,7 @@ enum { WERR_EMPTY = 41, WERR_FULL = 42, WERR_ACC = 43 };
 // kind::f16 instruction descriptor with both operands MN-major (bits 15, 16), fp16 in, fp32 accumulate
 __host__ __device__ constexpr uint32_t wg_idesc(uint32_t m, uint32_t n) { return umma_idesc_f16(m, n) | (1u << 15) | (1u << 16); }
 
+template <bool XLO>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
                      const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CUtensorMap tmD_lo,
@@ -37,10 +39,12 @@ wgrad3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t s0 = smem_u32(smem);
-    constexpr uint32_t STAGE = 2 * (kWgXPlane + kWgDPlane);
+    constexpr int kWgStages = XLO ? kWgStagesXlo : kWgStagesHi;
+    constexpr int XPL = XLO ? 2 : 1;                       // x planes staged per tile
+    constexpr uint32_t STAGE = XPL * kWgXPlane + 2 * kWgDPlane;
     auto sXhi = [&](int s) { return s0 + s * STAGE; };
     auto sXlo = [&](int s) { return s0 + s * STAGE + kWgXPlane; };
-    auto sDhi = [&](int s) { return s0 + s * STAGE + 2 * kWgXPlane; };
+    auto sDhi = [&](int s) { return s0 + s * STAGE + XPL * kWgXPlane; };
 
     __shared__ __align__(8) uint64_t bars[2 * kWgStages + 1];
     __shared__ uint32_t tmem_slot;
@@ -60,8 +64,11 @@ wgrad3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
     const int split = item / a.OB;
     const int t0 = tg == 0 ? 0 : 5, t1 = tg == 0 ? 5 : 9;
 
+    // CTAs of Cin block 0 / tap group 0 also sum their dy tiles over the pixels (bias gradient) on the epilogue warps,
+    // which otherwise idle until the accumulator is complete; those warps then take part in releasing a stage.
+    const bool do_bias = a.bias_partial != nullptr && cb == 0 && tg == 0;
     if (tid == 0) {
-        for (int s = 0; s < kWgStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        for (int s = 0; s < kWgStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), do_bias ? 5 : 1); }
         mbar_init(acc_full, 1);
         fence_mbar_init();
         tma_prefetch_desc(&tmX_hi); tma_prefetch_desc(&tmX_lo); tma_prefetch_desc(&tmD_hi); tma_prefetch_desc(&tmD_lo);
@@ -81,9 +88,9 @@ wgrad3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
                 const int r = tile / a.tiles_x;
                 const int ty = r % a.tiles_y, n = r / a.tiles_y;
                 const int x0 = tx * kWgTW, y0 = ty * kWgTH;
-                mbar_expect_tx(full(st), 2 * (kWgXBox + kWgDPlane));
+                mbar_expect_tx(full(st), XPL * kWgXBox + 2 * kWgDPlane);
                 tma_load_4d(sXhi(st), &tmX_hi, full(st), a.x_coff + cb * 64, x0 - 1, y0 - 1, n);
-                tma_load_4d(sXlo(st), &tmX_lo, full(st), a.x_coff + cb * 64, x0 - 1, y0 - 1, n);
+                if (XLO) tma_load_4d(sXlo(st), &tmX_lo, full(st), a.x_coff + cb * 64, x0 - 1, y0 - 1, n);
                 tma_load_4d(sDhi(st), &tmD_hi, full(st), a.dy_coff + ob * 64, x0, y0, n);
                 tma_load_4d(sDhi(st) + kWgDPlane, &tmD_lo, full(st), a.dy_coff + ob * 64, x0, y0, n);
                 if (++st == kWgStages) { st = 0; ph ^= 1; }
@@ -116,7 +123,7 @@ wgrad3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
                         const uint32_t ao = ty * (kWgTW * 128 / 16);                               // 16 rows of 128 B, >> 4
                         const uint32_t bo = static_cast<uint32_t>((ty + ky) * (kWgTW + 2) + kx) * 8u;
                         umma_f16_lohi(d_tmem, dA + ao, dBh + bo, desc_hi, idesc, ty == 0 ? first : 1u);
-                        umma_f16_lohi(d_tmem, dA + ao, dBl + bo, desc_hi, idesc, 1u);
+                        if (XLO) umma_f16_lohi(d_tmem, dA + ao, dBl + bo, desc_hi, idesc, 1u);
                     }
                 }
                 umma_commit(empty(st));
@@ -132,7 +139,49 @@ wgrad3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
         const int half = r >> 6, co = r & 63;
         const bool have_tiles = split < a.num_tiles;
         bool ok = true;
-        if (have_tiles) ok = __all_sync(0xffffffffu, mbar_wait(acc_full, 0, a.err, WERR_ACC));
+        if (do_bias) {
+            // thread e: 16-byte chunk c (8 channels) of rows rg, rg+16, ..; chunk c of row r sits at c ^ (r & 7) (128B swizzle)
+            const int e = tid - 64, c = e & 7, rg = e >> 3;
+            const uint32_t off = rg * 128 + ((c ^ (rg & 7)) << 4);
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+            uint32_t st = 0, ph = 0;
+            for (int tile = split; tile < a.num_tiles && ok; tile += a.S) {
+                ok = __all_sync(0xffffffffu, mbar_wait(full(st), ph, a.err, WERR_FULL));
+                if (!ok) break;
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        uint32_t w0, w1, w2, w3;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                                     : "r"(sDhi(st) + pl * kWgDPlane + off + i * 2048) : "memory");
+                        const uint32_t wv[4] = {w0, w1, w2, w3};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wv[q]));
+                            acc[2 * q] += f.x;
+                            acc[2 * q + 1] += f.y;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty(st));
+                if (++st == kWgStages) { st = 0; ph ^= 1; }
+            }
+            __shared__ float bsum[16][64];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bsum[rg][c * 8 + j] = acc[j];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (e < 64) {
+                float v = 0.f;
+#pragma unroll
+                for (int g = 0; g < 16; ++g) v += bsum[g][e];
+                a.bias_partial[static_cast<size_t>(split) * a.cout_pad + ob * 64 + e] = v;
+            }
+        }
+        if (have_tiles && ok) ok = __all_sync(0xffffffffu, mbar_wait(acc_full, 0, a.err, WERR_ACC));
         tc_fence_after();
         float* dst = a.partial + (static_cast<size_t>(2 * split + half) * 9) * a.cin_pad * a.cout_pad + ob * 64 + co;
         for (int t = t0; t < t1; ++t) {
@@ -158,10 +207,19 @@ wgrad3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
 }
 
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int slots, int cin_pad, int cout_pad, int cin, int cout,
-                                    float scale, float* __restrict__ g) {
+                                    float scale, float* __restrict__ g, const float* __restrict__ bias_partial, int splits,
+                                    float* __restrict__ gb) {
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     const size_t total = static_cast<size_t>(9) * cin * cout;
-    if (i >= total) return;
+    if (i >= total) {
+        const size_t co = i - total;          // trailing threads fold the bias-gradient partials of the splits
+        if (gb && co < static_cast<size_t>(cout)) {
+            float acc = 0.f;
+            for (int s = 0; s < splits; ++s) acc += bias_partial[static_cast<size_t>(s) * cout_pad + co];
+            gb[co] = acc * scale;
+        }
+        return;
+    }
     const int co = i % cout;
     size_t r = i / cout;
     const int ci = r % cin;
@@ -173,40 +231,9 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int slots
     g[i] = acc * scale;
 }
 
-// Column sums of a (hi, lo) gradient tensor: stage 1 = one block per 256 pixels, thread = channel; stage 2 folds the
-// block partials in order.
-__global__ void bias_grad_partial_kernel(const __half* __restrict__ dy, size_t plane, int cs, int coff, size_t npix, int cout,
-                                         float* __restrict__ ws) {
-    const int c = threadIdx.x;
-    if (c >= cout) return;
-    const size_t p0 = static_cast<size_t>(blockIdx.x) * 256;
-    const size_t p1 = p0 + 256 < npix ? p0 + 256 : npix;
-    float acc = 0.f;
-    for (size_t p = p0; p < p1; ++p) {
-        const size_t o = p * cs + coff + c;
-        acc += __half2float(dy[o]) + __half2float(dy[plane + o]);
-    }
-    ws[static_cast<size_t>(blockIdx.x) * cout + c] = acc;
-}
-__global__ void bias_grad_final_kernel(const float* __restrict__ ws, int nblk, int cout, float scale, float* __restrict__ gb) {
-    const int c = blockIdx.x;
-    double acc = 0;
-    for (int b = threadIdx.x; b < nblk; b += blockDim.x) acc += ws[static_cast<size_t>(b) * cout + c];
-    __shared__ double red[8];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double v = 0;
-        for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) v += red[w];
-        gb[c] = static_cast<float>(v * scale);
-    }
-}
-
 }  // namespace
 
-void plan_wgrad(int N, int H, int W, int CB, int OB, int num_sms, WgradLaunch* L) {
+void plan_wgrad(int N, int H, int W, int CB, int OB, int num_sms, bool exact, WgradLaunch* L) {
     WgradArgs& a = L->args;
     a.N = N; a.H = H; a.W = W; a.CB = CB; a.OB = OB;
     a.tiles_x = (W + kWgTW - 1) / kWgTW;
@@ -220,34 +247,36 @@ void plan_wgrad(int N, int H, int W, int CB, int OB, int num_sms, WgradLaunch* L
     a.cin_pad = CB * 64; a.cout_pad = OB * 64;
     a.lbo_a = kWgDPlane >> 4;
     a.variant = 0;
+    // x's lo plane: leaving it out rounds the forward activation to fp16 inside this product only, a zero-mean term of
+    // relative size <= 2^-12 per summand (measured: ~1e-4 of a weight-gradient tensor, the level the tensor core's
+    // truncating fp32 accumulation already sets, tools/accum_probe.py) for half the MMAs and 30 % less smem traffic.
+    // dy keeps both planes (gradients span many octaves).  Small layers cost nothing: they keep the exact product.
+    L->x_lo = exact || static_cast<long long>(N) * H * W < kWgXloMaxPixels;
     L->grid = per_split * S;
-    L->partial_floats = static_cast<size_t>(2 * S) * 9 * a.cin_pad * a.cout_pad;
+    L->bias_offset = static_cast<size_t>(2 * S) * 9 * a.cin_pad * a.cout_pad;
+    L->partial_floats = L->bias_offset + static_cast<size_t>(S) * a.cout_pad;
 }
 
 cudaError_t wgrad3x3_init() {
-    return cudaFuncSetAttribute(wgrad3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
+    cudaError_t e = cudaFuncSetAttribute(wgrad3x3_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemXlo);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(wgrad3x3_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemHi);
+    return e;
 }
 
 cudaError_t launch_wgrad3x3(const WgradLaunch& L, cudaStream_t stream) {
-    wgrad3x3_umma_kernel<<<L.grid, kWgThreads, kWgSmem, stream>>>(L.tmX_hi, L.tmX_lo, L.tmD_hi, L.tmD_lo, L.args);
+    if (L.x_lo)
+        wgrad3x3_umma_kernel<true><<<L.grid, kWgThreads, kWgSmemXlo, stream>>>(L.tmX_hi, L.tmX_lo, L.tmD_hi, L.tmD_lo, L.args);
+    else
+        wgrad3x3_umma_kernel<false><<<L.grid, kWgThreads, kWgSmemHi, stream>>>(L.tmX_hi, L.tmX_lo, L.tmD_hi, L.tmD_lo, L.args);
     return cudaGetLastError();
 }
 
-void launch_wgrad_reduce(const float* partial, int slots, int cin_pad, int cout_pad, int cin, int cout, float scale, float* g,
+void launch_wgrad_reduce(const WgradLaunch& L, const float* partial, int cin, int cout, float scale, float* g, float* gb,
                          cudaStream_t st) {
-    const size_t total = static_cast<size_t>(9) * cin * cout;
-    wgrad_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(partial, slots, cin_pad, cout_pad, cin, cout,
-                                                                                    scale, g);
-}
-
-size_t bias_grad_workspace(size_t npix, int cout) { return ((npix + 255) / 256) * cout * sizeof(float); }
-
-void launch_bias_grad(const __half* dy, size_t plane, int cs, int coff, size_t npix, int cout, float scale, float* workspace,
-                      float* gb, cudaStream_t st) {
-    const int nblk = static_cast<int>((npix + 255) / 256);
-    const int threads = (cout + 31) / 32 * 32;
-    bias_grad_partial_kernel<<<nblk, threads, 0, st>>>(dy, plane, cs, coff, npix, cout, workspace);
-    bias_grad_final_kernel<<<cout, 256, 0, st>>>(workspace, nblk, cout, scale, gb);
+    const size_t total = static_cast<size_t>(9) * cin * cout + (gb ? cout : 0);
+    wgrad_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+        partial, 2 * L.args.S, L.args.cin_pad, L.args.cout_pad, cin, cout, scale, g, partial + L.bias_offset, L.args.S, gb);
 }
 
 }  // namespace fisr

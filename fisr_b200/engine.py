@@ -348,6 +348,11 @@ class Engine:
     def set_loss_scale(self, scale: float) -> None:
         self._check(self.lib.fisr_set_loss_scale(self.h, float(scale)), "fisr_set_loss_scale")
 
+    def set_wgrad_exact(self, exact: bool) -> None:
+        """Weight gradients with both planes of the forward activation everywhere (default: hi plane only for layers
+        with >= 16384 pixels)."""
+        self._check(self.lib.fisr_set_wgrad_exact(self.h, int(bool(exact))), "fisr_set_wgrad_exact")
+
     def profile_train(self, B: int, h: int, w: int, reps: int = 2):
         """Per-op device time of the backward pass (after one :meth:`train_backward` at that shape)."""
         torch.cuda.synchronize(self.device)

@@ -142,6 +142,9 @@ int fisr_train_step(fisr_ctx* ctx, const float* d_data, const float* d_flow, con
  * makes fisr_train_backward return FISR_E_KERNEL. */
 int fisr_set_loss_scale(fisr_ctx* ctx, float scale);
 float fisr_get_loss_scale(fisr_ctx* ctx, int B, int h, int w);
+/* Weight gradients of layers with >= 16384 pixels multiply dy (hi, lo) by the hi plane of the forward activation only
+ * (half the MMAs; adds ~1e-4 relative rounding noise per gradient tensor).  exact = 1 uses both planes everywhere. */
+int fisr_set_wgrad_exact(fisr_ctx* ctx, int exact);
 long long fisr_adam_steps(const fisr_ctx* ctx);
 int fisr_adam_reset(fisr_ctx* ctx, long long step);
 

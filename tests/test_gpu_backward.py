@@ -58,6 +58,27 @@ def test_gradients_match_float64_autograd(engine, B, h, w, seed):
     assert all(np.abs(v).max() > 0 for v in engine.get_grads().values())
 
 
+def test_exact_wgrad_mode(engine):
+    """fisr_set_wgrad_exact: both planes of x in every weight gradient; the default drops x's lo plane on big layers."""
+    engine.set_precision("f16x3")
+    params = O.init_params(71)
+    engine.set_params(params)
+    batch = _batch(2, 64, 64, 72)                      # level-3 layers have 8 * 64 * 64 = 32768 pixels: fast path by default
+    p64 = {k: v.double() for k, v in params.items()}
+    _, _, ref_g = L.training_forward(p64, *[t.double() for t in batch], grad=True)
+    dev = [t.cuda() for t in batch]
+    engine.train_backward(*dev)
+    fast = _grad_errors(engine.get_grads(), ref_g)[1]
+    engine.set_wgrad_exact(True)
+    try:
+        engine.train_backward(*dev)
+        exact = _grad_errors(engine.get_grads(), ref_g)[1]
+    finally:
+        engine.set_wgrad_exact(False)
+    print("whole-gradient relative L2 error: default %.3e, exact wgrad %.3e" % (fast, exact))
+    assert exact < 5e-4 and fast < 1e-3
+
+
 def test_custom_lambdas_and_loss_scale_invariance(engine):
     engine.set_precision("f16x3")
     params = O.init_params(41)
