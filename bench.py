@@ -258,7 +258,7 @@ def run_b200(args):
         all_ms = sum(o["ms"] for o in ops)
         conv_flops = sum(o["flops"] for o in conv)
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12
-        mma_factor = 3 if eng.precision == "f16x3" else 1
+        mma_factor = {"f16x3": 3, "f16f8": 2, "f16": 1}[eng.precision]      # tensor-pipe time per K slice in fp16-rate MMA units
         top = max(conv, key=lambda o: o["ms"])
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["tflops_sustained"], "traffic": None,
@@ -273,7 +273,7 @@ def run_b200(args):
         info = eng.plan_info(T, 544, 992)
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warm,
                 "ms_per_step": t_s / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 via fp16 (hi,lo) split operands, fp32 accumulate" if eng.precision == "f16x3" else "f16 operands, f32 accumulate",
+                "dtype": {"f16x3": "f32 via fp16 (hi,lo) split operands, fp32 accumulate", "f16f8": "f32 via fp16 main term + fp8 (e5m2 x e4m3) cross terms, fp32 accumulate", "f16": "f16 operands, f32 accumulate"}[eng.precision],
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "windows_per_step": B, "units_per_rank_per_step": len(my_units),
                            "input": f"{B} x (frames u8 [1080,1920,9] + flow f32 [..,8] + warp f32 [..,12])",
@@ -303,7 +303,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="f16x3", choices=["f16x3", "f16"],
+    ap.add_argument("--precision", default="f16x3", choices=["f16x3", "f16", "f16f8"],
                     help="f16x3 = fp32-class parity mode (default, what the parity tests hold to 1e-4); f16 = fast mode")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     args = ap.parse_args()

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libfisr_b200.so")
 FISR_OK = 0
 PREC_F16X3 = 0      # fp16 (hi, lo) split operands, fp32-class result (default)
 PREC_F16 = 1        # single fp16 operands, fast mode
+PREC_F16F8 = 2      # fp16 main term + fp8 cross terms (2 MMA units per K slice), inference only
 
 _lib: Optional[C.CDLL] = None
 

@@ -21,6 +21,10 @@ __device__ __forceinline__ void load8(const __half* p, size_t plane, float (&f)[
         unpack8(*reinterpret_cast<const uint4*>(p + plane), l);
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = join_f16(h[i], l[i]);
+    } else if (PLANES == 3) {
+        const uint2 b = *reinterpret_cast<const uint2*>(f8_row_ptr(p + plane));      // 8 e5m2 bytes of 16 * lo
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = join_f8(h[i], static_cast<uint8_t>(((i < 4 ? b.x : b.y) >> (8 * (i & 3))) & 0xFF));
     } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = __half2float(h[i]);
@@ -33,6 +37,11 @@ __device__ __forceinline__ void store8(__half* p, size_t plane, const float (&f)
     for (int q = 0; q < 4; ++q) split2_f32(f[2 * q], f[2 * q + 1], hi[q], lo[q]);
     *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     if (PLANES == 2) *reinterpret_cast<uint4*>(p + plane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    if (PLANES == 3) {
+        uint8_t* q = f8_row_ptr(p + plane);
+        *reinterpret_cast<uint2*>(q) = make_uint2(f8_pack_lo4(lo[0], lo[1]), f8_pack_lo4(lo[2], lo[3]));
+        *reinterpret_cast<uint2*>(q + 64) = make_uint2(f8_pack_hi4(hi[0], hi[1]), f8_pack_hi4(hi[2], hi[3]));
+    }
 }
 
 }  // namespace fisr

@@ -25,6 +25,15 @@ __global__ void prep_weights_kernel(const float* __restrict__ w, __half* __restr
     const int ci = kb * 64 + cl;
     float v = 0.f;
     if (ci < cin && co < cout) v = w[(static_cast<size_t>(tap) * cin + ci) * cout + co];
+    if (planes == 3) {   // f16f8: fp16(128 w) plane + 8-bit rows [e4m3(wh / 16) x 64 | e5m2(128 w - wh) x 64] (common.cuh)
+        const float ws = v * kF8WScale;
+        const __half wh = __float2half_rn(ws);
+        out[i] = wh;
+        uint8_t* row = reinterpret_cast<uint8_t*>(out + per_plane) + (i >> 6) * 128;
+        row[cl] = static_cast<uint8_t>(__nv_cvt_float_to_fp8(__half2float(wh) * (kF8WHiScale / kF8WScale), __NV_SATFINITE, __NV_E4M3));
+        row[64 + cl] = static_cast<uint8_t>(__nv_cvt_float_to_fp8(ws - __half2float(wh), __NV_SATFINITE, __NV_E5M2));
+        return;
+    }
     const SplitHalf s = split_f32(v);
     out[i] = s.hi;
     if (planes == 2) out[per_plane + i] = s.lo;
@@ -45,18 +54,28 @@ __global__ void pack_input_kernel(const float* __restrict__ img, int N, int H, i
     const int x = pix % W;
     const int y = (pix / W) % H;
     const int n = pix / (static_cast<size_t>(W) * H);
-    const SplitHalf s = split_f32(img[pix * cin + c]);
+    const float v = img[pix * cin + c];
+    const SplitHalf s = split_f32(v);
+    const uint8_t b_lo = PLANES == 3 ? f8_lo_byte(v - __half2float(s.hi)) : 0, b_hi = PLANES == 3 ? f8_hi_byte(v) : 0;
+    auto put8 = [&](__half* plane1, size_t q) {       // 8-bit row of pixel q (64 channels = one block)
+        uint8_t* row = reinterpret_cast<uint8_t*>(plane1 + q * 64);
+        row[c] = b_lo;
+        row[64 + c] = b_hi;
+    };
     l3[pix * 64 + c] = s.hi;
     if (PLANES == 2) l3[p3 + pix * 64 + c] = s.lo;
+    if (PLANES == 3) put8(l3 + p3, pix);
     if (((x | y) & 1) == 0) {
         const size_t q = (static_cast<size_t>(n) * (H / 2) + y / 2) * (W / 2) + x / 2;
         l2[q * 64 + c] = s.hi;
         if (PLANES == 2) l2[p2 + q * 64 + c] = s.lo;
+        if (PLANES == 3) put8(l2 + p2, q);
     }
     if (((x | y) & 3) == 0) {
         const size_t q = (static_cast<size_t>(n) * (H / 4) + y / 4) * (W / 4) + x / 4;
         l1[q * 64 + c] = s.hi;
         if (PLANES == 2) l1[p1 + q * 64 + c] = s.lo;
+        if (PLANES == 3) put8(l1 + p1, q);
     }
 }
 
@@ -135,6 +154,11 @@ __global__ void act_from_f32_kernel(const float* __restrict__ src, int C, __half
     const SplitHalf s = split_f32(v);
     dst[i] = s.hi;
     if (PLANES == 2) dst[plane + i] = s.lo;
+    if (PLANES == 3) {
+        uint8_t* q = f8_row_ptr(dst + plane + i);
+        q[0] = f8_lo_byte(v - __half2float(s.hi));
+        q[64] = f8_hi_byte(v);
+    }
 }
 template <int PLANES>
 __global__ void act_to_f32_kernel(const __half* __restrict__ src, size_t plane, int cs, int coff, float* __restrict__ dst,
@@ -144,7 +168,8 @@ __global__ void act_to_f32_kernel(const __half* __restrict__ src, size_t plane, 
     const int c = i % C;
     const size_t pix = i / C;
     const size_t s = pix * cs + coff + c;
-    dst[i] = PLANES == 2 ? join_f16(src[s], src[plane + s]) : __half2float(src[s]);
+    dst[i] = PLANES == 2 ? join_f16(src[s], src[plane + s])
+             : PLANES == 3 ? join_f8(src[s], *f8_row_ptr(src + plane + s)) : __half2float(src[s]);
 }
 
 // ---------------------------------------------------------------- tiled video path
@@ -324,7 +349,10 @@ void launch_prep_weights(const float* w, __half* out, int cin, int cout, int KB,
 void launch_pack_input(const float* img, int N, int H, int W, int cin, ActBuf l3, ActBuf l2, ActBuf l1, int planes,
                        cudaStream_t st) {
     const size_t total = static_cast<size_t>(N) * H * W * 32;
-    if (planes == 2)
+    if (planes == 3)
+        pack_input_kernel<3><<<blocks_for(total, 256), 256, 0, st>>>(img, N, H, W, cin, l3.p, l3.plane, l2.p, l2.plane,
+                                                                     l1.p, l1.plane);
+    else if (planes == 2)
         pack_input_kernel<2><<<blocks_for(total, 256), 256, 0, st>>>(img, N, H, W, cin, l3.p, l3.plane, l2.p, l2.plane,
                                                                      l1.p, l1.plane);
     else
@@ -334,7 +362,9 @@ void launch_pack_input(const float* img, int N, int H, int W, int cin, ActBuf l3
 
 void launch_upsample2(ActBuf in, ActBuf out, int N, int h, int w, int C, int planes, cudaStream_t st) {
     const size_t total = static_cast<size_t>(N) * 4 * h * w * (C / 8);
-    if (planes == 2)
+    if (planes == 3)
+        upsample2_kernel<3><<<blocks_for(total, 256), 256, 0, st>>>(in.p, in.plane, out.p, out.plane, N, h, w, C);
+    else if (planes == 2)
         upsample2_kernel<2><<<blocks_for(total, 256), 256, 0, st>>>(in.p, in.plane, out.p, out.plane, N, h, w, C);
     else
         upsample2_kernel<1><<<blocks_for(total, 256), 256, 0, st>>>(in.p, in.plane, out.p, out.plane, N, h, w, C);
@@ -342,21 +372,27 @@ void launch_upsample2(ActBuf in, ActBuf out, int N, int h, int w, int C, int pla
 
 void launch_maxpool2(ActBuf in, int cs, int coff, ActBuf out, int N, int H, int W, int C, int planes, cudaStream_t st) {
     const size_t total = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
-    if (planes == 2)
+    if (planes == 3)
+        maxpool2_kernel<3><<<blocks_for(total, 256), 256, 0, st>>>(in.p, in.plane, cs, coff, out.p, out.plane, N, H, W, C);
+    else if (planes == 2)
         maxpool2_kernel<2><<<blocks_for(total, 256), 256, 0, st>>>(in.p, in.plane, cs, coff, out.p, out.plane, N, H, W, C);
     else
         maxpool2_kernel<1><<<blocks_for(total, 256), 256, 0, st>>>(in.p, in.plane, cs, coff, out.p, out.plane, N, H, W, C);
 }
 
 void launch_act_from_f32(const float* src, int C, ActBuf dst, int cs, size_t npix, int planes, cudaStream_t st) {
-    if (planes == 2)
+    if (planes == 3)
+        act_from_f32_kernel<3><<<blocks_for(npix * cs, 256), 256, 0, st>>>(src, C, dst.p, dst.plane, cs, npix);
+    else if (planes == 2)
         act_from_f32_kernel<2><<<blocks_for(npix * cs, 256), 256, 0, st>>>(src, C, dst.p, dst.plane, cs, npix);
     else
         act_from_f32_kernel<1><<<blocks_for(npix * cs, 256), 256, 0, st>>>(src, C, dst.p, dst.plane, cs, npix);
 }
 
 void launch_act_to_f32(ActBuf src, int cs, int coff, float* dst, int C, size_t npix, int planes, cudaStream_t st) {
-    if (planes == 2)
+    if (planes == 3)
+        act_to_f32_kernel<3><<<blocks_for(npix * C, 256), 256, 0, st>>>(src.p, src.plane, cs, coff, dst, C, npix);
+    else if (planes == 2)
         act_to_f32_kernel<2><<<blocks_for(npix * C, 256), 256, 0, st>>>(src.p, src.plane, cs, coff, dst, C, npix);
     else
         act_to_f32_kernel<1><<<blocks_for(npix * C, 256), 256, 0, st>>>(src.p, src.plane, cs, coff, dst, C, npix);
@@ -365,7 +401,10 @@ void launch_act_to_f32(ActBuf src, int cs, int coff, float* dst, int C, size_t n
 void launch_tile_pack(const uint8_t* frames, const float* flow, const float* warp, int fh, int fw, const TileList& tiles,
                       int th, int tw, const float* lut255, ActBuf l3, ActBuf l2, ActBuf l1, int planes, cudaStream_t st) {
     const size_t total = static_cast<size_t>(tiles.count) * th * tw * 4;
-    if (planes == 2)
+    if (planes == 3)
+        tile_pack_kernel<3><<<blocks_for(total, 256), 256, 0, st>>>(frames, flow, warp, fh, fw, tiles, th, tw, lut255, l3.p,
+                                                                    l3.plane, l2.p, l2.plane, l1.p, l1.plane);
+    else if (planes == 2)
         tile_pack_kernel<2><<<blocks_for(total, 256), 256, 0, st>>>(frames, flow, warp, fh, fw, tiles, th, tw, lut255, l3.p,
                                                                     l3.plane, l2.p, l2.plane, l1.p, l1.plane);
     else

@@ -5,6 +5,7 @@
 #include <string>
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
 namespace fisr {
@@ -13,7 +14,20 @@ namespace fisr {
 //   F16X3: activations and weights are stored as an fp16 (hi, lo) pair, x = hi + lo (22-bit mantissa);
 //          each K-slice issues 3 MMAs hi*hi + lo*hi + hi*lo with fp32 TMEM accumulation (fp32-class result).
 //   F16  : hi plane only, 1 MMA per K-slice (fast mode, ~7e-4 max-abs on the 138-conv cascade).
-enum Precision { PREC_F16X3 = 0, PREC_F16 = 1 };
+//   F16F8: fp16 hi plane + an 8-bit plane; the main product hi*hi runs as fp16 MMAs, the two cross terms lo*hi + hi*lo as
+//          fp8 MMAs (kind::f8f6f4, twice the fp16 rate) into the same accumulator: 2 MMA units per K-slice instead of 3.
+//          The cross terms are ~2^-11 of the main term, so their 2..3-bit mantissas leave ~2^-14 relative error per conv
+//          (tools/precision_study_fp8.py: 2.5e-5 max-abs on the 138-conv cascade, 40x inside the 1e-3 bar).
+//          8-bit plane of an activation, per pixel and 64-channel block (128 B, same footprint as the fp16 lo plane):
+//              bytes [0,64)  = e5m2(16 * lo[c])      bytes [64,128) = e4m3(hi[c])
+//          weights: fp16 plane = fp16(128 * w) =: wh, 8-bit plane row = [e4m3(wh / 16) x 64 | e5m2(128 w - wh) x 64];
+//          every product term carries the factor 128, which the epilogue removes.
+enum Precision { PREC_F16X3 = 0, PREC_F16 = 1, PREC_F16F8 = 2 };
+constexpr float kF8ActLoScale = 16.f;     // activation lo part -> e5m2
+constexpr float kF8WScale = 128.f;        // weights -> fp16 plane and e5m2 lo part
+constexpr float kF8WHiScale = 8.f;        // weight hi part -> e4m3   (16 * 8 = 1 * 128 = 128)
+// number of 2-byte planes an activation buffer holds for a given kernel PLANES parameter (1 = f16, 2 = f16x3, 3 = f16f8)
+__host__ __device__ constexpr int act_planes(int planes) { return planes == 1 ? 1 : 2; }
 
 struct SplitHalf {
     __half hi, lo;
@@ -35,6 +49,38 @@ __device__ __forceinline__ void split2_f32(float x0, float x1, uint32_t& hi, uin
 }
 __device__ __forceinline__ float join_f16(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
 
+// ---- F16F8 8-bit plane helpers
+// Byte address of the 8-bit row entry that belongs to the element p1 points at in the second plane (same element index
+// as in the hi plane).  Buffers are >= 128-B aligned and pixel strides are multiples of 64 channels, so the channel
+// index inside the 64-channel block is ((address >> 1) & 63): block base + c for the lo byte, + 64 + c for the hi byte.
+__device__ __forceinline__ uint8_t* f8_row_ptr(const __half* p1) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p1);
+    return reinterpret_cast<uint8_t*>(a - ((a >> 1) & 63));
+}
+__device__ __forceinline__ uint8_t f8_lo_byte(float lo) {
+    return static_cast<uint8_t>(__nv_cvt_float_to_fp8(lo * kF8ActLoScale, __NV_SATFINITE, __NV_E5M2));
+}
+__device__ __forceinline__ uint8_t f8_hi_byte(float x) {
+    return static_cast<uint8_t>(__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3));
+}
+// l01 / l23: packed fp16 lo parts of 4 consecutive channels -> 4 e5m2 bytes of 16 * lo (channel order = byte order)
+__device__ __forceinline__ uint32_t f8_pack_lo4(uint32_t l01, uint32_t l23) {
+    const __half2 s = __floats2half2_rn(kF8ActLoScale, kF8ActLoScale);
+    const __half2 a = __hmul2(*reinterpret_cast<const __half2*>(&l01), s), b = __hmul2(*reinterpret_cast<const __half2*>(&l23), s);
+    const uint32_t x = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(a), __NV_SATFINITE, __NV_E5M2);
+    const uint32_t y = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(b), __NV_SATFINITE, __NV_E5M2);
+    return x | (y << 16);
+}
+__device__ __forceinline__ uint32_t f8_pack_hi4(uint32_t h01, uint32_t h23) {
+    const uint32_t x = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(*reinterpret_cast<const __half2*>(&h01)), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t y = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(*reinterpret_cast<const __half2*>(&h23)), __NV_SATFINITE, __NV_E4M3);
+    return x | (y << 16);
+}
+// value an (hi, 8-bit row) pair stands for: hi + e5m2 byte / 16 (an e5m2 byte is the upper byte of the fp16 with the same value)
+__device__ __forceinline__ float join_f8(__half hi, uint8_t lo_byte) {
+    return __half2float(hi) + __half2float(__ushort_as_half(static_cast<unsigned short>(lo_byte) << 8)) * (1.f / kF8ActLoScale);
+}
+
 // Everything the 3x3 conv kernel needs besides the tensor maps (see conv_umma.cu).
 struct ConvArgs {
     const float* bias;        // [cout_pad]
@@ -47,8 +93,10 @@ struct ConvArgs {
     int cin_off, KB;          // first input channel in the source buffer, number of 64-channel K blocks
     int ksteps_last;          // 16-channel K slices of the last block that hold real input channels (1..4)
     int cout, NB;             // true output channels, number of N blocks (cout_pad = NB * NT)
-    int P, TH, TW;            // patch pitch (= TW + 2), output rows / cols per tile
-    int inv_p;                // ceil(2^20 / P): q / P == (q * inv_p) >> 20 for q < 2^20 / P
+    int P, TH, TW;            // patch pitch (= TW + 2), output rows / cols per tile (TW = 8 * CX, TH = 16 * CY)
+    int cx;                   // chunks side by side in x (1 or 2); a chunk is 8 px wide x 16 rows = 128 MMA rows
+    unsigned chunk_off;       // A-descriptor offset of chunk 1 relative to chunk 0, in 16-byte units
+    unsigned a_desc_hi;       // high word of the A descriptors: SBO = P * 128 B (one image row of the patch per 8-row group)
     int tiles_x, tiles_y, num_tiles;
     int raw_cs, raw_off0, raw_off1, raw_split;   // fp32 output channel stride / channel map
     int act_cs, act_off0, act_off1, act_split;   // fp16 output channel stride / channel map

@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "conv_umma.h"
+#include "sm100_ptx.cuh"
 
 namespace fisr {
 
@@ -17,6 +18,7 @@ cudaError_t launch_family(const ConvLaunch& L, int num_sms, cudaStream_t stream)
     template <> cudaError_t init_family<NT_, PL_>();            \
     template <> cudaError_t launch_family<NT_, PL_>(const ConvLaunch&, int, cudaStream_t);
 FISR_DECL(16, 1) FISR_DECL(64, 1) FISR_DECL(128, 1) FISR_DECL(16, 2) FISR_DECL(64, 2) FISR_DECL(128, 2)
+FISR_DECL(16, 3) FISR_DECL(64, 3) FISR_DECL(128, 3)
 #undef FISR_DECL
 }  // namespace convk
 
@@ -29,12 +31,19 @@ cudaError_t conv3x3_init() {
     if (e == cudaSuccess) e = init_family<16, 2>();
     if (e == cudaSuccess) e = init_family<64, 2>();
     if (e == cudaSuccess) e = init_family<128, 2>();
+    if (e == cudaSuccess) e = init_family<16, 3>();
+    if (e == cudaSuccess) e = init_family<64, 3>();
+    if (e == cudaSuccess) e = init_family<128, 3>();
     return e;
 }
 
 cudaError_t launch_conv3x3(const ConvLaunch& L, int num_sms, cudaStream_t stream) {
     using namespace convk;
-    if (L.planes == 2) {
+    if (L.planes == 3) {
+        if (L.NT == 16) return launch_family<16, 3>(L, num_sms, stream);
+        if (L.NT == 64) return launch_family<64, 3>(L, num_sms, stream);
+        if (L.NT == 128) return launch_family<128, 3>(L, num_sms, stream);
+    } else if (L.planes == 2) {
         if (L.NT == 16) return launch_family<16, 2>(L, num_sms, stream);
         if (L.NT == 64) return launch_family<64, 2>(L, num_sms, stream);
         if (L.NT == 128) return launch_family<128, 2>(L, num_sms, stream);
@@ -55,42 +64,40 @@ bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int n
     if (cout_pad >= 128 && (long)H * W >= 64L * 64) NT = 128;
     int chunks = 2;
     {
-        const long tiles2 = (long)n_img * ((H * (long)W + 223) / 224) * (cout_pad / NT);
+        const long tiles2 = (long)n_img * ((H * (long)W + 255) / 256) * (cout_pad / NT);
         if (tiles2 < num_sms) chunks = 1;
     }
-    const int M = chunks * 128;
+    if (const char* e = getenv("FISR_CHUNKS")) { if (atoi(e) == 1 || atoi(e) == 2) chunks = atoi(e); }   // tuning knob
+    const int apl = act_planes(planes);
     const bool stack = planes == 2 && NT <= 64;
     const int slot_bytes = stack ? 2 * NT * 128 : NT * 128;
-    int min_slots = 3;
-    if (const char* e = getenv("FISR_MIN_SLOTS")) min_slots = atoi(e) > 0 ? atoi(e) : min_slots;   // tuning knob
-    const int fixed = 1024 /*align*/ + 2048 /*bias*/ + convk::kStageBytes /*epilogue transpose*/;
+    const int fixed = 128 /*align*/ + convk::kStageBytes /*epilogue transpose*/;
+    // A chunk is 8 px x 16 rows (one 128-row MMA, one image row of the patch per 8-row group); two chunks sit side by
+    // side (16 x 16 tile, patch 18 x 18) or on top of each other (8 x 32, patch 10 x 34), whichever covers the image better.
+    int cx = 1, cy = 1;
     double best_eff = -1;
-    int bestP = 0;
-    for (int P = 4; P <= 130 && P <= M; ++P) {
-        const int a_plane = (((M + 2 * P + 2) * 128) + 1023) / 1024 * 1024;
-        if (fixed + 2 * planes * a_plane + min_slots * slot_bytes > kConvMaxSmem) break;
-        const int TW = P - 2, TH = M / P;
-        if (TH < 1 || TH + 2 > 256) continue;
-        const long tiles = (long)((W + TW - 1) / TW) * ((H + TH - 1) / TH);
-        const double eff = (double)H * W / ((double)tiles * M);
-        if (eff > best_eff + 1e-9) { best_eff = eff; bestP = P; }
+    for (int cand = 0; cand < (chunks == 2 ? 2 : 1); ++cand) {
+        const int ccx = chunks == 2 && cand == 0 ? 2 : 1, ccy = chunks / ccx;
+        const long tiles = (long)((W + 8 * ccx - 1) / (8 * ccx)) * ((H + 16 * ccy - 1) / (16 * ccy));
+        const double eff = (double)H * W / ((double)tiles * 128 * chunks);
+        if (eff > best_eff + 1e-9) { best_eff = eff; cx = ccx; cy = ccy; }
     }
-    if (bestP == 0) return false;
-    const int P = bestP;
     ConvArgs& a = L->args;
-    a.P = P; a.TW = P - 2; a.TH = M / P;
-    a.inv_p = ((1 << 20) + P - 1) / P;
+    a.TW = 8 * cx; a.TH = 16 * cy; a.P = a.TW + 2; a.cx = cx;
+    a.chunk_off = static_cast<unsigned>(cx == 2 ? 8 : 16 * a.P) * 8u;     // (rows of 128 B) * 128 >> 4
+    a.a_desc_hi = umma_desc_hi_sw128(static_cast<uint32_t>(a.P) * 128u);
     a.tiles_x = (W + a.TW - 1) / a.TW;
     a.tiles_y = (H + a.TH - 1) / a.TH;
     a.NB = cout_pad / NT;
     a.num_tiles = n_img * a.tiles_x * a.tiles_y * a.NB;
-    a.a_plane_bytes = (((M + 2 * P + 2) * 128) + 1023) / 1024 * 1024;
+    a.a_plane_bytes = (a.TH + 2) * a.P * 128;
     a.a_stages = 2;
-    int slots = (kConvMaxSmem - fixed - 2 * planes * a.a_plane_bytes) / slot_bytes;
+    int slots = (kConvMaxSmem - fixed - 2 * apl * a.a_plane_bytes) / slot_bytes;
     if (slots > convk::kMaxBSlots) slots = convk::kMaxBSlots;
+    if (slots < 2) return false;
     a.b_slots = slots;
     L->NT = NT; L->chunks = chunks; L->planes = planes;
-    L->smem_bytes = fixed + 2 * planes * a.a_plane_bytes + slots * slot_bytes;
+    L->smem_bytes = fixed + 2 * apl * a.a_plane_bytes + slots * slot_bytes;
     L->efficiency = best_eff;
     return true;
 }

@@ -4,8 +4,8 @@
 
 namespace fisr {
 
-// opt-in dynamic shared memory budget per CTA (227 KB minus the kernel's static barriers)
-constexpr int kConvMaxSmem = 230400;
+// opt-in dynamic shared memory budget per CTA: 227 KB (232448 B) minus 512 B for the kernel's static barriers
+constexpr int kConvMaxSmem = 231936;
 
 struct ConvLaunch {
     CUtensorMap tmA_hi, tmA_lo, tmB;
@@ -13,7 +13,7 @@ struct ConvLaunch {
     int NT, chunks, planes;
     int epi;                // epilogue variant: 1 residual in, 2 fp32 out, 4 depth-to-space (convk::EPI_*)
     int smem_bytes;
-    double efficiency;      // useful fraction of the MMA rows issued (tile quantisation + halo columns)
+    double efficiency;      // useful fraction of the MMA rows issued (tile quantisation at the image edges)
 };
 
 // Chooses NT / chunk count / patch pitch for an H x W x n_img conv and fills the geometry fields of L->args.

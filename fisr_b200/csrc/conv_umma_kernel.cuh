@@ -12,13 +12,21 @@
 //   weights     : [plane][kb][tap][cout_pad][64] fp16 (K-major rows of 128 B), hi/lo planes.
 //   residual / pre-activation outputs : NHWC fp32.
 //
-// One CTA tile = TH x TW output pixels x NT output channels.  Per 64-channel K block the producer
-// TMA-loads ONE halo'd input patch (TH+2) x (TW+2) x 64ch (4-D box, out-of-bounds = SAME zero padding)
-// into 128B-swizzled shared memory with pixel pitch P = TW+2.  GEMM row m of the tile is patch position
-// m (row-major with pitch P), so the A operand of tap (ky,kx) is the same patch read through a UMMA
-// descriptor whose start address is advanced by (ky*P+kx) rows of 128 B: no im2col re-read, every
-// activation byte crosses L2->SMEM once per tile (plus halo).  Rows with (m % P) >= TW are computed
-// and discarded.  Weights stream per tap through a ring of slots.
+// One CTA tile = TH x TW output pixels x NT output channels, made of CHUNKS chunks of 8 px x 16 rows (= the 128
+// rows of one MMA).  Per 64-channel K block the producer TMA-loads ONE halo'd input patch (TH+2) x (TW+2) x 64ch
+// (4-D box, out-of-bounds = SAME zero padding) into 128B-swizzled shared memory with pixel pitch P = TW+2.
+// The A operand of tap (ky,kx) of a chunk is that patch read through a UMMA descriptor whose start address is
+// advanced by (ky*P+kx) rows of 128 B and whose stride between 8-row groups (SBO) is P*128 B: MMA row m is
+// pixel (m & 7) of image row (m >> 3) of the chunk, so no halo position is ever multiplied (row efficiency 1 up to
+// image-edge tiles), there is no im2col re-read, and every activation byte crosses L2->SMEM once per tile (plus
+// halo).  tests/cuda/umma_probe2.cu established on B200 that group starts need not be 1024-B aligned (the 128-B
+// swizzle is a function of the absolute shared-memory address for TMA and UMMA alike).  Weights stream per tap
+// through a ring of slots.
+//
+// PLANES = 3 ("f16f8"): activations are (fp16 hi plane, 8-bit plane [e5m2(16 lo) x64 | e4m3(hi) x64] per 64-channel
+// block), weights (fp16(128 w) plane, 8-bit plane [e4m3(8 w_hi) | e5m2(128 w_lo)]).  Per tap the main product is 4
+// kind::f16 MMAs and both cross terms are 4 kind::f8f6f4 MMAs (K = 32, mixed formats) K-concatenated in the same
+// 128-B rows, all into ONE accumulator that holds 128 x the result: 2 MMA units per K slice instead of 3.
 //
 // STACK (split mode, NT <= 64): the weight slot of a tap holds [B_hi; B_lo] as one 2*NT-row operand, so
 //   D[:, 0:NT] = A_hi * B_hi + A_lo * B_hi        D[:, NT:2NT] = A_hi * B_lo
@@ -44,6 +52,7 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxBSlots = 12;
 constexpr int kMaxAStages = 2;
 constexpr int kStageBytesPerWarp = 32 * 64;   // [32 px][16 ch] fp32, 16-B groups XOR-swizzled (conflict-free both ways)
+constexpr float kF8AccScale = 1.f / 128.f;    // PLANES = 3: the accumulator holds 128 x the convolution (common.cuh, F8 scales)
 
 // epilogue variants (template flags)
 // backward (dgrad) variants: EPI_MASK multiplies the accumulator by [mask > 0] (the ReLU gradient, read from the hi plane
@@ -81,18 +90,27 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // Narrow head outputs (Cout = 6 / 3, FISRnet.py:100,106): thread = pixel, channel-mapped scalar stores into the
 // 9-channel pred tensor and into channels 29.. of the next level's input (FISRnet.py:107-108,113,144).
 template <int PLANES>
-__device__ __forceinline__ void epilogue_scalar16(const ConvArgs& a, const float* __restrict__ sBias, const uint32_t (&v)[16],
-                                                  int pix) {
+__device__ __forceinline__ void epilogue_scalar16(const ConvArgs& a, const uint32_t (&v)[16], int pix) {
 #pragma unroll
     for (int ch = 0; ch < 16; ++ch) {
         if (ch < a.cout) {
-            const float f = __uint_as_float(v[ch]) + sBias[ch];
+            float f = __uint_as_float(v[ch]);
+            if (PLANES == 3) f *= kF8AccScale;
+            f += __ldg(a.bias + ch);
             if (a.out_raw) a.out_raw[static_cast<size_t>(pix) * a.raw_cs + ch + (ch < a.raw_split ? a.raw_off0 : a.raw_off1)] = f;
             if (a.out_act) {
-                const SplitHalf s = split_f32(a.act_relu ? fmaxf(f, 0.f) : f);
-                __half* d = a.out_act + static_cast<size_t>(pix) * a.act_cs + ch + (ch < a.act_split ? a.act_off0 : a.act_off1);
+                const float g = a.act_relu ? fmaxf(f, 0.f) : f;
+                const SplitHalf s = split_f32(g);
+                const int c = ch + (ch < a.act_split ? a.act_off0 : a.act_off1);
+                __half* d = a.out_act + static_cast<size_t>(pix) * a.act_cs + c;
                 d[0] = s.hi;
                 if (PLANES == 2) d[a.act_plane] = s.lo;
+                if (PLANES == 3) {
+                    uint8_t* q = reinterpret_cast<uint8_t*>(a.out_act + a.act_plane + static_cast<size_t>(pix) * a.act_cs) +
+                                 (c >> 6) * 128 + (c & 63);
+                    q[0] = f8_lo_byte(g - __half2float(s.hi));
+                    q[64] = f8_hi_byte(g);
+                }
             }
         }
     }
@@ -103,23 +121,24 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvArgs a) {
     constexpr bool STACK = (PLANES == 2) && (NT <= 64);
+    constexpr bool F8 = PLANES == 3;
+    constexpr int APL = PLANES == 1 ? 1 : 2;                    // activation planes staged in shared memory
     constexpr int DCOLS = STACK ? 2 * NT : NT;                  // accumulator columns per 128-row chunk
     constexpr int ACC_COLS = CHUNKS * DCOLS;                    // fp32 columns of one accumulator stage
     constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
     static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns must be a power of two <= 512");
     constexpr int PLANE_BYTES = NT * 128;                       // one weight plane of one tap
     constexpr int B_SLOT_BYTES = STACK ? 2 * PLANE_BYTES : PLANE_BYTES;
-    constexpr int SLOTS_PER_TAP = STACK ? 1 : PLANES;
+    constexpr int SLOTS_PER_TAP = STACK ? 1 : APL;
     constexpr bool NARROW = NT < 32;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t a_stage_bytes = PLANES * a.a_plane_bytes;
+    // 128-B alignment is all the swizzled operands need (absolute-address swizzle): planes and slots are packed tightly
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    const uint32_t a_stage_bytes = APL * a.a_plane_bytes;
     const uint32_t sA = smem_u32(smem);
     const uint32_t sB = sA + a.a_stages * a_stage_bytes;
-    float* sBias = reinterpret_cast<float*>(smem + a.a_stages * a_stage_bytes + a.b_slots * B_SLOT_BYTES);
-    const uint32_t sBias32 = sB + a.b_slots * B_SLOT_BYTES;
-    const uint32_t sStage32 = sBias32 + 2048;      // kEpiWarps x [32 px][16 ch] fp32 transpose buffers
+    const uint32_t sStage32 = sB + a.b_slots * B_SLOT_BYTES;      // kEpiWarps x [32 px][16 ch] fp32 transpose buffers
 
     __shared__ __align__(8) uint64_t bars[2 * kMaxAStages + 2 * kMaxBSlots + 4];
     __shared__ uint32_t tmem_slot;
@@ -140,11 +159,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), kEpiWarps); }
         fence_mbar_init();
         tma_prefetch_desc(&tmA_hi);
-        if (PLANES == 2) tma_prefetch_desc(&tmA_lo);
+        if (APL == 2) tma_prefetch_desc(&tmA_lo);
         tma_prefetch_desc(&tmB);
     }
     if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
-    for (int i = tid; i < a.NB * NT; i += kThreads) sBias[i] = a.bias[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -164,10 +182,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 if (pf_tile >= a.num_tiles) return true;
                 if (!mbar_wait(a_empty(as), aph ^ 1, a.err, ERR_A_EMPTY)) return false;
                 const TileCoord t = decode_tile(a, pf_tile);
-                mbar_expect_tx(a_full(as), PLANES * box_bytes);
+                mbar_expect_tx(a_full(as), APL * box_bytes);
                 const uint32_t dst = sA + as * a_stage_bytes;
                 tma_load_4d(dst, &tmA_hi, a_full(as), a.cin_off + pf_kb * 64, t.x0 - 1, t.y0 - 1, t.n);
-                if (PLANES == 2)
+                if (APL == 2)
                     tma_load_4d(dst + a.a_plane_bytes, &tmA_lo, a_full(as), a.cin_off + pf_kb * 64, t.x0 - 1, t.y0 - 1, t.n);
                 if (++as == (uint32_t)a.a_stages) { as = 0; aph ^= 1; }
                 if (++pf_kb == a.KB) { pf_kb = 0; pf_tile += gridDim.x; }
@@ -203,7 +221,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         // uniform registers); only the tcgen05 instructions are predicated on one elected lane.
         constexpr uint32_t idesc = umma_idesc_f16(128, NT);
         constexpr uint32_t idesc2 = umma_idesc_f16(128, STACK ? 2 * NT : NT);
+        constexpr uint32_t idesc8a = umma_idesc_f8(128, NT, kF8E5M2, kF8E4M3);   // bytes [0,64):   e5m2(16 x_lo) * e4m3(8 w_hi)
+        constexpr uint32_t idesc8b = umma_idesc_f8(128, NT, kF8E4M3, kF8E5M2);   // bytes [64,128): e4m3(x_hi) * e5m2(128 w_lo)
         const bool lead = elect_one();
+        const uint32_t a_hi_word = a.a_desc_hi;
         uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
         bool ok = true;
         for (int tile = blockIdx.x; tile < a.num_tiles && ok; tile += gridDim.x) {
@@ -218,6 +239,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 const uint32_t a_lo0 = umma_desc_lo(sA + as * a_stage_bytes + a.a_plane_bytes);
                 uint32_t first = kb == 0 ? 0u : 1u;          // accumulate flag of the very first MMA of the tile
                 const int ksteps = kb == a.KB - 1 ? a.ksteps_last : 4;   // 16-channel K slices that hold real channels
+                const int k8steps = (ksteps + 1) >> 1;                   // 32-channel slices of each half of the 8-bit rows
 #pragma unroll 1
                 for (int ky = 0; ky < 3 && ok; ++ky) {
 #pragma unroll 1
@@ -232,15 +254,16 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                             if (lead) {
 #pragma unroll
                                 for (int c = 0; c < CHUNKS; ++c) {
+                                    const uint32_t co = c ? a.chunk_off : 0u;
 #pragma unroll
                                     for (int k = 0; k < 4; ++k) {
                                         if (k >= ksteps) break;
                                         // A_hi * [B_hi (; B_lo)]
-                                        umma_f16_lohi(d_tmem + c * DCOLS, ah + c * 1024 + k * 2, b0 + k * 2, kUmmaDescHiSw128,
-                                                      idesc2, k == 0 ? first : 1u);
+                                        umma_f16_lohi2(d_tmem + c * DCOLS, ah + co + k * 2, a_hi_word, b0 + k * 2, kUmmaDescHiSw128,
+                                                       idesc2, k == 0 ? first : 1u);
                                         if (PLANES == 2)   // A_lo * B_hi
-                                            umma_f16_lohi(d_tmem + c * DCOLS, al + c * 1024 + k * 2, b0 + k * 2,
-                                                          kUmmaDescHiSw128, idesc, 1u);
+                                            umma_f16_lohi2(d_tmem + c * DCOLS, al + co + k * 2, a_hi_word, b0 + k * 2,
+                                                           kUmmaDescHiSw128, idesc, 1u);
                                     }
                                 }
                                 umma_commit(b_empty(bs));
@@ -248,7 +271,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                             first = 1u;
                             if (++bs == (uint32_t)a.b_slots) { bs = 0; bph ^= 1; }
                         }
-                        if (PLANES == 2 && !STACK) {   // separate lo weight plane: A_hi * B_lo
+                        if (APL == 2 && !STACK) {   // second weight plane: A_hi * B_lo (f16x3) or the 8-bit cross terms (f16f8)
                             ok = __all_sync(0xffffffffu, mbar_wait(b_full(bs), bph, a.err, ERR_B_FULL));
                             if (!ok) break;
                             tc_fence_after();
@@ -256,11 +279,21 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                             if (lead) {
 #pragma unroll
                                 for (int c = 0; c < CHUNKS; ++c) {
+                                    const uint32_t co = c ? a.chunk_off : 0u;
+                                    if (F8) {
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        if (k >= ksteps) break;
-                                        umma_f16_lohi(d_tmem + c * DCOLS, ah + c * 1024 + k * 2, b0 + k * 2, kUmmaDescHiSw128,
-                                                      idesc, 1u);
+                                        for (int k = 0; k < 4; ++k) {
+                                            if ((k & 1) >= k8steps) continue;
+                                            umma_f8_lohi2(d_tmem + c * DCOLS, al + co + k * 2, a_hi_word, b0 + k * 2, kUmmaDescHiSw128,
+                                                          k < 2 ? idesc8a : idesc8b, 1u);
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) {
+                                            if (k >= ksteps) break;
+                                            umma_f16_lohi2(d_tmem + c * DCOLS, ah + co + k * 2, a_hi_word, b0 + k * 2, kUmmaDescHiSw128,
+                                                           idesc, 1u);
+                                        }
                                     }
                                 }
                                 umma_commit(b_empty(bs));
@@ -294,6 +327,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         //   read : lane -> row (lane >> 2) + 8*i, group lane & 3 -> 2 rows x 4 groups per phase, again all different
         const uint32_t wr_base = stg + lane * 64, wr_sw = (lane >> 1) & 3;
         const uint32_t rd_row = lane >> 2, rd_grp = lane & 3;
+        // chunk origin inside the tile: chunks sit side by side (cx == 2) or on top of each other; MMA row m of a chunk
+        // is pixel (m & 7) of row (m >> 3)
+        const int ch_x0 = a.cx == 2 ? my_c * 8 : 0, ch_y0 = a.cx == 2 ? 0 : my_c * 16;
 
         for (int tile = blockIdx.x; tile < a.num_tiles && ok; tile += gridDim.x) {
             const TileCoord t = decode_tile(a, tile);
@@ -303,10 +339,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 if (!ok) break;
                 tc_fence_after();
                 if (!idle) {
-                    const int q = my_c * 128 + q4 * 32 + lane;
-                    const int ty = (q * a.inv_p) >> 20, tx = q - ty * a.P;
+                    const int ty = ch_y0 + q4 * 4 + (lane >> 3), tx = ch_x0 + (lane & 7);
                     const int y = t.y0 + ty, x = t.x0 + tx;
-                    const bool valid = (tx < a.TW) && (ty < a.TH) && (y < a.H) && (x < a.W);
+                    const bool valid = (y < a.H) && (x < a.W);
                     uint32_t v[16];
                     tmem_ld_32x16(tacc, v);
                     if (STACK) {
@@ -318,7 +353,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                     } else {
                         tmem_ld_wait();
                     }
-                    if (valid) epilogue_scalar16<PLANES>(a, sBias, v, (t.n * a.H + y) * a.W + x);
+                    if (valid) epilogue_scalar16<PLANES>(a, v, (t.n * a.H + y) * a.W + x);
                 }
             } else {
                 // After the transpose lane l serves pixels (l >> 2) + 8*i of this warp's 32-pixel group, channels
@@ -328,10 +363,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 uint32_t vmask = 0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int q = my_c * 128 + q4 * 32 + 8 * i + rd_row;
-                    const int ty = (q * a.inv_p) >> 20, tx = q - ty * a.P;
+                    const int ty = ch_y0 + q4 * 4 + i, tx = ch_x0 + static_cast<int>(rd_row);
                     const int y = t.y0 + ty, x = t.x0 + tx;
-                    const bool valid = (tx < a.TW) && (ty < a.TH) && (y < a.H) && (x < a.W);
+                    const bool valid = (y < a.H) && (x < a.W);
                     vmask |= (valid ? 1u : 0u) << i;
                     const uint32_t pix = valid ? static_cast<uint32_t>((t.n * a.H + y) * a.W + x) : 0u;
                     if (EPI & EPI_RES) o_res[i] = pix * a.res_cs + cg_lane;
@@ -375,7 +409,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                             if ((vmask >> i) & 1) mk[i] = __ldg(reinterpret_cast<const uint2*>(a.mask + o_msk[i] + c0));
                         }
                     }
-                    const float4 b4 = lds128(sBias32 + (cg_lane + c0) * 4);
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + cg_lane + c0));
                     uint32_t v[16];
                     tmem_ld_32x16(tacc + c_begin + c0, v);
                     if (STACK) {
@@ -397,7 +431,13 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                         const uint32_t r = rd_row + 8 * i;
                         const float4 val = lds128(stg + r * 64 + ((rd_grp ^ ((r >> 1) & 3)) << 4));
                         if ((vmask >> i) & 1) {
-                            float f0 = val.x + b4.x, f1 = val.y + b4.y, f2 = val.z + b4.z, f3 = val.w + b4.w;
+                            float f0, f1, f2, f3;
+                            if (F8) {
+                                f0 = fmaf(val.x, kF8AccScale, b4.x); f1 = fmaf(val.y, kF8AccScale, b4.y);
+                                f2 = fmaf(val.z, kF8AccScale, b4.z); f3 = fmaf(val.w, kF8AccScale, b4.w);
+                            } else {
+                                f0 = val.x + b4.x; f1 = val.y + b4.y; f2 = val.z + b4.z; f3 = val.w + b4.w;
+                            }
                             if (EPI & EPI_MASK) {   // fp16 bit patterns 0x0001..0x7FFF are the positive values (post-ReLU: never negative)
                                 if ((mk[i].x & 0x7FFFu) == 0u) f0 = 0.f;
                                 if ((mk[i].x & 0x7FFF0000u) == 0u) f1 = 0.f;
@@ -420,6 +460,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                             }
                             *reinterpret_cast<uint2*>(d) = make_uint2(h01, h23);
                             if (PLANES == 2) *reinterpret_cast<uint2*>(d + a.act_plane) = make_uint2(l01, l23);
+                            if (F8) {   // 8-bit plane: [e5m2(16 lo) x 64 | e4m3(hi) x 64] per 64-channel block of the pixel
+                                uint8_t* q = f8_row_ptr(d + a.act_plane);
+                                *reinterpret_cast<uint32_t*>(q) = f8_pack_lo4(l01, l23);
+                                *reinterpret_cast<uint32_t*>(q + 64) = f8_pack_hi4(h01, h23);
+                            }
                         }
                     }
                     __syncwarp();

@@ -280,7 +280,7 @@ struct Builder {
         ActBuf b;
         const size_t elems = static_cast<size_t>(N) * H * W * C;
         b.plane = (elems + 511) / 512 * 512;
-        b.p = static_cast<__half*>(alloc(b.plane * plan->planes * sizeof(__half), zero));
+        b.p = static_cast<__half*>(alloc(b.plane * act_planes(plan->planes) * sizeof(__half), zero));
         return b;
     }
     float* f32(int N, int H, int W, int C) { return static_cast<float*>(alloc(static_cast<size_t>(N) * H * W * C * 4, false)); }
@@ -377,11 +377,11 @@ struct Builder {
         a.ksteps_last = (p.cin - (p.KB - 1) * 64 + 15) / 16;       // padded input channels beyond this are zeros: skip their MMAs
         if (a.ksteps_last < 1 || a.ksteps_last > 4) a.ksteps_last = 4;
         if (!encode_act(&L.tmA_hi, in.p, in_cs, N, H, W, a.P, a.TH + 2)) return false;
-        if (!encode_act(&L.tmA_lo, in.p + (plan->planes == 2 ? in.plane : 0), in_cs, N, H, W, a.P, a.TH + 2)) return false;
-        if (!encode_w(&L.tmB, p.wp, static_cast<size_t>(plan->planes) * p.KB * 9 * p.cout_pad, L.NT)) return false;
+        if (!encode_act(&L.tmA_lo, in.p + (plan->planes >= 2 ? in.plane : 0), in_cs, N, H, W, a.P, a.TH + 2)) return false;
+        if (!encode_w(&L.tmB, p.wp, static_cast<size_t>(act_planes(plan->planes)) * p.KB * 9 * p.cout_pad, L.NT)) return false;
         op.flops = 2.0 * 9 * p.cin * p.cout * static_cast<double>(H) * W * N;
         {   // algorithmic HBM bytes: input + weights once, every output / residual once
-            const double px = static_cast<double>(N) * H * W, eb = 2.0 * plan->planes;
+            const double px = static_cast<double>(N) * H * W, eb = 2.0 * act_planes(plan->planes);
             op.bytes = px * p.KB * 64 * eb + 9.0 * p.KB * 64 * p.cout_pad * eb + (o.res ? px * p.cout * 4 : 0) +
                        (o.raw ? px * p.cout * 4 : 0) + (o.act.p ? px * p.cout * eb : 0) + (o.mask.p ? px * p.cout * 2 : 0);
         }
@@ -391,14 +391,14 @@ struct Builder {
     void upsample(ActBuf in, ActBuf out, int N, int h, int w, int C) {
         Op op{};
         op.kind = OP_UPSAMPLE; op.in = in; op.out = out; op.N = N; op.H = h; op.W = w; op.C = C;
-        op.bytes = static_cast<double>(N) * h * w * C * 2.0 * plan->planes * 5;
+        op.bytes = static_cast<double>(N) * h * w * C * 2.0 * act_planes(plan->planes) * 5;
         snprintf(op.name, sizeof op.name, "upsample2 %dx%dx%d", h, w, C);
         plan->ops.push_back(op);
     }
     void pool(ActBuf in, int cs, int coff, ActBuf out, int N, int H, int W, int C) {
         Op op{};
         op.kind = OP_POOL; op.in = in; op.out = out; op.N = N; op.H = H; op.W = W; op.C = C; op.cs = cs; op.coff = coff;
-        op.bytes = static_cast<double>(N) * H * W * C * 2.0 * plan->planes * 1.25;
+        op.bytes = static_cast<double>(N) * H * W * C * 2.0 * act_planes(plan->planes) * 1.25;
         snprintf(op.name, sizeof op.name, "maxpool2 %dx%dx%d", H, W, C);
         plan->ops.push_back(op);
     }
@@ -1076,8 +1076,9 @@ const char* fisr_last_error(const fisr_ctx* ctx) { return ctx ? ctx->err.c_str()
 
 int fisr_set_precision(fisr_ctx* ctx, int precision) {
     if (!ctx) return FISR_E_INVALID;
-    if (precision != FISR_PREC_F16X3 && precision != FISR_PREC_F16) return fail(ctx, FISR_E_INVALID, "unknown precision %d", precision);
-    const int planes = precision == FISR_PREC_F16X3 ? 2 : 1;
+    if (precision != FISR_PREC_F16X3 && precision != FISR_PREC_F16 && precision != FISR_PREC_F16F8)
+        return fail(ctx, FISR_E_INVALID, "unknown precision %d", precision);
+    const int planes = precision == FISR_PREC_F16X3 ? 2 : precision == FISR_PREC_F16F8 ? 3 : 1;   // kernel PLANES parameter
     if (planes != ctx->planes) {
         Guard guard(ctx->device);
         cudaDeviceSynchronize();
@@ -1088,7 +1089,9 @@ int fisr_set_precision(fisr_ctx* ctx, int precision) {
     }
     return FISR_OK;
 }
-int fisr_get_precision(const fisr_ctx* ctx) { return ctx && ctx->planes == 1 ? FISR_PREC_F16 : FISR_PREC_F16X3; }
+int fisr_get_precision(const fisr_ctx* ctx) {
+    return ctx && ctx->planes == 1 ? FISR_PREC_F16 : ctx && ctx->planes == 3 ? FISR_PREC_F16F8 : FISR_PREC_F16X3;
+}
 
 int fisr_num_params(void) { return static_cast<int>(param_names().size()); }
 const char* fisr_param_name(int index) {
@@ -1381,7 +1384,7 @@ int fisr_conv3x3(fisr_ctx* ctx, const float* d_x, const float* d_w, const float*
     const int cs = p.KB * 64;
     ActBuf xin = b.act(N, H, W, cs);
     const int oc = d2s ? Cout / 4 : Cout, oH = d2s ? 2 * H : H, oW = d2s ? 2 * W : W;
-    const int ocs = Cout <= 16 ? 16 : oc;
+    const int ocs = Cout <= 16 ? (ctx->planes == 3 ? 64 : 16) : oc;      // the 8-bit plane is organised in 64-channel blocks
     ActBuf yact = b.act(N, oH, oW, ocs, true);
     if (b.rc != FISR_OK) return b.rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(p.d_b, d_b, Cout * 4, cudaMemcpyDeviceToDevice, st));

@@ -13,9 +13,10 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import FisrError, PREC_F16, PREC_F16X3
+from ._lib import FisrError, PREC_F16, PREC_F16F8, PREC_F16X3
 
-_PREC = {"f16x3": PREC_F16X3, "fp32": PREC_F16X3, "f16": PREC_F16, "fast": PREC_F16}
+_PREC = {"f16x3": PREC_F16X3, "fp32": PREC_F16X3, "f16": PREC_F16, "fast": PREC_F16, "f16f8": PREC_F16F8}
+_PREC_NAME = {PREC_F16X3: "f16x3", PREC_F16: "f16", PREC_F16F8: "f16f8"}
 
 
 def param_inventory() -> "OrderedDict[str, Tuple[int, ...]]":
@@ -82,7 +83,7 @@ class Engine:
         if precision not in _PREC:
             raise FisrError(f"unknown precision {precision!r}; use one of {sorted(_PREC)}")
         self._check(self.lib.fisr_set_precision(self.h, _PREC[precision]), "fisr_set_precision")
-        self.precision = "f16" if _PREC[precision] == PREC_F16 else "f16x3"
+        self.precision = _PREC_NAME[_PREC[precision]]
 
     @property
     def launch_count(self) -> int:

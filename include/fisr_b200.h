@@ -35,7 +35,9 @@ enum {
 /* Arithmetic of the conv stack (DESIGN.md "Numerics").  The reference computes in fp32 (cuDNN on Pascal). */
 enum {
     FISR_PREC_F16X3 = 0,    /* fp16 (hi,lo) split operands, 3 tcgen05 MMAs per K-slice, fp32 accumulate: fp32-class */
-    FISR_PREC_F16 = 1       /* single fp16 operands, 1 MMA per K-slice: fast mode, ~7e-4 max-abs on the cascade   */
+    FISR_PREC_F16 = 1,      /* single fp16 operands, 1 MMA per K-slice: fast mode, ~7e-4 max-abs on the cascade   */
+    FISR_PREC_F16F8 = 2     /* fp16 main term + both cross terms as fp8 (e5m2 x e4m3) MMAs at twice the rate: 2 MMA units
+                               per K-slice, ~3e-5 max-abs on the cascade; inference only (training needs F16X3)     */
 };
 
 /* ---- lifetime --------------------------------------------------------------------------------------------- */

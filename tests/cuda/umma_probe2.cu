@@ -41,11 +41,11 @@ constexpr int A_ALLOC = (A_BYTES + 1023) / 1024 * 1024;
 constexpr int B_BYTES = 9 * CO * 128;
 
 __global__ void __launch_bounds__(128, 1)
-sbo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* out, int H, int W, int* err) {
+sbo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* out, int H, int W, int* err, int a_shift) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + A_ALLOC;
+    uint8_t* sA = smem + a_shift;          // a_shift = 128..896: is the TMA / UMMA swizzle a function of the absolute address?
+    uint8_t* sB = smem + A_ALLOC + 1024;
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_slot;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, n = blockIdx.z;
@@ -163,7 +163,7 @@ static float dec8(uint8_t b, bool e5m2) {
     return __half2float(hh);
 }
 
-static int test_sbo() {
+static int test_sbo(int a_shift) {
     const int N = 2, H = 32, W = 24;
     std::vector<__half> hx((size_t)N * H * W * C), hw((size_t)9 * CO * C);
     srand(123);
@@ -195,9 +195,9 @@ static int test_sbo() {
         if (r != CUDA_SUCCESS) { printf("encode B failed %d\n", (int)r); return 2; }
     }
     dim3 grid(W / TW, H / TH, N);
-    const int smem = 1024 + A_ALLOC + B_BYTES;
+    const int smem = 2048 + A_ALLOC + B_BYTES;
     CK(cudaFuncSetAttribute(sbo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    sbo_kernel<<<grid, 128, smem>>>(tmA, tmB, dout, H, W, derr);
+    sbo_kernel<<<grid, 128, smem>>>(tmA, tmB, dout, H, W, derr, a_shift);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     int herr = 0;
@@ -219,7 +219,7 @@ static int test_sbo() {
         if (!(e <= 1e-2)) ++bad;
         if (e > maxerr || std::isnan(g)) maxerr = std::isnan(g) ? 1e30 : e;
     }
-    printf("PROBE2 sbo (SBO = %d B, unaligned group starts) err_flag=%d max_abs_err=%.3e bad=%zu/%zu -> %s\n", P * 128, herr, maxerr,
+    printf("PROBE2 sbo (SBO = %d B, unaligned group starts, patch base +%d B) err_flag=%d max_abs_err=%.3e bad=%zu/%zu -> %s\n", P * 128, a_shift, herr, maxerr,
            bad, ho.size(), (herr == 0 && bad == 0) ? "PASS" : "FAIL");
     return (herr == 0 && bad == 0) ? 0 : 1;
 }
@@ -277,7 +277,7 @@ int main(int argc, char** argv) {
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&g_encode, cudaEnableDefault, &qres));
     if (!g_encode) { printf("no cuTensorMapEncodeTiled\n"); return 2; }
     const char* which = argc > 1 ? argv[1] : "sbo";
-    if (!strcmp(which, "sbo")) return test_sbo();
+    if (!strcmp(which, "sbo")) return test_sbo(argc > 2 ? atoi(argv[2]) : 0);
     if (!strcmp(which, "f8")) return test_f8();
     printf("usage: umma_probe2 sbo|f8\n");
     return 2;

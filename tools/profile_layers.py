@@ -9,7 +9,7 @@ prec = sys.argv[4] if len(sys.argv) > 4 else "f16x3"
 eng = fisr_b200.Engine(0, precision=prec)
 eng.set_params(xavier_params(0, 0.01))
 ops = eng.profile_ops(n, h, w, reps=3)
-mult = 3 if prec == "f16x3" else 1
+mult = {"f16x3": 3, "f16f8": 2}.get(prec, 1)
 tot = sum(o["ms"] for o in ops)
 print(f"# plan {n}x{h}x{w} {prec}: {len(ops)} launches, {tot:.3f} ms launch-by-launch, "
       f"{sum(o['flops'] for o in ops)/tot/1e9:.1f} TFLOP/s algorithmic")
