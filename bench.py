@@ -303,7 +303,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="f16x3", choices=["f16x3", "f16", "f16f8"],
+    ap.add_argument("--precision", default="f16f8", choices=["f16x3", "f16", "f16f8"],
                     help="f16x3 = fp32-class parity mode (default, what the parity tests hold to 1e-4); f16 = fast mode")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     args = ap.parse_args()

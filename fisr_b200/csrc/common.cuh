@@ -93,10 +93,8 @@ struct ConvArgs {
     int cin_off, KB;          // first input channel in the source buffer, number of 64-channel K blocks
     int ksteps_last;          // 16-channel K slices of the last block that hold real input channels (1..4)
     int cout, NB;             // true output channels, number of N blocks (cout_pad = NB * NT)
-    int P, TH, TW;            // patch pitch (= TW + 2), output rows / cols per tile (TW = 8 * CX, TH = 16 * CY)
-    int cx;                   // chunks side by side in x (1 or 2); a chunk is 8 px wide x 16 rows = 128 MMA rows
-    unsigned chunk_off;       // A-descriptor offset of chunk 1 relative to chunk 0, in 16-byte units
-    unsigned a_desc_hi;       // high word of the A descriptors: SBO = P * 128 B (one image row of the patch per 8-row group)
+    int P, TH, TW;            // patch pitch (= TW + 2), output rows / cols per tile (TW = 8 * CHUNKS, TH = 16): host-side copy of
+                              // the kernel's compile-time geometry, used for the TMA box and the tile grid
     int tiles_x, tiles_y, num_tiles;
     int raw_cs, raw_off0, raw_off1, raw_split;   // fp32 output channel stride / channel map
     int act_cs, act_off0, act_off1, act_split;   // fp16 output channel stride / channel map

@@ -72,20 +72,16 @@ bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int n
     const bool stack = planes == 2 && NT <= 64;
     const int slot_bytes = stack ? 2 * NT * 128 : NT * 128;
     const int fixed = 128 /*align*/ + convk::kStageBytes /*epilogue transpose*/;
-    // A chunk is 8 px x 16 rows (one 128-row MMA, one image row of the patch per 8-row group); two chunks sit side by
-    // side (16 x 16 tile, patch 18 x 18) or on top of each other (8 x 32, patch 10 x 34), whichever covers the image better.
-    int cx = 1, cy = 1;
-    double best_eff = -1;
-    for (int cand = 0; cand < (chunks == 2 ? 2 : 1); ++cand) {
-        const int ccx = chunks == 2 && cand == 0 ? 2 : 1, ccy = chunks / ccx;
-        const long tiles = (long)((W + 8 * ccx - 1) / (8 * ccx)) * ((H + 16 * ccy - 1) / (16 * ccy));
-        const double eff = (double)H * W / ((double)tiles * 128 * chunks);
-        if (eff > best_eff + 1e-9) { best_eff = eff; cx = ccx; cy = ccy; }
+    // A chunk is 8 px x 16 rows (one 128-row MMA, one image row of the patch per 8-row group); two chunks sit side by side:
+    // tile 16 x 16, patch 18 x 18.  The geometry is a compile-time function of CHUNKS in the kernel.
+    const int cx = chunks, cy = 1;
+    double best_eff;
+    {
+        const long tiles = (long)((W + 8 * cx - 1) / (8 * cx)) * ((H + 15) / 16);
+        best_eff = (double)H * W / ((double)tiles * 128 * chunks);
     }
     ConvArgs& a = L->args;
-    a.TW = 8 * cx; a.TH = 16 * cy; a.P = a.TW + 2; a.cx = cx;
-    a.chunk_off = static_cast<unsigned>(cx == 2 ? 8 : 16 * a.P) * 8u;     // (rows of 128 B) * 128 >> 4
-    a.a_desc_hi = umma_desc_hi_sw128(static_cast<uint32_t>(a.P) * 128u);
+    a.TW = 8 * cx; a.TH = 16 * cy; a.P = a.TW + 2;
     a.tiles_x = (W + a.TW - 1) / a.TW;
     a.tiles_y = (H + a.TH - 1) / a.TH;
     a.NB = cout_pad / NT;

@@ -34,7 +34,7 @@
 // products: an N = 64 MMA needs 48 cycles of shared-memory operand reads for 32 cycles of math (ncu:
 // pipe_tc 80 % busy at 50 % tensor math), so the narrow layers are bound by exactly that traffic.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 =
+// Warp roles (352 threads): warp 0 = TMA producer, warp 1 = MMA issuer of chunk 0 + TMEM owner, warp 10 = MMA issuer of chunk 1, warps 2-9 =
 // epilogue (TMEM -> registers -> smem transpose -> bias/residual/ReLU/split -> coalesced HBM stores).
 // Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.  The epilogue
 // is CUDA-core work on every output element; 8 warps (two per TMEM lane quarter) keep the four schedulers
@@ -48,7 +48,8 @@ namespace fisr {
 namespace convk {
 
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kThreads = 64 + 32 * kEpiWarps + 32;     // + a second MMA issuer (last warp), see "MMA issue" below
+constexpr int kIssuer2Warp = kThreads / 32 - 1;
 constexpr int kMaxBSlots = 12;
 constexpr int kMaxAStages = 2;
 constexpr int kStageBytesPerWarp = 32 * 64;   // [32 px][16 ch] fp32, 16-B groups XOR-swizzled (conflict-free both ways)
@@ -131,6 +132,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     constexpr int B_SLOT_BYTES = STACK ? 2 * PLANE_BYTES : PLANE_BYTES;
     constexpr int SLOTS_PER_TAP = STACK ? 1 : APL;
     constexpr bool NARROW = NT < 32;
+    // tile geometry is a function of CHUNKS alone: two 8 x 16 chunks side by side (16 x 16 tile, patch pitch 18) or one chunk
+    constexpr int TWc = 8 * CHUNKS, THc = 16, Pc = TWc + 2;
+    constexpr uint32_t CHUNK_OFF = 8u * 128u >> 4;                      // chunk 1 starts 8 pixels to the right of chunk 0
+    constexpr uint32_t A_DESC_HI = umma_desc_hi_sw128(Pc * 128u);       // SBO = one patch row
 
     extern __shared__ uint8_t smem_raw[];
     // 128-B alignment is all the swizzled operands need (absolute-address swizzle): planes and slots are packed tightly
@@ -154,9 +159,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // broadcast: lets ptxas treat the role branches as warp-uniform
 
     if (tid == 0) {
-        for (int s = 0; s < a.a_stages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-        for (int s = 0; s < a.b_slots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), kEpiWarps); }
+        // every chunk has its own MMA issuer warp: operand buffers are released, and accumulators published, by all of them
+        for (int s = 0; s < a.a_stages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), CHUNKS); }
+        for (int s = 0; s < a.b_slots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), CHUNKS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), CHUNKS); mbar_init(acc_empty(s), kEpiWarps); }
         fence_mbar_init();
         tma_prefetch_desc(&tmA_hi);
         if (APL == 2) tma_prefetch_desc(&tmA_lo);
@@ -168,7 +174,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    const int box_bytes = (a.TH + 2) * a.P * 128;
+    constexpr int box_bytes = (THc + 2) * Pc * 128;
     const int cout_pad = a.NB * NT;
 
     if (warp == 0) {
@@ -215,16 +221,21 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 }
             }
         }
-    } else if (warp == 1) {
-        // ============================== MMA issuer ==============================
+    } else if (warp == 1 || (CHUNKS == 2 && warp == kIssuer2Warp)) {
+        // ============================== MMA issuers ==============================
+        // One issuer warp per chunk (warp 1: chunk 0, last warp: chunk 1).  A single thread needs ~70 cycles per
+        // tcgen05.mma (descriptor arithmetic on the uniform datapath, ncu source view), more than the 32..64 cycles an
+        // N = 64 / 128 MMA occupies the tensor pipe; two issuers, each feeding its own accumulator, keep the pipe full and
+        // the per-accumulator issue order -- hence the fp32 summation order -- fixed.
         // The whole warp walks the pipeline convergently (waits, stage counters and descriptor words stay in
         // uniform registers); only the tcgen05 instructions are predicated on one elected lane.
+        const int c = warp == 1 ? 0 : 1;
         constexpr uint32_t idesc = umma_idesc_f16(128, NT);
         constexpr uint32_t idesc2 = umma_idesc_f16(128, STACK ? 2 * NT : NT);
         constexpr uint32_t idesc8a = umma_idesc_f8(128, NT, kF8E5M2, kF8E4M3);   // bytes [0,64):   e5m2(16 x_lo) * e4m3(8 w_hi)
         constexpr uint32_t idesc8b = umma_idesc_f8(128, NT, kF8E4M3, kF8E5M2);   // bytes [64,128): e4m3(x_hi) * e5m2(128 w_lo)
         const bool lead = elect_one();
-        const uint32_t a_hi_word = a.a_desc_hi;
+        constexpr uint32_t a_hi_word = A_DESC_HI;
         uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
         bool ok = true;
         for (int tile = blockIdx.x; tile < a.num_tiles && ok; tile += gridDim.x) {
@@ -244,7 +255,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 for (int ky = 0; ky < 3 && ok; ++ky) {
 #pragma unroll 1
                     for (int kx = 0; kx < 3 && ok; ++kx) {
-                        const uint32_t a_off = static_cast<uint32_t>(ky * a.P + kx) * 8u;      // rows of 128 B, >> 4
+                        const uint32_t a_off = static_cast<uint32_t>(ky * Pc + kx) * 8u;      // rows of 128 B, >> 4
                         const uint32_t ah = a_hi0 + a_off, al = a_lo0 + a_off;
                         ok = __all_sync(0xffffffffu, mbar_wait(b_full(bs), bph, a.err, ERR_B_FULL));
                         if (!ok) break;
@@ -252,9 +263,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                         {
                             const uint32_t b0 = umma_desc_lo(sB + bs * B_SLOT_BYTES);
                             if (lead) {
-#pragma unroll
-                                for (int c = 0; c < CHUNKS; ++c) {
-                                    const uint32_t co = c ? a.chunk_off : 0u;
+                                {
+                                    const uint32_t co = c * CHUNK_OFF;
 #pragma unroll
                                     for (int k = 0; k < 4; ++k) {
                                         if (k >= ksteps) break;
@@ -277,9 +287,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                             tc_fence_after();
                             const uint32_t b0 = umma_desc_lo(sB + bs * B_SLOT_BYTES);
                             if (lead) {
-#pragma unroll
-                                for (int c = 0; c < CHUNKS; ++c) {
-                                    const uint32_t co = c ? a.chunk_off : 0u;
+                                {
+                                    const uint32_t co = c * CHUNK_OFF;
                                     if (F8) {
 #pragma unroll
                                         for (int k = 0; k < 4; ++k) {
@@ -308,7 +317,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             if (lead && ok) umma_commit(acc_full(cs));
             if (++cs == 2) { cs = 0; cph ^= 1; }
         }
-    } else {
+    } else if (warp < 2 + kEpiWarps) {
         // ============================== epilogue ==============================
         const int ew = warp - 2;             // 0..7
         const int q4 = warp & 3;             // TMEM lane quarter this warp may read
@@ -327,9 +336,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         //   read : lane -> row (lane >> 2) + 8*i, group lane & 3 -> 2 rows x 4 groups per phase, again all different
         const uint32_t wr_base = stg + lane * 64, wr_sw = (lane >> 1) & 3;
         const uint32_t rd_row = lane >> 2, rd_grp = lane & 3;
-        // chunk origin inside the tile: chunks sit side by side (cx == 2) or on top of each other; MMA row m of a chunk
-        // is pixel (m & 7) of row (m >> 3)
-        const int ch_x0 = a.cx == 2 ? my_c * 8 : 0, ch_y0 = a.cx == 2 ? 0 : my_c * 16;
+        // chunk origin inside the tile (chunks sit side by side); MMA row m of a chunk is pixel (m & 7) of row (m >> 3)
+        const int ch_x0 = my_c * 8, ch_y0 = 0;
 
         for (int tile = blockIdx.x; tile < a.num_tiles && ok; tile += gridDim.x) {
             const TileCoord t = decode_tile(a, tile);
