@@ -87,13 +87,16 @@ bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int n
     a.NB = cout_pad / NT;
     a.num_tiles = n_img * a.tiles_x * a.tiles_y * a.NB;
     a.a_plane_bytes = (a.TH + 2) * a.P * 128;
-    a.a_stages = 2;
-    int slots = (kConvMaxSmem - fixed - 2 * apl * a.a_plane_bytes) / slot_bytes;
+    a.a_stages = planes == 3 ? 1 : 2;      // f16f8 keeps one buffer per activation plane (phase-split main loop)
+    a.pf16 = 3; a.pf8 = 12;
+    if (const char* e = getenv("FISR_PF16")) a.pf16 = atoi(e);      // tuning knobs
+    if (const char* e = getenv("FISR_PF8")) a.pf8 = atoi(e);
+    int slots = (kConvMaxSmem - fixed - a.a_stages * apl * a.a_plane_bytes) / slot_bytes;
     if (slots > convk::kMaxBSlots) slots = convk::kMaxBSlots;
     if (slots < 2) return false;
     a.b_slots = slots;
     L->NT = NT; L->chunks = chunks; L->planes = planes;
-    L->smem_bytes = fixed + 2 * apl * a.a_plane_bytes + slots * slot_bytes;
+    L->smem_bytes = fixed + a.a_stages * apl * a.a_plane_bytes + slots * slot_bytes;
     L->efficiency = best_eff;
     return true;
 }

@@ -160,7 +160,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 
     if (tid == 0) {
         // every chunk has its own MMA issuer warp: operand buffers are released, and accumulators published, by all of them
-        for (int s = 0; s < a.a_stages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), CHUNKS); }
+        for (int s = 0; s < kMaxAStages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), CHUNKS); }
         for (int s = 0; s < a.b_slots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), CHUNKS); }
         for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), CHUNKS); mbar_init(acc_empty(s), kEpiWarps); }
         fence_mbar_init();
@@ -179,6 +179,43 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
+        if constexpr (F8) {
+            // f16f8: every (tile, K block) item runs as two phases -- A: the 9 taps of the 8-bit cross terms (8-bit patch,
+            // 8-bit weight plane), B: the 9 taps of the fp16 main term.  Each activation plane therefore sits idle during the
+            // other phase, which is when its next patch is loaded: ONE buffer per plane instead of two stages of two planes.
+            // The 83 KB this frees hold 8 weight slots (NT = 128) instead of 3, enough to cover the L2 latency of the weight stream.
+            if (elect_one()) {
+                uint32_t e16 = 0, e8 = 0, bs = 0, bph = 0;
+                bool ok = true;
+                auto issue_plane = [&](int buf, const CUtensorMap* tm, int tile, int kb, uint32_t& eph) -> bool {
+                    if (!mbar_wait(a_empty(buf), eph ^ 1, a.err, ERR_A_EMPTY)) return false;
+                    eph ^= 1;
+                    const TileCoord t = decode_tile(a, tile);
+                    mbar_expect_tx(a_full(buf), box_bytes);
+                    tma_load_4d(sA + buf * a.a_plane_bytes, tm, a_full(buf), a.cin_off + kb * 64, t.x0 - 1, t.y0 - 1, t.n);
+                    return true;
+                };
+                if (blockIdx.x < a.num_tiles) ok = issue_plane(1, &tmA_lo, blockIdx.x, 0, e8);
+                for (int tile = blockIdx.x; tile < a.num_tiles && ok; tile += gridDim.x) {
+                    const int nb = tile % a.NB;
+                    for (int kb = 0; kb < a.KB && ok; ++kb) {
+                        int ntile = tile, nkb = kb + 1;
+                        if (nkb == a.KB) { nkb = 0; ntile += gridDim.x; }
+                        for (int sl = 0; sl < 18 && ok; ++sl) {
+                            if (sl == a.pf16) ok = issue_plane(0, &tmA_hi, tile, kb, e16);
+                            if (sl == a.pf8 && ntile < a.num_tiles && ok) ok = issue_plane(1, &tmA_lo, ntile, nkb, e8);
+                            if (!ok) break;
+                            const int plane = sl < 9 ? 1 : 0, tap = sl < 9 ? sl : sl - 9;
+                            ok = mbar_wait(b_empty(bs), bph ^ 1, a.err, ERR_B_EMPTY);
+                            if (!ok) break;
+                            mbar_expect_tx(b_full(bs), B_SLOT_BYTES);
+                            tma_load_2d(sB + bs * B_SLOT_BYTES, &tmB, b_full(bs), 0, ((plane * a.KB + kb) * 9 + tap) * cout_pad + nb * NT);
+                            if (++bs == (uint32_t)a.b_slots) { bs = 0; bph ^= 1; }
+                        }
+                    }
+                }
+            }
+        } else
         if (elect_one()) {
             uint32_t as = 0, aph = 0, bs = 0, bph = 0;
             bool ok = true;
@@ -238,6 +275,62 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         constexpr uint32_t a_hi_word = A_DESC_HI;
         uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
         bool ok = true;
+        if constexpr (F8) {
+            uint32_t f16ph = 0, f8ph = 0;
+            const uint32_t co = c * CHUNK_OFF;
+            for (int tile = blockIdx.x; tile < a.num_tiles && ok; tile += gridDim.x) {
+                ok = __all_sync(0xffffffffu, mbar_wait(acc_empty(cs), cph ^ 1, a.err, ERR_ACC_EMPTY));
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + cs * ACC_COLS + c * DCOLS;
+                for (int kb = 0; kb < a.KB && ok; ++kb) {
+                    const int ksteps = kb == a.KB - 1 ? a.ksteps_last : 4;   // 16-channel K slices that hold real channels
+                    const int k8steps = (ksteps + 1) >> 1;                   // 32-channel slices of each half of the 8-bit rows
+#pragma unroll 1
+                    for (int phase = 0; phase < 2 && ok; ++phase) {           // 0: 8-bit cross terms, 1: fp16 main term
+                        const int buf = phase == 0 ? 1 : 0;
+                        ok = __all_sync(0xffffffffu, mbar_wait(a_full(buf), phase == 0 ? f8ph : f16ph, a.err, ERR_A_FULL));
+                        if (!ok) break;
+                        if (phase == 0) f8ph ^= 1; else f16ph ^= 1;
+                        const uint32_t a0 = umma_desc_lo(sA + buf * a.a_plane_bytes) + co;
+                        uint32_t first = (kb == 0 && phase == 0) ? 0u : 1u;  // accumulate flag of the very first MMA of the tile
+#pragma unroll 1
+                        for (int ky = 0; ky < 3 && ok; ++ky) {
+#pragma unroll 1
+                            for (int kx = 0; kx < 3 && ok; ++kx) {
+                                const uint32_t at = a0 + static_cast<uint32_t>(ky * Pc + kx) * 8u;      // rows of 128 B, >> 4
+                                ok = __all_sync(0xffffffffu, mbar_wait(b_full(bs), bph, a.err, ERR_B_FULL));
+                                if (!ok) break;
+                                tc_fence_after();
+                                const uint32_t b0 = umma_desc_lo(sB + bs * B_SLOT_BYTES);
+                                if (lead) {
+                                    if (phase == 0) {
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) {
+                                            if ((k & 1) >= k8steps) continue;
+                                            umma_f8_lohi2(d_tmem, at + k * 2, a_hi_word, b0 + k * 2, kUmmaDescHiSw128,
+                                                          k < 2 ? idesc8a : idesc8b, k == 0 ? first : 1u);
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) {
+                                            if (k >= ksteps) break;
+                                            umma_f16_lohi2(d_tmem, at + k * 2, a_hi_word, b0 + k * 2, kUmmaDescHiSw128, idesc, 1u);
+                                        }
+                                    }
+                                    umma_commit(b_empty(bs));
+                                }
+                                first = 1u;
+                                if (++bs == (uint32_t)a.b_slots) { bs = 0; bph ^= 1; }
+                            }
+                        }
+                        if (lead && ok) umma_commit(a_empty(buf));
+                    }
+                }
+                if (lead && ok) umma_commit(acc_full(cs));
+                if (++cs == 2) { cs = 0; cph ^= 1; }
+            }
+        } else {
         for (int tile = blockIdx.x; tile < a.num_tiles && ok; tile += gridDim.x) {
             ok = __all_sync(0xffffffffu, mbar_wait(acc_empty(cs), cph ^ 1, a.err, ERR_ACC_EMPTY));
             if (!ok) break;
@@ -316,6 +409,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             }
             if (lead && ok) umma_commit(acc_full(cs));
             if (++cs == 2) { cs = 0; cph ^= 1; }
+        }
         }
     } else if (warp < 2 + kEpiWarps) {
         // ============================== epilogue ==============================
