@@ -227,8 +227,11 @@ def run_b200(args):
     canvases = [torch.empty((oh, ow, 9), dtype=torch.uint8).pin_memory() for _ in range(2)]
     pin_np = [p.numpy() for p in pin]
     e2e_steps = max(2, min(steps, 10))
-    for _ in range(2):
-        eng.window_host(pin_np[0], pin_np[1], pin_np[2], GRID, out=canvases[0].numpy())
+    for k in range(4):       # warm-up through the same pipelined entry points (slot staging buffers, copy streams, events)
+        eng.window_submit(k & 1, pin_np[0], pin_np[1], pin_np[2], GRID, out=canvases[k & 1].numpy())
+        if k > 0:
+            eng.window_wait((k - 1) & 1)
+    eng.window_wait(1)
     barrier()
     # two windows in flight (what FISRnet.FISR_for_video does): every window still pays its H2D and D2H inside the timed
     # region, on copy streams that overlap the previous / next window's kernels
