@@ -9,7 +9,9 @@ Documented deviations from the reference:
   * ``FISR_for_video`` sorts the frame list (the reference's unsorted ``glob`` at FISRnet.py:953 returns a
     file-system-dependent order; the shipped scene1 outputs correspond to the sorted order, like ``test()`` :762).
   * the tile loop runs as one batched forward instead of growing a TF graph per tile (FISRnet.py:1039-1041).
-  * checkpoints are ``.npz`` files keyed by the TF variable names (no TensorFlow in this stack).
+  * checkpoints are ``.npz`` files keyed by the TF variable names (no TensorFlow in this stack); a training checkpoint
+    carries the weights and the step, not the Adam moments (they restart at zero after a resume).
+  * ``train`` prints what the reference prints; the TensorBoard summaries (FISRnet.py:533-578) are not written.
   * the printed "Estimated Inference Time" is per window from CUDA-synchronised wall time.
 """
 from __future__ import annotations
@@ -74,11 +76,134 @@ class FISRnet(object):
 
     # ------------------------------------------------------------------ training (FISRnet.py:175-743)
     def build_model(self):
-        raise NotImplementedError("the training graph (multi-scale temporal loss + backward + Adam, FISRnet.py:175-491) is "
-                                  "not part of this round's B200 path; see DESIGN.md 'Scope'")
+        """Reads the training set and fixes the schedule (FISRnet.py:175-248).  The graph itself -- four weight-shared
+        forwards, multi-scale temporal loss, backward, Adam (FISRnet.py:250-491) -- is ``fisr_train_step`` in the library."""
+        print(" Start to read 4K data.")
+        data, label = utils.read_mat_file(self.train_data_path, self.train_label_path, 'LR_data', 'HR_data')  # [B,N_seq,H,W,C]
+        print(" Successfully load.")
+        data, label = merge_seq_dim(data), merge_seq_dim(label)          # [B,h,w,15], [B,2h,2w,21]
+        self.data_sz, self.label_sz = data.shape, label.shape
+        print(" Start to read flow data.")
+        flow = merge_seq_dim(read_flo_file_5dim(self.train_flow_data_path)) / self.data_sz[1] / 2          # FISRnet.py:195-197
+        flow_ss2 = merge_seq_dim(read_flo_file_5dim(self.train_flow_ss2_data_path)) / self.data_sz[1] / 2  # :199-202
+        print(" Successfully load.")
+        print(" Start to read warped data.")
+        warp = merge_seq_dim(read_mat_file_warp(self.train_warped_data_path, 'pred'))
+        warp_ss2 = merge_seq_dim(read_mat_file_warp(self.train_wapred_ss2_data_path, 'pred'))
+        print(" Successfully load.")
+        v = self.val_data_size                                           # split val / train, FISRnet.py:213-227
+        as32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        self.data_val, self.label_val, self.flow_val, self.warp_val = (as32(a[-v:]) for a in (data, label, flow, warp))
+        self.flow_ss2_val, self.warp_ss2_val = as32(flow_ss2[-v:]), as32(warp_ss2[-v:])
+        self.data, self.label, self.flow, self.flow_ss2, self.warp, self.warp_ss2 = (
+            as32(a[:-v]) for a in (data, label, flow, flow_ss2, warp, warp_ss2))
+        self.train_iter = math.floor((self.data_sz[0] - v) / self.batch_size)
+        self.val_iter = math.floor(v / self.val_batch_size)
+        self.global_step = 0
+        if self.lr_type == "stair_decay":                                # tf.train.piecewise_constant, FISRnet.py:233-240
+            self.epoch_lr_to_be_decayed_boundaries = [y * self.train_iter for y in self.lr_stair_decay_points]
+            self.epoch_lr_to_be_decayed_value = [self.init_lr * (self.lr_decreasing_factor ** y)
+                                                 for y in range(len(self.lr_stair_decay_points) + 1)]
+            print("lr_type: stair_decay")
+        elif self.lr_type == "linear_decay":
+            print("lr_type: linear_decay")
+        else:
+            print("lr_type: no decay")
+        self.lambdas = {"recn": self.recn_lambda, "tm1": self.tm1_lambda, "tm2": self.tm2_lambda, "tmm": self.tmm_lambda,
+                        "td": self.td_lambda, "ss2": self.ss2_lambda}    # main.py:80-85
+        self._built = True
+
+    def _lr(self, epoch):
+        """Learning rate of the step about to run: piecewise constant in global_step (x <= boundary keeps the earlier value,
+        like tf.train.piecewise_constant), linear decay in the epoch (FISRnet.py:631-633), or constant."""
+        if self.lr_type == "stair_decay":
+            k = sum(1 for b in self.epoch_lr_to_be_decayed_boundaries if self.global_step > b)
+            return self.epoch_lr_to_be_decayed_value[k]
+        if self.lr_type == "linear_decay" and epoch >= self.lr_linear_decay_point:
+            return self.init_lr * (self.epoch - epoch) / (self.epoch - self.lr_linear_decay_point)
+        return self.init_lr
+
+    def validate(self, data, label, flow, warp):
+        """Validation graph of FISRnet.py:492-531 on one batch: three stride-1 windows through the shared network,
+        ``Groups2Ovlp``, then L2 and ``tf.image.psnr`` (per image, then mean) against the 7 GT frames."""
+        import torch
+        dev = "cuda:%d" % self.engine.device
+        d, f, w = (torch.as_tensor(a, dtype=torch.float32, device=dev) for a in (data, flow, warp))
+        gt = torch.as_tensor(label, dtype=torch.float32, device=dev)
+        B, H2, W2, _ = gt.shape
+        # window i: frames i..i+2, flows 4i..4i+8, warps 6i..6i+12 (ops.py:90-116), the three windows as one batch
+        x = torch.cat([torch.cat((d[..., 3 * i:3 * i + 9], f[..., 4 * i:4 * i + 8], w[..., 6 * i:6 * i + 12]), dim=3)
+                       for i in range(3)], dim=0)
+        pred = self.engine.forward(x, want=(False, False, True))[2]      # [3B, 2h, 2w, 9], windows 0, 1, 2 stacked
+        seq = self.engine.groups2ovlp(pred)                              # [B, 7, 2h, 2w, 3]
+        gt = gt.reshape(B, H2, W2, 7, 3).permute(0, 3, 1, 2, 4)           # tf_split_seq_dim
+        err = (seq - gt) ** 2
+        recn = float(err.mean())                                         # L2_loss, ops.py:30-32
+        mse = err.mean(dim=(2, 3, 4))                                    # tf.image.psnr: last three dims of [B, 7, H, W, 3]
+        return recn, float((-10.0 * torch.log10(mse)).mean())
 
     def train(self):
-        raise NotImplementedError("see build_model")
+        if not getattr(self, "_built", False):
+            self.build_model()
+        self._ensure_variables()                                         # tf.global_variables_initializer().run()
+        self.engine.set_precision("f16x3")                               # the backward kernels need the split operand planes
+        could_load, checkpoint_counter = self.load(self.checkpoint_dir)  # FISRnet.py:593-604
+        if could_load:
+            start_epoch = int(checkpoint_counter / self.train_iter)
+            counter = checkpoint_counter
+            self.global_step = checkpoint_counter
+            self.engine.adam_reset(checkpoint_counter)                   # Adam moments restart at zero (not in the .npz)
+            print(" [*] Load SUCCESS")
+        else:
+            start_epoch, counter = 0, 1
+            self.engine.adam_reset(0)
+            print(" [!] Load failed...")
+        import torch
+        dev = "cuda:%d" % self.engine.device
+        names = self.engine.LOSS_NAMES
+        start_time = time.time()
+        for epoch in range(start_epoch, self.epoch):
+            hist = {k: [] for k in names}
+            rand_idx = np.random.permutation(self.data_sz[0] - self.val_data_size)      # FISRnet.py:622
+            lr = self._lr(epoch)
+            for idx in range(self.train_iter):
+                sel = rand_idx[self.batch_size * idx:self.batch_size * (idx + 1)]
+                lr = self._lr(epoch)
+                batch = [torch.from_numpy(a[sel]).to(dev, non_blocking=True)            # the feed_dict of FISRnet.py:634-639
+                         for a in (self.data, self.flow, self.flow_ss2, self.warp, self.warp_ss2, self.label)]
+                s = self.engine.train_step(*batch, lr, self.lambdas)
+                self.global_step += 1
+                if np.mod(idx, self.freq_display) == 0:
+                    print("Epoch: [%3d], [%4d/%4d]-th batch, time: %4.2f(min.), "
+                          "train_PSNR: %.3f, recnLoss: %.6f, tmLoss: %.6f, tmmLoss: %.6f, tdLoss: %.6f, "
+                          "totalLoss_s1: %.6f,recnLoss_ss2: %.6f,"
+                          "tdLoss_ss2: %.6f, tmLoss_ss2: %.6f, totalLoss_ss2: %.6f, total_loss: %.6f"
+                          % (epoch, idx, self.train_iter, (time.time() - start_time) / 60, s["train_PSNR"], s["recnLoss"],
+                             s["tmLoss"], s["tmmLoss"], s["tdLoss"], s["totalLoss_s1"], s["recnLoss_ss2"], s["tdLoss_ss2"],
+                             s["tmLoss_ss2"], s["totalLoss_ss2"], s["total_loss"]))
+                counter += 1
+                for k in names:
+                    hist[k].append(s[k])
+            m = {k: float(np.mean(hist[k])) if hist[k] else float("nan") for k in names}
+            print("# (average) Epoch: [%4d], LR: %1.10f, time: %4.2f(minutes), "
+                  "train_PSNR: %.3f, recnLoss: %.6f, tmLoss: %.6f, tmmLoss: %.6f, tdLoss: %.6f, "
+                  "totalLoss_s1: %.6f,recnLoss_ss2: %.6f,"
+                  "tdLoss_ss2: %.6f, tmLoss_ss2: %.6f, totalLoss_ss2: %.6f, total_loss: %.6f"
+                  % (epoch, lr, (time.time() - start_time) / 60, m["train_PSNR"], m["recnLoss"], m["tmLoss"], m["tmmLoss"],
+                     m["tdLoss"], m["totalLoss_s1"], m["recnLoss_ss2"], m["tdLoss_ss2"], m["tmLoss_ss2"], m["totalLoss_ss2"],
+                     m["total_loss"]))
+            val_recn, val_psnr = [], []                                  # FISRnet.py:706-722
+            for val_idx in range(self.val_iter):
+                sl = slice(self.val_batch_size * val_idx, self.val_batch_size * (val_idx + 1))
+                r, p_ = self.validate(self.data_val[sl], self.label_val[sl], self.flow_val[sl], self.warp_val[sl])
+                val_recn.append(r)
+                val_psnr.append(p_)
+            print("######### Validation (average),Epoch: [%4d/%4d]-th epoch, time: %4.2f(min.), val_PSNR: %.3f[dB], "
+                  "recnLoss: %.6f #########"
+                  % (epoch, self.epoch, (time.time() - start_time) / 60,
+                     float(np.mean(val_psnr)) if val_psnr else float("nan"), float(np.mean(val_recn)) if val_recn else float("nan")))
+            self.save_checkpoint(self.checkpoint_dir, self.global_step)  # FISRnet.py:737
+        self.save_checkpoint(self.checkpoint_dir, self.global_step)      # FISRnet.py:743
 
     # ------------------------------------------------------------------ shared inner loop
     def _window(self, frames_u8, flow_sample, warp_sample, num_patch):
@@ -195,7 +320,8 @@ class FISRnet(object):
         ckpt_name = None
         if os.path.exists(state):
             m = re.search(r'model_checkpoint_path:\s*"([^"]+)"', open(state).read())
-            if m and os.path.exists(os.path.join(checkpoint_dir, os.path.basename(m.group(1)))):
+            if m and (os.path.exists(os.path.join(checkpoint_dir, os.path.basename(m.group(1)))) or
+                      os.path.exists(os.path.join(checkpoint_dir, os.path.basename(m.group(1)) + ".index"))):
                 ckpt_name = os.path.basename(m.group(1))
         if ckpt_name and ckpt_name.endswith(".npz"):
             data = np.load(os.path.join(checkpoint_dir, ckpt_name))
@@ -206,6 +332,14 @@ class FISRnet(object):
             self.engine.set_params(params)
             self._initialized = True
             counter = int(next(re.finditer(r"(\d+)(?!.*\d)", ckpt_name)).group(0))
+            print(" [*] Success to read {}".format(ckpt_name))
+            return True, counter
+        if ckpt_name and os.path.exists(os.path.join(checkpoint_dir, ckpt_name + ".index")):
+            # a checkpoint written by the reference itself (tf.train.Saver V2 bundle, e.g. the released FISRnet-122000)
+            from .tf_checkpoint import fisrnet_weights
+            self.engine.set_params(fisrnet_weights(os.path.join(checkpoint_dir, ckpt_name)))
+            self._initialized = True
+            counter = int(next(re.finditer(r"(\d+)(?!.*\d)", ckpt_name)).group(0))       # FISRnet.py:1110
             print(" [*] Success to read {}".format(ckpt_name))
             return True, counter
         print(" [*] Failed to find a checkpoint")           # like the reference, not an error (FISRnet.py:1113-1115)

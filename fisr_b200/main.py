@@ -5,6 +5,7 @@
 from __future__ import annotations
 
 import argparse
+import os
 
 from .FISRnet import FISRnet
 from .utils import check_folder
@@ -65,8 +66,9 @@ def parse_args(argv=None):
     p.add_argument('--FISR_input_size', type=_pair, default=(1080, 1920))
     p.add_argument('--frame_num', type=int, default=5)
     p.add_argument('--FISR_test_patch', type=_pair, default=(2, 2))
-    p.add_argument('--precision', type=str, default='f16x3', choices=['f16x3', 'f16'],
-                   help='B200 path only: fp32-class split operands (default) or single-fp16 fast mode')
+    p.add_argument('--precision', type=str, default='f16x3', choices=['f16x3', 'f16', 'f16f8'],
+                   help='B200 path only: f16x3 = fp32-class split operands (default; training always uses it), f16f8 = fp16 main '
+                        'term + fp8 cross terms (inference, ~3e-5 max-abs, 1.2x faster), f16 = single-fp16 fast mode')
     p.add_argument('--device', type=int, default=0, help='B200 path only: CUDA device index')
     args = p.parse_args(argv)
     for d in (args.checkpoint_dir, args.text_dir, args.log_dir, args.test_img_dir):         # main.py:108-121
@@ -78,8 +80,19 @@ def main(argv=None):
     args = parse_args(argv)
     net = FISRnet(args.device, args)
     if args.phase == 'train':
+        with open(args.text_dir + '/exp_' + str(args.exp_num) + '.txt', 'a') as log:        # main.py:131-134
+            log.write('----- Model parameters -----\n')
+            for arg in vars(args):
+                log.write('{} : {}\n'.format(arg, getattr(args, arg)))
+        print("[*] Exp: ", args.exp_num)
         net.build_model()
+        print("[*] Training starts")
         net.train()
+        print("[*] Training finished! ")
+        if args.test_data_path and os.path.isdir(args.test_data_path):                        # "test after training", main.py:159-181
+            print("[*] Testing starts")
+            net.test()
+            print("[*] Testing finished! ")
     elif args.phase == 'test':
         net.test()
     else:                                                                                    # main.py:206-236

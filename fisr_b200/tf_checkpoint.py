@@ -1,0 +1,402 @@
+"""TensorFlow checkpoint ("tensor bundle", V2 format) reader / writer without TensorFlow.
+
+The reference restores ``FISRnet-122000`` with ``tf.train.Saver.restore`` (FISRnet.py:1101-1115, README.md:56-66).  A V2
+checkpoint is two kinds of files:
+
+  ``<prefix>.index``                  a LevelDB-format *table* (sorted string table): key "" -> ``BundleHeaderProto``,
+                                      key <variable name> -> ``BundleEntryProto`` (dtype, shape, shard, offset, size, crc32c)
+  ``<prefix>.data-SSSSS-of-NNNNN``    the raw little-endian tensor bytes the entries point into
+
+Table layout (LevelDB ``table_format.md``): blocks of prefix-compressed entries
+``varint32 shared | varint32 non_shared | varint32 value_len | key suffix | value`` followed by a restart array
+(``uint32`` offsets, then their count) and a 5-byte trailer (compression type, masked crc32c); the file ends with a 48-byte
+footer = metaindex handle + index handle (varint64 offset, size each, zero-padded to 40 bytes) + magic
+``0xdb4775248b80fb57``.  The index block maps a separator key to the handle of each data block.
+
+PARITY NOTE: TensorFlow is not installable in this environment, so this module is validated by its
+own writer/reader round trip and by hand-assembled fixtures of the published format, not against files written by
+TensorFlow itself.  Snappy-compressed blocks (TensorFlow writes the index uncompressed) are decoded by a small built-in
+decompressor.
+"""
+from __future__ import annotations
+
+import os
+import re
+import struct
+from collections import OrderedDict
+from typing import Dict, Iterator, List, Optional, Tuple
+
+import numpy as np
+
+TABLE_MAGIC = 0xdb4775248b80fb57
+DT_FLOAT, DT_DOUBLE, DT_INT32, DT_INT64, DT_HALF = 1, 2, 3, 9, 19
+_NP_OF_DT = {DT_FLOAT: np.float32, DT_DOUBLE: np.float64, DT_INT32: np.int32, DT_INT64: np.int64, DT_HALF: np.float16}
+_DT_OF_NP = {np.dtype(v): k for k, v in _NP_OF_DT.items()}
+
+
+# ------------------------------------------------------------------------------------------ primitives
+def _varint(buf: bytes, pos: int) -> Tuple[int, int]:
+    out = shift = 0
+    while True:
+        b = buf[pos]
+        pos += 1
+        out |= (b & 0x7F) << shift
+        if b < 0x80:
+            return out, pos
+        shift += 7
+
+
+def _put_varint(v: int) -> bytes:
+    out = bytearray()
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+_CRC_TABLES: Optional[List[List[int]]] = None
+
+
+def _crc_tables() -> List[List[int]]:
+    global _CRC_TABLES
+    if _CRC_TABLES is None:
+        t0 = []
+        for i in range(256):
+            c = i
+            for _ in range(8):
+                c = (c >> 1) ^ 0x82F63B78 if c & 1 else c >> 1
+            t0.append(c)
+        tabs = [t0]
+        for k in range(1, 8):                            # slicing-by-8: table k advances a byte k positions further
+            prev = tabs[-1]
+            tabs.append([t0[prev[i] & 0xFF] ^ (prev[i] >> 8) for i in range(256)])
+        _CRC_TABLES = tabs
+    return _CRC_TABLES
+
+
+def crc32c(data: bytes, crc: int = 0) -> int:
+    """CRC-32C (Castagnoli), the checksum of LevelDB blocks and bundle entries (pure Python, slicing-by-8)."""
+    t0, t1, t2, t3, t4, t5, t6, t7 = _crc_tables()
+    c = crc ^ 0xFFFFFFFF
+    n8 = len(data) // 8
+    if n8:
+        for (lo, hi) in struct.iter_unpack("<II", memoryview(data)[:n8 * 8]):
+            lo ^= c
+            c = (t7[lo & 0xFF] ^ t6[(lo >> 8) & 0xFF] ^ t5[(lo >> 16) & 0xFF] ^ t4[lo >> 24] ^
+                 t3[hi & 0xFF] ^ t2[(hi >> 8) & 0xFF] ^ t1[(hi >> 16) & 0xFF] ^ t0[hi >> 24])
+    for b in data[n8 * 8:]:
+        c = t0[(c ^ b) & 0xFF] ^ (c >> 8)
+    return c ^ 0xFFFFFFFF
+
+
+def mask_crc(crc: int) -> int:
+    return (((crc >> 15) | (crc << 17)) + 0xa282ead8) & 0xFFFFFFFF
+
+
+def snappy_decompress(buf: bytes) -> bytes:
+    """Raw snappy block format (a varint length, then literal / copy elements)."""
+    n, pos = _varint(buf, 0)
+    out = bytearray()
+    while pos < len(buf):
+        tag = buf[pos]
+        pos += 1
+        kind = tag & 3
+        if kind == 0:                                   # literal
+            ln = tag >> 2
+            if ln >= 60:
+                nb = ln - 59
+                ln = int.from_bytes(buf[pos:pos + nb], "little")
+                pos += nb
+            ln += 1
+            out += buf[pos:pos + ln]
+            pos += ln
+            continue
+        if kind == 1:
+            ln = ((tag >> 2) & 7) + 4
+            off = ((tag >> 5) << 8) | buf[pos]
+            pos += 1
+        elif kind == 2:
+            ln = (tag >> 2) + 1
+            off = buf[pos] | (buf[pos + 1] << 8)
+            pos += 2
+        else:
+            ln = (tag >> 2) + 1
+            off = int.from_bytes(buf[pos:pos + 4], "little")
+            pos += 4
+        if off == 0 or off > len(out):
+            raise ValueError("corrupt snappy stream")
+        for _ in range(ln):                              # copies may overlap their own output
+            out.append(out[-off])
+    if len(out) != n:
+        raise ValueError("snappy length mismatch")
+    return bytes(out)
+
+
+# ------------------------------------------------------------------------------------------ protobuf (the two messages used)
+def _proto_fields(buf: bytes) -> Iterator[Tuple[int, int, object]]:
+    pos = 0
+    while pos < len(buf):
+        key, pos = _varint(buf, pos)
+        field, wire = key >> 3, key & 7
+        if wire == 0:
+            v, pos = _varint(buf, pos)
+        elif wire == 1:
+            v = buf[pos:pos + 8]
+            pos += 8
+        elif wire == 2:
+            ln, pos = _varint(buf, pos)
+            v = buf[pos:pos + ln]
+            pos += ln
+        elif wire == 5:
+            v = buf[pos:pos + 4]
+            pos += 4
+        else:
+            raise ValueError(f"unsupported protobuf wire type {wire}")
+        yield field, wire, v
+
+
+def _signed64(v: int) -> int:
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def parse_entry(buf: bytes) -> dict:
+    """``BundleEntryProto`` (tensorflow/core/protobuf/tensor_bundle.proto): 1 dtype, 2 shape, 3 shard_id, 4 offset, 5 size,
+    6 crc32c (fixed32, masked), 7 slices."""
+    e = {"dtype": 0, "shape": [], "shard_id": 0, "offset": 0, "size": 0, "crc32c": None, "slices": 0}
+    for field, _, v in _proto_fields(buf):
+        if field == 1:
+            e["dtype"] = v
+        elif field == 2:                                 # TensorShapeProto: 2 = repeated Dim {1: size, 2: name}, 3 = unknown_rank
+            for f2, _, v2 in _proto_fields(v):
+                if f2 == 2:
+                    size = 0
+                    for f3, _, v3 in _proto_fields(v2):
+                        if f3 == 1:
+                            size = _signed64(v3)
+                    e["shape"].append(size)
+        elif field == 3:
+            e["shard_id"] = v
+        elif field == 4:
+            e["offset"] = v
+        elif field == 5:
+            e["size"] = v
+        elif field == 6:
+            e["crc32c"] = struct.unpack("<I", v)[0]
+        elif field == 7:
+            e["slices"] += 1
+    return e
+
+
+def parse_header(buf: bytes) -> dict:
+    """``BundleHeaderProto``: 1 num_shards, 2 endianness (0 = little), 3 version {1 producer, 2 min_consumer}."""
+    h = {"num_shards": 1, "endianness": 0}
+    for field, _, v in _proto_fields(buf):
+        if field == 1:
+            h["num_shards"] = v
+        elif field == 2:
+            h["endianness"] = v
+    return h
+
+
+def _tag(field: int, wire: int) -> bytes:
+    return _put_varint((field << 3) | wire)
+
+
+def build_entry(dtype: int, shape, shard_id: int, offset: int, size: int, crc: int) -> bytes:
+    dims = b"".join(_tag(2, 2) + _put_varint(len(d)) + d for d in (_tag(1, 0) + _put_varint(int(s)) for s in shape))
+    out = _tag(1, 0) + _put_varint(dtype) + _tag(2, 2) + _put_varint(len(dims)) + dims
+    if shard_id:
+        out += _tag(3, 0) + _put_varint(shard_id)
+    if offset:
+        out += _tag(4, 0) + _put_varint(offset)
+    out += _tag(5, 0) + _put_varint(size) + _tag(6, 5) + struct.pack("<I", crc)
+    return out
+
+
+def build_header(num_shards: int = 1) -> bytes:
+    version = _tag(1, 0) + _put_varint(1)                # VersionDef.producer = 1 (kTensorBundleVersion)
+    return _tag(1, 0) + _put_varint(num_shards) + _tag(3, 2) + _put_varint(len(version)) + version
+
+
+# ------------------------------------------------------------------------------------------ table reader
+def _read_block(buf: bytes, offset: int, size: int, verify: bool) -> bytes:
+    raw, ctype = buf[offset:offset + size], buf[offset + size]
+    if verify:
+        stored = struct.unpack("<I", buf[offset + size + 1:offset + size + 5])[0]
+        if mask_crc(crc32c(buf[offset:offset + size + 1])) != stored:
+            raise ValueError(f"table block at {offset}: crc32c mismatch")
+    if ctype == 0:
+        return raw
+    if ctype == 1:
+        return snappy_decompress(raw)
+    raise ValueError(f"table block at {offset}: unknown compression type {ctype}")
+
+
+def _block_entries(block: bytes) -> Iterator[Tuple[bytes, bytes]]:
+    num_restarts = struct.unpack("<I", block[-4:])[0]
+    end = len(block) - 4 - 4 * num_restarts
+    pos, key = 0, b""
+    while pos < end:
+        shared, pos = _varint(block, pos)
+        non_shared, pos = _varint(block, pos)
+        vlen, pos = _varint(block, pos)
+        key = key[:shared] + block[pos:pos + non_shared]
+        pos += non_shared
+        yield key, block[pos:pos + vlen]
+        pos += vlen
+
+
+def read_table(path: str, verify: bool = False) -> "OrderedDict[bytes, bytes]":
+    buf = open(path, "rb").read()
+    if len(buf) < 48 or struct.unpack("<Q", buf[-8:])[0] != TABLE_MAGIC:
+        raise ValueError(f"{path} is not a LevelDB-format table (bad magic)")
+    footer = buf[-48:]
+    _, pos = _varint(footer, 0)                          # metaindex handle (unused)
+    _, pos = _varint(footer, pos)
+    idx_off, pos = _varint(footer, pos)
+    idx_size, pos = _varint(footer, pos)
+    out: "OrderedDict[bytes, bytes]" = OrderedDict()
+    for _, handle in _block_entries(_read_block(buf, idx_off, idx_size, verify)):
+        off, p = _varint(handle, 0)
+        size, _ = _varint(handle, p)
+        for k, v in _block_entries(_read_block(buf, off, size, verify)):
+            out[k] = v
+    return out
+
+
+# ------------------------------------------------------------------------------------------ public API
+def _data_path(prefix: str, shard: int, num_shards: int) -> str:
+    return f"{prefix}.data-{shard:05d}-of-{num_shards:05d}"
+
+
+def list_variables(prefix: str) -> "OrderedDict[str, Tuple[int, Tuple[int, ...]]]":
+    """name -> (dtype enum, shape), like ``tf.train.list_variables``."""
+    out: "OrderedDict[str, Tuple[int, Tuple[int, ...]]]" = OrderedDict()
+    for k, v in read_table(prefix + ".index").items():
+        if k:
+            e = parse_entry(v)
+            out[k.decode()] = (e["dtype"], tuple(e["shape"]))
+    return out
+
+
+def load_checkpoint(prefix: str, names=None, verify_crc: bool = False) -> "OrderedDict[str, np.ndarray]":
+    """Every (or the named) variable of the V2 checkpoint ``prefix`` as numpy arrays, like
+    ``tf.train.load_checkpoint(prefix).get_tensor(name)``."""
+    table = read_table(prefix + ".index", verify=verify_crc)
+    if b"" not in table:
+        raise ValueError(f"{prefix}.index has no bundle header entry")
+    header = parse_header(table[b""])
+    if header["endianness"] != 0:
+        raise ValueError("big-endian tensor bundles are not supported")
+    want = set(names) if names is not None else None
+    files: Dict[int, np.memmap] = {}
+    out: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    for k, v in table.items():
+        name = k.decode()
+        if not k or (want is not None and name not in want):
+            continue
+        e = parse_entry(v)
+        if e["slices"]:
+            raise ValueError(f"{name}: partitioned (sliced) variables are not supported")
+        if e["dtype"] not in _NP_OF_DT:
+            raise ValueError(f"{name}: unsupported dtype enum {e['dtype']}")
+        dt = np.dtype(_NP_OF_DT[e["dtype"]])
+        count = int(np.prod(e["shape"], dtype=np.int64)) if e["shape"] else 1
+        if count * dt.itemsize != e["size"]:
+            raise ValueError(f"{name}: entry size {e['size']} does not match shape {e['shape']}")
+        if e["shard_id"] not in files:
+            files[e["shard_id"]] = np.memmap(_data_path(prefix, e["shard_id"], header["num_shards"]), dtype=np.uint8, mode="r")
+        raw = files[e["shard_id"]][e["offset"]:e["offset"] + e["size"]]
+        if verify_crc and e["crc32c"] is not None and mask_crc(crc32c(raw.tobytes())) != e["crc32c"]:
+            raise ValueError(f"{name}: crc32c mismatch")
+        out[name] = np.frombuffer(raw.tobytes(), dtype=dt).reshape(e["shape"]).copy()
+    if want is not None and want - set(out):
+        raise KeyError(f"not in checkpoint: {sorted(want - set(out))[:3]}")
+    return out
+
+
+def _build_block(entries: List[Tuple[bytes, bytes]], restart_interval: int = 16) -> bytes:
+    out, restarts, prev = bytearray(), [], b""
+    for i, (k, v) in enumerate(entries):
+        shared = 0
+        if i % restart_interval == 0:
+            restarts.append(len(out))
+        else:
+            while shared < min(len(prev), len(k)) and prev[shared] == k[shared]:
+                shared += 1
+        out += _put_varint(shared) + _put_varint(len(k) - shared) + _put_varint(len(v)) + k[shared:] + v
+        prev = k
+    if not restarts:
+        restarts = [0]
+    out += b"".join(struct.pack("<I", r) for r in restarts) + struct.pack("<I", len(restarts))
+    return bytes(out)
+
+
+def save_checkpoint(prefix: str, tensors: Dict[str, np.ndarray], block_size: int = 4096) -> None:
+    """Writes ``tensors`` as a single-shard V2 checkpoint (uncompressed table blocks, crc32c on blocks and entries)."""
+    os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
+    items = sorted(((k.encode(), np.require(np.asarray(v), requirements="C")) for k, v in tensors.items()), key=lambda kv: kv[0])
+    entries: List[Tuple[bytes, bytes]] = [(b"", build_header(1))]
+    offset = 0
+    with open(_data_path(prefix, 0, 1), "wb") as f:
+        for k, a in items:
+            if a.dtype not in _DT_OF_NP:
+                raise ValueError(f"{k.decode()}: unsupported dtype {a.dtype}")
+            raw = a.tobytes()
+            f.write(raw)
+            entries.append((k, build_entry(_DT_OF_NP[a.dtype], a.shape, 0, offset, len(raw), mask_crc(crc32c(raw)))))
+            offset += len(raw)
+    table, index_entries, cur, cur_bytes = bytearray(), [], [], 0
+
+    def flush():
+        nonlocal cur, cur_bytes
+        if not cur:
+            return
+        block = _build_block(cur)
+        handle = _put_varint(len(table)) + _put_varint(len(block))
+        table.extend(block + b"\x00" + struct.pack("<I", mask_crc(crc32c(block + b"\x00"))))
+        index_entries.append((cur[-1][0], handle))       # the last key of a block is a valid separator
+        cur, cur_bytes = [], 0
+
+    for k, v in entries:
+        cur.append((k, v))
+        cur_bytes += len(k) + len(v) + 3
+        if cur_bytes >= block_size:
+            flush()
+    flush()
+    meta = _build_block([])
+    meta_handle = _put_varint(len(table)) + _put_varint(len(meta))
+    table.extend(meta + b"\x00" + struct.pack("<I", mask_crc(crc32c(meta + b"\x00"))))
+    index = _build_block(index_entries, restart_interval=1)
+    index_handle = _put_varint(len(table)) + _put_varint(len(index))
+    table.extend(index + b"\x00" + struct.pack("<I", mask_crc(crc32c(index + b"\x00"))))
+    footer = meta_handle + index_handle
+    table.extend(footer + b"\x00" * (40 - len(footer)) + struct.pack("<Q", TABLE_MAGIC))
+    with open(prefix + ".index", "wb") as f:
+        f.write(bytes(table))
+
+
+def latest_checkpoint(checkpoint_dir: str) -> Optional[str]:
+    """``tf.train.latest_checkpoint``: the prefix named by the text-proto state file ``<dir>/checkpoint``."""
+    state = os.path.join(checkpoint_dir, "checkpoint")
+    if not os.path.exists(state):
+        return None
+    m = re.search(r'model_checkpoint_path:\s*"([^"]+)"', open(state).read())
+    if not m:
+        return None
+    name = m.group(1)
+    return name if os.path.isabs(name) else os.path.join(checkpoint_dir, name)
+
+
+def fisrnet_weights(prefix: str, scope: str = "FISRnet") -> "OrderedDict[str, np.ndarray]":
+    """The 276 trainable variables of FISRnet (``<scope>/level_k/.../{w,b}``) from a reference checkpoint, leaving out the
+    optimizer slots (``.../Adam``, ``.../Adam_1``, ``beta1_power``, ``beta2_power``) and ``global_step``."""
+    from .engine import param_inventory
+    names = list(param_inventory())
+    avail = list_variables(prefix)
+    missing = [n for n in names if n not in avail]
+    if missing:
+        raise KeyError(f"checkpoint {prefix} lacks {len(missing)} FISRnet variables, e.g. {missing[0]}")
+    got = load_checkpoint(prefix, names)
+    return OrderedDict((n, got[n].astype(np.float32, copy=False)) for n in names)
