@@ -84,31 +84,36 @@ __global__ void pack_input_kernel(const float* __restrict__ img, int N, int H, i
 template <int PLANES>
 __global__ void upsample2_kernel(const __half* __restrict__ in, size_t pin, __half* __restrict__ out, size_t pout,
                                  int N, int h, int w, int C) {
+    // thread = one input pixel x 8 channels -> its 2 x 2 output block (4 loads, 4 stores; every input is read by at most
+    // 4 threads, through L1/L2)
     const int cv = C / 8;
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-    const size_t total = static_cast<size_t>(N) * (2 * h) * (2 * w) * cv;
+    const size_t total = static_cast<size_t>(N) * h * w * cv;
     if (i >= total) return;
     const int c8 = (i % cv) * 8;
     size_t r = i / cv;
-    const int X = r % (2 * w); r /= (2 * w);
-    const int Y = r % (2 * h);
-    const int n = r / (2 * h);
-    const int y0 = Y >> 1, x0 = X >> 1;
-    const int y1 = (Y & 1) ? min(y0 + 1, h - 1) : y0;
-    const int x1 = (X & 1) ? min(x0 + 1, w - 1) : x0;
+    const int x0 = r % w; r /= w;
+    const int y0 = r % h;
+    const int n = r / h;
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
     const __half* base = in + static_cast<size_t>(n) * h * w * C + c8;
     float a[8], b[8], c[8], d[8], o[8];
     load8<PLANES>(base + (static_cast<size_t>(y0) * w + x0) * C, pin, a);
     load8<PLANES>(base + (static_cast<size_t>(y1) * w + x0) * C, pin, b);
     load8<PLANES>(base + (static_cast<size_t>(y0) * w + x1) * C, pin, c);
     load8<PLANES>(base + (static_cast<size_t>(y1) * w + x1) * C, pin, d);
+    __half* ob = out + ((static_cast<size_t>(n) * 2 * h + 2 * y0) * 2 * w + 2 * x0) * C + c8;
+    const size_t row = static_cast<size_t>(2) * w * C;
+    store8<PLANES>(ob, pout, a);                                                  // (2y, 2x)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float v0 = (Y & 1) ? 0.5f * (a[j] + b[j]) : a[j];
-        const float v1 = (Y & 1) ? 0.5f * (c[j] + d[j]) : c[j];
-        o[j] = (X & 1) ? 0.5f * (v0 + v1) : v0;
-    }
-    store8<PLANES>(out + ((static_cast<size_t>(n) * 2 * h + Y) * 2 * w + X) * C + c8, pout, o);
+    for (int j = 0; j < 8; ++j) o[j] = 0.5f * (a[j] + c[j]);
+    store8<PLANES>(ob + C, pout, o);                                              // (2y, 2x+1)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.5f * (a[j] + b[j]);
+    store8<PLANES>(ob + row, pout, o);                                            // (2y+1, 2x)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.5f * (0.5f * (a[j] + b[j]) + 0.5f * (c[j] + d[j]));
+    store8<PLANES>(ob + row + C, pout, o);                                        // (2y+1, 2x+1)
 }
 
 // ---------------------------------------------------------------- 2x2 max pool (ops.py:54)
@@ -361,7 +366,7 @@ void launch_pack_input(const float* img, int N, int H, int W, int cin, ActBuf l3
 }
 
 void launch_upsample2(ActBuf in, ActBuf out, int N, int h, int w, int C, int planes, cudaStream_t st) {
-    const size_t total = static_cast<size_t>(N) * 4 * h * w * (C / 8);
+    const size_t total = static_cast<size_t>(N) * h * w * (C / 8);
     if (planes == 3)
         upsample2_kernel<3><<<blocks_for(total, 256), 256, 0, st>>>(in.p, in.plane, out.p, out.plane, N, h, w, C);
     else if (planes == 2)

@@ -492,6 +492,13 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 ok = __all_sync(0xffffffffu, mbar_wait(acc_full(cs), cph, a.err, ERR_ACC_FULL));
                 if (!ok) break;
                 tc_fence_after();
+                // TMEM loads and bias loads run one step ahead: the LDTM of step it+1 is in flight while step it is transposed,
+                // converted and stored (with two epilogue warps per scheduler nothing else would hide its latency)
+                uint32_t v[16], v2[16];
+                float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + cg_lane));
+                tmem_ld_32x16(tacc + c_begin, v);
+                if (STACK) tmem_ld_32x16(tacc + NT + c_begin, v2);
+                tmem_ld_wait();
 #pragma unroll
                 for (int it = 0; it < ITERS; ++it) {
                     const int c0 = it * 16;
@@ -511,23 +518,21 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                             if ((vmask >> i) & 1) mk[i] = __ldg(reinterpret_cast<const uint2*>(a.mask + o_msk[i] + c0));
                         }
                     }
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + cg_lane + c0));
-                    uint32_t v[16];
-                    tmem_ld_32x16(tacc + c_begin + c0, v);
                     if (STACK) {
-                        uint32_t v2[16];
-                        tmem_ld_32x16(tacc + NT + c_begin + c0, v2);
-                        tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
-                    } else {
-                        tmem_ld_wait();
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         sts128(wr_base + ((j ^ wr_sw) << 4), __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                     __syncwarp();
+                    float4 bn = b4;
+                    if (it + 1 < ITERS) {      // the registers of v are free again: fetch the next 16 columns
+                        tmem_ld_32x16(tacc + c_begin + c0 + 16, v);
+                        if (STACK) tmem_ld_32x16(tacc + NT + c_begin + c0 + 16, v2);
+                        bn = __ldg(reinterpret_cast<const float4*>(a.bias + cg_lane + c0 + 16));
+                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t r = rd_row + 8 * i;
@@ -570,6 +575,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                         }
                     }
                     __syncwarp();
+                    if (it + 1 < ITERS) {
+                        tmem_ld_wait();
+                        b4 = bn;
+                    }
                     if ((EPI & EPI_RES) && it + 1 < ITERS) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) rr[i] = rn[i];
