@@ -39,6 +39,31 @@ __global__ void prep_weights_kernel(const float* __restrict__ w, __half* __restr
     if (planes == 2) out[per_plane + i] = s.lo;
 }
 
+// conv/2 of the heads (FISRnet.py:100,106) runs on relu(depth_to_space(conv/1)) at 2R resolution with 64 input channels.
+// Evaluated at R resolution on the 256-channel pre-shuffle tensor it is a 3x3 conv with 4 * cout output columns (one group per
+// output sub-pixel) whose weights are a scatter of the original ones:
+//   output sub-pixel (i,j), 2R tap (ky,kx):  r = i + ky - 1 -> R-tap dy = floor(r / 2), source sub-row i' = r mod 2  (same in x)
+//   W'[(dy+1)*3 + (dx+1)][(2i'+j')*64 + c][(2i+j)*cout + co] = w[ky*3 + kx][c][co]
+// 16 of the 36 (R-tap, source group) pairs are non-zero; SAME padding at the 2R border equals SAME padding at the R border.
+__global__ void expand_ps_weights_kernel(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ wps,
+                                         float* __restrict__ bps, int cout) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = 9 * 4 * 64 * cout;
+    if (i < 4 * cout) bps[i] = b[i % cout];
+    if (i >= total) return;
+    const int co = i % cout;
+    int r = i / cout;
+    const int c = r % 64; r /= 64;
+    const int sub = r % 4;
+    const int tap = r / 4;
+    const int ky = tap / 3, kx = tap % 3, si = sub >> 1, sj = sub & 1;
+    const int ry = si + ky - 1, rx = sj + kx - 1;                 // -1 .. 2
+    const int dy = (ry + 2) / 2 - 1, dx = (rx + 2) / 2 - 1;       // floor division
+    const int iy = ry - 2 * dy, ix = rx - 2 * dx;
+    const int tap2 = (dy + 1) * 3 + (dx + 1), cin2 = (2 * iy + ix) * 64 + c, cout4 = 4 * cout;
+    wps[(static_cast<size_t>(tap2) * 256 + cin2) * cout4 + sub * cout + co] = w[(static_cast<size_t>(tap) * 64 + c) * cout + co];
+}
+
 // ---------------------------------------------------------------- input pack
 // img fp32 NHWC [N,H,W,29] -> level-3 input (full res), level-2 (x[::2, ::2]) and level-1 (x[::4, ::4]) buffers,
 // fp16 (hi, lo), 64 channels each; only channels [0, cin) are written (FISRnet.py:81,112,144).
@@ -225,6 +250,11 @@ __global__ void tile_pack_kernel(const uint8_t* __restrict__ frames, const float
 
 // pred_l3 of T tiles [T,2th,2tw,9] fp32 -> trim the halo (utils.py:138-159), clip [0,1], uint8(x*255) with the
 // reference's float64 truncation (FISRnet.py:1060-1064), paste into the [OH,OW,9] canvas (FISRnet.py:1056-1057).
+// channel k of a prediction pixel: float k of a 9-float record, or float (k / 3) * 4 + k % 3 of a 12-float record (the layout
+// the depth_to_space-folded heads write, conv_umma_kernel.cuh epilogue_scalar_ps)
+__device__ __forceinline__ int pred_slot(int k, int cs) { return cs == 12 ? (k / 3) * 4 + k % 3 : k; }
+
+template <int CS>
 __global__ void tile_unpack_u8_kernel(const float* __restrict__ pred, TileList tiles, int th2, int tw2,
                                       uint8_t* __restrict__ canvas, int OH, int OW, int core_h, int core_w) {
     // thread = 4 consecutive pixels of one row: 9 float4 loads, 9 packed 32-bit stores (all offsets are multiples of 4 px)
@@ -237,23 +267,36 @@ __global__ void tile_unpack_u8_kernel(const float* __restrict__ pred, TileList t
     const int y = r % core_h;
     const int t = r / core_h;
     const float4* src = reinterpret_cast<const float4*>(
-        pred + ((static_cast<size_t>(t) * th2 + tiles.trim_y[t] + y) * tw2 + tiles.trim_x[t] + x) * 9);
+        pred + ((static_cast<size_t>(t) * th2 + tiles.trim_y[t] + y) * tw2 + tiles.trim_x[t] + x) * CS);
     uint32_t* dst = reinterpret_cast<uint32_t*>(
         canvas + ((static_cast<size_t>(tiles.out_img[t]) * OH + tiles.out_y[t] + y) * OW + tiles.out_x[t] + x) * 9);
+    float f[36];                                     // 4 pixels x 9 channels, in output order
+    if (CS == 9) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const float4 v = __ldg(src + j);
+            f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
+        }
+    } else {                                         // 12-float records: three 16-byte groups of 3 channels per pixel
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            const float4 v = __ldg(src + j);
+            const int q = j / 3, g = j % 3;
+            f[q * 9 + g * 3] = v.x; f[q * 9 + g * 3 + 1] = v.y; f[q * 9 + g * 3 + 2] = v.z;
+        }
+    }
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
-        const float4 v = __ldg(src + j);
-        const float f[4] = {v.x, v.y, v.z, v.w};
         uint32_t w = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const double cl = fmin(fmax(static_cast<double>(f[k]), 0.0), 1.0);
+            const double cl = fmin(fmax(static_cast<double>(f[4 * j + k]), 0.0), 1.0);
             w |= static_cast<uint32_t>(static_cast<int>(cl * 255.0)) << (8 * k);
         }
         dst[j] = w;
     }
 }
-__global__ void tile_unpack_u8_scalar_kernel(const float* __restrict__ pred, TileList tiles, int th2, int tw2,
+__global__ void tile_unpack_u8_scalar_kernel(const float* __restrict__ pred, int cs, TileList tiles, int th2, int tw2,
                                              uint8_t* __restrict__ canvas, int OH, int OW, int core_h, int core_w) {
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     const size_t total = static_cast<size_t>(tiles.count) * core_h * core_w * 9;
@@ -263,13 +306,13 @@ __global__ void tile_unpack_u8_scalar_kernel(const float* __restrict__ pred, Til
     const int x = r % core_w; r /= core_w;
     const int y = r % core_h;
     const int t = r / core_h;
-    const float v = pred[((static_cast<size_t>(t) * th2 + tiles.trim_y[t] + y) * tw2 + tiles.trim_x[t] + x) * 9 + c];
+    const float v = pred[((static_cast<size_t>(t) * th2 + tiles.trim_y[t] + y) * tw2 + tiles.trim_x[t] + x) * cs + pred_slot(c, cs)];
     const double cl = fmin(fmax(static_cast<double>(v), 0.0), 1.0);
     canvas[((static_cast<size_t>(tiles.out_img[t]) * OH + tiles.out_y[t] + y) * OW + tiles.out_x[t] + x) * 9 + c] =
         static_cast<uint8_t>(static_cast<int>(cl * 255.0));
 }
 // same, but keeps fp32 (for parity tests against the oracle's float canvas)
-__global__ void tile_unpack_f32_kernel(const float* __restrict__ pred, TileList tiles, int th2, int tw2,
+__global__ void tile_unpack_f32_kernel(const float* __restrict__ pred, int cs, TileList tiles, int th2, int tw2,
                                        float* __restrict__ canvas, int OH, int OW, int core_h, int core_w) {
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     const size_t total = static_cast<size_t>(tiles.count) * core_h * core_w * 9;
@@ -280,7 +323,15 @@ __global__ void tile_unpack_f32_kernel(const float* __restrict__ pred, TileList 
     const int y = r % core_h;
     const int t = r / core_h;
     canvas[((static_cast<size_t>(tiles.out_img[t]) * OH + tiles.out_y[t] + y) * OW + tiles.out_x[t] + x) * 9 + c] =
-        pred[((static_cast<size_t>(t) * th2 + tiles.trim_y[t] + y) * tw2 + tiles.trim_x[t] + x) * 9 + c];
+        pred[((static_cast<size_t>(t) * th2 + tiles.trim_y[t] + y) * tw2 + tiles.trim_x[t] + x) * cs + pred_slot(c, cs)];
+}
+
+// 12-float prediction records -> the [.., 9] tensor FISRnet.model returns
+__global__ void pred_compact_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t npix) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= npix * 9) return;
+    const int k = i % 9;
+    dst[i] = src[(i / 9) * 12 + pred_slot(k, 12)];
 }
 
 // ---------------------------------------------------------------- flow warp
@@ -351,6 +402,12 @@ void launch_prep_weights(const float* w, __half* out, int cin, int cout, int KB,
     prep_weights_kernel<<<blocks_for(total, 256), 256, 0, st>>>(w, out, cin, cout, KB, cout_pad, planes);
 }
 
+void launch_expand_ps_weights(const float* w, const float* b, float* wps, float* bps, int cout, cudaStream_t st) {
+    cudaMemsetAsync(wps, 0, static_cast<size_t>(9) * 256 * 4 * cout * sizeof(float), st);
+    const int total = 9 * 4 * 64 * cout;
+    expand_ps_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, b, wps, bps, cout);
+}
+
 void launch_pack_input(const float* img, int N, int H, int W, int cin, ActBuf l3, ActBuf l2, ActBuf l1, int planes,
                        cudaStream_t st) {
     const size_t total = static_cast<size_t>(N) * H * W * 32;
@@ -417,23 +474,28 @@ void launch_tile_pack(const uint8_t* frames, const float* flow, const float* war
                                                                     l3.plane, l2.p, l2.plane, l1.p, l1.plane);
 }
 
-void launch_tile_unpack_u8(const float* pred, const TileList& tiles, int th2, int tw2, uint8_t* canvas, int OH, int OW,
+void launch_pred_compact(const float* src, float* dst, size_t npix, cudaStream_t st) {
+    pred_compact_kernel<<<blocks_for(npix * 9, 256), 256, 0, st>>>(src, dst, npix);
+}
+
+void launch_tile_unpack_u8(const float* pred, int cs, const TileList& tiles, int th2, int tw2, uint8_t* canvas, int OH, int OW,
                            int core_h, int core_w, cudaStream_t st) {
     // vector path needs every row segment to start on a 4-pixel boundary (36-byte groups are then 4-byte aligned)
     bool vec = (core_w % 4 == 0) && (tw2 % 4 == 0) && (OW % 4 == 0);
     for (int t = 0; t < tiles.count; ++t) vec = vec && (tiles.trim_x[t] % 4 == 0) && (tiles.out_x[t] % 4 == 0);
     if (vec) {
         const size_t total = static_cast<size_t>(tiles.count) * core_h * (core_w / 4);
-        tile_unpack_u8_kernel<<<blocks_for(total, 256), 256, 0, st>>>(pred, tiles, th2, tw2, canvas, OH, OW, core_h, core_w);
+        if (cs == 12) tile_unpack_u8_kernel<12><<<blocks_for(total, 256), 256, 0, st>>>(pred, tiles, th2, tw2, canvas, OH, OW, core_h, core_w);
+        else tile_unpack_u8_kernel<9><<<blocks_for(total, 256), 256, 0, st>>>(pred, tiles, th2, tw2, canvas, OH, OW, core_h, core_w);
     } else {
         const size_t total = static_cast<size_t>(tiles.count) * core_h * core_w * 9;
-        tile_unpack_u8_scalar_kernel<<<blocks_for(total, 256), 256, 0, st>>>(pred, tiles, th2, tw2, canvas, OH, OW, core_h, core_w);
+        tile_unpack_u8_scalar_kernel<<<blocks_for(total, 256), 256, 0, st>>>(pred, cs, tiles, th2, tw2, canvas, OH, OW, core_h, core_w);
     }
 }
-void launch_tile_unpack_f32(const float* pred, const TileList& tiles, int th2, int tw2, float* canvas, int OH, int OW,
+void launch_tile_unpack_f32(const float* pred, int cs, const TileList& tiles, int th2, int tw2, float* canvas, int OH, int OW,
                             int core_h, int core_w, cudaStream_t st) {
     const size_t total = static_cast<size_t>(tiles.count) * core_h * core_w * 9;
-    tile_unpack_f32_kernel<<<blocks_for(total, 256), 256, 0, st>>>(pred, tiles, th2, tw2, canvas, OH, OW, core_h, core_w);
+    tile_unpack_f32_kernel<<<blocks_for(total, 256), 256, 0, st>>>(pred, cs, tiles, th2, tw2, canvas, OH, OW, core_h, core_w);
 }
 
 void launch_warp_yuv(const uint8_t* yuv, const float* flow, float flow_scale, float* out, int h, int w, float out_scale,

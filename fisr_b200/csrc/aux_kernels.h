@@ -22,6 +22,8 @@ struct TileList {
 };
 
 void launch_prep_weights(const float* w, __half* out, int cin, int cout, int KB, int cout_pad, int planes, cudaStream_t st);
+// depth_to_space-folded weights / bias of a conv/2 head: w [3,3,64,cout], b [cout] -> wps [3,3,256,4*cout], bps [4*cout]
+void launch_expand_ps_weights(const float* w, const float* b, float* wps, float* bps, int cout, cudaStream_t st);
 void launch_pack_input(const float* img, int N, int H, int W, int cin, ActBuf l3, ActBuf l2, ActBuf l1, int planes, cudaStream_t st);
 void launch_upsample2(ActBuf in, ActBuf out, int N, int h, int w, int C, int planes, cudaStream_t st);
 void launch_maxpool2(ActBuf in, int cs, int coff, ActBuf out, int N, int H, int W, int C, int planes, cudaStream_t st);
@@ -30,9 +32,11 @@ void launch_act_to_f32(ActBuf src, int cs, int coff, float* dst, int C, size_t n
 void launch_tile_pack(const uint8_t* frames, const float* flow, const float* warp, int fh, int fw, const TileList& tiles,
                       int th, int tw, const float* lut255, ActBuf l3, ActBuf l2, ActBuf l1, int planes, cudaStream_t st);
 // canvas: images of OH x OW x 9, tile t lands in image out_img[t] at (out_y[t], out_x[t])
-void launch_tile_unpack_u8(const float* pred, const TileList& tiles, int th2, int tw2, uint8_t* canvas, int OH, int OW,
+// pred: fp32 records of cs floats per pixel (9, or the 12-float layout of the depth_to_space-folded heads)
+void launch_pred_compact(const float* src, float* dst, size_t npix, cudaStream_t st);
+void launch_tile_unpack_u8(const float* pred, int cs, const TileList& tiles, int th2, int tw2, uint8_t* canvas, int OH, int OW,
                            int core_h, int core_w, cudaStream_t st);
-void launch_tile_unpack_f32(const float* pred, const TileList& tiles, int th2, int tw2, float* canvas, int OH, int OW,
+void launch_tile_unpack_f32(const float* pred, int cs, const TileList& tiles, int th2, int tw2, float* canvas, int OH, int OW,
                             int core_h, int core_w, cudaStream_t st);
 void launch_warp_yuv(const uint8_t* yuv, const float* flow, float flow_scale, float* out, int h, int w, float out_scale,
                      cudaStream_t st);

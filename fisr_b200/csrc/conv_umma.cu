@@ -18,7 +18,7 @@ cudaError_t launch_family(const ConvLaunch& L, int num_sms, cudaStream_t stream)
     template <> cudaError_t init_family<NT_, PL_>();            \
     template <> cudaError_t launch_family<NT_, PL_>(const ConvLaunch&, int, cudaStream_t);
 FISR_DECL(16, 1) FISR_DECL(64, 1) FISR_DECL(128, 1) FISR_DECL(16, 2) FISR_DECL(64, 2) FISR_DECL(128, 2)
-FISR_DECL(16, 3) FISR_DECL(64, 3) FISR_DECL(128, 3)
+FISR_DECL(16, 3) FISR_DECL(32, 3) FISR_DECL(64, 3) FISR_DECL(128, 3)
 #undef FISR_DECL
 }  // namespace convk
 
@@ -32,6 +32,7 @@ cudaError_t conv3x3_init() {
     if (e == cudaSuccess) e = init_family<64, 2>();
     if (e == cudaSuccess) e = init_family<128, 2>();
     if (e == cudaSuccess) e = init_family<16, 3>();
+    if (e == cudaSuccess) e = init_family<32, 3>();
     if (e == cudaSuccess) e = init_family<64, 3>();
     if (e == cudaSuccess) e = init_family<128, 3>();
     return e;
@@ -41,6 +42,7 @@ cudaError_t launch_conv3x3(const ConvLaunch& L, int num_sms, cudaStream_t stream
     using namespace convk;
     if (L.planes == 3) {
         if (L.NT == 16) return launch_family<16, 3>(L, num_sms, stream);
+        if (L.NT == 32) return launch_family<32, 3>(L, num_sms, stream);
         if (L.NT == 64) return launch_family<64, 3>(L, num_sms, stream);
         if (L.NT == 128) return launch_family<128, 3>(L, num_sms, stream);
     } else if (L.planes == 2) {
@@ -57,7 +59,7 @@ cudaError_t launch_conv3x3(const ConvLaunch& L, int num_sms, cudaStream_t stream
 
 // Host-side tile geometry / shared-memory carve-up for one conv launch.
 bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int num_sms, ConvLaunch* L) {
-    int NT = cout_pad <= 16 ? 16 : 64;
+    int NT = cout_pad <= 16 ? 16 : cout_pad <= 32 ? 32 : 64;
     // Wide N tiles halve the A re-reads and balance shared-memory operand traffic against MMA math.  The choice
     // depends on the per-image geometry only (never on the batch), so results are bit-identical however a
     // window's tiles are sharded over batches / GPUs (NT decides the fp32 summation order, see STACK).
@@ -87,10 +89,15 @@ bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int n
     a.NB = cout_pad / NT;
     a.num_tiles = n_img * a.tiles_x * a.tiles_y * a.NB;
     a.a_plane_bytes = (a.TH + 2) * a.P * 128;
-    a.a_stages = planes == 3 ? 1 : 2;      // f16f8 keeps one buffer per activation plane (phase-split main loop)
-    a.pf16 = 3; a.pf8 = 12;
+    // f16f8 (phase-split main loop): one buffer per activation plane (a second one measured no better, even where it fits)
+    a.a_stages = planes == 3 ? 1 : 2;
+    if (const char* e = getenv("FISR_ASTAGES")) { if (planes == 3 && NT < 128 && (atoi(e) == 1 || atoi(e) == 2)) a.a_stages = atoi(e); }
+    a.pf16 = planes == 3 && a.a_stages == 2 ? 0 : 3;        // with two buffers per plane the next item's patches are
+    a.pf8 = planes == 3 && a.a_stages == 2 ? 0 : 12;         // requested as soon as their buffers drain
     if (const char* e = getenv("FISR_PF16")) a.pf16 = atoi(e);      // tuning knobs
     if (const char* e = getenv("FISR_PF8")) a.pf8 = atoi(e);
+    for (int i = 0; i < 8; ++i) a.tapmask[i] = 0x1FFu;
+    a.ps_cout = 0;
     int slots = (kConvMaxSmem - fixed - a.a_stages * apl * a.a_plane_bytes) / slot_bytes;
     if (slots > convk::kMaxBSlots) slots = convk::kMaxBSlots;
     if (slots < 2) return false;

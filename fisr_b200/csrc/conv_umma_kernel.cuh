@@ -34,7 +34,8 @@
 // products: an N = 64 MMA needs 48 cycles of shared-memory operand reads for 32 cycles of math (ncu:
 // pipe_tc 80 % busy at 50 % tensor math), so the narrow layers are bound by exactly that traffic.
 //
-// Warp roles (352 threads): warp 0 = TMA producer, warp 1 = MMA issuer of chunk 0 + TMEM owner, warp 10 = MMA issuer of chunk 1, warps 2-9 =
+// Warp roles (352 threads; 384 for f16f8, whose warp 11 requests the activation patches while warp 0 streams the weights):
+// warp 0 = TMA producer, warp 1 = MMA issuer of chunk 0 + TMEM owner, warp 10 = MMA issuer of chunk 1, warps 2-9 =
 // epilogue (TMEM -> registers -> smem transpose -> bias/residual/ReLU/split -> coalesced HBM stores).
 // Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.  The epilogue
 // is CUDA-core work on every output element; 8 warps (two per TMEM lane quarter) keep the four schedulers
@@ -48,10 +49,11 @@ namespace fisr {
 namespace convk {
 
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps + 32;     // + a second MMA issuer (last warp), see "MMA issue" below
-constexpr int kIssuer2Warp = kThreads / 32 - 1;
+constexpr int kIssuer2Warp = 2 + kEpiWarps;            // second MMA issuer, see "MMA issuers" below
+constexpr int kPatchWarp = kIssuer2Warp + 1;           // f16f8 only: activation-patch producer
+__host__ __device__ constexpr int conv_threads(int planes) { return 32 * (planes == 3 ? kPatchWarp + 1 : kIssuer2Warp + 1); }
 constexpr int kMaxBSlots = 12;
-constexpr int kMaxAStages = 2;
+constexpr int kMaxAStages = 4;                // activation buffers with their own barrier pair (f16f8: plane * 2 + stage)
 constexpr int kStageBytesPerWarp = 32 * 64;   // [32 px][16 ch] fp32, 16-B groups XOR-swizzled (conflict-free both ways)
 constexpr float kF8AccScale = 1.f / 128.f;    // PLANES = 3: the accumulator holds 128 x the convolution (common.cuh, F8 scales)
 
@@ -90,24 +92,26 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 
 // Narrow head outputs (Cout = 6 / 3, FISRnet.py:100,106): thread = pixel, channel-mapped scalar stores into the
 // 9-channel pred tensor and into channels 29.. of the next level's input (FISRnet.py:107-108,113,144).
-template <int PLANES>
-__device__ __forceinline__ void epilogue_scalar16(const ConvArgs& a, const uint32_t (&v)[16], int pix) {
+template <int PLANES, int NCOL>
+__device__ __forceinline__ void epilogue_scalar(const ConvArgs& a, const uint32_t (&v)[NCOL], int n, int y, int x) {
+    const int pix = (n * a.H + y) * a.W + x;
 #pragma unroll
-    for (int ch = 0; ch < 16; ++ch) {
+    for (int ch = 0; ch < NCOL; ++ch) {
         if (ch < a.cout) {
             float f = __uint_as_float(v[ch]);
             if (PLANES == 3) f *= kF8AccScale;
             f += __ldg(a.bias + ch);
-            if (a.out_raw) a.out_raw[static_cast<size_t>(pix) * a.raw_cs + ch + (ch < a.raw_split ? a.raw_off0 : a.raw_off1)] = f;
+            const int co = ch, opix = pix;
+            if (a.out_raw) a.out_raw[static_cast<size_t>(opix) * a.raw_cs + co + (co < a.raw_split ? a.raw_off0 : a.raw_off1)] = f;
             if (a.out_act) {
                 const float g = a.act_relu ? fmaxf(f, 0.f) : f;
                 const SplitHalf s = split_f32(g);
-                const int c = ch + (ch < a.act_split ? a.act_off0 : a.act_off1);
-                __half* d = a.out_act + static_cast<size_t>(pix) * a.act_cs + c;
+                const int c = co + (co < a.act_split ? a.act_off0 : a.act_off1);
+                __half* d = a.out_act + static_cast<size_t>(opix) * a.act_cs + c;
                 d[0] = s.hi;
                 if (PLANES == 2) d[a.act_plane] = s.lo;
                 if (PLANES == 3) {
-                    uint8_t* q = reinterpret_cast<uint8_t*>(a.out_act + a.act_plane + static_cast<size_t>(pix) * a.act_cs) +
+                    uint8_t* q = reinterpret_cast<uint8_t*>(a.out_act + a.act_plane + static_cast<size_t>(opix) * a.act_cs) +
                                  (c >> 6) * 128 + (c & 63);
                     q[0] = f8_lo_byte(g - __half2float(s.hi));
                     q[64] = f8_hi_byte(g);
@@ -117,8 +121,52 @@ __device__ __forceinline__ void epilogue_scalar16(const ConvArgs& a, const uint3
     }
 }
 
+// conv/2 head with the depth_to_space folded into its weights (fisr_api.cu, conv_ps): GEMM column sub * COUT + co of input
+// pixel (y, x) is channel co of output pixel (2y + (sub >> 1), 2x + (sub & 1)).  The fp32 prediction is stored as 12-float
+// records per output pixel, [FI-SR 0..2, -, SR 0..2, -, FI-SR 3..5, -], so that each head writes whole 16-byte groups
+// (raw_off0 / raw_off1 = float offset of this head's first / second group).
+template <int PLANES, int COUT>
+__device__ __forceinline__ void epilogue_scalar_ps(const ConvArgs& a, const uint32_t (&v)[COUT == 6 ? 32 : 16], int n, int y, int x) {
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+        const size_t opix = (static_cast<size_t>(n) * 2 * a.H + 2 * y + (sub >> 1)) * (2 * a.W) + 2 * x + (sub & 1);
+        float f[COUT];
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+            f[co] = __uint_as_float(v[sub * COUT + co]);
+            if (PLANES == 3) f[co] *= kF8AccScale;
+            f[co] += __ldg(a.bias + sub * COUT + co);
+        }
+        if (a.out_raw) {
+            float* rec = a.out_raw + opix * a.raw_cs;
+            if (COUT == 6) {
+                *reinterpret_cast<float4*>(rec + a.raw_off0) = make_float4(f[0], f[1], f[2], 0.f);
+                *reinterpret_cast<float4*>(rec + a.raw_off1) = make_float4(f[3], f[4], f[5], 0.f);
+            } else {
+                *reinterpret_cast<float4*>(rec + a.raw_off1) = make_float4(f[0], f[1], f[2], 0.f);
+            }
+        }
+        if (a.out_act) {
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                const float g = a.act_relu ? fmaxf(f[co], 0.f) : f[co];
+                const SplitHalf s = split_f32(g);
+                const int c = co + (co < a.act_split ? a.act_off0 : a.act_off1);
+                __half* d = a.out_act + opix * a.act_cs + c;
+                d[0] = s.hi;
+                if (PLANES == 2) d[a.act_plane] = s.lo;
+                if (PLANES == 3) {
+                    uint8_t* q = reinterpret_cast<uint8_t*>(a.out_act + a.act_plane + opix * a.act_cs) + (c >> 6) * 128 + (c & 63);
+                    q[0] = f8_lo_byte(g - __half2float(s.hi));
+                    q[64] = f8_hi_byte(g);
+                }
+            }
+        }
+    }
+}
+
 template <int NT, int CHUNKS, int PLANES, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(conv_threads(PLANES), 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvArgs a) {
     constexpr bool STACK = (PLANES == 2) && (NT <= 64);
@@ -131,7 +179,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     constexpr int PLANE_BYTES = NT * 128;                       // one weight plane of one tap
     constexpr int B_SLOT_BYTES = STACK ? 2 * PLANE_BYTES : PLANE_BYTES;
     constexpr int SLOTS_PER_TAP = STACK ? 1 : APL;
-    constexpr bool NARROW = NT < 32;
+    constexpr bool NARROW = NT <= 32;
     // tile geometry is a function of CHUNKS alone: two 8 x 16 chunks side by side (16 x 16 tile, patch pitch 18) or one chunk
     constexpr int TWc = 8 * CHUNKS, THc = 16, Pc = TWc + 2;
     constexpr uint32_t CHUNK_OFF = 8u * 128u >> 4;                      // chunk 1 starts 8 pixels to the right of chunk 0
@@ -180,32 +228,19 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     if (warp == 0) {
         // ============================== TMA producer ==============================
         if constexpr (F8) {
-            // f16f8: every (tile, K block) item runs as two phases -- A: the 9 taps of the 8-bit cross terms (8-bit patch,
-            // 8-bit weight plane), B: the 9 taps of the fp16 main term.  Each activation plane therefore sits idle during the
-            // other phase, which is when its next patch is loaded: ONE buffer per plane instead of two stages of two planes.
-            // The 83 KB this frees hold 8 weight slots (NT = 128) instead of 3, enough to cover the L2 latency of the weight stream.
+            // f16f8: every (tile, K block) item runs as two phases -- A: the taps of the 8-bit cross terms (8-bit patch, 8-bit
+            // weight plane), B: the taps of the fp16 main term.  This warp streams the weight slots; the patches come from
+            // the patch-producer warp below.
             if (elect_one()) {
-                uint32_t e16 = 0, e8 = 0, bs = 0, bph = 0;
+                uint32_t bs = 0, bph = 0;
                 bool ok = true;
-                auto issue_plane = [&](int buf, const CUtensorMap* tm, int tile, int kb, uint32_t& eph) -> bool {
-                    if (!mbar_wait(a_empty(buf), eph ^ 1, a.err, ERR_A_EMPTY)) return false;
-                    eph ^= 1;
-                    const TileCoord t = decode_tile(a, tile);
-                    mbar_expect_tx(a_full(buf), box_bytes);
-                    tma_load_4d(sA + buf * a.a_plane_bytes, tm, a_full(buf), a.cin_off + kb * 64, t.x0 - 1, t.y0 - 1, t.n);
-                    return true;
-                };
-                if (blockIdx.x < a.num_tiles) ok = issue_plane(1, &tmA_lo, blockIdx.x, 0, e8);
                 for (int tile = blockIdx.x; tile < a.num_tiles && ok; tile += gridDim.x) {
                     const int nb = tile % a.NB;
                     for (int kb = 0; kb < a.KB && ok; ++kb) {
-                        int ntile = tile, nkb = kb + 1;
-                        if (nkb == a.KB) { nkb = 0; ntile += gridDim.x; }
+                        const uint32_t mask = a.tapmask[kb & 7];
                         for (int sl = 0; sl < 18 && ok; ++sl) {
-                            if (sl == a.pf16) ok = issue_plane(0, &tmA_hi, tile, kb, e16);
-                            if (sl == a.pf8 && ntile < a.num_tiles && ok) ok = issue_plane(1, &tmA_lo, ntile, nkb, e8);
-                            if (!ok) break;
                             const int plane = sl < 9 ? 1 : 0, tap = sl < 9 ? sl : sl - 9;
+                            if (!((mask >> tap) & 1u)) continue;      // all-zero weights (fused depth_to_space heads)
                             ok = mbar_wait(b_empty(bs), bph ^ 1, a.err, ERR_B_EMPTY);
                             if (!ok) break;
                             mbar_expect_tx(b_full(bs), B_SLOT_BYTES);
@@ -258,6 +293,33 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 }
             }
         }
+    } else if (F8 && warp == kPatchWarp) {
+        // ============================== f16f8 patch producer ==============================
+        // Each activation plane sits idle during the other phase of an item, which is when its next patch is loaded: D = 1
+        // buffer per plane under the 16 KB weight slots of NT = 128 (the 83 KB this frees hold 8 weight slots instead of 3,
+        // enough to cover the L2 latency of the weight stream), D = 2 where shared memory allows.  Buffers drain in the order
+        // 8-bit(i), fp16(i), 8-bit(i+1), ..., so one thread with blocking waits requests every patch the moment its buffer is free.
+        if (elect_one()) {
+            const uint32_t D = a.a_stages;
+            const int my_tiles = blockIdx.x < a.num_tiles ? (a.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            bool ok = true;
+            uint32_t cnt = 0;
+            for (int ti = 0; ti < my_tiles && ok; ++ti) {
+                const TileCoord t = decode_tile(a, blockIdx.x + ti * gridDim.x);
+                for (int kb = 0; kb < a.KB && ok; ++kb, ++cnt) {
+                    const uint32_t st = cnt & (D - 1), par = ((cnt >> (D - 1)) & 1) ^ 1;
+#pragma unroll
+                    for (int pl = 1; pl >= 0 && ok; --pl) {           // 8-bit plane first: phase A consumes it first
+                        const uint32_t buf = pl * 2 + st;
+                        ok = mbar_wait(a_empty(buf), par, a.err, ERR_A_EMPTY);
+                        if (!ok) break;
+                        mbar_expect_tx(a_full(buf), box_bytes);
+                        tma_load_4d(sA + (st * 2 + pl) * a.a_plane_bytes, pl ? &tmA_lo : &tmA_hi, a_full(buf), a.cin_off + kb * 64,
+                                    t.x0 - 1, t.y0 - 1, t.n);
+                    }
+                }
+            }
+        }
     } else if (warp == 1 || (CHUNKS == 2 && warp == kIssuer2Warp)) {
         // ============================== MMA issuers ==============================
         // One issuer warp per chunk (warp 1: chunk 0, last warp: chunk 1).  A single thread needs ~70 cycles per
@@ -276,28 +338,30 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
         bool ok = true;
         if constexpr (F8) {
-            uint32_t f16ph = 0, f8ph = 0;
+            uint32_t items = 0;                           // (tile, K block) items consumed so far = patches consumed per plane
+            const uint32_t D = a.a_stages;
             const uint32_t co = c * CHUNK_OFF;
             for (int tile = blockIdx.x; tile < a.num_tiles && ok; tile += gridDim.x) {
                 ok = __all_sync(0xffffffffu, mbar_wait(acc_empty(cs), cph ^ 1, a.err, ERR_ACC_EMPTY));
                 if (!ok) break;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + cs * ACC_COLS + c * DCOLS;
+                uint32_t first = 0u;                                          // accumulate flag: 0 for the first MMA of the tile
                 for (int kb = 0; kb < a.KB && ok; ++kb) {
                     const int ksteps = kb == a.KB - 1 ? a.ksteps_last : 4;   // 16-channel K slices that hold real channels
                     const int k8steps = (ksteps + 1) >> 1;                   // 32-channel slices of each half of the 8-bit rows
 #pragma unroll 1
                     for (int phase = 0; phase < 2 && ok; ++phase) {           // 0: 8-bit cross terms, 1: fp16 main term
-                        const int buf = phase == 0 ? 1 : 0;
-                        ok = __all_sync(0xffffffffu, mbar_wait(a_full(buf), phase == 0 ? f8ph : f16ph, a.err, ERR_A_FULL));
+                        const int pl = phase == 0 ? 1 : 0;
+                        const uint32_t st = items & (D - 1), buf = pl * 2 + st;
+                        ok = __all_sync(0xffffffffu, mbar_wait(a_full(buf), (items >> (D - 1)) & 1, a.err, ERR_A_FULL));
                         if (!ok) break;
-                        if (phase == 0) f8ph ^= 1; else f16ph ^= 1;
-                        const uint32_t a0 = umma_desc_lo(sA + buf * a.a_plane_bytes) + co;
-                        uint32_t first = (kb == 0 && phase == 0) ? 0u : 1u;  // accumulate flag of the very first MMA of the tile
+                        const uint32_t a0 = umma_desc_lo(sA + (st * 2 + pl) * a.a_plane_bytes) + co;
 #pragma unroll 1
                         for (int ky = 0; ky < 3 && ok; ++ky) {
 #pragma unroll 1
                             for (int kx = 0; kx < 3 && ok; ++kx) {
+                                if (!((a.tapmask[kb & 7] >> (ky * 3 + kx)) & 1u)) continue;
                                 const uint32_t at = a0 + static_cast<uint32_t>(ky * Pc + kx) * 8u;      // rows of 128 B, >> 4
                                 ok = __all_sync(0xffffffffu, mbar_wait(b_full(bs), bph, a.err, ERR_B_FULL));
                                 if (!ok) break;
@@ -326,6 +390,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                         }
                         if (lead && ok) umma_commit(a_empty(buf));
                     }
+                    ++items;
                 }
                 if (lead && ok) umma_commit(acc_full(cs));
                 if (++cs == 2) { cs = 0; cph ^= 1; }
@@ -444,18 +509,23 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                     const int ty = ch_y0 + q4 * 4 + (lane >> 3), tx = ch_x0 + (lane & 7);
                     const int y = t.y0 + ty, x = t.x0 + tx;
                     const bool valid = (y < a.H) && (x < a.W);
-                    uint32_t v[16];
-                    tmem_ld_32x16(tacc, v);
+                    uint32_t v[NT];
+#pragma unroll
+                    for (int c0 = 0; c0 < NT; c0 += 16) tmem_ld_32x16(tacc + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[c0]));
                     if (STACK) {
-                        uint32_t v2[16];
-                        tmem_ld_32x16(tacc + NT, v2);
+                        uint32_t v2[NT];
+#pragma unroll
+                        for (int c0 = 0; c0 < NT; c0 += 16) tmem_ld_32x16(tacc + NT + c0, *reinterpret_cast<uint32_t(*)[16]>(&v2[c0]));
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+                        for (int j = 0; j < NT; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
                     } else {
                         tmem_ld_wait();
                     }
-                    if (valid) epilogue_scalar16<PLANES>(a, v, (t.n * a.H + y) * a.W + x);
+                    if (valid) {
+                        if (a.ps_cout > 0) epilogue_scalar_ps<PLANES, NT == 32 ? 6 : 3>(a, v, t.n, y, x);
+                        else epilogue_scalar<PLANES, NT>(a, v, t.n, y, x);
+                    }
                 }
             } else {
                 // After the transpose lane l serves pixels (l >> 2) + 8*i of this warp's 32-pixel group, channels
@@ -606,7 +676,7 @@ cudaError_t init_inst() {
 template <int NT, int CHUNKS, int PLANES, int EPI>
 cudaError_t launch_inst(const ConvLaunch& L, int num_sms, cudaStream_t stream) {
     const int grid = L.args.num_tiles < num_sms ? L.args.num_tiles : num_sms;
-    conv3x3_umma_kernel<NT, CHUNKS, PLANES, EPI><<<grid, kThreads, L.smem_bytes, stream>>>(L.tmA_hi, L.tmA_lo, L.tmB, L.args);
+    conv3x3_umma_kernel<NT, CHUNKS, PLANES, EPI><<<grid, conv_threads(PLANES), L.smem_bytes, stream>>>(L.tmA_hi, L.tmA_lo, L.tmB, L.args);
     return cudaGetLastError();
 }
 
@@ -636,7 +706,7 @@ cudaError_t launch_family(const ConvLaunch& L, int num_sms, cudaStream_t stream)
     M(NT_, PL_, 1, 0) M(NT_, PL_, 2, 0) M(NT_, PL_, 1, EPI_RAW) M(NT_, PL_, 2, EPI_RAW)                      \
     M(NT_, PL_, 1, EPI_RES) M(NT_, PL_, 2, EPI_RES) M(NT_, PL_, 1, EPI_RES | EPI_RAW) M(NT_, PL_, 2, EPI_RES | EPI_RAW) \
     M(NT_, PL_, 1, EPI_D2S) M(NT_, PL_, 2, EPI_D2S)
-#define FISR_FOR_EPI_NARROW(M, NT_, PL_) M(NT_, PL_, 1, 0) M(NT_, PL_, 2, 0)
+#define FISR_FOR_EPI_NARROW(M, NT_, PL_) M(NT_, PL_, 1, 0) M(NT_, PL_, 2, 0)      // NT = 16 / 32: scalar epilogue
 // dgrad variants (training, split mode only): mask | mask+res | mask+res+raw | mask+raw (| mask+s2d for the 64-wide tile)
 #define FISR_FOR_EPI_BWD(M, NT_, PL_)                                                                       \
     M(NT_, PL_, 1, EPI_MASK) M(NT_, PL_, 2, EPI_MASK) M(NT_, PL_, 1, EPI_MASK | EPI_RES) M(NT_, PL_, 2, EPI_MASK | EPI_RES) \

@@ -101,6 +101,12 @@ struct ConvParam {
     __half* d_wpT = nullptr;
     bool packedT = false;
     float *g_w = nullptr, *g_b = nullptr;
+    // conv/2 heads under f16f8: the conv evaluated at input resolution with depth_to_space folded into the weights
+    // (aux_kernels.cu, expand_ps_weights_kernel): fp32 [3,3,256,4*cout] + bias [32], packed planes, cout_pad 16 or 32
+    bool head2 = false;
+    float *d_wps = nullptr, *d_bps = nullptr;
+    __half* d_wpps = nullptr;
+    int ps_cout_pad = 0;
 };
 
 // Buffers of one forward level that the backward pass reads again (activations = ReLU masks and wgrad operands).
@@ -141,6 +147,8 @@ struct Plan {
     std::vector<Op> ops;
     ActBuf in_lvl[3];
     float* pred[3] = {nullptr, nullptr, nullptr};
+    int pred_cs = 9;                 // floats per prediction pixel: 9, or 12 (padded groups) under f16f8
+    float* pred9[3] = {nullptr, nullptr, nullptr};      // compact copies for fisr_forward when pred_cs == 12
     std::map<std::string, DebugTensor> debug;
     cudaGraphExec_t graph = nullptr;
     double flops = 0, eff_weighted = 0;
@@ -251,6 +259,17 @@ int ensure_packed(fisr_ctx* ctx, ConvParam& p, cudaStream_t st) {
     if (p.packed) return FISR_OK;
     launch_prep_weights(p.d_w, p.d_wp, p.cin, p.cout, p.KB, p.cout_pad, ctx->planes, st);
     ctx->launches++;
+    if (p.head2 && ctx->planes == 3) {
+        if (!p.d_wps) {
+            CUDA_TRY(ctx, cudaMalloc(&p.d_wps, static_cast<size_t>(9) * 256 * 4 * p.cout * sizeof(float)));
+            CUDA_TRY(ctx, cudaMalloc(&p.d_bps, 32 * sizeof(float)));
+            CUDA_TRY(ctx, cudaMemset(p.d_bps, 0, 32 * sizeof(float)));
+            CUDA_TRY(ctx, cudaMalloc(&p.d_wpps, static_cast<size_t>(2) * 4 * 9 * p.ps_cout_pad * 64 * sizeof(__half)));
+        }
+        launch_expand_ps_weights(p.d_w, p.d_b, p.d_wps, p.d_bps, p.cout, st);
+        launch_prep_weights(p.d_wps, p.d_wpps, 256, 4 * p.cout, 4, p.ps_cout_pad, 3, st);
+        ctx->launches += 2;
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     p.packed = true;
     return FISR_OK;
@@ -322,6 +341,7 @@ struct Builder {
         ActBuf act;
         int act_cs = 0, act_off0 = 0, act_off1 = 0, act_split = 0;
         bool relu = true, d2s = false, scalar = false;
+        bool ps = false;          // conv/2 head at input resolution: output columns are (sub-pixel, channel) pairs
         ActBuf mask;              // dgrad: ReLU gate (hi plane of a forward activation), mask_cs channels per pixel
         int mask_cs = 0, mask_off = 0;
         bool s2d = false;         // dgrad of conv/2: store space-to-depth into a 256-channel buffer
@@ -333,6 +353,7 @@ struct Builder {
         const float* bias;
     };
     WView fwd_view(const ConvParam& p) const { return WView{p.d_wp, p.KB, p.cout_pad, p.cout, p.cin, p.d_b}; }
+    WView ps_view(const ConvParam& p) const { return WView{p.d_wpps, 4, p.ps_cout_pad, 4 * p.cout, 256, p.d_bps}; }
     WView bwd_view(const ConvParam& p) const { return WView{p.d_wpT, p.OBk, p.cin_pad, p.cin, p.cout, ctx->d_zero_bias}; }
 
     // One conv launch: input = channels [cin_off, cin_off + KB*64) of `in` (cs channels, N x H x W).
@@ -341,6 +362,26 @@ struct Builder {
         Op op{};
         if (!make_conv(fwd_view(p), in, in_cs, cin_off, N, H, W, o, name, &op)) return;
         if (o.raw && !o.scalar) plan->debug[name] = DebugTensor{o.raw, N, H, W, o.raw_cs};
+        plan->flops += op.flops;
+        plan->eff_weighted += op.flops * op.conv.efficiency;
+        plan->ops.push_back(op);
+    }
+    // conv/2 head with folded depth_to_space (planes == 3): 256 -> 4 * cout at input resolution, writes [N,2H,2W,*] outputs
+    void conv_ps(const ConvParam& p, ActBuf in, int N, int H, int W, const ConvOut& o, const std::string& name) {
+        Op op{};
+        if (!make_conv(ps_view(p), in, 256, 0, N, H, W, o, name, &op)) return;
+        ConvArgs& a = op.conv.args;
+        a.ps_cout = p.cout;
+        for (int g = 0; g < 4; ++g) {          // source group g = 2i'+j' is read by R-taps dy in {0,1} (i' = 0) or {-1,0} (i' = 1), same in x
+            unsigned m = 0;
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const bool ay = (g >> 1) == 0 ? (dy >= 0) : (dy <= 0), ax = (g & 1) == 0 ? (dx >= 0) : (dx <= 0);
+                    if (ay && ax) m |= 1u << ((dy + 1) * 3 + dx + 1);
+                }
+            a.tapmask[g] = m;
+        }
+        op.flops = 2.0 * 9 * 64 * p.cout * static_cast<double>(2 * H) * (2 * W) * N;      // algorithmic: the 64 -> cout conv at 2R
         plan->flops += op.flops;
         plan->eff_weighted += op.flops * op.conv.efficiency;
         plan->ops.push_back(op);
@@ -369,7 +410,7 @@ struct Builder {
         if (!o.scalar && !o.act.p) { rc = fail(ctx, FISR_E_INVALID, "conv %s: the wide epilogue always writes an activation", name.c_str()); return false; }
         if (o.s2d && (p.cout_pad != 64 || (H & 1) || (W & 1))) { rc = fail(ctx, FISR_E_INVALID, "conv %s: space-to-depth needs 64 output channels and even H, W", name.c_str()); return false; }
         {   // the epilogue indexes with 32-bit element offsets
-            const double px = static_cast<double>(N) * H * W * (o.d2s ? 4 : 1);
+            const double px = static_cast<double>(N) * H * W * ((o.d2s || o.ps) ? 4 : 1);
             const int cs_max = std::max(std::max(std::max(o.raw_cs, o.res_cs), o.act_cs), o.mask_cs);
             if (px * cs_max >= 4294967296.0) { rc = fail(ctx, FISR_E_INVALID, "conv %s: %d x %d x %d x %d exceeds 32-bit offsets; split the batch", name.c_str(), N, H, W, cs_max); return false; }
         }
@@ -472,6 +513,22 @@ struct Builder {
         conv(P(p + "/res_block/0/conv/0"), a0, c, 0, N, H, W, o, p + "/res_block/0/conv/0");
         o = ConvOut{}; o.res = m0; o.res_cs = c; o.act = a2; o.act_cs = c;
         conv(P(p + "/res_block/0/conv/1"), a1, c, 0, N, H, W, o, p + "/res_block/0/conv/1");
+        if (plan->planes == 3) {
+            // f16f8 (inference): conv/1 keeps its 256 channels at input resolution and conv/2 runs there too, with the
+            // depth_to_space folded into its weights: 16 instead of 36 (tap, K block) products per output group, no 2R-resolution
+            // activation tensor, and conv/1 stores plain NHWC rows.
+            ActBuf t256 = act(N, H, W, 4 * c);
+            o = ConvOut{}; o.act = t256; o.act_cs = 4 * c;             // relu commutes with depth_to_space (FISRnet.py:99,105)
+            conv(P(p + "/conv/1"), a2, c, 0, N, H, W, o, p + "/conv/1");
+            o = ConvOut{}; o.scalar = true; o.relu = false; o.ps = true;
+            o.raw = pred; o.raw_cs = 12;                               // 12-float records: [FI-SR 0..2 -, SR 0..2 -, FI-SR 3..5 -]
+            o.act = next; o.act_cs = 64;
+            if (cout == 6) { o.raw_off0 = 0; o.raw_off1 = 8; o.act_split = 3; o.act_off0 = IN_CH; o.act_off1 = IN_CH + 3; }
+            else           { o.raw_off1 = 4; o.act_split = 0; o.act_off1 = IN_CH + 3; }
+            conv_ps(P(p + "/conv/2"), t256, N, H, W, o, p + "/conv/2");
+            *rec = HeadRec{p, x, a0, a1, a2, t256, cout};
+            return;
+        }
         ActBuf shuf = act(N, 2 * H, 2 * W, c);
         o = ConvOut{}; o.act = shuf; o.act_cs = c; o.d2s = true;       // relu + depth_to_space (FISRnet.py:99,105)
         conv(P(p + "/conv/1"), a2, c, 0, N, H, W, o, p + "/conv/1");
@@ -768,9 +825,10 @@ int get_plan(fisr_ctx* ctx, int N, int H, int W, Plan** out) {
     plan->in_lvl[0] = b.act(N, H / 4, W / 4, 64, true);
     plan->in_lvl[1] = b.act(N, H / 2, W / 2, 64, true);
     plan->in_lvl[2] = b.act(N, H, W, 64, true);
-    plan->pred[0] = b.f32(N, H / 2, W / 2, 9);
-    plan->pred[1] = b.f32(N, H, W, 9);
-    plan->pred[2] = b.f32(N, 2 * H, 2 * W, 9);
+    plan->pred_cs = ctx->planes == 3 ? 12 : 9;
+    plan->pred[0] = b.f32(N, H / 2, W / 2, plan->pred_cs);
+    plan->pred[1] = b.f32(N, H, W, plan->pred_cs);
+    plan->pred[2] = b.f32(N, 2 * H, 2 * W, plan->pred_cs);
     b.level(1, plan->in_lvl[0], N, H / 4, W / 4, plan->pred[0], plan->in_lvl[1]);
     b.level(2, plan->in_lvl[1], N, H / 2, W / 2, plan->pred[1], plan->in_lvl[2]);
     b.level(3, plan->in_lvl[2], N, H, W, plan->pred[2], ActBuf{});
@@ -876,9 +934,9 @@ int units_impl(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, cons
         rc = run_plan(ctx, plan, st);
         if (rc != FISR_OK) return rc;
         if (d_canvas_u8)
-            launch_tile_unpack_u8(plan->pred[2], tl, 2 * th, 2 * tw, d_canvas_u8, OH, OW, 2 * g.sH, 2 * g.sW, st);
+            launch_tile_unpack_u8(plan->pred[2], plan->pred_cs, tl, 2 * th, 2 * tw, d_canvas_u8, OH, OW, 2 * g.sH, 2 * g.sW, st);
         if (d_canvas_f32)
-            launch_tile_unpack_f32(plan->pred[2], tl, 2 * th, 2 * tw, d_canvas_f32, OH, OW, 2 * g.sH, 2 * g.sW, st);
+            launch_tile_unpack_f32(plan->pred[2], plan->pred_cs, tl, 2 * th, 2 * tw, d_canvas_f32, OH, OW, 2 * g.sH, 2 * g.sW, st);
         ctx->launches++;
         CUDA_TRY(ctx, cudaGetLastError());
     }
@@ -1030,6 +1088,8 @@ int fisr_create(int device, fisr_ctx** out) {
         p.cout_pad = p.cout <= 16 ? 16 : (p.cout + 63) / 64 * 64;
         p.cin_pad = p.KB * 64;
         p.OBk = (p.cout + 63) / 64;
+        p.head2 = p.cin == 64 && p.cout <= 16;                 // FI-SR/conv/2 (64 -> 6) and SR/conv/2 (64 -> 3)
+        p.ps_cout_pad = 4 * p.cout <= 16 ? 16 : 32;
         const size_t wn = static_cast<size_t>(9) * p.cin * p.cout;
         CUDA_TRY(nullptr, cudaMalloc(&p.d_w, wn * 4));
         CUDA_TRY(nullptr, cudaMemset(p.d_w, 0, wn * 4));
@@ -1049,7 +1109,7 @@ void fisr_destroy(fisr_ctx* ctx) {
     cudaDeviceSynchronize();
     ctx->plans.clear();
     for (auto& p : ctx->params) {
-        cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); cudaFree(p.m_w); cudaFree(p.v_w); cudaFree(p.m_b); cudaFree(p.v_b);
+        cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); cudaFree(p.d_wps); cudaFree(p.d_bps); cudaFree(p.d_wpps); cudaFree(p.m_w); cudaFree(p.v_w); cudaFree(p.m_b); cudaFree(p.v_b);
         cudaFree(p.d_wpT); cudaFree(p.g_w); cudaFree(p.g_b);
     }
     cudaFree(ctx->d_scalars);
@@ -1132,9 +1192,9 @@ int fisr_set_param(fisr_ctx* ctx, const char* name, const float* h_data, size_t 
     // landed, and the context stream is non-blocking, so the pack kernel would race with it.
     CUDA_TRY(ctx, cudaDeviceSynchronize());
     CUDA_TRY(ctx, cudaMemcpyAsync(is_w ? p.d_w : p.d_b, h_data, count * 4, cudaMemcpyHostToDevice, ctx->stream));
-    if (is_w) {
+    if (is_w || p.head2) {
         p.packed = false;
-        p.packedT = false;
+        if (is_w) p.packedT = false;
         // plans hold pointers to the packed planes, which are rewritten in place: re-pack now
         rc = ensure_packed(ctx, p, ctx->stream);
         if (rc != FISR_OK) return rc;
@@ -1157,6 +1217,27 @@ int fisr_get_param(fisr_ctx* ctx, const char* name, float* h_data, size_t count)
     return FISR_OK;
 }
 
+// FISRnet.model's three outputs as dense [.., 9] tensors: the plan's buffers themselves, or compacted copies of the 12-float records.
+int compact_preds(fisr_ctx* ctx, Plan* plan, const float* src[3], cudaStream_t st) {
+    const size_t npx[3] = {static_cast<size_t>(plan->N) * (plan->H / 2) * (plan->W / 2), static_cast<size_t>(plan->N) * plan->H * plan->W,
+                           static_cast<size_t>(plan->N) * plan->H * plan->W * 4};
+    for (int l = 0; l < 3; ++l) {
+        src[l] = plan->pred[l];
+        if (plan->pred_cs == 9) continue;
+        if (!plan->pred9[l]) {
+            void* p = nullptr;
+            CUDA_TRY(ctx, cudaMalloc(&p, npx[l] * 9 * sizeof(float)));
+            plan->allocs.push_back(p);
+            plan->pred9[l] = static_cast<float*>(p);
+        }
+        launch_pred_compact(plan->pred[l], plan->pred9[l], npx[l], st);
+        ctx->launches++;
+        src[l] = plan->pred9[l];
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FISR_OK;
+}
+
 int fisr_forward(fisr_ctx* ctx, const float* d_img, int N, int H, int W, float* d_l1, float* d_l2, float* d_l3,
                  void* stream) {
     if (!ctx || !d_img) return FISR_E_INVALID;
@@ -1170,9 +1251,11 @@ int fisr_forward(fisr_ctx* ctx, const float* d_img, int N, int H, int W, float* 
     rc = run_plan(ctx, plan, st);
     if (rc != FISR_OK) return rc;
     const size_t n1 = static_cast<size_t>(N) * (H / 2) * (W / 2) * 9, n2 = static_cast<size_t>(N) * H * W * 9, n3 = n2 * 4;
-    if (d_l1) CUDA_TRY(ctx, cudaMemcpyAsync(d_l1, plan->pred[0], n1 * 4, cudaMemcpyDeviceToDevice, st));
-    if (d_l2) CUDA_TRY(ctx, cudaMemcpyAsync(d_l2, plan->pred[1], n2 * 4, cudaMemcpyDeviceToDevice, st));
-    if (d_l3) CUDA_TRY(ctx, cudaMemcpyAsync(d_l3, plan->pred[2], n3 * 4, cudaMemcpyDeviceToDevice, st));
+    const float* src[3];
+    if ((rc = compact_preds(ctx, plan, src, st)) != FISR_OK) return rc;
+    if (d_l1) CUDA_TRY(ctx, cudaMemcpyAsync(d_l1, src[0], n1 * 4, cudaMemcpyDeviceToDevice, st));
+    if (d_l2) CUDA_TRY(ctx, cudaMemcpyAsync(d_l2, src[1], n2 * 4, cudaMemcpyDeviceToDevice, st));
+    if (d_l3) CUDA_TRY(ctx, cudaMemcpyAsync(d_l3, src[2], n3 * 4, cudaMemcpyDeviceToDevice, st));
     return FISR_OK;
 }
 
@@ -1192,9 +1275,11 @@ int fisr_forward_host(fisr_ctx* ctx, const float* h_img, int N, int H, int W, fl
     rc = run_plan(ctx, plan, st);
     if (rc != FISR_OK) return rc;
     const size_t n1 = static_cast<size_t>(N) * (H / 2) * (W / 2) * 9, n2 = static_cast<size_t>(N) * H * W * 9, n3 = n2 * 4;
-    if (h_l1) CUDA_TRY(ctx, cudaMemcpyAsync(h_l1, plan->pred[0], n1 * 4, cudaMemcpyDeviceToHost, st));
-    if (h_l2) CUDA_TRY(ctx, cudaMemcpyAsync(h_l2, plan->pred[1], n2 * 4, cudaMemcpyDeviceToHost, st));
-    if (h_l3) CUDA_TRY(ctx, cudaMemcpyAsync(h_l3, plan->pred[2], n3 * 4, cudaMemcpyDeviceToHost, st));
+    const float* src[3];
+    if ((rc = compact_preds(ctx, plan, src, st)) != FISR_OK) return rc;
+    if (h_l1) CUDA_TRY(ctx, cudaMemcpyAsync(h_l1, src[0], n1 * 4, cudaMemcpyDeviceToHost, st));
+    if (h_l2) CUDA_TRY(ctx, cudaMemcpyAsync(h_l2, src[1], n2 * 4, cudaMemcpyDeviceToHost, st));
+    if (h_l3) CUDA_TRY(ctx, cudaMemcpyAsync(h_l3, src[2], n3 * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return check_kernel_error(ctx);
 }

@@ -48,6 +48,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe (mbarrier.try_wait may suspend the thread for a system-dependent time before it gives up).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as an error flag, never as a hung GPU.
 // Returns false after ~4 s without progress (caller records it and bails out).
 __device__ __forceinline__ unsigned long long global_timer_ns() {
