@@ -226,7 +226,7 @@ class FISRnet(object):
         test_img_dir = check_folder(os.path.join(self.test_img_dir, self.model_dir))
         n_in_seq, n_test_in_seq = 3, 5
         n_GT_seq, n_test_label_seq = n_in_seq * 2 - 3, 2 * n_test_in_seq - 3
-        psnr_fisr, psnr_sr, inf_time = [], [], []
+        psnr_fisr, psnr_sr, ssim_fisr, ssim_sr, inf_time = [], [], [], [], []
         start_time = time.time()
         H, W = self.test_input_size
         h = H - np.remainder(H, 32 * num_patch[0])
@@ -250,16 +250,25 @@ class FISRnet(object):
                       "fr2 (SR) %.8f[dB], fr3 (FI-SR) %.8f[dB]  "
                       % (scene_i * 3 + sample_i, len(test_data_path) / n_test_in_seq * 3, scene_i, sample_i,
                          (time.time() - start_time) / 60, test_PSNR[0], test_PSNR[1], test_PSNR[2]))
+                label_u8 = (label * 255).astype('uint8')                                       # FISRnet.py:890-891
+                test_SSIM = [utils.compare_ssim(pred[:, :, 3 * s:3 * (s + 1)], label_u8[:, :, 3 * s:3 * (s + 1)])
+                             for s in range(n_GT_seq)]
+                print(" --------------------------------------------------------------- test_SSIM: fr1 (FI-SR) %.8f, "
+                      "fr2 (SR) %.8f, fr3 (FI-SR) %.8f  " % (test_SSIM[0], test_SSIM[1], test_SSIM[2]))
                 for s in range(n_GT_seq):
                     fr_name = os.path.basename(test_label_path[scene_i * n_test_label_seq + sample_i * 2 + s])[3:]
                     rgb_img = utils.YUV2RGB_matlab(pred[:, :, s * 3:(s + 1) * 3])
                     Image.fromarray(rgb_img.astype('uint8')).save(os.path.join(test_img_dir, 'pred_{}'.format(fr_name)))
                 psnr_fisr.append(test_PSNR[0])
                 psnr_sr.append(test_PSNR[1])
+                ssim_fisr.append(test_SSIM[0])
+                ssim_sr.append(test_SSIM[1])
                 if sample_i == 2:
                     psnr_fisr.append(test_PSNR[2])
+                    ssim_fisr.append(test_SSIM[2])
         print("######### Test (average) test_PSNR: FISR %.8f[dB], SR %.8f[dB]  #########"
               % (np.mean(psnr_fisr), np.mean(psnr_sr)))
+        print("######### Test (average) test_SSIM: FISR %.8f, SR %.8f #########" % (np.mean(ssim_fisr), np.mean(ssim_sr)))
         print("######### Estimated Inference Time (per window = three 4K frames): %.8f[s]  #########" % np.mean(inf_time))
 
     # ------------------------------------------------------------------ FISR_for_video (FISRnet.py:937-1084)

@@ -27,6 +27,37 @@ def _compute_psnr(img_orig, img_out, peak):        # utils.py:23-26
 FLO_MAGIC = np.float32(202021.25)
 
 
+def compare_ssim(image_0, image_1, tile_size=7):
+    """SSIM as the reference's ``test()`` measures it (FISRnet.py:5,890-891: ``SSIM_PIL.compare_ssim`` on uint8 images).
+
+    SSIM-PIL 1.0.x is not vendored with the reference and not installable here, so this restates its published algorithm
+    (parity unpinned): the image is cut into NON-overlapping ``tile_size`` x ``tile_size`` tiles
+    (the ragged border is dropped); for every tile and channel
+        ssim = (2 m0 m1 + c1) (2 cov + c2) / ((m0^2 + m1^2 + c1) (var0 + var1 + c2)),
+    with population statistics (divide by the pixel count), c1 = (0.01 * 255)^2, c2 = (0.03 * 255)^2, and the result is the
+    mean over tiles and channels.  Accepts PIL images or uint8 arrays [H, W] / [H, W, C]."""
+    a = np.asarray(image_0, dtype=np.float64)
+    b = np.asarray(image_1, dtype=np.float64)
+    if a.shape != b.shape:
+        raise AttributeError('The images do not have the same resolution.')
+    if a.ndim == 2:
+        a, b = a[..., None], b[..., None]
+    t = int(tile_size)
+    h, w = a.shape[0] // t * t, a.shape[1] // t * t
+    if h == 0 or w == 0:
+        raise ValueError('image smaller than one tile')
+    tiles = lambda x: x[:h, :w].reshape(h // t, t, w // t, t, -1)
+    a, b = tiles(a), tiles(b)
+    n = float(t * t)
+    s0, s1 = a.sum(axis=(1, 3)), b.sum(axis=(1, 3))
+    s00, s11, s01 = (a * a).sum(axis=(1, 3)), (b * b).sum(axis=(1, 3)), (a * b).sum(axis=(1, 3))
+    m0, m1 = s0 / n, s1 / n
+    var0, var1, cov = s00 / n - m0 * m0, s11 / n - m1 * m1, s01 / n - m0 * m1
+    c1, c2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+    ssim = (2 * m0 * m1 + c1) * (2 * cov + c2) / ((m0 * m0 + m1 * m1 + c1) * (var0 + var1 + c2))
+    return float(ssim.mean())
+
+
 def read_flo_file_5dim(filename):
     """utils.py:57-74: float32 magic, int32 N, N_seq, h, w, then N*N_seq*h*w*2 float32 -> [N, N_seq, h, w, 2]."""
     with open(filename, 'rb') as f:

@@ -1,13 +1,14 @@
 #!/bin/bash
-# One GPU call: bench line, per-layer table, ncu launch list, ncu --set full of the top conv kernel.
+# round-end measurement set: GPU tests, bench lines (both precisions + reference arm), per-layer tables, training table,
+# ncu launch list, DRAM traffic of every conv launch of one forward, full captures of four representative convs
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
-timeout 300 python tools/profile_layers.py 4 544 992 f16x3 > gpurun_out/layers_f16x3.txt 2>&1; head -3 gpurun_out/layers_f16x3.txt
-timeout 300 python tools/profile_layers.py 8 192 192 f16x3 > gpurun_out/layers_cfg2_f16x3.txt 2>&1; head -2 gpurun_out/layers_cfg2_f16x3.txt
-timeout 300 python tools/profile_layers.py 4 544 992 f16 > gpurun_out/layers_f16.txt 2>&1; head -2 gpurun_out/layers_f16.txt
-if [ "$1" != "nonCU" ]; then
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches.csv python tools/ncu_target.py 4 544 992 > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv3x3_umma -s 232 -c 4 -o gpurun_out/prof_conv -f python tools/ncu_target.py 4 544 992 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
-fi
-ls -la gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python bench.py > gpurun_out/bench_f16f8.json 2> gpurun_out/bench_f16f8.err; cut -c1-200 gpurun_out/bench_f16f8.json
+python bench.py --precision f16x3 > gpurun_out/bench_f16x3.json 2>/dev/null
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null
+for p in f16f8 f16x3; do python tools/profile_layers.py 4 544 992 $p > gpurun_out/layers_tile_$p.txt 2>&1; python tools/profile_layers.py 8 192 192 $p > gpurun_out/layers_cfg2_$p.txt 2>&1; done
+python tools/profile_train.py > gpurun_out/train_cfg3.txt 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_f16f8.csv python bench.py --steps 2 --warmup 1 > gpurun_out/ncu_bench.log 2>&1
+python tools/summarize_launches.py gpurun_out/launches_f16f8.csv > gpurun_out/launches_f16f8.txt
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv3x3_umma -s 138 -c 138 --csv --log-file gpurun_out/traffic_f16f8.csv python tools/ncu_target.py 4 544 992 f16f8 2 > gpurun_out/ncu_traffic.log 2>&1
+tools/gpu_ncu.sh f16f8 conv64 93 2 conv128 98 2 head 131 2
