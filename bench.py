@@ -263,8 +263,20 @@ def run_b200(args):
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12
         mma_factor = {"f16x3": 3, "f16f8": 2, "f16": 1}[eng.precision]      # tensor-pipe time per K slice in fp16-rate MMA units
         top = max(conv, key=lambda o: o["ms"])
+        # DRAM bytes of the same 138 launches from the committed ncu capture (profiles/r01_traffic.json), next to the
+        # algorithmic bytes (every input plane, weight and output once per launch)
+        traffic = None
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
+                t = json.load(f).get(eng.precision)
+            if t:
+                traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+        except (OSError, ValueError, KeyError):
+            pass
+        alg_bytes = sum(o["bytes"] for o in conv)
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+                    "frac": achieved / peaks["tflops_sustained"], "traffic": traffic, "algorithmic_bytes": alg_bytes,
+                    "traffic_note": "DRAM read+write bytes of the 138 conv launches of one forward, summed (ncu, profiles/r01_traffic.json)",
                     "kernel": "conv3x3_umma_kernel (138 launches per forward, summed)",
                     "peak_source": peaks["source"] + ", bf16 sustained (fp16 operands run at the bf16 rate)",
                     "issued_tflops": achieved * mma_factor, "issued_frac": achieved * mma_factor / peaks["tflops_sustained"],

@@ -58,12 +58,13 @@ cudaError_t launch_conv3x3(const ConvLaunch& L, int num_sms, cudaStream_t stream
 }
 
 // Host-side tile geometry / shared-memory carve-up for one conv launch.
-bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int num_sms, ConvLaunch* L) {
+bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int num_sms, ConvLaunch* L, int kb) {
     int NT = cout_pad <= 16 ? 16 : cout_pad <= 32 ? 32 : 64;
     // Wide N tiles halve the A re-reads and balance shared-memory operand traffic against MMA math.  The choice
     // depends on the per-image geometry only (never on the batch), so results are bit-identical however a
     // window's tiles are sharded over batches / GPUs (NT decides the fp32 summation order, see STACK).
     if (cout_pad >= 128 && (long)H * W >= 64L * 64) NT = 128;
+    if (const char* e = getenv("FISR_KB1_NT")) { if (kb == 1 && NT == 128 && atoi(e) == 64) NT = 64; }     // tuning knob
     int chunks = 2;
     {
         const long tiles2 = (long)n_img * ((H * (long)W + 255) / 256) * (cout_pad / NT);

@@ -17,7 +17,7 @@ struct ConvLaunch {
 };
 
 // Chooses NT / chunk count / patch pitch for an H x W x n_img conv and fills the geometry fields of L->args.
-bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int num_sms, ConvLaunch* L);
+bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int num_sms, ConvLaunch* L, int kb = 0);
 
 cudaError_t conv3x3_init();
 cudaError_t launch_conv3x3(const ConvLaunch& L, int num_sms, cudaStream_t stream);

@@ -603,10 +603,15 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                         if (STACK) tmem_ld_32x16(tacc + NT + c_begin + c0 + 16, v2);
                         bn = __ldg(reinterpret_cast<const float4*>(a.bias + cg_lane + c0 + 16));
                     }
+                    float4 vals[4];      // all four shared-memory reads in flight before the first use
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t r = rd_row + 8 * i;
-                        const float4 val = lds128(stg + r * 64 + ((rd_grp ^ ((r >> 1) & 3)) << 4));
+                        vals[i] = lds128(stg + r * 64 + ((rd_grp ^ ((r >> 1) & 3)) << 4));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 val = vals[i];
                         if ((vmask >> i) & 1) {
                             float f0, f1, f2, f3;
                             if (F8) {

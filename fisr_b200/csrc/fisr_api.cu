@@ -392,7 +392,7 @@ struct Builder {
         Op& op = *out;
         op.kind = OP_CONV;
         ConvLaunch& L = op.conv;
-        if (!plan_conv_geometry(H, W, N, p.cout_pad, plan->planes, ctx->num_sms, &L)) {
+        if (!plan_conv_geometry(H, W, N, p.cout_pad, plan->planes, ctx->num_sms, &L, p.KB)) {
             rc = fail(ctx, FISR_E_INVALID, "no tile geometry for conv %s (%dx%d)", name.c_str(), H, W);
             return false;
         }
