@@ -19,7 +19,7 @@ namespace fisr {
 //          The cross terms are ~2^-11 of the main term, so their 2..3-bit mantissas leave ~2^-14 relative error per conv
 //          (tools/precision_study_fp8.py: 2.5e-5 max-abs on the 138-conv cascade, 40x inside the 1e-3 bar).
 //          8-bit plane of an activation, per pixel and 64-channel block (128 B, same footprint as the fp16 lo plane):
-//              bytes [0,64)  = e5m2(16 * lo[c])      bytes [64,128) = e4m3(hi[c])
+//              bytes [0,64)  = e5m2(16 * lo[c])      bytes [64,128) = e5m2(hi[c])       (e5m2 = rounded upper byte of an fp16)
 //          weights: fp16 plane = fp16(128 * w) =: wh, 8-bit plane row = [e4m3(wh / 16) x 64 | e5m2(128 w - wh) x 64];
 //          every product term carries the factor 128, which the epilogue removes.
 enum Precision { PREC_F16X3 = 0, PREC_F16 = 1, PREC_F16F8 = 2 };
@@ -57,24 +57,29 @@ __device__ __forceinline__ uint8_t* f8_row_ptr(const __half* p1) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p1);
     return reinterpret_cast<uint8_t*>(a - ((a >> 1) & 63));
 }
-__device__ __forceinline__ uint8_t f8_lo_byte(float lo) {
-    return static_cast<uint8_t>(__nv_cvt_float_to_fp8(lo * kF8ActLoScale, __NV_SATFINITE, __NV_E5M2));
+__device__ __forceinline__ uint8_t f8_lo_byte(float lo) {    // e5m2 of fp16(lo) * 16 (same arithmetic as f8_pack_lo4)
+    const uint32_t h = __half_as_ushort(__hmul(__float2half_rn(lo), __float2half_rn(kF8ActLoScale)));
+    return static_cast<uint8_t>((h + 0x7Fu + ((h >> 8) & 1u)) >> 8);
 }
-__device__ __forceinline__ uint8_t f8_hi_byte(float x) {
-    return static_cast<uint8_t>(__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3));
+__device__ __forceinline__ uint8_t f8_hi_byte(float x) {     // e5m2 of the fp16 hi part (same rounding as f8_pack_hi4)
+    const uint32_t h = __half_as_ushort(__float2half_rn(x));
+    return static_cast<uint8_t>((h + 0x7Fu + ((h >> 8) & 1u)) >> 8);
 }
+// Two packed fp16 -> two e5m2 bytes (left in byte 1 and byte 3 of the result): an e5m2 number is the upper byte of the fp16
+// with the same value, so the conversion is a round-to-nearest-even of the low byte, done with integer adds.  (The
+// cvt.rn.satfinite.e5m2x2.f16x2 instruction runs on the quarter-rate XU pipe: ncu showed it at 179 % of its sustained peak
+// in the f16f8 epilogue, which made the K = 576 layers epilogue bound.)  No carry can cross the halves for finite inputs.
+__device__ __forceinline__ uint32_t f16x2_round_to_e5m2(uint32_t w) { return w + 0x007F007Fu + ((w >> 8) & 0x00010001u); }
 // l01 / l23: packed fp16 lo parts of 4 consecutive channels -> 4 e5m2 bytes of 16 * lo (channel order = byte order)
 __device__ __forceinline__ uint32_t f8_pack_lo4(uint32_t l01, uint32_t l23) {
     const __half2 s = __floats2half2_rn(kF8ActLoScale, kF8ActLoScale);
     const __half2 a = __hmul2(*reinterpret_cast<const __half2*>(&l01), s), b = __hmul2(*reinterpret_cast<const __half2*>(&l23), s);
-    const uint32_t x = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(a), __NV_SATFINITE, __NV_E5M2);
-    const uint32_t y = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(b), __NV_SATFINITE, __NV_E5M2);
-    return x | (y << 16);
+    return __byte_perm(f16x2_round_to_e5m2(*reinterpret_cast<const uint32_t*>(&a)),
+                       f16x2_round_to_e5m2(*reinterpret_cast<const uint32_t*>(&b)), 0x7531);
 }
+// h01 / h23: packed fp16 hi parts of 4 consecutive channels -> 4 e5m2 bytes of hi
 __device__ __forceinline__ uint32_t f8_pack_hi4(uint32_t h01, uint32_t h23) {
-    const uint32_t x = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(*reinterpret_cast<const __half2*>(&h01)), __NV_SATFINITE, __NV_E4M3);
-    const uint32_t y = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(*reinterpret_cast<const __half2*>(&h23)), __NV_SATFINITE, __NV_E4M3);
-    return x | (y << 16);
+    return __byte_perm(f16x2_round_to_e5m2(h01), f16x2_round_to_e5m2(h23), 0x7531);
 }
 // value an (hi, 8-bit row) pair stands for: hi + e5m2 byte / 16 (an e5m2 byte is the upper byte of the fp16 with the same value)
 __device__ __forceinline__ float join_f8(__half hi, uint8_t lo_byte) {

@@ -23,7 +23,7 @@
 // swizzle is a function of the absolute shared-memory address for TMA and UMMA alike).  Weights stream per tap
 // through a ring of slots.
 //
-// PLANES = 3 ("f16f8"): activations are (fp16 hi plane, 8-bit plane [e5m2(16 lo) x64 | e4m3(hi) x64] per 64-channel
+// PLANES = 3 ("f16f8"): activations are (fp16 hi plane, 8-bit plane [e5m2(16 lo) x64 | e5m2(hi) x64] per 64-channel
 // block), weights (fp16(128 w) plane, 8-bit plane [e4m3(8 w_hi) | e5m2(128 w_lo)]).  Per tap the main product is 4
 // kind::f16 MMAs and both cross terms are 4 kind::f8f6f4 MMAs (K = 32, mixed formats) K-concatenated in the same
 // 128-B rows, all into ONE accumulator that holds 128 x the result: 2 MMA units per K slice instead of 3.
@@ -332,7 +332,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         constexpr uint32_t idesc = umma_idesc_f16(128, NT);
         constexpr uint32_t idesc2 = umma_idesc_f16(128, STACK ? 2 * NT : NT);
         constexpr uint32_t idesc8a = umma_idesc_f8(128, NT, kF8E5M2, kF8E4M3);   // bytes [0,64):   e5m2(16 x_lo) * e4m3(8 w_hi)
-        constexpr uint32_t idesc8b = umma_idesc_f8(128, NT, kF8E4M3, kF8E5M2);   // bytes [64,128): e4m3(x_hi) * e5m2(128 w_lo)
+        constexpr uint32_t idesc8b = umma_idesc_f8(128, NT, kF8E5M2, kF8E5M2);   // bytes [64,128): e5m2(x_hi) * e5m2(128 w_lo)
         const bool lead = elect_one();
         constexpr uint32_t a_hi_word = A_DESC_HI;
         uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
@@ -642,7 +642,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                             }
                             *reinterpret_cast<uint2*>(d) = make_uint2(h01, h23);
                             if (PLANES == 2) *reinterpret_cast<uint2*>(d + a.act_plane) = make_uint2(l01, l23);
-                            if (F8) {   // 8-bit plane: [e5m2(16 lo) x 64 | e4m3(hi) x 64] per 64-channel block of the pixel
+                            if (F8) {   // 8-bit plane: [e5m2(16 lo) x 64 | e5m2(hi) x 64] per 64-channel block of the pixel
                                 uint8_t* q = f8_row_ptr(d + a.act_plane);
                                 *reinterpret_cast<uint32_t*>(q) = f8_pack_lo4(l01, l23);
                                 *reinterpret_cast<uint32_t*>(q + 64) = f8_pack_hi4(h01, h23);
