@@ -18,7 +18,7 @@ cudaError_t launch_family(const ConvLaunch& L, int num_sms, cudaStream_t stream)
     template <> cudaError_t init_family<NT_, PL_>();            \
     template <> cudaError_t launch_family<NT_, PL_>(const ConvLaunch&, int, cudaStream_t);
 FISR_DECL(16, 1) FISR_DECL(64, 1) FISR_DECL(128, 1) FISR_DECL(16, 2) FISR_DECL(64, 2) FISR_DECL(128, 2)
-FISR_DECL(16, 3) FISR_DECL(32, 3) FISR_DECL(64, 3) FISR_DECL(128, 3)
+FISR_DECL(16, 3) FISR_DECL(32, 3) FISR_DECL(64, 3) FISR_DECL(128, 3) FISR_DECL(64, 4) FISR_DECL(128, 4)
 #undef FISR_DECL
 }  // namespace convk
 
@@ -35,12 +35,17 @@ cudaError_t conv3x3_init() {
     if (e == cudaSuccess) e = init_family<32, 3>();
     if (e == cudaSuccess) e = init_family<64, 3>();
     if (e == cudaSuccess) e = init_family<128, 3>();
+    if (e == cudaSuccess) e = init_family<64, 4>();
+    if (e == cudaSuccess) e = init_family<128, 4>();
     return e;
 }
 
 cudaError_t launch_conv3x3(const ConvLaunch& L, int num_sms, cudaStream_t stream) {
     using namespace convk;
-    if (L.planes == 3) {
+    if (L.planes == 3 && L.pair) {
+        if (L.NT == 64) return launch_family<64, 4>(L, num_sms, stream);
+        if (L.NT == 128) return launch_family<128, 4>(L, num_sms, stream);
+    } else if (L.planes == 3) {
         if (L.NT == 16) return launch_family<16, 3>(L, num_sms, stream);
         if (L.NT == 32) return launch_family<32, 3>(L, num_sms, stream);
         if (L.NT == 64) return launch_family<64, 3>(L, num_sms, stream);
@@ -73,19 +78,28 @@ bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int n
     if (const char* e = getenv("FISR_CHUNKS")) { if (atoi(e) == 1 || atoi(e) == 2) chunks = atoi(e); }   // tuning knob
     const int apl = act_planes(planes);
     const bool stack = planes == 2 && NT <= 64;
-    const int slot_bytes = stack ? 2 * NT * 128 : NT * 128;
+    // f16f8 layers with wide outputs can run on CTA pairs (cluster of 2, cta_group::2, M = 256): each CTA keeps half of a tap's
+    // weight rows, i.e. half the L2 -> smem weight traffic and half the shared-memory B reads per MMA.  Measured on B200
+    // (profiles/r01_pair_mode.txt): bit-identical results, 1-3 % faster on act-only layers, 5-9 % slower on the residual
+    // layers (the slower epilogue of the two CTAs gates both), 26.73 vs 26.78 ms per forward -- so it is opt-in (FISR_PAIR=1).
+    bool pair = false;
+    if (const char* e = getenv("FISR_PAIR")) pair = planes == 3 && NT >= 64 && atoi(e) != 0;
+    const int slot_bytes = stack ? 2 * NT * 128 : (pair ? NT / 2 : NT) * 128;
     const int fixed = 128 /*align*/ + convk::kStageBytes /*epilogue transpose*/;
     // A chunk is 8 px x 16 rows (one 128-row MMA, one image row of the patch per 8-row group); two chunks sit side by side:
     // tile 16 x 16, patch 18 x 18.  The geometry is a compile-time function of CHUNKS in the kernel.
     const int cx = chunks, cy = 1;
     double best_eff;
     {
-        const long tiles = (long)((W + 8 * cx - 1) / (8 * cx)) * ((H + 15) / 16);
+        long tx = (W + 8 * cx - 1) / (8 * cx);
+        if (pair) tx = (tx + 1) / 2 * 2;          // a pair whose right tile lies past the image edge still issues its rows
+        const long tiles = tx * ((H + 15) / 16);
         best_eff = (double)H * W / ((double)tiles * 128 * chunks);
     }
     ConvArgs& a = L->args;
     a.TW = 8 * cx; a.TH = 16 * cy; a.P = a.TW + 2;
     a.tiles_x = (W + a.TW - 1) / a.TW;
+    if (pair) a.tiles_x = (a.tiles_x + 1) / 2;
     a.tiles_y = (H + a.TH - 1) / a.TH;
     a.NB = cout_pad / NT;
     a.num_tiles = n_img * a.tiles_x * a.tiles_y * a.NB;
@@ -103,7 +117,7 @@ bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int n
     if (slots > convk::kMaxBSlots) slots = convk::kMaxBSlots;
     if (slots < 2) return false;
     a.b_slots = slots;
-    L->NT = NT; L->chunks = chunks; L->planes = planes;
+    L->NT = NT; L->chunks = chunks; L->planes = planes; L->pair = pair;
     L->smem_bytes = fixed + a.a_stages * apl * a.a_plane_bytes + slots * slot_bytes;
     L->efficiency = best_eff;
     return true;

@@ -11,6 +11,7 @@ struct ConvLaunch {
     CUtensorMap tmA_hi, tmA_lo, tmB;
     ConvArgs args;
     int NT, chunks, planes;
+    bool pair;              // f16f8 on CTA pairs (cluster of 2, M = 256 MMAs): args.tiles_x / num_tiles count PAIRS of x-adjacent tiles
     int epi;                // epilogue variant: 1 residual in, 2 fp32 out, 4 depth-to-space (convk::EPI_*)
     int smem_bytes;
     double efficiency;      // useful fraction of the MMA rows issued (tile quantisation at the image edges)

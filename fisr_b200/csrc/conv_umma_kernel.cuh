@@ -51,7 +51,7 @@ namespace convk {
 constexpr int kEpiWarps = 8;
 constexpr int kIssuer2Warp = 2 + kEpiWarps;            // second MMA issuer, see "MMA issuers" below
 constexpr int kPatchWarp = kIssuer2Warp + 1;           // f16f8 only: activation-patch producer
-__host__ __device__ constexpr int conv_threads(int planes) { return 32 * (planes == 3 ? kPatchWarp + 1 : kIssuer2Warp + 1); }
+__host__ __device__ constexpr int conv_threads(int planes) { return 32 * (planes >= 3 ? kPatchWarp + 1 : kIssuer2Warp + 1); }
 constexpr int kMaxBSlots = 12;
 constexpr int kMaxAStages = 4;                // activation buffers with their own barrier pair (f16f8: plane * 2 + stage)
 constexpr int kStageBytesPerWarp = 32 * 64;   // [32 px][16 ch] fp32, 16-B groups XOR-swizzled (conflict-free both ways)
@@ -68,7 +68,9 @@ enum { ERR_A_EMPTY = 11, ERR_B_EMPTY = 12, ERR_A_FULL = 21, ERR_B_FULL = 22, ERR
 struct TileCoord {
     int n, y0, x0, nb;
 };
-__device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile) {
+// pair_rank < 0: one CTA per tile.  pair_rank = 0 / 1: the work item is a PAIR of x-adjacent tiles (a.tiles_x counts pairs) and
+// this CTA takes the left / right one; a right tile past the image edge is all padding (TMA zero fill, epilogue masks it).
+__device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile, int pair_rank = -1) {
     TileCoord t;
     t.nb = tile % a.NB;
     int s = tile / a.NB;
@@ -77,7 +79,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile) {
     const int ty = s % a.tiles_y;
     t.n = s / a.tiles_y;
     t.y0 = ty * a.TH;
-    t.x0 = tx * a.TW;
+    t.x0 = (pair_rank < 0 ? tx : 2 * tx + pair_rank) * a.TW;
     return t;
 }
 
@@ -99,7 +101,7 @@ __device__ __forceinline__ void epilogue_scalar(const ConvArgs& a, const uint32_
     for (int ch = 0; ch < NCOL; ++ch) {
         if (ch < a.cout) {
             float f = __uint_as_float(v[ch]);
-            if (PLANES == 3) f *= kF8AccScale;
+            if (PLANES >= 3) f *= kF8AccScale;
             f += __ldg(a.bias + ch);
             const int co = ch, opix = pix;
             if (a.out_raw) a.out_raw[static_cast<size_t>(opix) * a.raw_cs + co + (co < a.raw_split ? a.raw_off0 : a.raw_off1)] = f;
@@ -110,7 +112,7 @@ __device__ __forceinline__ void epilogue_scalar(const ConvArgs& a, const uint32_
                 __half* d = a.out_act + static_cast<size_t>(opix) * a.act_cs + c;
                 d[0] = s.hi;
                 if (PLANES == 2) d[a.act_plane] = s.lo;
-                if (PLANES == 3) {
+                if (PLANES >= 3) {
                     uint8_t* q = reinterpret_cast<uint8_t*>(a.out_act + a.act_plane + static_cast<size_t>(opix) * a.act_cs) +
                                  (c >> 6) * 128 + (c & 63);
                     q[0] = f8_lo_byte(g - __half2float(s.hi));
@@ -134,7 +136,7 @@ __device__ __forceinline__ void epilogue_scalar_ps(const ConvArgs& a, const uint
 #pragma unroll
         for (int co = 0; co < COUT; ++co) {
             f[co] = __uint_as_float(v[sub * COUT + co]);
-            if (PLANES == 3) f[co] *= kF8AccScale;
+            if (PLANES >= 3) f[co] *= kF8AccScale;
             f[co] += __ldg(a.bias + sub * COUT + co);
         }
         if (a.out_raw) {
@@ -155,7 +157,7 @@ __device__ __forceinline__ void epilogue_scalar_ps(const ConvArgs& a, const uint
                 __half* d = a.out_act + opix * a.act_cs + c;
                 d[0] = s.hi;
                 if (PLANES == 2) d[a.act_plane] = s.lo;
-                if (PLANES == 3) {
+                if (PLANES >= 3) {
                     uint8_t* q = reinterpret_cast<uint8_t*>(a.out_act + a.act_plane + opix * a.act_cs) + (c >> 6) * 128 + (c & 63);
                     q[0] = f8_lo_byte(g - __half2float(s.hi));
                     q[64] = f8_hi_byte(g);
@@ -170,13 +172,14 @@ __global__ void __launch_bounds__(conv_threads(PLANES), 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvArgs a) {
     constexpr bool STACK = (PLANES == 2) && (NT <= 64);
-    constexpr bool F8 = PLANES == 3;
+    constexpr bool F8 = PLANES >= 3;
+    constexpr bool PAIR = PLANES == 4;                          // f16f8 on CTA pairs: cluster of 2, tcgen05 cta_group::2, M = 256
     constexpr int APL = PLANES == 1 ? 1 : 2;                    // activation planes staged in shared memory
     constexpr int DCOLS = STACK ? 2 * NT : NT;                  // accumulator columns per 128-row chunk
     constexpr int ACC_COLS = CHUNKS * DCOLS;                    // fp32 columns of one accumulator stage
     constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
     static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns must be a power of two <= 512");
-    constexpr int PLANE_BYTES = NT * 128;                       // one weight plane of one tap
+    constexpr int PLANE_BYTES = (PAIR ? NT / 2 : NT) * 128;     // one weight plane of one tap (a CTA of a pair holds half the rows)
     constexpr int B_SLOT_BYTES = STACK ? 2 * PLANE_BYTES : PLANE_BYTES;
     constexpr int SLOTS_PER_TAP = STACK ? 1 : APL;
     constexpr bool NARROW = NT <= 32;
@@ -210,17 +213,22 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         // every chunk has its own MMA issuer warp: operand buffers are released, and accumulators published, by all of them
         for (int s = 0; s < kMaxAStages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), CHUNKS); }
         for (int s = 0; s < a.b_slots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), CHUNKS); }
-        for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), CHUNKS); mbar_init(acc_empty(s), kEpiWarps); }
+        // (pair: the epilogue warps of both CTAs release the leader's accumulator barrier)
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), CHUNKS); mbar_init(acc_empty(s), PAIR ? 2 * kEpiWarps : kEpiWarps); }
         fence_mbar_init();
         tma_prefetch_desc(&tmA_hi);
         if (APL == 2) tma_prefetch_desc(&tmA_lo);
         tma_prefetch_desc(&tmB);
     }
-    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
+    if (warp == 1) { if (PAIR) tmem_alloc_pair(smem_u32(&tmem_slot), TMEM_COLS); else tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS); }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();       // pair: both CTAs' barriers exist before anything signals across
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    // work distribution: one item per CTA, or per CTA pair (rank 0 = leader: issues the MMAs, owns the full / accumulator barriers)
+    const int prank = PAIR ? static_cast<int>(cluster_ctarank()) : -1;
+    const bool leader = !PAIR || prank == 0;
+    const int wid0 = PAIR ? blockIdx.x >> 1 : blockIdx.x, wstride = PAIR ? gridDim.x >> 1 : gridDim.x;
 
     constexpr int box_bytes = (THc + 2) * Pc * 128;
     const int cout_pad = a.NB * NT;
@@ -234,7 +242,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             if (elect_one()) {
                 uint32_t bs = 0, bph = 0;
                 bool ok = true;
-                for (int tile = blockIdx.x; tile < a.num_tiles && ok; tile += gridDim.x) {
+                for (int tile = wid0; tile < a.num_tiles && ok; tile += wstride) {
                     const int nb = tile % a.NB;
                     for (int kb = 0; kb < a.KB && ok; ++kb) {
                         const uint32_t mask = a.tapmask[kb & 7];
@@ -243,8 +251,14 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                             if (!((mask >> tap) & 1u)) continue;      // all-zero weights (fused depth_to_space heads)
                             ok = mbar_wait(b_empty(bs), bph ^ 1, a.err, ERR_B_EMPTY);
                             if (!ok) break;
-                            mbar_expect_tx(b_full(bs), B_SLOT_BYTES);
-                            tma_load_2d(sB + bs * B_SLOT_BYTES, &tmB, b_full(bs), 0, ((plane * a.KB + kb) * 9 + tap) * cout_pad + nb * NT);
+                            const int row = ((plane * a.KB + kb) * 9 + tap) * cout_pad + nb * NT;
+                            if (PAIR) {      // each CTA loads its half of the tap's rows; both credit the leader's barrier
+                                if (leader) mbar_expect_tx(b_full(bs), 2 * B_SLOT_BYTES);
+                                tma_load_2d_pair(sB + bs * B_SLOT_BYTES, &tmB, mapa_shared(b_full(bs), 0), 0, row + prank * (NT / 2));
+                            } else {
+                                mbar_expect_tx(b_full(bs), B_SLOT_BYTES);
+                                tma_load_2d(sB + bs * B_SLOT_BYTES, &tmB, b_full(bs), 0, row);
+                            }
                             if (++bs == (uint32_t)a.b_slots) { bs = 0; bph ^= 1; }
                         }
                     }
@@ -301,11 +315,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         // 8-bit(i), fp16(i), 8-bit(i+1), ..., so one thread with blocking waits requests every patch the moment its buffer is free.
         if (elect_one()) {
             const uint32_t D = a.a_stages;
-            const int my_tiles = blockIdx.x < a.num_tiles ? (a.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            const int my_tiles = wid0 < a.num_tiles ? (a.num_tiles - wid0 + wstride - 1) / wstride : 0;
             bool ok = true;
             uint32_t cnt = 0;
             for (int ti = 0; ti < my_tiles && ok; ++ti) {
-                const TileCoord t = decode_tile(a, blockIdx.x + ti * gridDim.x);
+                const TileCoord t = decode_tile(a, wid0 + ti * wstride, prank);
                 for (int kb = 0; kb < a.KB && ok; ++kb, ++cnt) {
                     const uint32_t st = cnt & (D - 1), par = ((cnt >> (D - 1)) & 1) ^ 1;
 #pragma unroll
@@ -313,14 +327,20 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                         const uint32_t buf = pl * 2 + st;
                         ok = mbar_wait(a_empty(buf), par, a.err, ERR_A_EMPTY);
                         if (!ok) break;
-                        mbar_expect_tx(a_full(buf), box_bytes);
-                        tma_load_4d(sA + (st * 2 + pl) * a.a_plane_bytes, pl ? &tmA_lo : &tmA_hi, a_full(buf), a.cin_off + kb * 64,
-                                    t.x0 - 1, t.y0 - 1, t.n);
+                        if (PAIR) {
+                            if (leader) mbar_expect_tx(a_full(buf), 2 * box_bytes);
+                            tma_load_4d_pair(sA + (st * 2 + pl) * a.a_plane_bytes, pl ? &tmA_lo : &tmA_hi, mapa_shared(a_full(buf), 0),
+                                             a.cin_off + kb * 64, t.x0 - 1, t.y0 - 1, t.n);
+                        } else {
+                            mbar_expect_tx(a_full(buf), box_bytes);
+                            tma_load_4d(sA + (st * 2 + pl) * a.a_plane_bytes, pl ? &tmA_lo : &tmA_hi, a_full(buf), a.cin_off + kb * 64,
+                                        t.x0 - 1, t.y0 - 1, t.n);
+                        }
                     }
                 }
             }
         }
-    } else if (warp == 1 || (CHUNKS == 2 && warp == kIssuer2Warp)) {
+    } else if ((warp == 1 || (CHUNKS == 2 && warp == kIssuer2Warp)) && leader) {
         // ============================== MMA issuers ==============================
         // One issuer warp per chunk (warp 1: chunk 0, last warp: chunk 1).  A single thread needs ~70 cycles per
         // tcgen05.mma (descriptor arithmetic on the uniform datapath, ncu source view), more than the 32..64 cycles an
@@ -331,8 +351,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const int c = warp == 1 ? 0 : 1;
         constexpr uint32_t idesc = umma_idesc_f16(128, NT);
         constexpr uint32_t idesc2 = umma_idesc_f16(128, STACK ? 2 * NT : NT);
-        constexpr uint32_t idesc8a = umma_idesc_f8(128, NT, kF8E5M2, kF8E4M3);   // bytes [0,64):   e5m2(16 x_lo) * e4m3(8 w_hi)
-        constexpr uint32_t idesc8b = umma_idesc_f8(128, NT, kF8E5M2, kF8E5M2);   // bytes [64,128): e5m2(x_hi) * e5m2(128 w_lo)
+        constexpr uint32_t MM = PAIR ? 256 : 128;                                // MMA M: a CTA pair issues both CTAs' rows at once
+        constexpr uint32_t idesc8a = umma_idesc_f8(MM, NT, kF8E5M2, kF8E4M3);    // bytes [0,64):   e5m2(16 x_lo) * e4m3(8 w_hi)
+        constexpr uint32_t idesc8b = umma_idesc_f8(MM, NT, kF8E5M2, kF8E5M2);    // bytes [64,128): e5m2(x_hi) * e5m2(128 w_lo)
+        constexpr uint32_t idesc16p = umma_idesc_f16(MM, NT);
         const bool lead = elect_one();
         constexpr uint32_t a_hi_word = A_DESC_HI;
         uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
@@ -341,7 +363,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             uint32_t items = 0;                           // (tile, K block) items consumed so far = patches consumed per plane
             const uint32_t D = a.a_stages;
             const uint32_t co = c * CHUNK_OFF;
-            for (int tile = blockIdx.x; tile < a.num_tiles && ok; tile += gridDim.x) {
+            auto commit = [&](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
+            for (int tile = wid0; tile < a.num_tiles && ok; tile += wstride) {
                 ok = __all_sync(0xffffffffu, mbar_wait(acc_empty(cs), cph ^ 1, a.err, ERR_ACC_EMPTY));
                 if (!ok) break;
                 tc_fence_after();
@@ -372,27 +395,30 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 #pragma unroll
                                         for (int k = 0; k < 4; ++k) {
                                             if ((k & 1) >= k8steps) continue;
-                                            umma_f8_lohi2(d_tmem, at + k * 2, a_hi_word, b0 + k * 2, kUmmaDescHiSw128,
-                                                          k < 2 ? idesc8a : idesc8b, k == 0 ? first : 1u);
+                                            if (PAIR) umma_f8_pair(d_tmem, at + k * 2, a_hi_word, b0 + k * 2, kUmmaDescHiSw128,
+                                                                   k < 2 ? idesc8a : idesc8b, k == 0 ? first : 1u);
+                                            else umma_f8_lohi2(d_tmem, at + k * 2, a_hi_word, b0 + k * 2, kUmmaDescHiSw128,
+                                                               k < 2 ? idesc8a : idesc8b, k == 0 ? first : 1u);
                                         }
                                     } else {
 #pragma unroll
                                         for (int k = 0; k < 4; ++k) {
                                             if (k >= ksteps) break;
-                                            umma_f16_lohi2(d_tmem, at + k * 2, a_hi_word, b0 + k * 2, kUmmaDescHiSw128, idesc, 1u);
+                                            if (PAIR) umma_f16_pair(d_tmem, at + k * 2, a_hi_word, b0 + k * 2, kUmmaDescHiSw128, idesc16p, 1u);
+                                            else umma_f16_lohi2(d_tmem, at + k * 2, a_hi_word, b0 + k * 2, kUmmaDescHiSw128, idesc, 1u);
                                         }
                                     }
-                                    umma_commit(b_empty(bs));
+                                    commit(b_empty(bs));
                                 }
                                 first = 1u;
                                 if (++bs == (uint32_t)a.b_slots) { bs = 0; bph ^= 1; }
                             }
                         }
-                        if (lead && ok) umma_commit(a_empty(buf));
+                        if (lead && ok) commit(a_empty(buf));
                     }
                     ++items;
                 }
-                if (lead && ok) umma_commit(acc_full(cs));
+                if (lead && ok) commit(acc_full(cs));
                 if (++cs == 2) { cs = 0; cph ^= 1; }
             }
         } else {
@@ -476,7 +502,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             if (++cs == 2) { cs = 0; cph ^= 1; }
         }
         }
-    } else if (warp < 2 + kEpiWarps) {
+    } else if (warp >= 2 && warp < 2 + kEpiWarps) {
         // ============================== epilogue ==============================
         const int ew = warp - 2;             // 0..7
         const int q4 = warp & 3;             // TMEM lane quarter this warp may read
@@ -498,8 +524,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         // chunk origin inside the tile (chunks sit side by side); MMA row m of a chunk is pixel (m & 7) of row (m >> 3)
         const int ch_x0 = my_c * 8, ch_y0 = 0;
 
-        for (int tile = blockIdx.x; tile < a.num_tiles && ok; tile += gridDim.x) {
-            const TileCoord t = decode_tile(a, tile);
+        const uint32_t acc_empty_dst0 = PAIR ? mapa_shared(acc_empty(0), 0) : 0u, acc_empty_dst1 = PAIR ? mapa_shared(acc_empty(1), 0) : 0u;
+        for (int tile = (F8 ? wid0 : static_cast<int>(blockIdx.x)); tile < a.num_tiles && ok; tile += (F8 ? wstride : static_cast<int>(gridDim.x))) {
+            const TileCoord t = decode_tile(a, tile, prank);
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + cs * ACC_COLS + my_c * DCOLS;
             if constexpr (NARROW) {
                 ok = __all_sync(0xffffffffu, mbar_wait(acc_full(cs), cph, a.err, ERR_ACC_FULL));
@@ -662,14 +689,17 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty(cs));
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_cluster(cs ? acc_empty_dst1 : acc_empty_dst0);      // the leader's barrier
+                else mbar_arrive(acc_empty(cs));
+            }
             if (++cs == 2) { cs = 0; cph ^= 1; }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) cluster_sync_all(); else __syncthreads();       // pair: no CTA leaves while its peer may still signal its barriers
+    if (warp == 1) { if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 template <int NT, int CHUNKS, int PLANES, int EPI>
@@ -680,6 +710,21 @@ cudaError_t init_inst() {
 
 template <int NT, int CHUNKS, int PLANES, int EPI>
 cudaError_t launch_inst(const ConvLaunch& L, int num_sms, cudaStream_t stream) {
+    if (PLANES == 4) {       // CTA pairs: L.args.num_tiles counts pairs of tiles, one cluster of 2 per pair in flight
+        const int pairs = num_sms / 2;
+        const int clusters = L.args.num_tiles < pairs ? L.args.num_tiles : pairs;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(conv_threads(PLANES));
+        cfg.dynamicSmemBytes = L.smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel<NT, CHUNKS, PLANES, EPI>, L.tmA_hi, L.tmA_lo, L.tmB, L.args);
+    }
     const int grid = L.args.num_tiles < num_sms ? L.args.num_tiles : num_sms;
     conv3x3_umma_kernel<NT, CHUNKS, PLANES, EPI><<<grid, conv_threads(PLANES), L.smem_bytes, stream>>>(L.tmA_hi, L.tmA_lo, L.tmB, L.args);
     return cudaGetLastError();

@@ -419,7 +419,7 @@ struct Builder {
         if (a.ksteps_last < 1 || a.ksteps_last > 4) a.ksteps_last = 4;
         if (!encode_act(&L.tmA_hi, in.p, in_cs, N, H, W, a.P, a.TH + 2)) return false;
         if (!encode_act(&L.tmA_lo, in.p + (plan->planes >= 2 ? in.plane : 0), in_cs, N, H, W, a.P, a.TH + 2)) return false;
-        if (!encode_w(&L.tmB, p.wp, static_cast<size_t>(act_planes(plan->planes)) * p.KB * 9 * p.cout_pad, L.NT)) return false;
+        if (!encode_w(&L.tmB, p.wp, static_cast<size_t>(act_planes(plan->planes)) * p.KB * 9 * p.cout_pad, L.pair ? L.NT / 2 : L.NT)) return false;
         op.flops = 2.0 * 9 * p.cin * p.cout * static_cast<double>(H) * W * N;
         {   // algorithmic HBM bytes: input + weights once, every output / residual once
             const double px = static_cast<double>(N) * H * W, eb = 2.0 * act_planes(plan->planes);

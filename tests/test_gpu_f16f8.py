@@ -124,3 +124,20 @@ def test_training_refuses_f16f8(eng8):
     z = lambda c, s=1: torch.zeros(1, 32 * s, 32 * s, c, device="cuda")
     with pytest.raises(fisr_b200.FisrError):
         eng8.train_backward(z(15), z(16), z(8), z(24), z(12), z(21, 2))
+
+
+def test_cta_pair_mode_is_bit_identical(eng8, monkeypatch):
+    """FISR_PAIR=1 runs the wide f16f8 layers on CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256 MMAs, half of each tap's
+    weight rows per CTA).  Every accumulator sees the same MMAs in the same order, so the outputs must not change by a bit;
+    shapes with odd tile counts exercise the all-padding right tile of the last pair."""
+    params = O.init_params(11)
+    eng8.set_params(params)
+    x = O.synthetic_input(1, 96, 160, 5)          # 160 / 16 = 10 tiles, 80 / 16 = 5 (odd), 40 / 16 -> 3 (odd)
+    base = [t.clone() for t in eng8.forward(x.cuda())]
+    monkeypatch.setenv("FISR_PAIR", "1")
+    eng8.set_precision("f16x3"); eng8.set_precision("f16f8")       # drops the cached plans: geometry is re-planned with pairs
+    paired = eng8.forward(x.cuda())
+    monkeypatch.delenv("FISR_PAIR")
+    for a, b in zip(base, paired):
+        assert torch.equal(a, b)
+    eng8.set_precision("f16x3"); eng8.set_precision("f16f8")
