@@ -186,13 +186,37 @@ def run_b200(args):
     frames, flow, warp = (torch.from_numpy(a).to(dev) for a in (frames_h, flow_h, warp_h))
     my_units = sharding.rank_units(rank, world, B, T)
     oh, ow, _ = eng.canvas_shape(H_IN, W_IN, GRID)
-    local_out = torch.zeros((len(my_units), oh // GRID[0], ow // GRID[1], 9), dtype=torch.uint8, device=dev)
-    gathered = torch.zeros((B * T, oh // GRID[0], ow // GRID[1], 9), dtype=torch.uint8, device=dev) if world > 1 else None
+    # two buffer sets: the all-gather of step k runs on NCCL's stream while the kernels of step k+1 already write the other set
+    local_out = [torch.zeros((len(my_units), oh // GRID[0], ow // GRID[1], 9), dtype=torch.uint8, device=dev) for _ in range(2)]
+    gathered = [torch.zeros((B * T, oh // GRID[0], ow // GRID[1], 9), dtype=torch.uint8, device=dev) if world > 1 else None
+                for _ in range(2)]
+    pending = [None, None]           # (gathered tensor, NCCL work) of the step that last used each buffer set
+    state = {"k": 0}
+
+    def finish(slot):
+        """Frames of the step that used buffer set `slot`: waits for its all-gather (stream-ordered) and pastes the tiles."""
+        g, work = pending[slot]
+        pending[slot] = None
+        if work is not None:
+            work.wait()
+        return sharding.assemble_frames(g, B, GRID)                 # [B, 2048, 3840, 9] uint8 on every rank
 
     def step():
-        eng.units(frames, flow, warp, my_units, GRID, layout="units", out=local_out)
-        g = sharding.gather_units(local_out, world, out=gathered)
-        return sharding.assemble_frames(g, B, GRID)                 # [B, 2048, 3840, 9] uint8 on every rank
+        """One step = this rank's 4 tile units + the all-gather of everybody's tiles + frame assembly.  The collective of step k
+        overlaps the kernels of step k+1; the frames returned are those of the PREVIOUS step (None on the first call), and
+        drain() returns the last ones, so K timed steps still complete K gathers and K assemblies inside the timed region."""
+        slot = state["k"] & 1
+        state["k"] += 1
+        eng.units(frames, flow, warp, my_units, GRID, layout="units", out=local_out[slot])
+        pending[slot] = sharding.gather_units(local_out[slot], world, out=gathered[slot], async_op=True)
+        return finish(slot ^ 1) if pending[slot ^ 1] is not None else None
+
+    def drain():
+        out = None
+        for slot in ((state["k"] & 1), (state["k"] & 1) ^ 1):        # older step first
+            if pending[slot] is not None:
+                out = finish(slot)
+        return out
 
     def barrier():
         if world > 1:
@@ -201,7 +225,8 @@ def run_b200(args):
 
     warm, steps = max(3, args.warmup), max(1, args.steps)
     for _ in range(warm):
-        out = step()
+        step()
+    out = drain()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -210,7 +235,8 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        out = step()
+        step()
+    out = drain()
     e1.record()
     barrier()
     launches = eng.launch_count - launches0

@@ -27,18 +27,20 @@ def rank_units(rank: int, world: int, n_windows: int, tiles_per_window: int) -> 
     return units[rank * k:(rank + 1) * k]
 
 
-def gather_units(local: torch.Tensor, world: int, out: torch.Tensor = None, group=None) -> torch.Tensor:
-    """All-gather of the per-rank unit-major tile buffers [k, sh, sw, 9] -> [world * k, sh, sw, 9] (rank order)."""
+def gather_units(local: torch.Tensor, world: int, out: torch.Tensor = None, group=None, async_op: bool = False):
+    """All-gather of the per-rank unit-major tile buffers [k, sh, sw, 9] -> [world * k, sh, sw, 9] (rank order).
+    ``async_op=True`` returns ``(out, work)``: the collective runs on NCCL's stream while the caller's stream goes on (the
+    next step's kernels); ``work.wait()`` orders the caller's stream behind it before ``out`` is read or ``local`` reused."""
     if world == 1:
-        return local
+        return (local, None) if async_op else local
     if out is None:
         out = local.new_empty((world * local.shape[0],) + tuple(local.shape[1:]))
     if dist.get_backend(group) == "nccl":
-        dist.all_gather_into_tensor(out, local, group=group)        # NCCL over NVLink 5 / NVSwitch
+        work = dist.all_gather_into_tensor(out, local, group=group, async_op=async_op)      # NCCL over NVLink 5 / NVSwitch
     else:                                                           # gloo (CPU tests)
         parts = list(out.chunk(world, dim=0))
-        dist.all_gather(parts, local.contiguous(), group=group)
-    return out
+        work = dist.all_gather(parts, local.contiguous(), group=group, async_op=async_op)
+    return (out, work) if async_op else out
 
 
 def assemble_frames(gathered: torch.Tensor, n_windows: int, grid: Tuple[int, int]) -> torch.Tensor:
