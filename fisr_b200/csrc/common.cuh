@@ -108,8 +108,6 @@ struct ConvArgs {
     unsigned tapmask[8];      // f16f8: bit t of tapmask[kb] = tap t of K block kb has non-zero weights (others are skipped)
     int ps_cout;              // > 0: the output is depth_to_space'd on the fly -- GEMM column ch = (2i+j) * ps_cout + co is channel co
                               // of output pixel (2y+i, 2x+j) (the conv/2 heads evaluated at input resolution, see fisr_api.cu)
-    int pf16, pf8;            // f16f8: weight-slot index (0..17) of an item at which the fp16 patch of this item / the 8-bit patch of
-                              // the next item is requested
     const __half* mask;       // dgrad: hi plane of the forward activation whose ReLU gradient gates this output, or nullptr
     int mask_cs, mask_off;
 };

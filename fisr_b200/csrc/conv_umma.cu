@@ -69,7 +69,7 @@ bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int n
     // depends on the per-image geometry only (never on the batch), so results are bit-identical however a
     // window's tiles are sharded over batches / GPUs (NT decides the fp32 summation order, see STACK).
     if (cout_pad >= 128 && (long)H * W >= 64L * 64) NT = 128;
-    if (const char* e = getenv("FISR_KB1_NT")) { if (kb == 1 && NT == 128 && atoi(e) == 64) NT = 64; }     // tuning knob
+    (void)kb;
     int chunks = 2;
     {
         const long tiles2 = (long)n_img * ((H * (long)W + 255) / 256) * (cout_pad / NT);
@@ -107,10 +107,6 @@ bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int n
     // f16f8 (phase-split main loop): one buffer per activation plane (a second one measured no better, even where it fits)
     a.a_stages = planes == 3 ? 1 : 2;
     if (const char* e = getenv("FISR_ASTAGES")) { if (planes == 3 && NT < 128 && (atoi(e) == 1 || atoi(e) == 2)) a.a_stages = atoi(e); }
-    a.pf16 = planes == 3 && a.a_stages == 2 ? 0 : 3;        // with two buffers per plane the next item's patches are
-    a.pf8 = planes == 3 && a.a_stages == 2 ? 0 : 12;         // requested as soon as their buffers drain
-    if (const char* e = getenv("FISR_PF16")) a.pf16 = atoi(e);      // tuning knobs
-    if (const char* e = getenv("FISR_PF8")) a.pf8 = atoi(e);
     for (int i = 0; i < 8; ++i) a.tapmask[i] = 0x1FFu;
     a.ps_cout = 0;
     int slots = (kConvMaxSmem - fixed - a.a_stages * apl * a.a_plane_bytes) / slot_bytes;

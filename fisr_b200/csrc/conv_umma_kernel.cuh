@@ -35,7 +35,8 @@
 // pipe_tc 80 % busy at 50 % tensor math), so the narrow layers are bound by exactly that traffic.
 //
 // Warp roles (352 threads; 384 for f16f8, whose warp 11 requests the activation patches while warp 0 streams the weights):
-// warp 0 = TMA producer, warp 1 = MMA issuer of chunk 0 + TMEM owner, warp 10 = MMA issuer of chunk 1, warps 2-9 =
+// warp 0 = TMA producer, warp 1 = MMA issuer of chunk 0 + TMEM owner, warp 10 = MMA issuer of chunk 1 (one thread can issue a
+// kind::f16 MMA only every ~150 cycles, tests/cuda/umma_rate_probe.cu, so every chunk gets its own issuer), warps 2-9 =
 // epilogue (TMEM -> registers -> smem transpose -> bias/residual/ReLU/split -> coalesced HBM stores).
 // Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.  The epilogue
 // is CUDA-core work on every output element; 8 warps (two per TMEM lane quarter) keep the four schedulers
