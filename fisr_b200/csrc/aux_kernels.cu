@@ -326,6 +326,42 @@ __global__ void tile_unpack_f32_kernel(const float* __restrict__ pred, int cs, T
         pred[((static_cast<size_t>(t) * th2 + tiles.trim_y[t] + y) * tw2 + tiles.trim_x[t] + x) * cs + pred_slot(c, cs)];
 }
 
+// 12-float prediction records of one level -> channels 29..37 of the next level's f16f8 input planes (FISRnet.py:113,144:
+// img_l2 = concat(bicubic(img), pred_l1), img_l3 = concat(img, pred_l2)).  One thread per pixel: 3 float4 loads, then the 18
+// bytes of the fp16 plane and the 2 x 9 bytes of the 8-bit row as 4 aligned stores each (offsets 58 / 29 / 93 in the 128-byte
+// rows), instead of 27 scattered scalar stores per pixel from the conv/2 epilogues.
+__global__ void pred_to_next_kernel(const float* __restrict__ pred, __half* __restrict__ next, size_t plane, size_t npix) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= npix) return;
+    const float4* src = reinterpret_cast<const float4*>(pred + i * 12);
+    const float4 g0 = __ldg(src), g1 = __ldg(src + 1), g2 = __ldg(src + 2);
+    const float f[9] = {g0.x, g0.y, g0.z, g1.x, g1.y, g1.z, g2.x, g2.y, g2.z};      // pred channels 0..8 -> input channels 29..37
+    unsigned short h[9];
+    uint8_t lo[9], hi[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const SplitHalf s = split_f32(f[k]);
+        h[k] = __half_as_ushort(s.hi);
+        lo[k] = f8_lo_byte(f[k] - __half2float(s.hi));
+        hi[k] = f8_hi_byte(f[k]);
+    }
+    uint8_t* ph = reinterpret_cast<uint8_t*>(next + i * 64) + 58;                    // fp16 plane, channel 29
+    *reinterpret_cast<unsigned short*>(ph) = h[0];
+    *reinterpret_cast<uint32_t*>(ph + 2) = h[1] | (static_cast<uint32_t>(h[2]) << 16);
+    *reinterpret_cast<uint2*>(ph + 6) = make_uint2(h[3] | (static_cast<uint32_t>(h[4]) << 16), h[5] | (static_cast<uint32_t>(h[6]) << 16));
+    *reinterpret_cast<uint32_t*>(ph + 14) = h[7] | (static_cast<uint32_t>(h[8]) << 16);
+    uint8_t* row = reinterpret_cast<uint8_t*>(next + plane + i * 64);                // 8-bit row of the pixel's only 64-channel block
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+        const uint8_t* b = part ? hi : lo;
+        uint8_t* q = row + part * 64 + 29;
+        q[0] = b[0];
+        *reinterpret_cast<unsigned short*>(q + 1) = static_cast<unsigned short>(b[1] | (b[2] << 8));
+        *reinterpret_cast<uint32_t*>(q + 3) = b[3] | (b[4] << 8) | (b[5] << 16) | (static_cast<uint32_t>(b[6]) << 24);
+        *reinterpret_cast<unsigned short*>(q + 7) = static_cast<unsigned short>(b[7] | (b[8] << 8));
+    }
+}
+
 // 12-float prediction records -> the [.., 9] tensor FISRnet.model returns
 __global__ void pred_compact_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t npix) {
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
@@ -472,6 +508,10 @@ void launch_tile_pack(const uint8_t* frames, const float* flow, const float* war
     else
         tile_pack_kernel<1><<<blocks_for(total, 256), 256, 0, st>>>(frames, flow, warp, fh, fw, tiles, th, tw, lut255, l3.p,
                                                                     l3.plane, l2.p, l2.plane, l1.p, l1.plane);
+}
+
+void launch_pred_to_next(const float* pred, ActBuf next, size_t npix, cudaStream_t st) {
+    pred_to_next_kernel<<<blocks_for(npix, 256), 256, 0, st>>>(pred, next.p, next.plane, npix);
 }
 
 void launch_pred_compact(const float* src, float* dst, size_t npix, cudaStream_t st) {

@@ -33,6 +33,8 @@ void launch_tile_pack(const uint8_t* frames, const float* flow, const float* war
                       int th, int tw, const float* lut255, ActBuf l3, ActBuf l2, ActBuf l1, int planes, cudaStream_t st);
 // canvas: images of OH x OW x 9, tile t lands in image out_img[t] at (out_y[t], out_x[t])
 // pred: fp32 records of cs floats per pixel (9, or the 12-float layout of the depth_to_space-folded heads)
+// f16f8: 12-float prediction records [npix] -> channels 29..37 of the next level's 64-channel input planes
+void launch_pred_to_next(const float* pred, ActBuf next, size_t npix, cudaStream_t st);
 void launch_pred_compact(const float* src, float* dst, size_t npix, cudaStream_t st);
 void launch_tile_unpack_u8(const float* pred, int cs, const TileList& tiles, int th2, int tw2, uint8_t* canvas, int OH, int OW,
                            int core_h, int core_w, cudaStream_t st);

@@ -129,11 +129,12 @@ struct DebugTensor {
     int N = 0, H = 0, W = 0, C = 0;
 };
 
-enum OpKind { OP_CONV, OP_UPSAMPLE, OP_POOL };
+enum OpKind { OP_CONV, OP_UPSAMPLE, OP_POOL, OP_PRED2NEXT };
 struct Op {
     OpKind kind;
     ConvLaunch conv;
     ActBuf in, out;
+    const float* pred = nullptr;   // OP_PRED2NEXT source
     int N, H, W, C, cs, coff;
     double flops;            // algorithmic conv FLOPs (0 for pool / upsample)
     double bytes;            // algorithmic HBM bytes of the launch
@@ -522,7 +523,7 @@ struct Builder {
             conv(P(p + "/conv/1"), a2, c, 0, N, H, W, o, p + "/conv/1");
             o = ConvOut{}; o.scalar = true; o.relu = false; o.ps = true;
             o.raw = pred; o.raw_cs = 12;                               // 12-float records: [FI-SR 0..2 -, SR 0..2 -, FI-SR 3..5 -]
-            o.act = next; o.act_cs = 64;
+            // (channels 29..37 of the next level's input are filled from pred by one pass after both heads, see level())
             if (cout == 6) { o.raw_off0 = 0; o.raw_off1 = 8; o.act_split = 3; o.act_off0 = IN_CH; o.act_off1 = IN_CH + 3; }
             else           { o.raw_off1 = 4; o.act_split = 0; o.act_off1 = IN_CH + 3; }
             conv_ps(P(p + "/conv/2"), t256, N, H, W, o, p + "/conv/2");
@@ -570,6 +571,13 @@ struct Builder {
         n = dec_level(p + "/dec/level_0", n, 2 * CH, CH, N, H, W, cat0, &R.dec[0]);
         head(p + "/FI-SR", n, N, H, W, 6, pred, next, &R.head[0]);
         head(p + "/SR", n, N, H, W, 3, pred, next, &R.head[1]);
+        if (plan->planes == 3 && next.p && rc == FISR_OK) {       // img_l{2,3} = concat(.., pred) (FISRnet.py:113,144)
+            Op op{};
+            op.kind = OP_PRED2NEXT; op.pred = pred; op.out = next; op.N = N; op.H = 2 * H; op.W = 2 * W;
+            op.bytes = static_cast<double>(N) * 4 * H * W * (48 + 36);
+            snprintf(op.name, sizeof op.name, "pred -> next level input %dx%d", 2 * H, 2 * W);
+            plan->ops.push_back(op);
+        }
     }
     // ================================================================ backward (see "Backward pass" in DESIGN.md)
     size_t max_partial = 0;
@@ -799,6 +807,7 @@ int run_ops(fisr_ctx* ctx, Plan* plan, cudaStream_t st, std::vector<cudaEvent_t>
             }
             case OP_UPSAMPLE: launch_upsample2(op.in, op.out, op.N, op.H, op.W, op.C, plan->planes, st); break;
             case OP_POOL: launch_maxpool2(op.in, op.cs, op.coff, op.out, op.N, op.H, op.W, op.C, plan->planes, st); break;
+            case OP_PRED2NEXT: launch_pred_to_next(op.pred, op.out, static_cast<size_t>(op.N) * op.H * op.W, st); break;
         }
     }
     if (marks) cudaEventRecord((*marks)[idx], st);
