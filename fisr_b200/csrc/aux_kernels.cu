@@ -12,8 +12,10 @@ namespace {
 
 // ---------------------------------------------------------------- weights
 // w: fp32 HWIO [3,3,cin,cout] (ops.py:8) -> [plane][kb][tap][cout_pad][64] fp16, zero padded.
+// gap_at / gap: input channels >= gap_at sit `gap` slots further in the activation buffer (f16f8: the 9 prediction channels of
+// the level-2/3 inputs start at slot 32, so that they are written as whole 32-byte sectors, see pred_to_next_kernel).
 __global__ void prep_weights_kernel(const float* __restrict__ w, __half* __restrict__ out, int cin, int cout, int KB,
-                                    int cout_pad, int planes) {
+                                    int cout_pad, int planes, int gap_at, int gap) {
     const size_t per_plane = static_cast<size_t>(KB) * 9 * cout_pad * 64;
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     if (i >= per_plane) return;
@@ -22,7 +24,8 @@ __global__ void prep_weights_kernel(const float* __restrict__ w, __half* __restr
     const int co = r % cout_pad; r /= cout_pad;
     const int tap = r % 9;
     const int kb = r / 9;
-    const int ci = kb * 64 + cl;
+    const int slot = kb * 64 + cl;
+    const int ci = slot < gap_at ? slot : (slot >= gap_at + gap ? slot - gap : cin);      // slots inside the gap carry zero weights
     float v = 0.f;
     if (ci < cin && co < cout) v = w[(static_cast<size_t>(tap) * cin + ci) * cout + co];
     if (planes == 3) {   // f16f8: fp16(128 w) plane + 8-bit rows [e4m3(wh / 16) x 64 | e5m2(128 w - wh) x 64] (common.cuh)
@@ -326,40 +329,39 @@ __global__ void tile_unpack_f32_kernel(const float* __restrict__ pred, int cs, T
         pred[((static_cast<size_t>(t) * th2 + tiles.trim_y[t] + y) * tw2 + tiles.trim_x[t] + x) * cs + pred_slot(c, cs)];
 }
 
-// 12-float prediction records of one level -> channels 29..37 of the next level's f16f8 input planes (FISRnet.py:113,144:
-// img_l2 = concat(bicubic(img), pred_l1), img_l3 = concat(img, pred_l2)).  One thread per pixel: 3 float4 loads, then the 18
-// bytes of the fp16 plane and the 2 x 9 bytes of the 8-bit row as 4 aligned stores each (offsets 58 / 29 / 93 in the 128-byte
-// rows), instead of 27 scattered scalar stores per pixel from the conv/2 epilogues.
+// 12-float prediction records of one level -> the prediction channels of the next level's f16f8 input planes (FISRnet.py:113,144:
+// img_l2 = concat(bicubic(img), pred_l1), img_l3 = concat(img, pred_l2)).  They occupy slots 32..40 of the 64-channel buffer
+// (kPredSlot; the weights of enc/level_0/conv/0 are packed with the matching gap), so that this pass owns whole 32-byte sectors
+// -- bytes 64..127 of the fp16 row, 32..63 and 96..127 of the 8-bit row -- and the tile packer owns the others: no partial
+// sector is ever written (the first version wrote 9 channels at slot 29 and ran at 0.57 TB/s on DRAM read-modify-writes).
+// One thread per pixel: 3 float4 loads, 8 x 16-byte stores.
 __global__ void pred_to_next_kernel(const float* __restrict__ pred, __half* __restrict__ next, size_t plane, size_t npix) {
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     if (i >= npix) return;
     const float4* src = reinterpret_cast<const float4*>(pred + i * 12);
     const float4 g0 = __ldg(src), g1 = __ldg(src + 1), g2 = __ldg(src + 2);
-    const float f[9] = {g0.x, g0.y, g0.z, g1.x, g1.y, g1.z, g2.x, g2.y, g2.z};      // pred channels 0..8 -> input channels 29..37
-    unsigned short h[9];
-    uint8_t lo[9], hi[9];
+    const float f[9] = {g0.x, g0.y, g0.z, g1.x, g1.y, g1.z, g2.x, g2.y, g2.z};      // pred channels 0..8 -> slots 32..40
+    uint32_t h[5] = {0, 0, 0, 0, 0}, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         const SplitHalf s = split_f32(f[k]);
-        h[k] = __half_as_ushort(s.hi);
-        lo[k] = f8_lo_byte(f[k] - __half2float(s.hi));
-        hi[k] = f8_hi_byte(f[k]);
+        h[k >> 1] |= static_cast<uint32_t>(__half_as_ushort(s.hi)) << (16 * (k & 1));
+        lo[k >> 2] |= static_cast<uint32_t>(f8_lo_byte(f[k] - __half2float(s.hi))) << (8 * (k & 3));
+        hi[k >> 2] |= static_cast<uint32_t>(f8_hi_byte(f[k])) << (8 * (k & 3));
     }
-    uint8_t* ph = reinterpret_cast<uint8_t*>(next + i * 64) + 58;                    // fp16 plane, channel 29
-    *reinterpret_cast<unsigned short*>(ph) = h[0];
-    *reinterpret_cast<uint32_t*>(ph + 2) = h[1] | (static_cast<uint32_t>(h[2]) << 16);
-    *reinterpret_cast<uint2*>(ph + 6) = make_uint2(h[3] | (static_cast<uint32_t>(h[4]) << 16), h[5] | (static_cast<uint32_t>(h[6]) << 16));
-    *reinterpret_cast<uint32_t*>(ph + 14) = h[7] | (static_cast<uint32_t>(h[8]) << 16);
-    uint8_t* row = reinterpret_cast<uint8_t*>(next + plane + i * 64);                // 8-bit row of the pixel's only 64-channel block
-#pragma unroll
-    for (int part = 0; part < 2; ++part) {
-        const uint8_t* b = part ? hi : lo;
-        uint8_t* q = row + part * 64 + 29;
-        q[0] = b[0];
-        *reinterpret_cast<unsigned short*>(q + 1) = static_cast<unsigned short>(b[1] | (b[2] << 8));
-        *reinterpret_cast<uint32_t*>(q + 3) = b[3] | (b[4] << 8) | (b[5] << 16) | (static_cast<uint32_t>(b[6]) << 24);
-        *reinterpret_cast<unsigned short*>(q + 7) = static_cast<unsigned short>(b[7] | (b[8] << 8));
-    }
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    uint4* ph = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(next + i * 64) + 64);       // fp16 plane, slots 32..63
+    ph[0] = make_uint4(h[0], h[1], h[2], h[3]);
+    ph[1] = make_uint4(h[4], 0u, 0u, 0u);
+    ph[2] = z;
+    ph[3] = z;
+    uint8_t* row = reinterpret_cast<uint8_t*>(next + plane + i * 64);                            // 8-bit row of the pixel's only block
+    uint4* pl = reinterpret_cast<uint4*>(row + 32);                                              // e5m2(16 lo), slots 32..63
+    pl[0] = make_uint4(lo[0], lo[1], lo[2], 0u);
+    pl[1] = z;
+    uint4* pq = reinterpret_cast<uint4*>(row + 96);                                              // e5m2(hi), slots 32..63
+    pq[0] = make_uint4(hi[0], hi[1], hi[2], 0u);
+    pq[1] = z;
 }
 
 // 12-float prediction records -> the [.., 9] tensor FISRnet.model returns
@@ -433,9 +435,9 @@ inline unsigned blocks_for(size_t total, int threads) { return static_cast<unsig
 
 // ================================================================ host launchers
 void launch_prep_weights(const float* w, __half* out, int cin, int cout, int KB, int cout_pad, int planes,
-                         cudaStream_t st) {
+                         cudaStream_t st, int gap_at, int gap) {
     const size_t total = static_cast<size_t>(KB) * 9 * cout_pad * 64;
-    prep_weights_kernel<<<blocks_for(total, 256), 256, 0, st>>>(w, out, cin, cout, KB, cout_pad, planes);
+    prep_weights_kernel<<<blocks_for(total, 256), 256, 0, st>>>(w, out, cin, cout, KB, cout_pad, planes, gap_at, gap);
 }
 
 void launch_expand_ps_weights(const float* w, const float* b, float* wps, float* bps, int cout, cudaStream_t st) {

@@ -21,7 +21,11 @@ struct TileList {
     int out_y[kMaxTiles], out_x[kMaxTiles];    // paste origin inside the destination image
 };
 
-void launch_prep_weights(const float* w, __half* out, int cin, int cout, int KB, int cout_pad, int planes, cudaStream_t st);
+// gap_at / gap: input channels >= gap_at are packed `gap` slots further (zero weights in between)
+void launch_prep_weights(const float* w, __half* out, int cin, int cout, int KB, int cout_pad, int planes, cudaStream_t st,
+                         int gap_at = 1 << 30, int gap = 0);
+// f16f8: slot of the first prediction channel in the 64-channel input buffers of levels 2 and 3 (29 real input channels, gap, 9)
+constexpr int kPredSlot = 32;
 // depth_to_space-folded weights / bias of a conv/2 head: w [3,3,64,cout], b [cout] -> wps [3,3,256,4*cout], bps [4*cout]
 void launch_expand_ps_weights(const float* w, const float* b, float* wps, float* bps, int cout, cudaStream_t st);
 void launch_pack_input(const float* img, int N, int H, int W, int cin, ActBuf l3, ActBuf l2, ActBuf l1, int planes, cudaStream_t st);

@@ -258,7 +258,10 @@ int check_kernel_error(fisr_ctx* ctx) {
 
 int ensure_packed(fisr_ctx* ctx, ConvParam& p, cudaStream_t st) {
     if (p.packed) return FISR_OK;
-    launch_prep_weights(p.d_w, p.d_wp, p.cin, p.cout, p.KB, p.cout_pad, ctx->planes, st);
+    // f16f8: the first conv of levels 2 and 3 (29 + 9 input channels) reads its 9 prediction channels from slot kPredSlot
+    const bool pred_in = ctx->planes == 3 && p.cin == IN_CH + 9;
+    launch_prep_weights(p.d_w, p.d_wp, p.cin, p.cout, p.KB, p.cout_pad, ctx->planes, st, pred_in ? IN_CH : 1 << 30,
+                        pred_in ? kPredSlot - IN_CH : 0);
     ctx->launches++;
     if (p.head2 && ctx->planes == 3) {
         if (!p.d_wps) {
@@ -416,7 +419,10 @@ struct Builder {
             if (px * cs_max >= 4294967296.0) { rc = fail(ctx, FISR_E_INVALID, "conv %s: %d x %d x %d x %d exceeds 32-bit offsets; split the batch", name.c_str(), N, H, W, cs_max); return false; }
         }
         a.cin_off = cin_off; a.KB = p.KB; a.cout = p.cout;
-        a.ksteps_last = (p.cin - (p.KB - 1) * 64 + 15) / 16;       // padded input channels beyond this are zeros: skip their MMAs
+        {   // padded input channels beyond the last real one are zeros: skip their MMAs (f16f8 level-2/3 inputs: 9 channels at slot 32)
+            const int cin_slots = (plan->planes == 3 && p.cin == IN_CH + 9 && p.KB == 1) ? kPredSlot + 9 : p.cin;
+            a.ksteps_last = (cin_slots - (p.KB - 1) * 64 + 15) / 16;
+        }
         if (a.ksteps_last < 1 || a.ksteps_last > 4) a.ksteps_last = 4;
         if (!encode_act(&L.tmA_hi, in.p, in_cs, N, H, W, a.P, a.TH + 2)) return false;
         if (!encode_act(&L.tmA_lo, in.p + (plan->planes >= 2 ? in.plane : 0), in_cs, N, H, W, a.P, a.TH + 2)) return false;
