@@ -41,6 +41,11 @@ def conv_hook(self, x, name):
         y = conv(xh, wh) + conv(xl, wh) + conv(xh, wl)
     elif Cfg.mode == "f16x2a":      # activation split only
         y = conv(xh, wh) + conv(xl, wh)
+    elif Cfg.mode == "built":       # the scheme as built (common.cuh): x = xh + xl; 8-bit row [e5m2(16 xl) | e5m2(xh)];
+        # weights W = 128 w: fp16 plane Wh, 8-bit row [e4m3(Wh / 16) | e5m2(W - Wh)]; accumulator holds 128 x the result
+        W = wk * 128.0
+        Wh = W.to(torch.float16).to(dt); Wl = W - Wh
+        y = (conv(xh, Wh) + conv(e5m2(xl, 16.0), e4m3(Wh, 1.0 / 16.0)) + conv(e5m2(xh, 1.0), e5m2(Wl, 1.0))) / 128.0
     elif Cfg.mode == "f16+f8":
         y = conv(xh, wh) + conv(q8(xl, Cfg.sx * Cfg.lo_shift), q8(wh, Cfg.sw)) + conv(q8(xh, Cfg.sx), q8(wl, Cfg.sw * Cfg.lo_shift))
     else:
@@ -67,7 +72,7 @@ for seed in (0, 1):
         outs = O.model(p64, x)
         errs = [(a.double() - b).abs().max().item() for a, b in zip(outs, ref)]
         print(f"  {tag:34s} maxabs l1/l2/l3 = {errs[0]:.2e} {errs[1]:.2e} {errs[2]:.2e}")
-    for mode in ("f16", "f16x2a", "f16x3"):
+    for mode in ("f16", "f16x2a", "f16x3", "built"):
         Cfg.mode = mode; rep(mode)
     Cfg.mode = "f16+f8"
     for q8, qn in ((e4m3, "e4m3"), (e5m2, "e5m2")):
