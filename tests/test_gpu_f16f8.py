@@ -141,3 +141,30 @@ def test_cta_pair_mode_is_bit_identical(eng8, monkeypatch):
     for a, b in zip(base, paired):
         assert torch.equal(a, b)
     eng8.set_precision("f16x3"); eng8.set_precision("f16f8")
+
+
+def test_full_size_window_deterministic_and_close_to_f16x3(eng8):
+    """BASELINE config 4 at full size (1080x1920 -> 2048x3840x9): the f16f8 window is bit-reproducible, equals its pipelined host
+    path, and differs from the fp32-class f16x3 frames by at most one grey level on < 1 % of the samples."""
+    import os
+    from conftest import GOLDEN
+    rng = np.random.default_rng(2)
+    base = np.load(os.path.join(GOLDEN, "scene1_lr_crop.npz"))["frames"]
+    H, W = 1080, 1920
+    reps = (-(-H // base.shape[1]), -(-W // base.shape[2]), 1)
+    frames = np.concatenate([np.tile(base[i], reps)[:H, :W] for i in range(3)], axis=2).astype(np.uint8)
+    flow = (rng.standard_normal((H, W, 8)) * 4).astype(np.float32)
+    warp = (frames[..., [3, 4, 5, 0, 1, 2, 6, 7, 8, 3, 4, 5]].astype(np.float32) / 255.
+            + 0.05 * rng.standard_normal((H, W, 12))).astype(np.float32)
+    eng8.set_params(O.init_params(10))
+    f, fl, wp = (torch.from_numpy(a).cuda() for a in (frames, flow, warp))
+    a = eng8.window(f, fl, wp, (2, 2))
+    assert tuple(a.shape) == (2048, 3840, 9)
+    assert torch.equal(a, eng8.window(f, fl, wp, (2, 2)))
+    host = eng8.window_host(frames, flow, warp, (2, 2))
+    assert np.array_equal(host, a.cpu().numpy())
+    eng8.set_precision("f16x3")
+    b = eng8.window(f, fl, wp, (2, 2))
+    eng8.set_precision("f16f8")
+    d = (a.to(torch.int16) - b.to(torch.int16)).abs()
+    assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 0.01
