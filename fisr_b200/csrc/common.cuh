@@ -106,6 +106,7 @@ struct ConvArgs {
     int act_relu, act_d2s, scalar_out, res_cs;
     int a_plane_bytes, a_stages, b_slots;        // smem carve-up (host computed)
     unsigned tapmask[8];      // f16f8: bit t of tapmask[kb] = tap t of K block kb has non-zero weights (others are skipped)
+    int tma_out;              // f16f8 activation-only epilogue: store through the output tensor maps (TMA) instead of the LSU
     int ps_cout;              // > 0: the output is depth_to_space'd on the fly -- GEMM column ch = (2i+j) * ps_cout + co is channel co
                               // of output pixel (2y+i, 2x+j) (the conv/2 heads evaluated at input resolution, see fisr_api.cu)
     const __half* mask;       // dgrad: hi plane of the forward activation whose ReLU gradient gates this output, or nullptr

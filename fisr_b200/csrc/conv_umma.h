@@ -9,6 +9,8 @@ constexpr int kConvMaxSmem = 231936;
 
 struct ConvLaunch {
     CUtensorMap tmA_hi, tmA_lo, tmB;
+    CUtensorMap tmO_hi, tmO_8;   // f16f8 activation-only epilogue: TMA-store maps of the fp16 plane and of the 8-bit rows
+    bool tma_out;                // the two maps above are valid
     ConvArgs args;
     int NT, chunks, planes;
     bool pair;              // f16f8 on CTA pairs (cluster of 2, M = 256 MMAs): args.tiles_x / num_tiles count PAIRS of x-adjacent tiles

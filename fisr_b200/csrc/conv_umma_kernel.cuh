@@ -171,7 +171,8 @@ __device__ __forceinline__ void epilogue_scalar_ps(const ConvArgs& a, const uint
 template <int NT, int CHUNKS, int PLANES, int EPI>
 __global__ void __launch_bounds__(conv_threads(PLANES), 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvArgs a) {
+                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO_hi,
+                    const __grid_constant__ CUtensorMap tmO_8, const __grid_constant__ ConvArgs a) {
     constexpr bool STACK = (PLANES == 2) && (NT <= 64);
     constexpr bool F8 = PLANES >= 3;
     constexpr bool PAIR = PLANES == 4;                          // f16f8 on CTA pairs: cluster of 2, tcgen05 cta_group::2, M = 256
@@ -555,6 +556,57 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                         else epilogue_scalar<PLANES, NT>(a, v, t.n, y, x);
                     }
                 }
+            } else if (EPI == 0 && F8 && a.tma_out) {
+                // Activation-only output through TMA stores.  All arithmetic happens in the TMEM layout (lane = pixel of this
+                // warp's 8 x 4 pixel block, 16 consecutive channels per step); each lane drops its 32 bytes of the fp16 plane
+                // and its 16 + 16 bytes of the 8-bit row into a pixel-major staging block, and one lane hands the two 1 KB
+                // blocks to the TMA unit (boxes {16 ch, 8 px, 4 rows} and {16 B, 2 half-rows, 8 px, 4 rows}).  No transposed
+                // shared-memory reads and no LSU store wavefronts (ncu: l1tex__data_pipe_lsu_wavefronts 78 % busy on the
+                // K = 576 layers, whose epilogue was the critical path); pixels outside the image are clipped by the TMA.
+                constexpr int ITERS = CSPAN / 16;
+                const int cg0 = a.act_off1 + t.nb * NT + c_begin;                // first output channel (slot) of this warp's span
+                const int bx = t.x0 + ch_x0, by = t.y0 + ch_y0 + q4 * 4;        // pixel block origin
+                ok = __all_sync(0xffffffffu, mbar_wait(acc_full(cs), cph, a.err, ERR_ACC_FULL));
+                if (!ok) break;
+                tc_fence_after();
+                uint32_t v[16];
+                tmem_ld_32x16(tacc + c_begin, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it) {
+                    const int c0 = it * 16;
+                    float f[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + t.nb * NT + c_begin + c0 + 4 * j));
+                        f[4 * j] = fmaxf(fmaf(__uint_as_float(v[4 * j]), kF8AccScale, b4.x), relu_floor);
+                        f[4 * j + 1] = fmaxf(fmaf(__uint_as_float(v[4 * j + 1]), kF8AccScale, b4.y), relu_floor);
+                        f[4 * j + 2] = fmaxf(fmaf(__uint_as_float(v[4 * j + 2]), kF8AccScale, b4.z), relu_floor);
+                        f[4 * j + 3] = fmaxf(fmaf(__uint_as_float(v[4 * j + 3]), kF8AccScale, b4.w), relu_floor);
+                    }
+                    if (it + 1 < ITERS) tmem_ld_32x16(tacc + c_begin + c0 + 16, v);     // next 16 columns in flight
+                    uint32_t h[8], l[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) split2_f32(f[2 * j], f[2 * j + 1], h[j], l[j]);
+                    if (lane == 0) bulk_wait_read0();                                 // the previous step's boxes have left the staging block
+                    __syncwarp();
+                    const uint32_t s16 = stg + lane * 32, s8 = stg + 1024 + lane * 32;
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s16), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s16 + 16), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s8), "r"(f8_pack_lo4(l[0], l[1])), "r"(f8_pack_lo4(l[2], l[3])),
+                                 "r"(f8_pack_lo4(l[4], l[5])), "r"(f8_pack_lo4(l[6], l[7])) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s8 + 16), "r"(f8_pack_hi4(h[0], h[1])), "r"(f8_pack_hi4(h[2], h[3])),
+                                 "r"(f8_pack_hi4(h[4], h[5])), "r"(f8_pack_hi4(h[6], h[7])) : "memory");
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int c = cg0 + c0;
+                        tma_store_4d(&tmO_hi, stg, c, bx, by, t.n);
+                        tma_store_5d(&tmO_8, stg + 1024, c & 63, 2 * (c >> 6), bx, by, t.n);
+                        bulk_commit();
+                    }
+                    if (it + 1 < ITERS) tmem_ld_wait();
+                }
             } else {
                 // After the transpose lane l serves pixels (l >> 2) + 8*i of this warp's 32-pixel group, channels
                 // 4*(l & 3) .. +3 of each 16-channel step: 4 lanes cover 64 contiguous bytes of fp32 per pixel.
@@ -698,6 +750,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         }
     }
 
+    if (EPI == 0 && F8 && lane == 0 && warp >= 2 && warp < 2 + kEpiWarps) bulk_wait0();     // outstanding TMA stores of this warp
     tc_fence_before();
     if (PAIR) cluster_sync_all(); else __syncthreads();       // pair: no CTA leaves while its peer may still signal its barriers
     if (warp == 1) { if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
@@ -724,10 +777,10 @@ cudaError_t launch_inst(const ConvLaunch& L, int num_sms, cudaStream_t stream) {
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel<NT, CHUNKS, PLANES, EPI>, L.tmA_hi, L.tmA_lo, L.tmB, L.args);
+        return cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel<NT, CHUNKS, PLANES, EPI>, L.tmA_hi, L.tmA_lo, L.tmB, L.tmO_hi, L.tmO_8, L.args);
     }
     const int grid = L.args.num_tiles < num_sms ? L.args.num_tiles : num_sms;
-    conv3x3_umma_kernel<NT, CHUNKS, PLANES, EPI><<<grid, conv_threads(PLANES), L.smem_bytes, stream>>>(L.tmA_hi, L.tmA_lo, L.tmB, L.args);
+    conv3x3_umma_kernel<NT, CHUNKS, PLANES, EPI><<<grid, conv_threads(PLANES), L.smem_bytes, stream>>>(L.tmA_hi, L.tmA_lo, L.tmB, L.tmO_hi, L.tmO_8, L.args);
     return cudaGetLastError();
 }
 

@@ -322,6 +322,29 @@ struct Builder {
         }
         return true;
     }
+    // TMA-store maps of an activation buffer (f16f8): fp16 plane as [N][H][W][cs] with boxes of 16 channels x 8 px x 4 rows, and
+    // the 8-bit rows as [N][H][W][2 * cs / 64 half-rows][64 bytes] with boxes of 16 bytes x (lo, hi half-row) x 8 px x 4 rows
+    bool encode_out(CUtensorMap* tm16, CUtensorMap* tm8, ActBuf buf, int cs, int N, int H, int W) {
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+            cuuint64_t strides[3] = {(cuuint64_t)cs * 2, (cuuint64_t)W * cs * 2, (cuuint64_t)H * W * cs * 2};
+            cuuint32_t box[4] = {16, 8, 4, 1};
+            cuuint32_t es[4] = {1, 1, 1, 1};
+            CUresult r = ctx->encode(tm16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, buf.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { rc = fail(ctx, FISR_E_CUDA, "cuTensorMapEncodeTiled(out fp16 %dx%dx%dx%d) failed: %d", N, H, W, cs, (int)r); return false; }
+        }
+        {
+            cuuint64_t dims[5] = {64, (cuuint64_t)(2 * (cs / 64)), (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+            cuuint64_t strides[4] = {64, (cuuint64_t)cs * 2, (cuuint64_t)W * cs * 2, (cuuint64_t)H * W * cs * 2};
+            cuuint32_t box[5] = {16, 2, 8, 4, 1};
+            cuuint32_t es[5] = {1, 1, 1, 1, 1};
+            CUresult r = ctx->encode(tm8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, buf.p + buf.plane, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { rc = fail(ctx, FISR_E_CUDA, "cuTensorMapEncodeTiled(out 8-bit %dx%dx%dx%d) failed: %d", N, H, W, cs, (int)r); return false; }
+        }
+        return true;
+    }
     bool encode_w(CUtensorMap* tm, const __half* base, size_t rows, int NT) {
         cuuint64_t dims[2] = {64, (cuuint64_t)rows};
         cuuint64_t strides[1] = {128};
@@ -426,6 +449,15 @@ struct Builder {
         if (a.ksteps_last < 1 || a.ksteps_last > 4) a.ksteps_last = 4;
         if (!encode_act(&L.tmA_hi, in.p, in_cs, N, H, W, a.P, a.TH + 2)) return false;
         if (!encode_act(&L.tmA_lo, in.p + (plan->planes >= 2 ? in.plane : 0), in_cs, N, H, W, a.P, a.TH + 2)) return false;
+        L.tma_out = false;
+        a.tma_out = 0;
+        memset(&L.tmO_hi, 0, sizeof L.tmO_hi);
+        memset(&L.tmO_8, 0, sizeof L.tmO_8);
+        if (plan->planes == 3 && L.epi == 0 && !o.scalar && o.act.p && o.act_cs % 64 == 0 && !getenv("FISR_NO_TMA_OUT")) {
+            if (!encode_out(&L.tmO_hi, &L.tmO_8, o.act, o.act_cs, N, H, W)) return false;
+            L.tma_out = true;
+            a.tma_out = 1;
+        }
         if (!encode_w(&L.tmB, p.wp, static_cast<size_t>(act_planes(plan->planes)) * p.KB * 9 * p.cout_pad, L.pair ? L.NT / 2 : L.NT)) return false;
         op.flops = 2.0 * 9 * p.cin * p.cout * static_cast<double>(H) * W * N;
         {   // algorithmic HBM bytes: input + weights once, every output / residual once
