@@ -154,7 +154,7 @@ def run_reference(args):
                              "sample": f"{steps} x FISRnet.model (oracle, torch-CPU fp32 oneDNN) on a {h}x{w} crop, scaled"},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    args.emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------- this repo's arm
@@ -335,7 +335,21 @@ def run_b200(args):
     if world > 1:
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        args.emit(json.dumps(line))
+
+
+def _json_only_stdout():
+    """Keeps stdout for the ONE JSON line: everything else that writes to file descriptor 1 (NCCL prints its version banner
+    there at communicator creation) is sent to stderr.  Returns the function that emits the line."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(text: str) -> None:
+        sys.stdout.flush()
+        os.write(keep, (text + "\n").encode())
+
+    return emit
 
 
 def main():
@@ -348,6 +362,7 @@ def main():
                     help="f16x3 = fp32-class parity mode (default, what the parity tests hold to 1e-4); f16 = fast mode")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     args = ap.parse_args()
+    args.emit = _json_only_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
