@@ -314,7 +314,7 @@ def run_b200(args):
         info = eng.plan_info(T, 544, 992)
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warm,
                 "ms_per_step": t_s / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"f16x3": "f32 via fp16 (hi,lo) split operands, fp32 accumulate", "f16f8": "f32 via fp16 main term + fp8 (e5m2 x e4m3) cross terms, fp32 accumulate", "f16": "f16 operands, f32 accumulate"}[eng.precision],
+                "dtype": {"f16x3": "f32 via fp16 (hi,lo) split operands, fp32 accumulate", "f16f8": "f32 via fp16 main term + fp8 cross terms (e5m2 activations x e4m3 / e5m2 weights), fp32 accumulate", "f16": "f16 operands, f32 accumulate"}[eng.precision],
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "windows_per_step": B, "units_per_rank_per_step": len(my_units),
                            "input": f"{B} x (frames u8 [1080,1920,9] + flow f32 [..,8] + warp f32 [..,12])",
