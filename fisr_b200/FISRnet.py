@@ -9,8 +9,10 @@ Documented deviations from the reference:
   * ``FISR_for_video`` sorts the frame list (the reference's unsorted ``glob`` at FISRnet.py:953 returns a
     file-system-dependent order; the shipped scene1 outputs correspond to the sorted order, like ``test()`` :762).
   * the tile loop runs as one batched forward instead of growing a TF graph per tile (FISRnet.py:1039-1041).
-  * checkpoints are ``.npz`` files keyed by the TF variable names (no TensorFlow in this stack); a training checkpoint
-    carries the weights and the step, not the Adam moments (they restart at zero after a resume).
+  * checkpoints are TensorFlow V2 bundles (``FISRnet-<step>.index`` / ``.data-00000-of-00001``) written by
+    ``fisr_b200.tf_checkpoint`` without TensorFlow, under the variable names the reference's Saver uses: the 276 weights,
+    the Adam slots ``<var>/Adam`` / ``<var>/Adam_1``, ``beta1_power`` / ``beta2_power`` and the global step, so a resumed
+    run continues seamlessly and the files go back to the reference.  ``.npz`` checkpoints of round 1 still load.
   * ``train`` prints what the reference prints; the TensorBoard summaries (FISRnet.py:533-578) are not written.
   * the printed "Estimated Inference Time" is per window from CUDA-synchronised wall time.
 """
@@ -151,8 +153,11 @@ class FISRnet(object):
         if could_load:
             start_epoch = int(checkpoint_counter / self.train_iter)
             counter = checkpoint_counter
-            self.global_step = checkpoint_counter
-            self.engine.adam_reset(checkpoint_counter)                   # Adam moments restart at zero (not in the .npz)
+            self.global_step = checkpoint_counter                        # lr schedule (tf.train.piecewise_constant)
+            if not self._adam_restored:
+                # a checkpoint without optimizer slots: zero moments need the bias correction of step 0 (with t ~ 1e5 the
+                # first updates would be ~3 lr sign(g), perturbing a trained model)
+                self.engine.adam_reset(0)
             print(" [*] Load SUCCESS")
         else:
             start_epoch, counter = 0, 1
@@ -205,13 +210,6 @@ class FISRnet(object):
             self.save_checkpoint(self.checkpoint_dir, self.global_step)  # FISRnet.py:737
         self.save_checkpoint(self.checkpoint_dir, self.global_step)      # FISRnet.py:743
 
-    # ------------------------------------------------------------------ shared inner loop
-    def _window(self, frames_u8, flow_sample, warp_sample, num_patch):
-        """One sliding window: crop / normalise / clip, tile grid with 32-px halo, paste, clip, uint8 (FISRnet.py:1003-1064)."""
-        t0 = time.time()
-        out = self.engine.window_host(frames_u8, flow_sample, warp_sample, tuple(int(v) for v in num_patch))
-        return out, time.time() - t0
-
     # ------------------------------------------------------------------ test (FISRnet.py:746-935)
     def test(self):
         self._ensure_variables()
@@ -240,10 +238,16 @@ class FISRnet(object):
                 label = np.clip(np.array(label[:h * 2, :w * 2, :], dtype=np.double) / 255., 0, 1)
                 flow_sample = flow[scene_i, :, :, 4 * sample_i:4 * sample_i + 8]
                 warp_sample = warp[scene_i, :, :, 6 * sample_i:6 * sample_i + 12]
-                pred, dt = self._window(img[:H, :W], flow_sample[:H, :W], warp_sample[:H, :W], num_patch)
-                inf_time.append(dt)
-                # the reference scores the clipped float prediction; uint8 truncation costs < 1/255 per sample
-                test_pred = pred.astype(np.double) / 255.
+                # frames, flow and warp cropped to (h, w) like the reference (FISRnet.py:826-840): files stored at the
+                # cropped size work too
+                t0 = time.time()
+                full = self.engine.window_host_f32(img[:h, :w], flow_sample[:h, :w], warp_sample[:h, :w],
+                                                   tuple(int(v) for v in num_patch))          # test_Pred_full, float
+                inf_time.append(time.time() - t0)
+                # the reference scores the CLIPPED FLOAT prediction (FISRnet.py:883-887) and truncates to uint8 only for the
+                # PNGs and SSIM (:888,901): scoring the uint8 canvas would cost ~(1/255)^2/3 of MSE (-1.2 dB at 48 dB)
+                test_pred = np.clip(full.astype(np.double), 0, 1)
+                pred = np.uint8(test_pred * 255)
                 test_PSNR = [utils._compute_psnr(test_pred[:, :, 3 * s:3 * (s + 1)], label[:, :, 3 * s:3 * (s + 1)], 1.)
                              for s in range(n_GT_seq)]
                 print(" <Test> [%4d/%4d]-th image, scene: %2d-%d, time: %4.4f(minutes), test_PSNR: fr1 (FI-SR) %.8f[dB], "
@@ -287,13 +291,15 @@ class FISRnet(object):
         num_patch = self.FISR_test_patch
         check_folder(os.path.join(self.test_img_dir, self.model_dir))
         H, W = self.FISR_input_size
+        h = H - np.remainder(H, 32 * num_patch[0])                                              # FISRnet.py:1006-1007
+        w = W - np.remainder(W, 32 * num_patch[1])
         inf_time = []
         start_time = time.time()
         digits = math.ceil(math.log10(2 * (num_fr - 1)))
         def windows():
             for fr in range(num_fr - 2):
                 img = np.concatenate([np.array(Image.open(test_data_path[fr + s])) for s in range(3)], axis=2)
-                yield img[:H, :W], flow[fr, :H, :W], warp[fr, :H, :W]
+                yield img[:h, :w], flow[fr, :h, :w], warp[fr, :h, :w]      # FISRnet.py:1008-1021
 
         # two windows in flight: the copies of window k+1 overlap the kernels of window k (fisr_window_submit / _wait)
         t_prev = time.time()
@@ -315,17 +321,22 @@ class FISRnet(object):
         return "{}_exp{}".format(self.model_name, self.exp_num)
 
     def save_checkpoint(self, checkpoint_dir, step):
+        """``self.saver.save(sess, <dir>/FISRnet, global_step=step)`` (FISRnet.py:1092-1099): a TensorFlow V2 bundle with the
+        weights and, once training has started, the optimizer state (Adam slots, beta powers, global step)."""
+        from .tf_checkpoint import save_fisrnet_checkpoint
         checkpoint_dir = os.path.join(checkpoint_dir, self.model_dir)
         os.makedirs(checkpoint_dir, exist_ok=True)
-        path = os.path.join(checkpoint_dir, "{}-{}.npz".format(self.model_name, int(step)))
-        np.savez(path, **{k.replace('/', '.'): v for k, v in self.engine.get_params().items()})
+        name = "{}-{}".format(self.model_name, int(step))
+        adam = self.engine.get_adam_state() if self.engine.adam_steps > 0 else None
+        save_fisrnet_checkpoint(os.path.join(checkpoint_dir, name), self.engine.get_params(), adam, int(step))
         with open(os.path.join(checkpoint_dir, "checkpoint"), "w") as f:
-            f.write('model_checkpoint_path: "{}"\n'.format(os.path.basename(path)))
+            f.write('model_checkpoint_path: "{}"\nall_model_checkpoint_paths: "{}"\n'.format(name, name))
 
     def load(self, checkpoint_dir):
         print(" [*] Reading checkpoints...")
         checkpoint_dir = os.path.join(checkpoint_dir, self.model_dir)
         state = os.path.join(checkpoint_dir, "checkpoint")
+        self._adam_restored = False
         ckpt_name = None
         if os.path.exists(state):
             m = re.search(r'model_checkpoint_path:\s*"([^"]+)"', open(state).read())
@@ -344,10 +355,15 @@ class FISRnet(object):
             print(" [*] Success to read {}".format(ckpt_name))
             return True, counter
         if ckpt_name and os.path.exists(os.path.join(checkpoint_dir, ckpt_name + ".index")):
-            # a checkpoint written by the reference itself (tf.train.Saver V2 bundle, e.g. the released FISRnet-122000)
-            from .tf_checkpoint import fisrnet_weights
-            self.engine.set_params(fisrnet_weights(os.path.join(checkpoint_dir, ckpt_name)))
+            # a tf.train.Saver V2 bundle: written by the reference itself (e.g. the released FISRnet-122000) or by save_checkpoint
+            from .tf_checkpoint import fisrnet_adam_state, fisrnet_weights
+            prefix = os.path.join(checkpoint_dir, ckpt_name)
+            self.engine.set_params(fisrnet_weights(prefix))
             self._initialized = True
+            adam = fisrnet_adam_state(prefix)
+            if adam is not None:                      # training checkpoint: m, v and beta1_power^t restored like Saver.restore
+                self.engine.set_adam_state(*adam)
+                self._adam_restored = True
             counter = int(next(re.finditer(r"(\d+)(?!.*\d)", ckpt_name)).group(0))       # FISRnet.py:1110
             print(" [*] Success to read {}".format(ckpt_name))
             return True, counter

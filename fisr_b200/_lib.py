@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfisr_b200.so")
 
 FISR_OK = 0
+FISR_E_OVERFLOW = -5   # non-finite gradient (loss scale too high)
 PREC_F16X3 = 0      # fp16 (hi, lo) split operands, fp32-class result (default)
 PREC_F16 = 1        # single fp16 operands, fast mode
 PREC_F16F8 = 2      # fp16 main term + fp8 cross terms (2 MMA units per K slice), inference only
@@ -52,6 +53,7 @@ def load() -> C.CDLL:
         "fisr_units_device": (i, [vp, vp, vp, vp, i, i, i, i, i, C.POINTER(i), i, i, vp, vp]),
         "fisr_window_device_f32": (i, [vp, vp, vp, vp, i, i, i, i, vp, vp]),
         "fisr_window_host": (i, [vp, vp, vp, vp, i, i, i, i, vp]),
+        "fisr_window_host_f32": (i, [vp, vp, vp, vp, i, i, i, i, vp]),
         "fisr_window_submit": (i, [vp, i, vp, vp, vp, i, i, i, i, vp]),
         "fisr_window_wait": (i, [vp, i]),
         "fisr_warp_device": (i, [vp, vp, vp, f, vp, i, i, f, vp]),
@@ -62,6 +64,9 @@ def load() -> C.CDLL:
         "fisr_adam_step": (i, [vp, C.POINTER(vp), i, f, f, f, f]),
         "fisr_adam_steps": (C.c_longlong, [vp]),
         "fisr_adam_reset": (i, [vp, C.c_longlong]),
+        "fisr_adam_set_steps": (i, [vp, C.c_longlong]),
+        "fisr_get_adam_slot": (i, [vp, C.c_char_p, i, vp, sz]),
+        "fisr_set_adam_slot": (i, [vp, C.c_char_p, i, vp, sz]),
         "fisr_conv3x3": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp]),
         "fisr_train_backward": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, C.POINTER(f), C.POINTER(f), vp]),
         "fisr_get_grad": (i, [vp, C.c_char_p, vp, sz]),
@@ -90,8 +95,8 @@ def load() -> C.CDLL:
 EXPORTS = [
     "fisr_create", "fisr_destroy", "fisr_last_error", "fisr_set_precision", "fisr_get_precision", "fisr_num_params",
     "fisr_param_name", "fisr_param_shape", "fisr_set_param", "fisr_get_param", "fisr_forward", "fisr_forward_host",
-    "fisr_window_device", "fisr_units_device", "fisr_window_device_f32", "fisr_window_host", "fisr_window_submit", "fisr_window_wait", "fisr_warp_device", "fisr_warp_host",
-    "fisr_groups2ovlp", "fisr_temporal_loss", "fisr_train_forward", "fisr_adam_step", "fisr_adam_steps", "fisr_adam_reset",
+    "fisr_window_device", "fisr_units_device", "fisr_window_device_f32", "fisr_window_host", "fisr_window_host_f32", "fisr_window_submit", "fisr_window_wait", "fisr_warp_device", "fisr_warp_host",
+    "fisr_groups2ovlp", "fisr_temporal_loss", "fisr_train_forward", "fisr_adam_step", "fisr_adam_steps", "fisr_adam_reset", "fisr_adam_set_steps", "fisr_get_adam_slot", "fisr_set_adam_slot",
     "fisr_train_backward", "fisr_get_grad", "fisr_adam_apply", "fisr_train_step", "fisr_set_loss_scale", "fisr_get_loss_scale", "fisr_set_wgrad_exact",
     "fisr_dgrad3x3", "fisr_profile_train", "fisr_conv3x3", "fisr_wgrad3x3", "fisr_debug_conv_output", "fisr_profile_ops", "fisr_launch_count", "fisr_plan_info",
 ]

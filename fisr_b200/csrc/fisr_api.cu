@@ -206,6 +206,10 @@ struct fisr_ctx {
     unsigned* d_gmax = nullptr;     // max |gradient| bits of the last backward (overflow check of the loss scale)
     float loss_scale_override = 0.f;
     bool wgrad_exact = false;       // multiply by x's lo plane in every wgrad launch (fisr_set_wgrad_exact)
+    std::vector<MtTensor> mt_host;  // multi-tensor optimiser tables (train_kernels.h)
+    MtTensor* d_mt = nullptr;
+    MtPack* d_mt_pack = nullptr;
+    size_t mt_pack_cap = 0;
 };
 
 namespace {
@@ -1051,32 +1055,91 @@ int run_backward(fisr_ctx* ctx, Plan* plan, cudaStream_t st) {
     return FISR_OK;
 }
 
-int adam_impl(fisr_ctx* ctx, const std::vector<const float*>& grads, float lr, float beta1, float beta2, float eps) {
-    cudaStream_t st = ctx->stream;
-    CUDA_TRY(ctx, cudaDeviceSynchronize());
+int ensure_adam_slots(fisr_ctx* ctx, cudaStream_t st) {
+    for (auto& p : ctx->params) {
+        if (p.m_w) continue;
+        const size_t wn = static_cast<size_t>(9) * p.cin * p.cout, bn = p.cout;
+        CUDA_TRY(ctx, cudaMalloc(&p.m_w, wn * 4)); CUDA_TRY(ctx, cudaMalloc(&p.v_w, wn * 4));
+        CUDA_TRY(ctx, cudaMalloc(&p.m_b, bn * 4)); CUDA_TRY(ctx, cudaMalloc(&p.v_b, bn * 4));
+        CUDA_TRY(ctx, cudaMemsetAsync(p.m_w, 0, wn * 4, st)); CUDA_TRY(ctx, cudaMemsetAsync(p.v_w, 0, wn * 4, st));
+        CUDA_TRY(ctx, cudaMemsetAsync(p.m_b, 0, bn * 4, st)); CUDA_TRY(ctx, cudaMemsetAsync(p.v_b, 0, bn * 4, st));
+    }
+    return FISR_OK;
+}
+
+// Device table over all 276 tensors for the multi-tensor kernels (rebuilt per call: the gradient pointers may be the caller's).
+int upload_mt_table(fisr_ctx* ctx, const std::vector<const float*>& grads, cudaStream_t st, unsigned* blocks) {
+    std::vector<MtTensor>& t = ctx->mt_host;
+    t.clear();
+    unsigned blk = 0;
+    for (size_t i = 0; i < ctx->params.size(); ++i) {
+        ConvParam& p = ctx->params[i];
+        const unsigned long long wn = static_cast<unsigned long long>(9) * p.cin * p.cout, bn = p.cout;
+        t.push_back(MtTensor{p.d_w, grads[2 * i], p.m_w, p.v_w, wn, blk});
+        blk += static_cast<unsigned>((wn + kMtChunk - 1) / kMtChunk);
+        t.push_back(MtTensor{p.d_b, grads[2 * i + 1], p.m_b, p.v_b, bn, blk});
+        blk += static_cast<unsigned>((bn + kMtChunk - 1) / kMtChunk);
+    }
+    if (!ctx->d_mt) CUDA_TRY(ctx, cudaMalloc(&ctx->d_mt, t.size() * sizeof(MtTensor)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_mt, t.data(), t.size() * sizeof(MtTensor), cudaMemcpyHostToDevice, st));
+    *blocks = blk;
+    return FISR_OK;
+}
+
+// Operand planes follow the fp32 master copies: one multi-tensor launch for the split-mode forward planes and (when the
+// training planes exist) the rotated-transposed dgrad planes; other precision modes re-pack conv by conv.
+int repack_all(fisr_ctx* ctx, cudaStream_t st) {
+    if (ctx->planes != 2) {
+        for (auto& p : ctx->params) {
+            p.packed = false; p.packedT = false;
+            const int rc = ensure_packed(ctx, p, st);
+            if (rc != FISR_OK) return rc;
+        }
+        return FISR_OK;
+    }
+    std::vector<MtPack> t;
+    unsigned blk = 0;
+    for (auto& p : ctx->params) {
+        const unsigned long long pf = static_cast<unsigned long long>(p.KB) * 9 * p.cout_pad * 64;
+        t.push_back(MtPack{p.d_w, p.d_wp, p.cin, p.cout, p.cout_pad, 0, pf, blk});
+        blk += static_cast<unsigned>((pf + kMtChunk - 1) / kMtChunk);
+        p.packed = true;
+        if (p.d_wpT) {
+            const unsigned long long pb = static_cast<unsigned long long>(p.OBk) * 9 * p.cin_pad * 64;
+            t.push_back(MtPack{p.d_w, p.d_wpT, p.cin, p.cout, p.cin_pad, 1, pb, blk});
+            blk += static_cast<unsigned>((pb + kMtChunk - 1) / kMtChunk);
+            p.packedT = true;
+        } else {
+            p.packedT = false;
+        }
+    }
+    if (ctx->mt_pack_cap < t.size()) {
+        if (ctx->d_mt_pack) cudaFree(ctx->d_mt_pack);
+        ctx->d_mt_pack = nullptr; ctx->mt_pack_cap = 0;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_mt_pack, t.size() * sizeof(MtPack)));
+        ctx->mt_pack_cap = t.size();
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_mt_pack, t.data(), t.size() * sizeof(MtPack), cudaMemcpyHostToDevice, st));
+    launch_mt_repack(ctx->d_mt_pack, static_cast<int>(t.size()), blk, st);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FISR_OK;
+}
+
+// tf.train.AdamOptimizer update of all 276 tensors (FISRnet.py:489-491) + operand re-pack, asynchronous on stream st:
+// 2 kernel launches (multi-tensor Adam, multi-tensor re-pack).
+int adam_impl(fisr_ctx* ctx, const std::vector<const float*>& grads, float lr, float beta1, float beta2, float eps, cudaStream_t st) {
+    int rc = ensure_adam_slots(ctx, st);
+    if (rc != FISR_OK) return rc;
     const long long t = ++ctx->adam_t;
     const float lr_t = static_cast<float>(lr * std::sqrt(1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(t))) /
                                           (1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(t))));
-    for (size_t i = 0; i < ctx->params.size(); ++i) {
-        ConvParam& p = ctx->params[i];
-        const size_t wn = static_cast<size_t>(9) * p.cin * p.cout, bn = p.cout;
-        if (!p.m_w) {
-            CUDA_TRY(ctx, cudaMalloc(&p.m_w, wn * 4)); CUDA_TRY(ctx, cudaMalloc(&p.v_w, wn * 4));
-            CUDA_TRY(ctx, cudaMalloc(&p.m_b, bn * 4)); CUDA_TRY(ctx, cudaMalloc(&p.v_b, bn * 4));
-            CUDA_TRY(ctx, cudaMemsetAsync(p.m_w, 0, wn * 4, st)); CUDA_TRY(ctx, cudaMemsetAsync(p.v_w, 0, wn * 4, st));
-            CUDA_TRY(ctx, cudaMemsetAsync(p.m_b, 0, bn * 4, st)); CUDA_TRY(ctx, cudaMemsetAsync(p.v_b, 0, bn * 4, st));
-        }
-        launch_adam_tf1(p.d_w, grads[2 * i], p.m_w, p.v_w, wn, lr_t, beta1, beta2, eps, st);
-        launch_adam_tf1(p.d_b, grads[2 * i + 1], p.m_b, p.v_b, bn, lr_t, beta1, beta2, eps, st);
-        p.packed = false;
-        p.packedT = false;
-        int rc = ensure_packed(ctx, p, st);          // operand planes follow the fp32 master copy
-        if (rc != FISR_OK) return rc;
-        ctx->launches += 2;
-    }
+    unsigned blocks = 0;
+    if ((rc = upload_mt_table(ctx, grads, st, &blocks)) != FISR_OK) return rc;
+    launch_mt_adam(ctx->d_mt, static_cast<int>(ctx->mt_host.size()), blocks, lr_t, beta1, beta2, eps, st);
+    ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    return FISR_OK;
+    return repack_all(ctx, st);
 }
 
 }  // namespace
@@ -1162,6 +1225,8 @@ void fisr_destroy(fisr_ctx* ctx) {
     cudaFree(ctx->d_scalars);
     cudaFree(ctx->d_zero_bias);
     cudaFree(ctx->d_gmax);
+    cudaFree(ctx->d_mt);
+    cudaFree(ctx->d_mt_pack);
     for (void* s : ctx->stage) if (s) cudaFree(s);
     for (auto& sl : ctx->slots) {
         for (void* b : sl.in) if (b) cudaFree(b);
@@ -1376,6 +1441,32 @@ int fisr_window_host(fisr_ctx* ctx, const uint8_t* h_frames, const float* h_flow
     rc = window_impl(ctx, static_cast<const uint8_t*>(ctx->stage[1]), static_cast<const float*>(ctx->stage[2]),
                      static_cast<const float*>(ctx->stage[3]), H, W, pH, pW, 0, pH * pW,
                      static_cast<uint8_t*>(ctx->stage[4]), nullptr, st);
+    if (rc != FISR_OK) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_canvas, ctx->stage[4], out_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return check_kernel_error(ctx);
+}
+
+int fisr_window_host_f32(fisr_ctx* ctx, const uint8_t* h_frames, const float* h_flow, const float* h_warp, int H, int W,
+                         int pH, int pW, float* h_canvas) {
+    if (!ctx || !h_frames || !h_flow || !h_warp || !h_canvas) return FISR_E_INVALID;
+    if (pH < 1 || pW < 1) return fail(ctx, FISR_E_INVALID, "bad tile grid");
+    Guard guard(ctx->device);
+    const size_t px = static_cast<size_t>(H) * W;
+    const int h = H - H % (32 * pH), w = W - W % (32 * pW);
+    const size_t out_bytes = static_cast<size_t>(2 * h) * (2 * w) * 9 * sizeof(float);
+    int rc;
+    if ((rc = ensure_stage(ctx, 1, px * 9)) != FISR_OK) return rc;
+    if ((rc = ensure_stage(ctx, 2, px * 8 * 4)) != FISR_OK) return rc;
+    if ((rc = ensure_stage(ctx, 3, px * 12 * 4)) != FISR_OK) return rc;
+    if ((rc = ensure_stage(ctx, 4, out_bytes)) != FISR_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage[1], h_frames, px * 9, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage[2], h_flow, px * 8 * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage[3], h_warp, px * 12 * 4, cudaMemcpyHostToDevice, st));
+    rc = window_impl(ctx, static_cast<const uint8_t*>(ctx->stage[1]), static_cast<const float*>(ctx->stage[2]),
+                     static_cast<const float*>(ctx->stage[3]), H, W, pH, pW, 0, pH * pW, nullptr,
+                     static_cast<float*>(ctx->stage[4]), st);
     if (rc != FISR_OK) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(h_canvas, ctx->stage[4], out_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -1734,7 +1825,54 @@ int fisr_adam_step(fisr_ctx* ctx, const float* const* d_grads, int n_grads, floa
     std::vector<const float*> g(d_grads, d_grads + n_grads);
     for (int i = 0; i < n_grads; ++i)
         if (!g[i]) return fail(ctx, FISR_E_INVALID, "gradient %d is NULL", i);
-    return adam_impl(ctx, g, lr, beta1, beta2, eps);
+    CUDA_TRY(ctx, cudaDeviceSynchronize());          // the caller's gradients may come from any stream
+    const int rc = adam_impl(ctx, g, lr, beta1, beta2, eps, ctx->stream);
+    if (rc != FISR_OK) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return FISR_OK;
+}
+
+// Adam slot variables "<var>/Adam" (m) and "<var>/Adam_1" (v) of the reference's training checkpoints (tf.train.Saver
+// saves them next to the weights, FISRnet.py:1092-1099): which = 0 -> m, 1 -> v.
+static int adam_slot_ptr(fisr_ctx* ctx, const char* name, int which, size_t count, float** out) {
+    int ci; bool is_w;
+    int rc = split_param_name(ctx, name, &ci, &is_w);
+    if (rc != FISR_OK) return rc;
+    if (which != 0 && which != 1) return fail(ctx, FISR_E_INVALID, "Adam slot must be 0 (m) or 1 (v)");
+    ConvParam& p = ctx->params[ci];
+    const size_t expect = is_w ? static_cast<size_t>(9) * p.cin * p.cout : static_cast<size_t>(p.cout);
+    if (count != expect) return fail(ctx, FISR_E_INVALID, "%s has %zu elements, got %zu", name, expect, count);
+    if ((rc = ensure_adam_slots(ctx, ctx->stream)) != FISR_OK) return rc;
+    *out = is_w ? (which ? p.v_w : p.m_w) : (which ? p.v_b : p.m_b);
+    return FISR_OK;
+}
+
+int fisr_get_adam_slot(fisr_ctx* ctx, const char* name, int which, float* h_data, size_t count) {
+    if (!ctx || !h_data) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    float* src = nullptr;
+    const int rc = adam_slot_ptr(ctx, name, which, count, &src);
+    if (rc != FISR_OK) return rc;
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    CUDA_TRY(ctx, cudaMemcpy(h_data, src, count * 4, cudaMemcpyDeviceToHost));
+    return FISR_OK;
+}
+
+int fisr_set_adam_slot(fisr_ctx* ctx, const char* name, int which, const float* h_data, size_t count) {
+    if (!ctx || !h_data) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    float* dst = nullptr;
+    const int rc = adam_slot_ptr(ctx, name, which, count, &dst);
+    if (rc != FISR_OK) return rc;
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    CUDA_TRY(ctx, cudaMemcpy(dst, h_data, count * 4, cudaMemcpyHostToDevice));
+    return FISR_OK;
+}
+
+int fisr_adam_set_steps(fisr_ctx* ctx, long long step) {
+    if (!ctx || step < 0) return FISR_E_INVALID;
+    ctx->adam_t = step;
+    return FISR_OK;
 }
 
 long long fisr_adam_steps(const fisr_ctx* ctx) { return ctx ? ctx->adam_t : 0; }
@@ -1773,17 +1911,24 @@ static int train_backward_impl(fisr_ctx* ctx, const float* d_data, const float* 
     if (lambdas) plan->lam = LossLambdas{lambdas[0], lambdas[1], lambdas[2], lambdas[3], lambdas[4], lambdas[5]};
     if ((rc = run_backward(ctx, plan, st)) != FISR_OK) return rc;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_gmax, 0, sizeof(unsigned), st));
-    for (auto& p : ctx->params) launch_grad_absmax(p.g_w, static_cast<size_t>(9) * p.cin * p.cout, ctx->d_gmax, st);
-    ctx->launches += static_cast<long long>(ctx->params.size());
+    {   // max |g| over every gradient tensor in one launch (overflow probe of the loss scale)
+        std::vector<const float*> g;
+        for (auto& p : ctx->params) { g.push_back(p.g_w); g.push_back(p.g_b); }
+        unsigned blocks = 0;
+        if ((rc = upload_mt_table(ctx, g, st, &blocks)) != FISR_OK) return rc;
+        launch_mt_absmax(ctx->d_mt, static_cast<int>(ctx->mt_host.size()), blocks, ctx->d_gmax, st);
+        ctx->launches++;
+    }
     const float* pred[3] = {plan->pred[0], plan->pred[1], plan->pred[2]};
     float scalars[11];
     if ((rc = loss_impl(ctx, pred, d_label, B, h, w, lambdas, scalars, st)) != FISR_OK) return rc;    // synchronises
     if (h_out) memcpy(h_out, scalars, sizeof scalars);
     unsigned gmax = 0;
     CUDA_TRY(ctx, cudaMemcpy(&gmax, ctx->d_gmax, sizeof gmax, cudaMemcpyDeviceToHost));
+    if ((rc = check_kernel_error(ctx)) != FISR_OK) return rc;
     if (gmax >= 0x7F800000u)
-        return fail(ctx, FISR_E_KERNEL, "non-finite gradient (loss scale %g overflowed the fp16 gradient planes): lower it with fisr_set_loss_scale", plan->loss_scale);
-    return check_kernel_error(ctx);
+        return fail(ctx, FISR_E_OVERFLOW, "non-finite gradient (loss scale %g overflowed the fp16 gradient planes): lower it with fisr_set_loss_scale", plan->loss_scale);
+    return FISR_OK;
 }
 
 int fisr_train_backward(fisr_ctx* ctx, const float* d_data, const float* d_flow, const float* d_flow_ss2, const float* d_warp,
@@ -1795,24 +1940,43 @@ int fisr_train_backward(fisr_ctx* ctx, const float* d_data, const float* d_flow,
     return train_backward_impl(ctx, d_data, d_flow, d_flow_ss2, d_warp, d_warp_ss2, d_label, B, h, w, lambdas, h_out, st);
 }
 
-int fisr_adam_apply(fisr_ctx* ctx, float lr, float beta1, float beta2, float eps) {
-    if (!ctx) return FISR_E_INVALID;
-    Guard guard(ctx->device);
+static int adam_apply_impl(fisr_ctx* ctx, float lr, float beta1, float beta2, float eps, cudaStream_t st) {
     std::vector<const float*> g;
     for (auto& p : ctx->params) {
         if (!p.g_w) return fail(ctx, FISR_E_INVALID, "no gradients yet: call fisr_train_backward first");
         g.push_back(p.g_w);
         g.push_back(p.g_b);
     }
-    return adam_impl(ctx, g, lr, beta1, beta2, eps);
+    return adam_impl(ctx, g, lr, beta1, beta2, eps, st);
 }
 
+int fisr_adam_apply(fisr_ctx* ctx, float lr, float beta1, float beta2, float eps) {
+    if (!ctx) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    // fisr_train_backward is synchronous, so the gradients are complete; later calls may use another stream: finish here
+    const int rc = adam_apply_impl(ctx, lr, beta1, beta2, eps, ctx->stream);
+    if (rc != FISR_OK) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return FISR_OK;
+}
+
+// One `sess.run(optim)`.  Dynamic loss scaling: when the fp16 gradient planes overflow, the update is skipped, the scale is
+// divided by 8 and the step is retried (up to 4 times); the lowered scale stays in force for the following steps.
 int fisr_train_step(fisr_ctx* ctx, const float* d_data, const float* d_flow, const float* d_flow_ss2, const float* d_warp,
                     const float* d_warp_ss2, const float* d_label, int B, int h, int w, const float* lambdas, float lr,
                     float* h_out, void* stream) {
-    int rc = fisr_train_backward(ctx, d_data, d_flow, d_flow_ss2, d_warp, d_warp_ss2, d_label, B, h, w, lambdas, h_out, stream);
+    if (!ctx) return FISR_E_INVALID;
+    int rc = FISR_OK;
+    for (int attempt = 0; attempt < 5; ++attempt) {
+        rc = fisr_train_backward(ctx, d_data, d_flow, d_flow_ss2, d_warp, d_warp_ss2, d_label, B, h, w, lambdas, h_out, stream);
+        if (rc != FISR_E_OVERFLOW || attempt == 4) break;
+        const float cur = fisr_get_loss_scale(ctx, B, h, w);
+        if ((rc = fisr_set_loss_scale(ctx, cur / 8.f)) != FISR_OK) return rc;
+    }
     if (rc != FISR_OK) return rc;
-    return fisr_adam_apply(ctx, lr, 0.9f, 0.999f, 1e-8f);
+    Guard guard(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return adam_apply_impl(ctx, lr, 0.9f, 0.999f, 1e-8f, st);      // asynchronous on the step's stream: 2 launches, no host sync
 }
 
 int fisr_get_grad(fisr_ctx* ctx, const char* name, float* h_data, size_t count) {

@@ -354,11 +354,8 @@ __global__ void upsample_bwd_kernel(const __half* __restrict__ gup, size_t pgup,
 // w fp32 HWIO [3,3,cin,cout] -> operand planes of the transposed, 180-degree rotated filter: the data gradient of a
 // SAME 3x3 conv is the SAME 3x3 conv of dy with w'[ky,kx,co,ci] = w[2-ky,2-kx,ci,co].
 // Layout [plane][kb over cout][tap][cin_pad][64] like the forward operand.
-__global__ void prep_weights_dgrad_kernel(const float* __restrict__ w, __half* __restrict__ out, int cin, int cout, int KBo,
-                                          int cin_pad) {
-    const size_t per_plane = static_cast<size_t>(KBo) * 9 * cin_pad * 64;
-    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-    if (i >= per_plane) return;
+__device__ __forceinline__ void prep_dgrad_element(const float* __restrict__ w, __half* __restrict__ out, int cin, int cout, int cin_pad,
+                                                   size_t per_plane, size_t i) {
     const int cl = i & 63;
     size_t r = i >> 6;
     const int ci = r % cin_pad; r /= cin_pad;
@@ -371,9 +368,83 @@ __global__ void prep_weights_dgrad_kernel(const float* __restrict__ w, __half* _
     out[i] = s.hi;
     out[per_plane + i] = s.lo;
 }
+__global__ void prep_weights_dgrad_kernel(const float* __restrict__ w, __half* __restrict__ out, int cin, int cout, int KBo,
+                                          int cin_pad) {
+    const size_t per_plane = static_cast<size_t>(KBo) * 9 * cin_pad * 64;
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= per_plane) return;
+    prep_dgrad_element(w, out, cin, cout, cin_pad, per_plane, i);
+}
 
-// max |g| over a gradient tensor, as the raw bits of a non-negative float (atomicMax on ints orders them); NaN / Inf
+// forward operand planes of the split mode (aux_kernels.cu, prep_weights_kernel with planes = 2), per element
+__device__ __forceinline__ void prep_fwd_split_element(const float* __restrict__ w, __half* __restrict__ out, int cin, int cout,
+                                                       int cout_pad, size_t per_plane, size_t i) {
+    const int cl = i & 63;
+    size_t r = i >> 6;
+    const int co = r % cout_pad; r /= cout_pad;
+    const int tap = r % 9;
+    const int ci = static_cast<int>(r / 9) * 64 + cl;
+    float v = 0.f;
+    if (ci < cin && co < cout) v = w[(static_cast<size_t>(tap) * cin + ci) * cout + co];
+    const SplitHalf s = split_f32(v);
+    out[i] = s.hi;
+    out[per_plane + i] = s.lo;
+}
+
+// ---------------------------------------------------------------- multi-tensor optimiser step
+// One launch over ALL 276 tensors (block -> tensor by binary search over MtTensor::block0, kMtChunk elements per block):
+// 3 launches per step (|g| max, Adam, operand re-pack) instead of 552 + 276 + 276.
+__device__ __forceinline__ int mt_find(const MtTensor* __restrict__ t, int n, unsigned blk) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (t[mid].block0 <= blk) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// max |g| over every gradient tensor, as the raw bits of a non-negative float (atomicMax on ints orders them); NaN / Inf
 // give bits >= 0x7F800000, which is how an overflowed loss scale is detected.
+__global__ void mt_absmax_kernel(const MtTensor* __restrict__ t, int n, unsigned* __restrict__ out) {
+    const MtTensor e = t[mt_find(t, n, blockIdx.x)];
+    const size_t base = static_cast<size_t>(blockIdx.x - e.block0) * kMtChunk;
+    unsigned m = 0;
+    for (size_t i = base + threadIdx.x; i < base + kMtChunk && i < e.n; i += blockDim.x)
+        m = max(m, __float_as_uint(e.g[i]) & 0x7FFFFFFFu);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// Adam, TF-1.13 formula (FISRnet.py:489-491): lr_t = lr sqrt(1 - b2^t) / (1 - b1^t) (host), theta -= lr_t m / (sqrt(v) + eps)
+__device__ __forceinline__ void adam_element(float& theta, float g, float& m, float& v, float lr_t, float beta1, float beta2, float eps) {
+    m = beta1 * m + (1.f - beta1) * g;
+    v = beta2 * v + (1.f - beta2) * g * g;
+    theta -= lr_t * m / (sqrtf(v) + eps);
+}
+__global__ void mt_adam_kernel(const MtTensor* __restrict__ t, int n, float lr_t, float beta1, float beta2, float eps) {
+    const MtTensor e = t[mt_find(t, n, blockIdx.x)];
+    const size_t base = static_cast<size_t>(blockIdx.x - e.block0) * kMtChunk;
+    for (size_t i = base + threadIdx.x; i < base + kMtChunk && i < e.n; i += blockDim.x) {
+        float th = e.theta[i], m = e.m[i], v = e.v[i];
+        adam_element(th, e.g[i], m, v, lr_t, beta1, beta2, eps);
+        e.theta[i] = th; e.m[i] = m; e.v[i] = v;
+    }
+}
+__global__ void mt_repack_kernel(const MtPack* __restrict__ t, int n) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (t[mid].block0 <= blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const MtPack e = t[lo];
+    const size_t base = static_cast<size_t>(blockIdx.x - e.block0) * kMtChunk;
+    for (size_t i = base + threadIdx.x; i < base + kMtChunk && i < e.per_plane; i += blockDim.x) {
+        if (e.dgrad) prep_dgrad_element(e.w, e.out, e.cin, e.cout, e.pad, e.per_plane, i);
+        else prep_fwd_split_element(e.w, e.out, e.cin, e.cout, e.pad, e.per_plane, i);
+    }
+}
+
 __global__ void grad_absmax_kernel(const float* __restrict__ g, size_t n, unsigned* __restrict__ out) {
     unsigned m = 0;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
@@ -383,17 +454,13 @@ __global__ void grad_absmax_kernel(const float* __restrict__ g, size_t n, unsign
     if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
-// ---------------------------------------------------------------- Adam, TF-1.13 formula (FISRnet.py:489-491)
 __global__ void adam_tf1_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ m,
                                 float* __restrict__ v, size_t n, float lr_t, float beta1, float beta2, float eps) {
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     if (i >= n) return;
-    const float gi = g[i];
-    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    theta[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    float th = theta[i], mi = m[i], vi = v[i];
+    adam_element(th, g[i], mi, vi, lr_t, beta1, beta2, eps);
+    theta[i] = th; m[i] = mi; v[i] = vi;
 }
 
 }  // namespace
@@ -476,6 +543,16 @@ void launch_grad_absmax(const float* g, size_t n, unsigned* out, cudaStream_t st
 void launch_adam_tf1(float* theta, const float* g, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,
                      float eps, cudaStream_t st) {
     adam_tf1_kernel<<<blocks_for(n, 256), 256, 0, st>>>(theta, g, m, v, n, lr_t, beta1, beta2, eps);
+}
+
+void launch_mt_absmax(const MtTensor* d_table, int n, unsigned blocks, unsigned* out, cudaStream_t st) {
+    mt_absmax_kernel<<<blocks, 256, 0, st>>>(d_table, n, out);
+}
+void launch_mt_adam(const MtTensor* d_table, int n, unsigned blocks, float lr_t, float beta1, float beta2, float eps, cudaStream_t st) {
+    mt_adam_kernel<<<blocks, 256, 0, st>>>(d_table, n, lr_t, beta1, beta2, eps);
+}
+void launch_mt_repack(const MtPack* d_table, int n, unsigned blocks, cudaStream_t st) {
+    mt_repack_kernel<<<blocks, 256, 0, st>>>(d_table, n);
 }
 
 }  // namespace fisr

@@ -29,6 +29,22 @@ void launch_pool_bwd(ActBuf skip, ActBuf gcat, int cs, int coff, ActBuf gpool, A
 void launch_upsample_bwd(ActBuf gup, ActBuf xin, ActBuf gout, float* rout, int N, int h, int w, int C, cudaStream_t st);
 void launch_prep_weights_dgrad(const float* w, __half* out, int cin, int cout, int KBo, int cin_pad, cudaStream_t st);
 void launch_grad_absmax(const float* g, size_t n, unsigned* out, cudaStream_t st);
+// Multi-tensor optimiser step: device tables over all 276 tensors, kMtChunk elements per block, block -> tensor by block0.
+constexpr int kMtChunk = 4096;
+struct MtTensor {
+    float* theta; const float* g; float* m; float* v;
+    unsigned long long n;
+    unsigned block0;
+};
+struct MtPack {          // operand re-pack of one conv (split mode): forward planes or rotated-transposed dgrad planes
+    const float* w; __half* out;
+    int cin, cout, pad, dgrad;        // pad = cout_pad (forward) or cin_pad (dgrad)
+    unsigned long long per_plane;
+    unsigned block0;
+};
+void launch_mt_absmax(const MtTensor* d_table, int n, unsigned blocks, unsigned* out, cudaStream_t st);
+void launch_mt_adam(const MtTensor* d_table, int n, unsigned blocks, float lr_t, float beta1, float beta2, float eps, cudaStream_t st);
+void launch_mt_repack(const MtPack* d_table, int n, unsigned blocks, cudaStream_t st);
 void launch_adam_tf1(float* theta, const float* g, float* m, float* v, size_t n, float lr_t, float beta1, float beta2, float eps,
                      cudaStream_t st);
 

@@ -211,6 +211,19 @@ class Engine:
                                               num_patch[0], num_patch[1], out.ctypes.data), "fisr_window_host")
         return out
 
+    def window_host_f32(self, frames: np.ndarray, flow: np.ndarray, warp: np.ndarray, num_patch=(2, 2)) -> np.ndarray:
+        """Float canvas [2h,2w,9] of one window before clipping (``test_Pred_full``, FISRnet.py:844-880), host buffers."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        flow = np.ascontiguousarray(flow, dtype=np.float32)
+        warp = np.ascontiguousarray(warp, dtype=np.float32)
+        H, W, _ = frames.shape
+        if flow.shape != (H, W, 8) or warp.shape != (H, W, 12) or frames.shape[2] != 9:
+            raise FisrError(f"window shapes: frames {frames.shape}, flow {flow.shape}, warp {warp.shape}")
+        out = np.empty(self.canvas_shape(H, W, num_patch), np.float32)
+        self._check(self.lib.fisr_window_host_f32(self.h, frames.ctypes.data, flow.ctypes.data, warp.ctypes.data, H, W,
+                                                  num_patch[0], num_patch[1], out.ctypes.data), "fisr_window_host_f32")
+        return out
+
     def window_submit(self, slot: int, frames: np.ndarray, flow: np.ndarray, warp: np.ndarray, num_patch=(2, 2),
                       out: Optional[np.ndarray] = None) -> np.ndarray:
         """Pipelined :meth:`window_host`: enqueue one window on slot 0/1 and return; :meth:`window_wait` delivers ``out``.
@@ -231,17 +244,38 @@ class Engine:
         self._check(self.lib.fisr_window_wait(self.h, slot), "fisr_window_wait")
         return self._inflight.pop(slot)[3]
 
+    def _pinned(self, slot: int, idx: int, shape, dtype) -> np.ndarray:
+        """Page-locked staging array of one pipeline slot (cudaMemcpyAsync from pageable memory blocks the host, so the two
+        windows in flight would not overlap)."""
+        cache = self.__dict__.setdefault("_pin_cache", {})
+        key = (slot, idx)
+        t = cache.get(key)
+        tdt = {np.dtype(np.uint8): torch.uint8, np.dtype(np.float32): torch.float32}[np.dtype(dtype)]
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != tdt:
+            t = torch.empty(tuple(shape), dtype=tdt).pin_memory()
+            cache[key] = t
+        return t.numpy()
+
     def video_windows(self, windows, num_patch=(2, 2)):
-        """Generator over uint8 canvases for an iterable of (frames, flow, warp) host windows, two windows in flight."""
+        """Generator over uint8 canvases for an iterable of (frames, flow, warp) host windows, two windows in flight:
+        each window is staged through the slot's pinned buffers, so its H2D copy overlaps the previous window's kernels
+        (the yielded canvas is a private copy of the slot's pinned output buffer)."""
         pending = []
         for k, (fr, fl, wp) in enumerate(windows):
-            self.window_submit(k & 1, np.ascontiguousarray(fr, np.uint8), np.ascontiguousarray(fl, np.float32),
-                               np.ascontiguousarray(wp, np.float32), num_patch)
-            pending.append(k & 1)
+            slot = k & 1
+            stage = []
+            for idx, (a, dt) in enumerate(((fr, np.uint8), (fl, np.float32), (wp, np.float32))):
+                buf = self._pinned(slot, idx, a.shape, dt)
+                np.copyto(buf, a, casting="same_kind")
+                stage.append(buf)
+            H, W, _ = stage[0].shape
+            out = self._pinned(slot, 3, self.canvas_shape(H, W, num_patch), np.uint8)
+            self.window_submit(slot, stage[0], stage[1], stage[2], num_patch, out=out)
+            pending.append(slot)
             if len(pending) == 2:
-                yield self.window_wait(pending.pop(0))
+                yield self.window_wait(pending.pop(0)).copy()
         while pending:
-            yield self.window_wait(pending.pop(0))
+            yield self.window_wait(pending.pop(0)).copy()
 
     # ------------------------------------------------------------------ flow warp
     def warp(self, yuv: torch.Tensor, flow: torch.Tensor, flow_scale: float = 0.5, out_scale: float = 1.0) -> torch.Tensor:
@@ -383,7 +417,31 @@ class Engine:
         return int(self.lib.fisr_adam_steps(self.h))
 
     def adam_reset(self, step: int = 0) -> None:
+        """Zero moments and step counter ``step`` (bias correction matches zero moments only for ``step = 0``)."""
         self._check(self.lib.fisr_adam_reset(self.h, step), "fisr_adam_reset")
+
+    @property
+    def adam_steps(self) -> int:
+        return int(self.lib.fisr_adam_steps(self.h))
+
+    def get_adam_state(self) -> dict:
+        """Optimizer state as the reference's Saver stores it: ``<var>/Adam`` (m), ``<var>/Adam_1`` (v), step counter t."""
+        out = {"t": self.adam_steps, "m": OrderedDict(), "v": OrderedDict()}
+        for name, shape in param_inventory().items():
+            for which, key in ((0, "m"), (1, "v")):
+                a = np.empty(shape, dtype=np.float32)
+                self._check(self.lib.fisr_get_adam_slot(self.h, name.encode(), which, a.ctypes.data, a.size), "fisr_get_adam_slot")
+                out[key][name] = a
+        return out
+
+    def set_adam_state(self, m: Dict[str, np.ndarray], v: Dict[str, np.ndarray], t: int) -> None:
+        for name, shape in param_inventory().items():
+            for which, src in ((0, m), (1, v)):
+                a = np.ascontiguousarray(src[name], dtype=np.float32)
+                if tuple(a.shape) != shape:
+                    raise FisrError(f"Adam slot of {name}: expected shape {shape}, got {tuple(a.shape)}")
+                self._check(self.lib.fisr_set_adam_slot(self.h, name.encode(), which, a.ctypes.data, a.size), "fisr_set_adam_slot")
+        self._check(self.lib.fisr_adam_set_steps(self.h, int(t)), "fisr_adam_set_steps")
 
     # ------------------------------------------------------------------ test hooks
     def conv3x3(self, x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, res: Optional[torch.Tensor] = None,

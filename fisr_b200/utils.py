@@ -131,27 +131,3 @@ def YUV2RGB_matlab(yuv):                           # utils.py:106-115
     for p in range(3):
         rgb[:, :, p] = T[p, 0] * yuv[:, :, 0] + T[p, 1] * yuv[:, :, 1] + T[p, 2] * yuv[:, :, 2] - offset[p]
     return np.clip(rgb, 0, 255)
-
-
-def get_HW_boundary(patch_boundary, h, w, pH, sH, pW, sW):          # utils.py:118-135
-    H_low_ind = max(pH * sH - patch_boundary, 0)
-    H_high_ind = min((pH + 1) * sH + patch_boundary, h)
-    W_low_ind = max(pW * sW - patch_boundary, 0)
-    W_high_ind = min((pW + 1) * sW + patch_boundary, w)
-    add_H = (patch_boundary if pH * sH >= patch_boundary else 0) + (patch_boundary if (pH + 1) * sH + patch_boundary <= h else 0)
-    add_W = (patch_boundary if pW * sW >= patch_boundary else 0) + (patch_boundary if (pW + 1) * sW + patch_boundary <= w else 0)
-    return H_low_ind, H_high_ind, W_low_ind, W_high_ind, add_H, add_W
-
-
-def trim_patch_boundary(img, patch_boundary, h, w, pH, sH, pW, sW, sf):   # utils.py:138-159
-    if patch_boundary == 0:
-        return img
-    if not pH * sH < patch_boundary:
-        img = img[:, patch_boundary * sf:, :, :]
-    if not (pH + 1) * sH + patch_boundary > h:
-        img = img[:, :-patch_boundary * sf, :, :]
-    if not pW * sW < patch_boundary:
-        img = img[:, :, patch_boundary * sf:, :]
-    if not (pW + 1) * sW + patch_boundary > w:
-        img = img[:, :, :-patch_boundary * sf, :]
-    return img

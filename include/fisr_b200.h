@@ -29,7 +29,8 @@ enum {
     FISR_E_INVALID = -1,    /* bad argument (shape not a multiple of 32, unknown parameter name, ...) */
     FISR_E_CUDA = -2,       /* CUDA runtime / driver error */
     FISR_E_KERNEL = -3,     /* a kernel reported a pipeline time-out through its error flag */
-    FISR_E_NOMEM = -4
+    FISR_E_NOMEM = -4,
+    FISR_E_OVERFLOW = -5    /* non-finite gradient: the loss scale overflowed the fp16 gradient planes (fisr_train_backward) */
 };
 
 /* Arithmetic of the conv stack (DESIGN.md "Numerics").  The reference computes in fp32 (cuDNN on Pascal). */
@@ -92,7 +93,10 @@ int fisr_window_host(fisr_ctx* ctx, const uint8_t* h_frames, const float* h_flow
 int fisr_window_submit(fisr_ctx* ctx, int slot, const uint8_t* h_frames, const float* h_flow, const float* h_warp, int H,
                        int W, int pH, int pW, uint8_t* h_canvas);
 int fisr_window_wait(fisr_ctx* ctx, int slot);
-/* float canvas [2h,2w,9] before clipping (what FISRnet.py:1057 accumulates), for parity tests */
+/* float canvas [2h,2w,9] before clipping: `test_Pred_full` of FISRnet.py:844,880 -- what FISRnet.test() clips and scores
+ * (PSNR on the float prediction, FISRnet.py:883-887) before it truncates to uint8 for the PNGs (:901). */
+int fisr_window_host_f32(fisr_ctx* ctx, const uint8_t* h_frames, const float* h_flow, const float* h_warp, int H, int W,
+                         int pH, int pW, float* h_canvas);
 int fisr_window_device_f32(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, const float* d_warp, int H,
                            int W, int pH, int pW, float* d_canvas, void* stream);
 
@@ -141,14 +145,22 @@ int fisr_train_step(fisr_ctx* ctx, const float* d_data, const float* d_flow, con
                     float* h_out, void* stream);
 /* Gradients travel through the network as fp16 (hi, lo) planes multiplied by a power-of-two loss scale (default:
  * 2^floor(log2(B*2h*2w*3)), divided out by the weight-gradient reduction).  0 restores the default; a non-finite gradient
- * makes fisr_train_backward return FISR_E_KERNEL. */
+ * makes fisr_train_backward return FISR_E_OVERFLOW.  fisr_train_step scales dynamically: on overflow it skips the update,
+ * divides the scale by 8 and retries the step (up to 4 times); the lowered scale stays in force. */
 int fisr_set_loss_scale(fisr_ctx* ctx, float scale);
 float fisr_get_loss_scale(fisr_ctx* ctx, int B, int h, int w);
 /* Weight gradients of layers with >= 16384 pixels multiply dy (hi, lo) by the hi plane of the forward activation only
  * (half the MMAs; adds ~1e-4 relative rounding noise per gradient tensor).  exact = 1 uses both planes everywhere. */
 int fisr_set_wgrad_exact(fisr_ctx* ctx, int exact);
 long long fisr_adam_steps(const fisr_ctx* ctx);
+/* Frees the moments (they restart at zero) and sets the step counter. */
 int fisr_adam_reset(fisr_ctx* ctx, long long step);
+/* Optimizer state of a training checkpoint: tf.train.Saver stores "<var>/Adam" (m), "<var>/Adam_1" (v) and the beta powers
+ * next to the weights (FISRnet.py:1092-1099), so a resumed run continues seamlessly.  which = 0 -> m, 1 -> v; names / shapes as
+ * fisr_get_param.  fisr_adam_set_steps sets t (beta1_power = beta1^t) without touching the moments. */
+int fisr_get_adam_slot(fisr_ctx* ctx, const char* name, int which, float* h_data, size_t count);
+int fisr_set_adam_slot(fisr_ctx* ctx, const char* name, int which, const float* h_data, size_t count);
+int fisr_adam_set_steps(fisr_ctx* ctx, long long step);
 
 /* ---- introspection / test hooks ---------------------------------------------------------------------------- */
 /* Single 3x3 SAME conv through the production kernel (ops.py:7-11 plus the fused epilogue):

@@ -9,6 +9,10 @@ from oracle import loss_oracle as L
 
 pytestmark = pytest.mark.gpu
 
+# whole-gradient / median per-tensor relative L2 error against float64 autograd (torch's fp32 autograd measures 1e-5 .. 3e-5)
+GRAD_TOL_DEFAULT = 1e-3
+GRAD_TOL_EXACT = 5e-4
+
 
 def _batch(B, h, w, seed):
     g = torch.Generator().manual_seed(seed)
@@ -56,6 +60,39 @@ def test_gradients_match_float64_autograd(engine, B, h, w, seed):
     assert errs[worst] < 3e-2, (worst, errs[worst])              # flipped ReLU gates on a 4x4 map (see _grad_errors)
     # and every tensor got a gradient (no dead branch): the oracle's is non-zero everywhere
     assert all(np.abs(v).max() > 0 for v in engine.get_grads().values())
+
+
+def test_gradients_at_config3_patch_size(engine):
+    """BASELINE configs[2] patch size (LR 192x192, HR label 384x384; batch 1 of its 16): all 276 gradients against float64
+    autograd, in the default and the exact wgrad mode, next to what torch's own fp32 autograd (the reference-class noise
+    floor) delivers on the same graph.  ~1 min of host time for the float64 oracle."""
+    engine.set_precision("f16x3")
+    params = O.init_params(91)
+    engine.set_params(params)
+    batch = _batch(1, 192, 192, 92)
+    p64 = {k: v.double() for k, v in params.items()}
+    ref_s, _, ref_g = L.training_forward(p64, *[t.double() for t in batch], grad=True)
+    _, _, g32 = L.training_forward(params, *batch, grad=True)
+    e32, tot32 = _grad_errors({k: v.numpy() for k, v in g32.items()}, ref_g)
+    dev = [t.cuda() for t in batch]
+    got_s = engine.train_backward(*dev)
+    for k in L.SCALAR_NAMES:
+        assert abs(got_s[k] - float(ref_s[k])) < 1e-4 * max(1.0, abs(float(ref_s[k]))), k
+    e_fast, tot_fast = _grad_errors(engine.get_grads(), ref_g)
+    engine.set_wgrad_exact(True)
+    try:
+        engine.train_backward(*dev)
+        e_exact, tot_exact = _grad_errors(engine.get_grads(), ref_g)
+    finally:
+        engine.set_wgrad_exact(False)
+    med = lambda e: float(np.median(list(e.values())))
+    print("192x192 whole-gradient rel-L2: default %.3e, exact wgrad %.3e, torch fp32 %.3e" % (tot_fast, tot_exact, tot32))
+    print("per-tensor rel-L2 median / worst: default %.3e / %.3e, exact %.3e / %.3e, torch fp32 %.3e / %.3e" %
+          (med(e_fast), max(e_fast.values()), med(e_exact), max(e_exact.values()), med(e32), max(e32.values())))
+    assert tot_fast < GRAD_TOL_DEFAULT and med(e_fast) < GRAD_TOL_DEFAULT
+    assert tot_exact < GRAD_TOL_EXACT and med(e_exact) < GRAD_TOL_EXACT
+    # no tensor may be far worse than the rest (a wrong tap / plane would show as O(1))
+    assert max(e_exact.values()) < 20 * GRAD_TOL_EXACT, max(e_exact, key=e_exact.get)
 
 
 def test_exact_wgrad_mode(engine):

@@ -54,7 +54,12 @@ def test_train_two_epochs_checkpoint_and_resume(engine, tmp_path, capsys):
     net.global_step = 3; assert net._lr(1) == pytest.approx(1e-5)
     net.global_step = 5; assert net._lr(2) == pytest.approx(1e-6)
     ckpt = os.path.join(d, "ckpt", "FISRnet_exp1")
-    assert os.path.exists(os.path.join(ckpt, "FISRnet-4.npz")) and os.path.exists(os.path.join(ckpt, "checkpoint"))
+    # a TensorFlow V2 bundle under the Saver's names (FISRnet.py:1092-1099), with the optimizer state
+    assert os.path.exists(os.path.join(ckpt, "FISRnet-4.index")) and os.path.exists(os.path.join(ckpt, "checkpoint"))
+    from fisr_b200 import tf_checkpoint as T
+    names = T.list_variables(os.path.join(ckpt, "FISRnet-4"))
+    assert "FISRnet/level_1/enc/level_0/conv/0/w/Adam_1" in names and "beta1_power" in names and T.GLOBAL_STEP_NAME in names
+    assert len(names) == 3 * 276 + 3
     trained = engine.get_params()
     # the weights moved, and a fresh object resumes from the checkpoint at step 4 with nothing left to do
     from fisr_b200.init import xavier_params
@@ -65,7 +70,75 @@ def test_train_two_epochs_checkpoint_and_resume(engine, tmp_path, capsys):
     ok, step = net2.load(net2.checkpoint_dir)
     assert ok and step == 4
     assert all(np.array_equal(engine.get_params()[n], trained[n]) for n in trained)
+    assert net2._adam_restored and engine.adam_steps == 4
     engine.set_precision("f16x3")
+
+
+def _batch(B, h, w, seed):
+    g = torch.Generator().manual_seed(seed)
+    data = torch.rand(B, h, w, 15, generator=g)
+    flow = (torch.randn(B, h, w, 16, generator=g) * 4 / 96 / 2).clamp(-1, 1)
+    flow2 = (torch.randn(B, h, w, 8, generator=g) * 8 / 96 / 2).clamp(-1, 1)
+    warp = torch.rand(B, h, w, 24, generator=g)
+    warp2 = torch.rand(B, h, w, 12, generator=g)
+    label = torch.rand(B, 2 * h, 2 * w, 21, generator=g)
+    return [t.cuda() for t in (data, flow, flow2, warp, warp2, label)]
+
+
+def test_resume_is_seamless(engine, tmp_path):
+    """Saver.restore brings back m, v and the beta powers (FISRnet.py:1101-1115): step 3 after a save / clobber / load must be
+    bit-identical to step 3 of the uninterrupted run; restarting Adam from zero moments instead moves the weights elsewhere."""
+    from fisr_b200 import FISRnet
+    from fisr_b200.init import xavier_params
+    engine.set_precision("f16x3")
+    net = FISRnet(engine, _args(str(tmp_path)))
+    engine.set_params(xavier_params(seed=5, bias_std=0.01))
+    net._initialized = True
+    engine.adam_reset(0)
+    for t in (1, 2):
+        engine.train_step(*_batch(1, 32, 32, 80 + t), lr=1e-4)
+    net.save_checkpoint(net.checkpoint_dir, 2)
+    engine.train_step(*_batch(1, 32, 32, 83), lr=1e-4)
+    straight = engine.get_params()
+
+    engine.set_params(xavier_params(seed=6, bias_std=0.0))            # clobber weights and optimizer state
+    engine.adam_reset(0)
+    ok, step = net.load(net.checkpoint_dir)
+    assert ok and step == 2 and net._adam_restored and engine.adam_steps == 2
+    engine.train_step(*_batch(1, 32, 32, 83), lr=1e-4)
+    resumed = engine.get_params()
+    assert all(np.array_equal(resumed[k], straight[k]) for k in straight)
+
+    net.load(net.checkpoint_dir)
+    engine.adam_reset(0)                                              # what round 1 did: zero moments after a resume
+    engine.train_step(*_batch(1, 32, 32, 83), lr=1e-4)
+    cold = engine.get_params()
+    k = "FISRnet/level_3/dec/level_0/conv/0/w"
+    assert np.abs(cold[k] - straight[k]).max() > 10 * np.abs(resumed[k] - straight[k]).max() + 1e-7
+    engine.adam_reset(0)
+
+
+def test_train_step_rescales_on_overflow(engine):
+    """Dynamic loss scaling: an absurd scale overflows the fp16 gradient planes; fisr_train_backward reports it, fisr_train_step
+    lowers the scale and still takes the step."""
+    import fisr_b200
+    from fisr_b200.init import xavier_params
+    engine.set_precision("f16x3")
+    engine.set_params(xavier_params(seed=7, bias_std=0.01))
+    engine.adam_reset(0)
+    batch = _batch(1, 32, 32, 90)
+    try:
+        engine.set_loss_scale(2.0 ** 40)
+        with pytest.raises(fisr_b200.FisrError, match="non-finite gradient"):
+            engine.train_backward(*batch)
+        before = engine.get_params()["FISRnet/level_3/SR/conv/2/w"].copy()
+        s = engine.train_step(*batch, lr=1e-4)
+        assert np.isfinite(s["total_loss"]) and engine.adam_steps == 1
+        after = engine.get_params()["FISRnet/level_3/SR/conv/2/w"]
+        assert np.isfinite(after).all() and np.abs(after - before).max() > 1e-6
+    finally:
+        engine.set_loss_scale(0.0)
+        engine.adam_reset(0)
 
 
 def test_validate_matches_torch(engine, tmp_path):

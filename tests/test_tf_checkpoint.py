@@ -129,3 +129,37 @@ def test_latest_checkpoint_state_file(tmp_path):
     (d / "checkpoint").write_text('model_checkpoint_path: "FISRnet-122000"\nall_model_checkpoint_paths: "FISRnet-122000"\n')
     assert T.latest_checkpoint(str(d)) == str(d / "FISRnet-122000")
     assert T.latest_checkpoint(str(tmp_path)) is None
+
+
+def test_training_checkpoint_round_trips_optimizer_state(tmp_path):
+    """What tf.train.Saver stores for a TRAINING run (FISRnet.py:489-491,1092-1099): weights + <var>/Adam + <var>/Adam_1 +
+    beta powers + the global step.  An inference-only export (weights alone) reports no optimizer state."""
+    from fisr_b200.engine import param_inventory
+    rng = np.random.default_rng(3)
+    small = lambda shape: (rng.standard_normal(shape) * 1e-3).astype(np.float32) if np.prod(shape) < 40000 else np.zeros(shape, np.float32)
+    params = {k: small(s) for k, s in param_inventory().items()}
+    adam = {"m": {k: small(s) for k, s in param_inventory().items()}, "v": {k: np.abs(small(s)) for k, s in param_inventory().items()}, "t": 37}
+    prefix = str(tmp_path / "FISRnet_exp1" / "FISRnet-37")
+    T.save_fisrnet_checkpoint(prefix, params, adam, global_step=37)
+    listed = T.list_variables(prefix)
+    assert len(listed) == 3 * 276 + 3 and listed[T.GLOBAL_STEP_NAME] == (T.DT_INT32, ())
+    b1 = T.load_checkpoint(prefix, ["beta1_power", "beta2_power", T.GLOBAL_STEP_NAME])
+    assert float(b1["beta1_power"]) == pytest.approx(0.9 ** 37, rel=1e-6) and float(b1["beta2_power"]) == pytest.approx(0.999 ** 37, rel=1e-6)
+    assert int(b1[T.GLOBAL_STEP_NAME]) == 37
+    m, v, t = T.fisrnet_adam_state(prefix)
+    assert t == 37
+    k = "FISRnet/level_2/SR/conv/2/w"
+    assert np.array_equal(m[k], adam["m"][k]) and np.array_equal(v[k], adam["v"][k])
+    w = T.fisrnet_weights(prefix)
+    assert np.array_equal(w[k], params[k])
+    prefix2 = str(tmp_path / "export" / "FISRnet-122000")
+    T.save_fisrnet_checkpoint(prefix2, params, None, global_step=122000)
+    assert T.fisrnet_adam_state(prefix2) is None and len(T.list_variables(prefix2)) == 277
+    # a corrupted small tensor is caught by the load path FISRnet.load uses (crc32c of the index and of tensors <= 64 KB)
+    path = prefix2 + ".data-00000-of-00001"
+    raw = bytearray(open(path, "rb").read())
+    off = T.parse_entry(T.read_table(prefix2 + ".index")[b"FISRnet/level_1/SR/conv/2/b"])["offset"]
+    raw[off] ^= 0x40
+    open(path, "wb").write(bytes(raw))
+    with pytest.raises(ValueError, match="crc32c"):
+        T.fisrnet_weights(prefix2)

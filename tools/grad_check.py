@@ -22,6 +22,8 @@ batch = (data, flow, flow2, warp, warp2, label)
 params = O.init_params(seed)
 eng = fisr_b200.Engine(0)
 eng.set_params(params)
+if os.environ.get("FISR_WGRAD_EXACT") == "1":
+    eng.set_wgrad_exact(True)
 p64 = {k: v.double() for k, v in params.items()}
 ref_s, _, ref_g = L.training_forward(p64, *[t.double() for t in batch], grad=True)
 got_s = eng.train_backward(*[t.cuda() for t in batch])
