@@ -109,6 +109,9 @@ struct ConvArgs {
     int tma_out;              // f16f8 activation-only epilogue: store through the output tensor maps (TMA) instead of the LSU
     int ps_cout;              // > 0: the output is depth_to_space'd on the fly -- GEMM column ch = (2i+j) * ps_cout + co is channel co
                               // of output pixel (2y+i, 2x+j) (the conv/2 heads evaluated at input resolution, see fisr_api.cu)
+    __half* pool_out;         // fused 2x2 max-pool of the (post-ReLU) activation output: [N, H/2, W/2, pool_cs] planes, or nullptr
+    unsigned long long pool_plane;
+    int pool_cs;
     const __half* mask;       // dgrad: hi plane of the forward activation whose ReLU gradient gates this output, or nullptr
     int mask_cs, mask_off;
 };

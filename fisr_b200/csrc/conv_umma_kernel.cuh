@@ -689,9 +689,13 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                         const uint32_t r = rd_row + 8 * i;
                         vals[i] = lds128(stg + r * 64 + ((rd_grp ^ ((r >> 1) & 3)) << 4));
                     }
+                    // fused 2x2 max-pool (closing conv of an encoder level, ops.py:52-54): post-ReLU values of this lane's 4 rows
+                    [[maybe_unused]] float pf[4][4];
+                    const bool pooling = (EPI == EPI_RES) && a.pool_out != nullptr;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float4 val = vals[i];
+                        if (EPI == EPI_RES) { pf[i][0] = pf[i][1] = pf[i][2] = pf[i][3] = 0.f; }
                         if ((vmask >> i) & 1) {
                             float f0, f1, f2, f3;
                             if (F8) {
@@ -710,6 +714,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                             if (EPI & EPI_RAW) *reinterpret_cast<float4*>(a.out_raw + o_raw[i] + c0) = make_float4(f0, f1, f2, f3);
                             f0 = fmaxf(f0, relu_floor); f1 = fmaxf(f1, relu_floor);
                             f2 = fmaxf(f2, relu_floor); f3 = fmaxf(f3, relu_floor);
+                            if (EPI == EPI_RES) { pf[i][0] = f0; pf[i][1] = f1; pf[i][2] = f2; pf[i][3] = f3; }
                             uint32_t h01, l01, h23, l23;
                             split2_f32(f0, f1, h01, l01);
                             split2_f32(f2, f3, h23, l23);
@@ -726,6 +731,35 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                                 uint8_t* q = f8_row_ptr(d + a.act_plane);
                                 *reinterpret_cast<uint32_t*>(q) = f8_pack_lo4(l01, l23);
                                 *reinterpret_cast<uint32_t*>(q + 64) = f8_pack_hi4(h01, h23);
+                            }
+                        }
+                    }
+                    if constexpr (EPI == EPI_RES) {
+                        if (pooling) {
+                            // rows (0,1) and (2,3) of this lane, columns x and x^1 of the lane 4 further: image sizes and tile
+                            // origins are even, so a 2x2 block is inside the image as a whole or not at all
+                            float m[2][4];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                m[0][c] = fmaxf(pf[0][c], pf[1][c]);
+                                m[1][c] = fmaxf(pf[2][c], pf[3][c]);
+                                m[0][c] = fmaxf(m[0][c], __shfl_xor_sync(0xffffffffu, m[0][c], 4));
+                                m[1][c] = fmaxf(m[1][c], __shfl_xor_sync(0xffffffffu, m[1][c], 4));
+                            }
+                            const int odd = rd_row & 1;                  // even columns store row pair 0, odd columns row pair 1
+                            if ((vmask >> (2 * odd)) & 1) {
+                                const int py = (t.y0 + ch_y0 + q4 * 4 + 2 * odd) >> 1, px = (t.x0 + ch_x0 + static_cast<int>(rd_row)) >> 1;
+                                __half* d = a.pool_out + (static_cast<size_t>(t.n * (a.H >> 1) + py) * (a.W >> 1) + px) * a.pool_cs + cg_lane + c0;
+                                uint32_t h01, l01, h23, l23;
+                                split2_f32(odd ? m[1][0] : m[0][0], odd ? m[1][1] : m[0][1], h01, l01);
+                                split2_f32(odd ? m[1][2] : m[0][2], odd ? m[1][3] : m[0][3], h23, l23);
+                                *reinterpret_cast<uint2*>(d) = make_uint2(h01, h23);
+                                if (PLANES == 2) *reinterpret_cast<uint2*>(d + a.pool_plane) = make_uint2(l01, l23);
+                                if (F8) {
+                                    uint8_t* q = f8_row_ptr(d + a.pool_plane);
+                                    *reinterpret_cast<uint32_t*>(q) = f8_pack_lo4(l01, l23);
+                                    *reinterpret_cast<uint32_t*>(q + 64) = f8_pack_hi4(h01, h23);
+                                }
                             }
                         }
                     }

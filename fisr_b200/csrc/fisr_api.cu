@@ -373,6 +373,8 @@ struct Builder {
         int act_cs = 0, act_off0 = 0, act_off1 = 0, act_split = 0;
         bool relu = true, d2s = false, scalar = false;
         bool ps = false;          // conv/2 head at input resolution: output columns are (sub-pixel, channel) pairs
+        ActBuf pool;              // fused 2x2 max-pool of the activation output (closing conv of an encoder level), pool_cs channels
+        int pool_cs = 0;
         ActBuf mask;              // dgrad: ReLU gate (hi plane of a forward activation), mask_cs channels per pixel
         int mask_cs = 0, mask_off = 0;
         bool s2d = false;         // dgrad of conv/2: store space-to-depth into a 256-channel buffer
@@ -435,10 +437,12 @@ struct Builder {
         a.act_cs = o.act_cs; a.act_off0 = o.act_off0; a.act_off1 = o.act_off1; a.act_split = o.act_split;
         a.act_relu = o.relu; a.act_d2s = o.d2s; a.scalar_out = o.scalar;
         a.mask = o.mask.p; a.mask_cs = o.mask_cs; a.mask_off = o.mask_off;
+        a.pool_out = o.pool.p; a.pool_plane = o.pool.plane; a.pool_cs = o.pool_cs;
         a.err = ctx->d_err;
         a.N = N; a.H = H; a.W = W;
         L.epi = o.scalar ? 0 : ((o.res ? 1 : 0) | (o.raw ? 2 : 0) | (o.d2s ? 4 : 0) | (o.mask.p ? 8 : 0) | (o.s2d ? 16 : 0));
         if (!o.scalar && !o.act.p) { rc = fail(ctx, FISR_E_INVALID, "conv %s: the wide epilogue always writes an activation", name.c_str()); return false; }
+        if (o.pool.p && (L.epi != 1 || (H & 1) || (W & 1))) { rc = fail(ctx, FISR_E_INVALID, "conv %s: the fused max-pool needs the residual epilogue and even H, W", name.c_str()); return false; }
         if (o.s2d && (p.cout_pad != 64 || (H & 1) || (W & 1))) { rc = fail(ctx, FISR_E_INVALID, "conv %s: space-to-depth needs 64 output channels and even H, W", name.c_str()); return false; }
         {   // the epilogue indexes with 32-bit element offsets
             const double px = static_cast<double>(N) * H * W * ((o.d2s || o.ps) ? 4 : 1);
@@ -467,7 +471,8 @@ struct Builder {
         {   // algorithmic HBM bytes: input + weights once, every output / residual once
             const double px = static_cast<double>(N) * H * W, eb = 2.0 * act_planes(plan->planes);
             op.bytes = px * p.KB * 64 * eb + 9.0 * p.KB * 64 * p.cout_pad * eb + (o.res ? px * p.cout * 4 : 0) +
-                       (o.raw ? px * p.cout * 4 : 0) + (o.act.p ? px * p.cout * eb : 0) + (o.mask.p ? px * p.cout * 2 : 0);
+                       (o.raw ? px * p.cout * 4 : 0) + (o.act.p ? px * p.cout * eb : 0) + (o.mask.p ? px * p.cout * 2 : 0) +
+                       (o.pool.p ? px / 4 * p.cout * eb : 0);
         }
         snprintf(op.name, sizeof op.name, "%s", name.c_str());
         return true;
@@ -500,7 +505,7 @@ struct Builder {
     // res_block (ops.py:39-44) x2 + trailing ReLU, given n0 (raw fp32) and relu(n0) (act): used by enc / dec levels.
     // Final activation relu(n2) goes to `dst` (channel offset dst_off of a dst_cs-channel buffer).
     ResRec two_res_blocks(const std::string& p, ActBuf a0, const float* n0, int c, int N, int H, int W, ActBuf dst,
-                          int dst_cs, int dst_off) {
+                          int dst_cs, int dst_off, ActBuf pooled = ActBuf{}) {
         ActBuf a1 = act(N, H, W, c), a2 = act(N, H, W, c), a3 = act(N, H, W, c);
         float* n1 = f32(N, H, W, c);
         ConvOut o;
@@ -511,6 +516,7 @@ struct Builder {
         o = ConvOut{}; o.act = a3; o.act_cs = c;
         conv(P(p + "/res_block/1/conv/0"), a2, c, 0, N, H, W, o, p + "/res_block/1/conv/0");
         o = ConvOut{}; o.res = n1; o.res_cs = c; o.act = dst; o.act_cs = dst_cs; o.act_off1 = dst_off;
+        o.pool = pooled; o.pool_cs = c;              // encoder levels: max_pool(skip) written by the same epilogue (ops.py:52-54)
         conv(P(p + "/res_block/1/conv/1"), a3, c, 0, N, H, W, o, p + "/res_block/1/conv/1");
         return ResRec{a1, a2, a3};
     }
@@ -522,9 +528,10 @@ struct Builder {
         float* n0 = f32(N, H, W, c);
         ConvOut o; o.raw = n0; o.raw_cs = c; o.act = a0; o.act_cs = c;
         conv(P(p + "/conv/0"), x, x_cs, 0, N, H, W, o, p + "/conv/0");
-        const ResRec rb = two_res_blocks(p, a0, n0, c, N, H, W, cat, 2 * c, c);
         ActBuf pooled = act(N, H / 2, W / 2, c);
-        pool(cat, 2 * c, c, pooled, N, H, W, c);
+        static const bool fuse_pool = !(getenv("FISR_NO_POOL_FUSION") && getenv("FISR_NO_POOL_FUSION")[0] == '1');
+        const ResRec rb = two_res_blocks(p, a0, n0, c, N, H, W, cat, 2 * c, c, fuse_pool ? pooled : ActBuf{});
+        if (!fuse_pool) pool(cat, 2 * c, c, pooled, N, H, W, c);
         *rec = EncRec{p, x, x_cs, c, H, W, a0, cat, pooled, rb};
         return pooled;
     }
@@ -1961,17 +1968,19 @@ int fisr_adam_apply(fisr_ctx* ctx, float lr, float beta1, float beta2, float eps
 }
 
 // One `sess.run(optim)`.  Dynamic loss scaling: when the fp16 gradient planes overflow, the update is skipped, the scale is
-// divided by 8 and the step is retried (up to 4 times); the lowered scale stays in force for the following steps.
+// lowered (to the default, then by 16 per retry, up to 5 retries) and the step is retried; the lowered scale stays in force for the following steps.
 int fisr_train_step(fisr_ctx* ctx, const float* d_data, const float* d_flow, const float* d_flow_ss2, const float* d_warp,
                     const float* d_warp_ss2, const float* d_label, int B, int h, int w, const float* lambdas, float lr,
                     float* h_out, void* stream) {
     if (!ctx) return FISR_E_INVALID;
     int rc = FISR_OK;
-    for (int attempt = 0; attempt < 5; ++attempt) {
+    for (int attempt = 0; attempt < 6; ++attempt) {
         rc = fisr_train_backward(ctx, d_data, d_flow, d_flow_ss2, d_warp, d_warp_ss2, d_label, B, h, w, lambdas, h_out, stream);
-        if (rc != FISR_E_OVERFLOW || attempt == 4) break;
+        if (rc != FISR_E_OVERFLOW || attempt == 5) break;
         const float cur = fisr_get_loss_scale(ctx, B, h, w);
-        if ((rc = fisr_set_loss_scale(ctx, cur / 8.f)) != FISR_OK) return rc;
+        const float def = static_cast<float>(std::exp2(std::floor(std::log2(static_cast<double>(B) * (2.0 * h) * (2.0 * w) * 3.0))));
+        // an override above the default falls back to the default first, then the scale drops by 16 per retry
+        if ((rc = fisr_set_loss_scale(ctx, cur > def ? def : cur / 16.f)) != FISR_OK) return rc;
     }
     if (rc != FISR_OK) return rc;
     Guard guard(ctx->device);

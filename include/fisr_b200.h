@@ -146,7 +146,7 @@ int fisr_train_step(fisr_ctx* ctx, const float* d_data, const float* d_flow, con
 /* Gradients travel through the network as fp16 (hi, lo) planes multiplied by a power-of-two loss scale (default:
  * 2^floor(log2(B*2h*2w*3)), divided out by the weight-gradient reduction).  0 restores the default; a non-finite gradient
  * makes fisr_train_backward return FISR_E_OVERFLOW.  fisr_train_step scales dynamically: on overflow it skips the update,
- * divides the scale by 8 and retries the step (up to 4 times); the lowered scale stays in force. */
+ * lowers the scale (to the default, then by 16 per retry, up to 5 retries) and repeats the step; the lowered scale stays in force. */
 int fisr_set_loss_scale(fisr_ctx* ctx, float scale);
 float fisr_get_loss_scale(fisr_ctx* ctx, int B, int h, int w);
 /* Weight gradients of layers with >= 16384 pixels multiply dy (hi, lo) by the hi plane of the forward activation only

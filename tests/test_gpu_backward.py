@@ -9,9 +9,13 @@ from oracle import loss_oracle as L
 
 pytestmark = pytest.mark.gpu
 
-# whole-gradient / median per-tensor relative L2 error against float64 autograd (torch's fp32 autograd measures 1e-5 .. 3e-5)
-GRAD_TOL_DEFAULT = 1e-3
-GRAD_TOL_EXACT = 5e-4
+# Whole-gradient / median per-tensor relative L2 error against float64 autograd at the config-3 patch size.  Measured on B200:
+# 1.0e-4 in both wgrad modes, next to 2.3e-5 for torch's own fp32 autograd on the same graph: 4.4x the reference-class noise
+# floor.  The floor is set by ReLU gates that flip within forward rounding (error ~ sqrt(forward max-abs error)): the f16x3
+# forward is 1-2e-5 from float64 where fp32 is 5e-7, because the tcgen05 accumulator truncates (tools/accum_probe.py:
+# -1.6e-5 relative after 864 accumulating MMAs) -- not by the gradient planes or by dropping x's lo plane.
+GRAD_TOL_DEFAULT = 3e-4
+GRAD_TOL_EXACT = 3e-4
 
 
 def _batch(B, h, w, seed):
