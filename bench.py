@@ -193,42 +193,86 @@ def run_b200(args):
     frames, flow, warp = (torch.from_numpy(a).to(dev) for a in (frames_h, flow_h, warp_h))
     my_units = sharding.rank_units(rank, world, B, T)
     oh, ow, _ = eng.canvas_shape(H_IN, W_IN, GRID)
-    # two buffer sets: the all-gather of step k runs on NCCL's stream while the kernels of step k+1 already write the other set
-    local_out = [torch.zeros((len(my_units), oh // GRID[0], ow // GRID[1], 9), dtype=torch.uint8, device=dev) for _ in range(2)]
-    gathered = [torch.zeros((B * T, oh // GRID[0], ow // GRID[1], 9), dtype=torch.uint8, device=dev) if world > 1 else None
-                for _ in range(2)]
-    pending = [None, None]           # (gathered tensor, NCCL work) of the step that last used each buffer set
-    state = {"k": 0}
-
-    def finish(slot):
-        """Frames of the step that used buffer set `slot`: waits for its all-gather (stream-ordered) and pastes the tiles."""
-        g, work = pending[slot]
-        pending[slot] = None
-        if work is not None:
-            work.wait()
-        return sharding.assemble_frames(g, B, GRID)                 # [B, 2048, 3840, 9] uint8 on every rank
-
-    def step():
-        """One step = this rank's 4 tile units + the all-gather of everybody's tiles + frame assembly.  The collective of step k
-        overlaps the kernels of step k+1; the frames returned are those of the PREVIOUS step (None on the first call), and
-        drain() returns the last ones, so K timed steps still complete K gathers and K assemblies inside the timed region."""
-        slot = state["k"] & 1
-        state["k"] += 1
-        eng.units(frames, flow, warp, my_units, GRID, layout="units", out=local_out[slot])
-        pending[slot] = sharding.gather_units(local_out[slot], world, out=gathered[slot], async_op=True)
-        return finish(slot ^ 1) if pending[slot ^ 1] is not None else None
-
-    def drain():
-        out = None
-        for slot in ((state["k"] & 1), (state["k"] & 1) ^ 1):        # older step first
-            if pending[slot] is not None:
-                out = finish(slot)
-        return out
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    class Exchange:
+        """One step = this rank's tile units computed straight into its own frames [B,2048,3840,9] + the exchange that completes
+        the frames on every rank.  "p2p" (default): finished tiles are pushed into every peer's frames by the copy engines over
+        NVLink peer memory (sharding.PeerFrames), overlapping the next step's kernels with no SM-resident collective.  "nccl":
+        unit-major send buffer, one ncclAllGather per step (async, second buffer set), frames re-assembled by a strided copy."""
+
+        def __init__(self, n_windows, units, mode):
+            self.B, self.units, self.k = n_windows, units, 0
+            self.mode = mode if world > 1 else "single"
+            self.peer = None
+            if self.mode == "p2p":
+                try:
+                    self.peer = sharding.PeerFrames(eng, rank, world, n_windows, oh, ow)
+                except Exception as e:                     # CUDA IPC unavailable in this container: fall back to NCCL
+                    print(f"[bench] peer-memory exchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
+                    self.mode = "nccl"
+                ok = torch.tensor([1 if self.mode == "p2p" else 0], device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok.item()) == 0 and self.mode == "p2p":
+                    self.peer.close()
+                    self.peer, self.mode = None, "nccl"
+            if self.mode == "single":
+                self.out = [torch.zeros((n_windows, oh, ow, 9), dtype=torch.uint8, device=dev)]
+            elif self.mode == "nccl":
+                shp = (oh // GRID[0], ow // GRID[1], 9)
+                self.local_out = [torch.zeros((len(units),) + shp, dtype=torch.uint8, device=dev) for _ in range(2)]
+                self.gathered = [torch.zeros((n_windows * T,) + shp, dtype=torch.uint8, device=dev) for _ in range(2)]
+                self.pending = [None, None]
+                self.last = None
+
+        def step(self, fr, fl, wp):
+            slot = self.k & 1
+            self.k += 1
+            if self.mode == "single":
+                eng.units(fr, fl, wp, self.units, GRID, layout="frames", out=self.out[0])
+            elif self.mode == "p2p":
+                eng.units(fr, fl, wp, self.units, GRID, layout="frames", out=self.peer.local(slot))
+                self.peer.publish(slot, self.units, GRID)
+            else:
+                eng.units(fr, fl, wp, self.units, GRID, layout="units", out=self.local_out[slot])
+                self.pending[slot] = sharding.gather_units(self.local_out[slot], world, out=self.gathered[slot], async_op=True)
+                if self.pending[slot ^ 1] is not None:
+                    self._finish(slot ^ 1)
+
+        def _finish(self, slot):
+            g, work = self.pending[slot]
+            self.pending[slot] = None
+            if work is not None:
+                work.wait()
+            self.last = sharding.assemble_frames(g, self.B, GRID)
+
+        def drain(self):
+            """Frames of the last step, complete on this rank once every rank has drained (the caller's barrier)."""
+            if self.mode == "single":
+                return self.out[0]
+            if self.mode == "p2p":
+                self.peer.drain()
+                return self.peer.local((self.k - 1) & 1)
+            for slot in ((self.k & 1), (self.k & 1) ^ 1):                # older step first
+                if self.pending[slot] is not None:
+                    self._finish(slot)
+            return self.last
+
+        def close(self):
+            if self.peer is not None:
+                self.peer.close()
+
+    ex = Exchange(B, my_units, args.exchange)
+
+    def step():
+        ex.step(frames, flow, warp)
+
+    def drain():
+        return ex.drain()
 
     warm, steps = max(3, args.warmup), max(1, args.steps)
     for _ in range(warm):
@@ -253,7 +297,36 @@ def run_b200(args):
     t_s = float(t_ms.item()) / 1e3
     clocks = sampler.stop() if sampler else None
     value = 2.0 * B * steps / t_s
-    checksum = int(out.sum().item())                                # forces / proves a real result
+    checksum = int(out.sum().item())                                # forces / proves a real result (complete frames: after the barrier)
+    exchange_mode = ex.mode
+
+    # ---- strong scaling / latency configuration: the tiles of ONE window spread over the ranks (2 windows at N = 8)
+    strong = None
+    if world > 1:
+        B2 = max(1, world // T)
+        units2 = sharding.rank_units(rank, world, B2, T)
+        ex2 = Exchange(B2, units2, ex.mode)
+        fr2, fl2, wp2 = frames[:B2].contiguous(), flow[:B2].contiguous(), warp[:B2].contiguous()
+        for _ in range(3):
+            ex2.step(fr2, fl2, wp2)
+        ex2.drain()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n2 = max(4, min(steps, 10))
+        s0.record()
+        for _ in range(n2):
+            ex2.step(fr2, fl2, wp2)
+        out2 = ex2.drain()
+        s1.record()
+        barrier()
+        t2 = torch.tensor([s0.elapsed_time(s1)], device=dev)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ms2 = float(t2.item()) / n2
+        strong = {"scaling": "strong", "windows_per_step": B2, "tiles_per_rank_per_step": len(units2), "ms_per_step": ms2,
+                  "value": 2.0 * B2 / (ms2 * 1e-3), "unit": "frames/s", "output_checksum": int(out2.sum().item()),
+                  "note": "latency configuration: every window's 4 tiles on 4 different ranks; ms_per_step is the time from a "
+                          "window's inputs in HBM to its complete frames on every rank (pipelined over steps)"}
+        ex2.close()
 
     # ---- e2e: host buffers -> fisr_window_host -> host canvas, each rank its own window (window-level sharding)
     pin = [torch.from_numpy(a[rank % B]).pin_memory() for a in (frames_h, flow_h, warp_h)]
@@ -333,7 +406,9 @@ def run_b200(args):
                 "config": {"workload": WORKLOAD, "windows_per_step": B, "units_per_rank_per_step": len(my_units),
                            "input": f"{B} x (frames u8 [1080,1920,9] + flow f32 [..,8] + warp f32 [..,12])",
                            "output": f"{B} x uint8 [2048,3840,9]", "precision": eng.precision, "weights": "random-init (Xavier)",
-                           "sharding": "tile-major (window,tile) units, one NCCL all-gather of uint8 tiles per step" if world > 1 else "single GPU, 4 tiles batched",
+                           "sharding": {"single": "single GPU, 4 tiles batched",
+                                        "p2p": "tile-major (window,tile) units computed into frame layout; finished tiles pushed to every peer's frames by the copy engines over NVLink peer memory (all-gather without an SM-resident collective)",
+                                        "nccl": "tile-major (window,tile) units, one NCCL all-gather of uint8 tiles per step + strided re-assembly"}[exchange_mode],
                            "l2": "inputs (185 MB/window) and the 35 GB activation workspace exceed the 126 MB L2; no flush needed",
                            "windows_per_s": B * steps / t_s, "conv_gflop_per_window": info["flops"] / 1e9,
                            "mma_row_efficiency": info["mma_row_efficiency"], "output_checksum": checksum},
@@ -343,8 +418,9 @@ def run_b200(args):
                         "output_checksum": e2e_checksum},
                 "gpu_launches": int(launches),
                 "roofline": roofline,
-                "cpu_baseline": cpu_baseline, "extra": extra}
+                "cpu_baseline": cpu_baseline, "extra": extra, "strong_scaling": strong}
     barrier()
+    ex.close()
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -372,24 +448,22 @@ def measure_extras(eng, dev, peaks, bench_precision):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    # ---- flow warp (FISR_for_video_warp_img_with_flo.py:61-67): 1080p, 8 buffer sets (384 MB) cycled so that nothing stays in L2
+    # ---- flow warp (FISR_for_video_warp_img_with_flo.py:61-67,112-128): the 16 warps of a 9-frame 1080p clip in one launch
+    # (fisr_warp_batch_device): 763 MB of traffic per launch, far beyond the 126 MB L2
     g = torch.Generator(device="cpu").manual_seed(5)
-    sets = 8
-    yuv = [torch.randint(0, 256, (H_IN, W_IN, 3), dtype=torch.uint8, generator=g).to(dev) for _ in range(sets)]
-    flo = [(torch.randn(H_IN, W_IN, 2, generator=g) * 4).to(dev) for _ in range(sets)]
-    k = {"i": 0}
-
-    def warp_once():
-        i = k["i"] % sets
-        k["i"] += 1
-        eng.warp(yuv[i], flo[i], 0.5, 1.0 / 255.0)
-    ms = timed(warp_once, 8, 64)
-    px = H_IN * W_IN
+    nfr = 9
+    jobs = 2 * (nfr - 1)
+    yuv = torch.randint(0, 256, (nfr, H_IN, W_IN, 3), dtype=torch.uint8, generator=g).to(dev)
+    flo = (torch.randn(jobs, H_IN, W_IN, 2, generator=g) * 4).to(dev)
+    src = [fr + 1 - (j & 1) for fr in range(nfr - 1) for j in range(2)]
+    ms = timed(lambda: eng.warp_batch(yuv, flo, src, 0.5, 1.0 / 255.0), 3, 10)
+    px = jobs * H_IN * W_IN
     by = px * (3 + 8 + 12)                      # u8 YUV source + f32 flow + f32 output, each once
-    out["warp_yuv_1080p"] = {"ms": ms, "algorithmic_bytes": by, "bytes_per_px": 23, "gbs": by / ms / 1e6,
+    out["warp_yuv_1080p"] = {"ms_per_launch": ms, "warps_per_launch": jobs, "us_per_1080p_warp": ms * 1e3 / jobs,
+                             "algorithmic_bytes": by, "bytes_per_px": 23, "gbs": by / ms / 1e6,
                              "frac_of_hbm_peak": by / ms / 1e6 / peak_gb,
                              "gbs_at_reference_layout_32B_per_px": px * 32 / ms / 1e6,
-                             "note": "64 launches over 8 rotating 1080p buffer sets (384 MB > L2), CUDA events, includes the output allocation of Engine.warp"}
+                             "note": "Engine.warp_batch: 16 warps (9-frame clip) per launch, 10 launches, CUDA events; 23 B/px = u8 source + f32 flow + f32 output"}
     del yuv, flo
 
     # ---- config 2: img [8,192,192,29] forward (FISRnet.py:747-748), both precision modes
@@ -487,6 +561,8 @@ def main():
     ap.add_argument("--precision", default="f16f8", choices=["f16x3", "f16", "f16f8"],
                     help="f16f8 (default) = fp16 main term + fp8 cross terms, 3-6e-5 max-abs vs the fp64 oracle (north-star bar 1e-3); "
                          "f16x3 = fp32-class mode (what training uses); f16 = fast mode, outside the bar")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: how the frames become complete on every rank -- p2p (copy engines over NVLink peer memory, default) or one NCCL all-gather per step")
     ap.add_argument("--no-extras", action="store_true", help="skip the `extra` block (configs 2 and 3, warp kernel, other precision mode)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     args = ap.parse_args()

@@ -58,6 +58,7 @@ def load() -> C.CDLL:
         "fisr_window_wait": (i, [vp, i]),
         "fisr_warp_device": (i, [vp, vp, vp, f, vp, i, i, f, vp]),
         "fisr_warp_host": (i, [vp, vp, vp, f, vp, i, i, f]),
+        "fisr_warp_batch_device": (i, [vp, vp, vp, vp, i, f, vp, i, i, f, vp]),
         "fisr_groups2ovlp": (i, [vp, vp, i, i, i, vp, vp]),
         "fisr_temporal_loss": (i, [vp, vp, vp, vp, vp, i, i, i, C.POINTER(f), C.POINTER(f), vp]),
         "fisr_train_forward": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, C.POINTER(f), C.POINTER(f), vp]),
@@ -81,6 +82,11 @@ def load() -> C.CDLL:
         "fisr_debug_conv_output": (i, [vp, C.c_char_p, vp, sz]),
         "fisr_profile_ops": (i, [vp, i, i, i, i, i, C.POINTER(f), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                  C.POINTER(i), C.c_char_p, i]),
+        "fisr_ipc_alloc": (i, [vp, sz, C.POINTER(vp), C.c_char_p]),
+        "fisr_ipc_open": (i, [vp, C.c_char_p, C.POINTER(vp)]),
+        "fisr_ipc_close": (i, [vp, vp]),
+        "fisr_ipc_free": (i, [vp, vp]),
+        "fisr_copy2d_async": (i, [vp, vp, sz, vp, sz, sz, sz, vp]),
         "fisr_launch_count": (C.c_longlong, [vp]),
         "fisr_plan_info": (i, [vp, i, i, i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i), C.POINTER(sz)]),
     }
@@ -95,8 +101,9 @@ def load() -> C.CDLL:
 EXPORTS = [
     "fisr_create", "fisr_destroy", "fisr_last_error", "fisr_set_precision", "fisr_get_precision", "fisr_num_params",
     "fisr_param_name", "fisr_param_shape", "fisr_set_param", "fisr_get_param", "fisr_forward", "fisr_forward_host",
-    "fisr_window_device", "fisr_units_device", "fisr_window_device_f32", "fisr_window_host", "fisr_window_host_f32", "fisr_window_submit", "fisr_window_wait", "fisr_warp_device", "fisr_warp_host",
+    "fisr_window_device", "fisr_units_device", "fisr_window_device_f32", "fisr_window_host", "fisr_window_host_f32", "fisr_window_submit", "fisr_window_wait", "fisr_warp_device", "fisr_warp_host", "fisr_warp_batch_device",
     "fisr_groups2ovlp", "fisr_temporal_loss", "fisr_train_forward", "fisr_adam_step", "fisr_adam_steps", "fisr_adam_reset", "fisr_adam_set_steps", "fisr_get_adam_slot", "fisr_set_adam_slot",
     "fisr_train_backward", "fisr_get_grad", "fisr_adam_apply", "fisr_train_step", "fisr_set_loss_scale", "fisr_get_loss_scale", "fisr_set_wgrad_exact",
     "fisr_dgrad3x3", "fisr_profile_train", "fisr_conv3x3", "fisr_wgrad3x3", "fisr_debug_conv_output", "fisr_profile_ops", "fisr_launch_count", "fisr_plan_info",
+    "fisr_ipc_alloc", "fisr_ipc_open", "fisr_ipc_close", "fisr_ipc_free", "fisr_copy2d_async",
 ]

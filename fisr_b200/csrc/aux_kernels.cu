@@ -379,53 +379,131 @@ __global__ void pred_compact_kernel(const float* __restrict__ src, float* __rest
 //   (cvRound = round-half-even of x*32), 4 taps weighted by the fp32 table (1-fy)(1-fx).., index-clamped border;
 //   --RGB2YUV (:48-57)--> float32 0..255 (not rounded).  `scale` multiplies the result (1/255 yields the
 //   network's warp input directly, utils.py:51).
-__device__ __forceinline__ void yuv2rgb(const uint8_t* p, double (&rgb)[3]) {
-    // T = 255 * Tinv, offset = T @ [16,128,128]  (float64 in the reference; evaluated in fp64 here too)
-    const double y = p[0], u = p[1], v = p[2];
-    const double t00 = 255 * 0.00456621, t02 = 255 * 0.00625893, t11 = 255 * -0.00153632, t12 = 255 * -0.00318811,
-                 t21 = 255 * 0.00791071;
-    const double o0 = t00 * 16 + t02 * 128, o1 = t00 * 16 + t11 * 128 + t12 * 128, o2 = t00 * 16 + t21 * 128;
-    const double r = t00 * y + 0.0 * u + t02 * v - o0;
-    const double g = t00 * y + t11 * u + t12 * v - o1;
-    const double b = t00 * y + t21 * u + 0.0 * v - o2;
-    rgb[0] = fmin(fmax(r, 0.0), 255.0);
-    rgb[1] = fmin(fmax(g, 0.0), 255.0);
-    rgb[2] = fmin(fmax(b, 0.0), 255.0);
+// Arithmetic: the reference converts in float64 (numpy) and cv2.remap interpolates the float64 image with its fp32 weight table;
+// every quantity is bounded by ~600 and the result is stored as float32, so fp32 FMAs reproduce it to ~1e-4 on the 0..255
+// scale (parity bar against cv2.remap: 2e-3, tests/test_gpu_window.py) without touching the FP64 pipe.  Instruction diet (the
+// kernel is issue bound, not HBM bound: ~160 instructions per pixel against 23 B): colours are carried in [0,1] so that every
+// clip(., 0, 255) of the reference is the free .SAT modifier of the FMA that produces the value, and bytes become floats through
+// the 2^23 mantissa trick (PRMT + FADD) instead of I2F.U8 on the quarter-rate XU pipe.
+// rgb / 255 of one YUV sample given as floats, T = 255 * Tinv, offset = T @ [16,128,128]  (..warp_img_with_flo.py:35-45): 7 FMAs
+__device__ __forceinline__ void yuv2rgb01(float y, float u, float v, float (&rgb)[3]) {
+    constexpr double t00 = 0.00456621, t02 = 0.00625893, t11 = -0.00153632, t12 = -0.00318811, t21 = 0.00791071;
+    constexpr double o0 = t00 * 16 + t02 * 128, o1 = t00 * 16 + t11 * 128 + t12 * 128, o2 = t00 * 16 + t21 * 128;
+    rgb[0] = __saturatef(fmaf(static_cast<float>(t02), v, fmaf(static_cast<float>(t00), y, -static_cast<float>(o0))));
+    rgb[1] = __saturatef(fmaf(static_cast<float>(t12), v, fmaf(static_cast<float>(t11), u, fmaf(static_cast<float>(t00), y, -static_cast<float>(o1)))));
+    rgb[2] = __saturatef(fmaf(static_cast<float>(t21), u, fmaf(static_cast<float>(t00), y, -static_cast<float>(o2))));
 }
 
-__global__ void warp_yuv_kernel(const uint8_t* __restrict__ yuv, const float* __restrict__ flow, float flow_scale,
-                                float* __restrict__ out, int h, int w, float out_scale) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    const size_t p = static_cast<size_t>(y) * w + x;
-    const float2 f = *reinterpret_cast<const float2*>(flow + p * 2);
+// byte k (0..3) of a 32-bit word as a float: PRMT builds the bit pattern of 2^23 + b in one instruction
+template <int K>
+__device__ __forceinline__ float word_byte_to_float(uint32_t w) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 | K)) - 8388608.f;
+}
+
+// The two horizontally adjacent taps (x0, x0 + 1) of one source row are 6 consecutive bytes at byte offset `off` of the frame.
+// WORDS: fetched as the two or three aligned 32-bit words that contain them (the third only when the run starts at byte 3 of a
+// word) -- a quarter of the L1 tag / sector work of six byte loads (ncu on the byte-gather version: L1/TEX 85 % busy, 88 % of the
+// sectors excessive).  Words are only touched when they hold a needed byte, so nothing outside the frame is read as long as
+// the frame starts on a 4-byte boundary and its size is a multiple of 4 (checked by the launcher; otherwise the byte path runs).
+// When `second` is false (BORDER_REPLICATE: both taps are the same column) tap b is computed from don't-care bytes and the
+// caller gives it weight zero.
+template <bool WORDS>
+__device__ __forceinline__ void load_tap_pair(const uint8_t* __restrict__ frame, int off, bool second, float (&a)[3], float (&b)[3]) {
+    if constexpr (WORDS) {
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(frame) + (off >> 2);
+        const uint32_t o = static_cast<uint32_t>(off & 3);
+        uint32_t w0 = __ldg(wp), w1 = 0u, w2 = 0u;
+        if (second || o > 1) w1 = __ldg(wp + 1);                         // predicated loads, no branches
+        if (second && o == 3) w2 = __ldg(wp + 2);
+        const uint32_t lo = __funnelshift_r(w0, w1, 8 * o);              // bytes off .. off+3 : y0 u0 v0 y1
+        const uint32_t hi = __funnelshift_r(w1, w2, 8 * o);              // bytes off+4 .. off+7: u1 v1 . .
+        yuv2rgb01(word_byte_to_float<0>(lo), word_byte_to_float<1>(lo), word_byte_to_float<2>(lo), a);
+        yuv2rgb01(word_byte_to_float<3>(lo), word_byte_to_float<0>(hi), word_byte_to_float<1>(hi), b);
+    } else {
+        const uint8_t* p = frame + off;
+        const uint8_t* q = second ? p + 3 : p;
+        yuv2rgb01(static_cast<float>(__ldg(p)), static_cast<float>(__ldg(p + 1)), static_cast<float>(__ldg(p + 2)), a);
+        yuv2rgb01(static_cast<float>(__ldg(q)), static_cast<float>(__ldg(q + 1)), static_cast<float>(__ldg(q + 2)), b);
+    }
+}
+
+// one warped pixel: source image `src` [h,w,3] u8 YUV (< 2 GB: 32-bit offsets), flow vector f of the destination pixel (x, y)
+// -> YUV float x out_scale
+template <bool WORDS>
+__device__ __forceinline__ void warp_pixel(const uint8_t* __restrict__ src, float2 f, float flow_scale, int x, int y, int h, int w,
+                                           float out_scale255, float (&o)[3]) {
     const float mx = f.x * flow_scale + static_cast<float>(x);      // ..warp_img_with_flo.py:64-65,123
     const float my = f.y * flow_scale + static_cast<float>(y);
-    const int ix = __float2int_rn(mx * 32.f), iy = __float2int_rn(my * 32.f);
+    const int ix = __float2int_rn(mx * 32.f), iy = __float2int_rn(my * 32.f);      // cvRound(x * INTER_TAB_SIZE)
     const int sx = ix >> 5, sy = iy >> 5;
-    const float fx = static_cast<float>(ix & 31) * (1.f / 32.f), fy = static_cast<float>(iy & 31) * (1.f / 32.f);
-    const int x0 = min(max(sx, 0), w - 1), x1 = min(max(sx + 1, 0), w - 1);
+    float fx = static_cast<float>(ix & 31) * (1.f / 32.f);
+    const float fy = static_cast<float>(iy & 31) * (1.f / 32.f);
+    const int x0 = min(max(sx, 0), w - 1), x1 = min(max(sx + 1, 0), w - 1);       // BORDER_REPLICATE
     const int y0 = min(max(sy, 0), h - 1), y1 = min(max(sy + 1, 0), h - 1);
-    double a[3], b[3], c[3], d[3];
-    yuv2rgb(yuv + (static_cast<size_t>(y0) * w + x0) * 3, a);
-    yuv2rgb(yuv + (static_cast<size_t>(y0) * w + x1) * 3, b);
-    yuv2rgb(yuv + (static_cast<size_t>(y1) * w + x0) * 3, c);
-    yuv2rgb(yuv + (static_cast<size_t>(y1) * w + x1) * 3, d);
+    const bool second = x1 != x0;
+    const int w3 = w * 3, c0 = x0 * 3;
+    float a[3], b[3], c[3], d[3];
+    load_tap_pair<WORDS>(src, y0 * w3 + c0, second, a, b);
+    load_tap_pair<WORDS>(src, y1 * w3 + c0, second, c, d);
+    // weights of cv2's table: (1-fy)(1-fx), (1-fy)fx, fy(1-fx), fy fx; with x1 == x0 the right taps ARE the left ones, so their
+    // weight moves over (a w00 + a w01 = a (1-fy) exactly as fx (1-fy) + (1-fx)(1-fy) rounds -- the sum is exact in fp32 for
+    // 5-bit fractions)
+    if (!second) fx = 0.f;
     const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
-    double rgb[3];
+    float rgb[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rgb[k] = fmaf(d[k], w11, fmaf(c[k], w10, fmaf(b[k], w01, a[k] * w00)));
+    // RGB2YUV (..warp_img_with_flo.py:48-57) on rgb / 255: yuv / 255 = (T / 255) rgb01 + off / 255, clip = .SAT, then x 255 x out_scale
+    constexpr float T[3][3] = {{static_cast<float>(65.481 / 255), static_cast<float>(128.553 / 255), static_cast<float>(24.966 / 255)},
+                               {static_cast<float>(-37.797 / 255), static_cast<float>(-74.203 / 255), static_cast<float>(112.0 / 255)},
+                               {static_cast<float>(112.0 / 255), static_cast<float>(-93.786 / 255), static_cast<float>(-18.214 / 255)}};
+    constexpr float off[3] = {static_cast<float>(16.0 / 255), static_cast<float>(128.0 / 255), static_cast<float>(128.0 / 255)};
 #pragma unroll
     for (int k = 0; k < 3; ++k)
-        rgb[k] = a[k] * w00 + b[k] * w01 + c[k] * w10 + d[k] * w11;
-    // RGB2YUV, T / 255 and offsets [16,128,128]
-    const double T[3][3] = {{65.481 / 255, 128.553 / 255, 24.966 / 255},
-                            {-37.797 / 255, -74.203 / 255, 112.0 / 255},
-                            {112.0 / 255, -93.786 / 255, -18.214 / 255}};
-    const double off[3] = {16, 128, 128};
+        o[k] = __saturatef(fmaf(T[k][2], rgb[2], fmaf(T[k][1], rgb[1], fmaf(T[k][0], rgb[0], off[k])))) * out_scale255;
+}
+
+// Warp job i (blockIdx.z): destination out[i] = frame yuv[src_idx[i]] sampled along flow[i].  A warp owns 32 CONSECUTIVE
+// destination pixels of kWarpRows rows: neighbouring lanes gather from the same one or two 128-byte lines, the flow load is one
+// coalesced 256-byte request, and the 96 output floats of a row segment are transposed through shared memory so that they
+// leave as three fully coalesced 128-byte stores.  23 B of HBM traffic per pixel (3 source + 8 flow + 12 destination).
+constexpr int kWarpRows = 2;
+template <bool WORDS>
+__global__ void __launch_bounds__(256) warp_yuv_kernel(const uint8_t* __restrict__ yuv, const float* __restrict__ flow, const int* __restrict__ src_idx,
+                                                       float flow_scale, float* __restrict__ out, int h, int w, float out_scale) {
+    __shared__ float stage[8][kWarpRows][96];
+    const int xb = blockIdx.x * 32, x = xb + threadIdx.x;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * kWarpRows;
+    if (y0 >= h) return;                         // warp-uniform
+    const size_t img = static_cast<size_t>(h) * w;
+    const int job = blockIdx.z;
+    const uint8_t* src = yuv + (src_idx ? static_cast<size_t>(__ldg(src_idx + job)) : static_cast<size_t>(job)) * img * 3;
+    out_scale *= 255.f;                          // colours are carried in [0,1] (warp_pixel)
+    const bool live = x < w;
+    float2 f[kWarpRows];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const double v = T[k][0] * rgb[0] + T[k][1] * rgb[1] + T[k][2] * rgb[2] + off[k];
-        out[p * 3 + k] = static_cast<float>(fmin(fmax(v, 0.0), 255.0)) * out_scale;
+    for (int r = 0; r < kWarpRows; ++r)          // both rows' flow vectors in flight before the dependent gathers
+        f[r] = (live && y0 + r < h) ? __ldg(reinterpret_cast<const float2*>(flow + (job * img + static_cast<size_t>(y0 + r) * w + x) * 2)) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < kWarpRows; ++r) {
+        if (live && y0 + r < h) {
+            float o[3];
+            warp_pixel<WORDS>(src, f[r], flow_scale, x, y0 + r, h, w, out_scale, o);
+            float* st = &stage[threadIdx.y][r][threadIdx.x * 3];
+            st[0] = o[0]; st[1] = o[1]; st[2] = o[2];
+        }
+    }
+    __syncwarp();
+    const int nfl = min(32, w - xb) * 3;         // floats of this row segment
+#pragma unroll
+    for (int r = 0; r < kWarpRows; ++r) {
+        if (y0 + r >= h) break;
+        float* d = out + (job * img + static_cast<size_t>(y0 + r) * w + xb) * 3;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int i = k * 32 + threadIdx.x;
+            if (i < nfl) d[i] = stage[threadIdx.y][r][i];
+        }
     }
 }
 
@@ -540,10 +618,13 @@ void launch_tile_unpack_f32(const float* pred, int cs, const TileList& tiles, in
     tile_unpack_f32_kernel<<<blocks_for(total, 256), 256, 0, st>>>(pred, cs, tiles, th2, tw2, canvas, OH, OW, core_h, core_w);
 }
 
-void launch_warp_yuv(const uint8_t* yuv, const float* flow, float flow_scale, float* out, int h, int w, float out_scale,
-                     cudaStream_t st) {
-    dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
-    warp_yuv_kernel<<<grid, block, 0, st>>>(yuv, flow, flow_scale, out, h, w, out_scale);
+void launch_warp_yuv(const uint8_t* yuv, const float* flow, const int* src_idx, int jobs, float flow_scale, float* out, int h, int w,
+                     float out_scale, cudaStream_t st) {
+    dim3 block(32, 8), grid((w + 31) / 32, (h + 8 * kWarpRows - 1) / (8 * kWarpRows), jobs);
+    // aligned word gathers need frames that start on a 4-byte boundary and are a multiple of 4 bytes long (every frame then is)
+    const bool words = (reinterpret_cast<uintptr_t>(yuv) & 3) == 0 && ((static_cast<size_t>(h) * w * 3) & 3) == 0;
+    if (words) warp_yuv_kernel<true><<<grid, block, 0, st>>>(yuv, flow, src_idx, flow_scale, out, h, w, out_scale);
+    else warp_yuv_kernel<false><<<grid, block, 0, st>>>(yuv, flow, src_idx, flow_scale, out, h, w, out_scale);
 }
 
 }  // namespace fisr

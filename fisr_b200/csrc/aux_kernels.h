@@ -44,7 +44,8 @@ void launch_tile_unpack_u8(const float* pred, int cs, const TileList& tiles, int
                            int core_h, int core_w, cudaStream_t st);
 void launch_tile_unpack_f32(const float* pred, int cs, const TileList& tiles, int th2, int tw2, float* canvas, int OH, int OW,
                             int core_h, int core_w, cudaStream_t st);
-void launch_warp_yuv(const uint8_t* yuv, const float* flow, float flow_scale, float* out, int h, int w, float out_scale,
-                     cudaStream_t st);
+// jobs warps in one launch: out[i] = frame yuv[src_idx[i]] (or yuv[i] when src_idx is null) sampled along flow[i]
+void launch_warp_yuv(const uint8_t* yuv, const float* flow, const int* src_idx, int jobs, float flow_scale, float* out, int h, int w,
+                     float out_scale, cudaStream_t st);
 
 }  // namespace fisr

@@ -70,12 +70,16 @@ bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int n
     // window's tiles are sharded over batches / GPUs (NT decides the fp32 summation order, see STACK).
     if (cout_pad >= 128 && (long)H * W >= 64L * 64) NT = 128;
     (void)kb;
-    int chunks = 2;
-    {
-        const long tiles2 = (long)n_img * ((H * (long)W + 255) / 256) * (cout_pad / NT);
-        if (tiles2 < num_sms) chunks = 1;
+    // Two chunks (16 x 16 tiles) unless the image is a single chunk wide.  Every chunk has its own MMA issuer warp and one
+    // thread issues a tcgen05.mma only every ~70-150 cycles (tests/cuda/umma_rate_probe.cu), so a one-chunk CTA is ISSUE
+    // bound at about half the rate of a two-chunk one: splitting small layers into 8-pixel-wide tiles to occupy more SMs
+    // (round 1) doubled the tile count without shortening a tile (ncu, profiles/r02_ncu_small_layers.md: level-1 bottleneck
+    // at 30 % tensor-active with 1 chunk against 57 % for the level-2 one with 2).
+    int chunks = W > 8 ? 2 : 1;
+    if (const char* e = getenv("FISR_CHUNKS")) {      // A/B knob (tools/window_time.py): 1 / 2 force, 3 = the round-1 rule
+        if (atoi(e) == 1 || atoi(e) == 2) chunks = atoi(e);
+        if (atoi(e) == 3) chunks = ((long)n_img * ((H * (long)W + 255) / 256) * (cout_pad / NT) < num_sms) ? 1 : 2;
     }
-    if (const char* e = getenv("FISR_CHUNKS")) { if (atoi(e) == 1 || atoi(e) == 2) chunks = atoi(e); }   // tuning knob
     const int apl = act_planes(planes);
     const bool stack = planes == 2 && NT <= 64;
     // f16f8 layers with wide outputs can run on CTA pairs (cluster of 2, cta_group::2, M = 256): each CTA keeps half of a tap's

@@ -1567,7 +1567,18 @@ int fisr_warp_device(fisr_ctx* ctx, const uint8_t* d_yuv, const float* d_flow, f
     if (!ctx || !d_yuv || !d_flow || !d_out || h < 1 || w < 1) return FISR_E_INVALID;
     Guard guard(ctx->device);
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
-    launch_warp_yuv(d_yuv, d_flow, flow_scale, d_out, h, w, out_scale, st);
+    launch_warp_yuv(d_yuv, d_flow, nullptr, 1, flow_scale, d_out, h, w, out_scale, st);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return FISR_OK;
+}
+
+int fisr_warp_batch_device(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, const int* d_src_index, int jobs,
+                           float flow_scale, float* d_out, int h, int w, float out_scale, void* stream) {
+    if (!ctx || !d_frames || !d_flow || !d_out || jobs < 1 || jobs > 65535 || h < 1 || w < 1) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    launch_warp_yuv(d_frames, d_flow, d_src_index, jobs, flow_scale, d_out, h, w, out_scale, st);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return FISR_OK;
@@ -1585,7 +1596,7 @@ int fisr_warp_host(fisr_ctx* ctx, const uint8_t* h_yuv, const float* h_flow, flo
     cudaStream_t st = ctx->stream;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage[5], h_yuv, px * 3, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage[6], h_flow, px * 8, cudaMemcpyHostToDevice, st));
-    launch_warp_yuv(static_cast<const uint8_t*>(ctx->stage[5]), static_cast<const float*>(ctx->stage[6]), flow_scale,
+    launch_warp_yuv(static_cast<const uint8_t*>(ctx->stage[5]), static_cast<const float*>(ctx->stage[6]), nullptr, 1, flow_scale,
                     static_cast<float*>(ctx->stage[7]), h, w, out_scale, st);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
@@ -2070,6 +2081,60 @@ int fisr_profile_train(fisr_ctx* ctx, int B, int h, int w, int reps, int max_ops
     }
     rc = check_kernel_error(ctx);
     return rc == FISR_OK ? n : rc;
+}
+
+// ---------------------------------------------------------------- multi-GPU frame exchange over peer memory
+int fisr_ipc_alloc(fisr_ctx* ctx, size_t bytes, void** d_ptr, unsigned char* handle64) {
+    if (!ctx || !d_ptr || !handle64 || bytes == 0) return FISR_E_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    Guard guard(ctx->device);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(ctx, FISR_E_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    cudaIpcMemHandle_t h;
+    if ((e = cudaIpcGetMemHandle(&h, p)) != cudaSuccess) {
+        cudaFree(p);
+        return fail(ctx, FISR_E_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    CUDA_TRY(ctx, cudaMemset(p, 0, bytes));
+    memcpy(handle64, &h, 64);
+    *d_ptr = p;
+    return FISR_OK;
+}
+
+int fisr_ipc_open(fisr_ctx* ctx, const unsigned char* handle64, void** d_ptr) {
+    if (!ctx || !handle64 || !d_ptr) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(ctx, FISR_E_CUDA, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+    *d_ptr = p;
+    return FISR_OK;
+}
+
+int fisr_ipc_close(fisr_ctx* ctx, void* d_ptr) {
+    if (!ctx || !d_ptr) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    CUDA_TRY(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return FISR_OK;
+}
+
+int fisr_ipc_free(fisr_ctx* ctx, void* d_ptr) {
+    if (!ctx || !d_ptr) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    CUDA_TRY(ctx, cudaFree(d_ptr));
+    return FISR_OK;
+}
+
+int fisr_copy2d_async(fisr_ctx* ctx, void* d_dst, size_t dst_pitch, const void* d_src, size_t src_pitch, size_t width_bytes,
+                      size_t rows, void* stream) {
+    if (!ctx || !d_dst || !d_src || width_bytes == 0 || rows == 0 || dst_pitch < width_bytes || src_pitch < width_bytes) return FISR_E_INVALID;
+    Guard guard(ctx->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_dst, dst_pitch, d_src, src_pitch, width_bytes, rows, cudaMemcpyDeviceToDevice, st));
+    return FISR_OK;
 }
 
 long long fisr_launch_count(const fisr_ctx* ctx) { return ctx ? ctx->launches : 0; }

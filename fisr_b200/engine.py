@@ -290,6 +290,23 @@ class Engine:
         self._exit()
         return out
 
+    def warp_batch(self, frames: torch.Tensor, flow: torch.Tensor, src_index, flow_scale: float = 0.5,
+                   out_scale: float = 1.0) -> torch.Tensor:
+        """All warps of a clip in one launch: frames u8 [F,h,w,3], flow f32 [J,h,w,2], ``src_index[j]`` = the frame job j
+        samples -> f32 [J,h,w,3] (the loop of ..warp_img_with_flo.py:112-128)."""
+        frames = self._dev(frames, torch.uint8)
+        flow = self._dev(flow, torch.float32)
+        J, h, w, _ = flow.shape
+        idx = torch.as_tensor(list(src_index), dtype=torch.int32, device=frames.device)
+        if idx.numel() != J or int(idx.min()) < 0 or int(idx.max()) >= frames.shape[0] or tuple(frames.shape[1:]) != (h, w, 3):
+            raise FisrError(f"warp_batch: {J} flows, {idx.numel()} source indices, frames {tuple(frames.shape)}")
+        out = torch.empty((J, h, w, 3), dtype=torch.float32, device=frames.device)
+        self._enter(frames, flow, idx, out)
+        self._check(self.lib.fisr_warp_batch_device(self.h, frames.data_ptr(), flow.data_ptr(), idx.data_ptr(), J, flow_scale,
+                                                    out.data_ptr(), h, w, out_scale, self._stream()), "fisr_warp_batch_device")
+        self._exit()
+        return out
+
     def warp_host(self, yuv: np.ndarray, flow: np.ndarray, flow_scale: float = 0.5, out_scale: float = 1.0) -> np.ndarray:
         yuv = np.ascontiguousarray(yuv, dtype=np.uint8)
         flow = np.ascontiguousarray(flow, dtype=np.float32)

@@ -20,13 +20,17 @@ def FISR_for_video_Warp_Img(args, flow_file_name, engine: Engine = None):
     num_fr = args.frame_num
     data_list = sorted(glob.glob(os.path.join(args.frame_folder_path, '*.png')))
     h, w = args.FISR_input_size[0], args.FISR_input_size[1]
-    pred = np.zeros((num_fr - 1, 2, h, w, 3), dtype=np.float32)
-    flow = read_flo_file_5dim(flow_file_name)
+    import torch
+    flow = read_flo_file_5dim(flow_file_name)                                   # [N-1, 2, h, w, 2]
+    frames = np.stack([np.ascontiguousarray(np.array(Image.open(data_list[fr]))[:h, :w], dtype=np.uint8) for fr in range(num_fr)])
+    # job 2*fr = frame fr+1 sampled along 0.5 * flow(fr -> fr+1)  (:121-124); job 2*fr+1 = frame fr along 0.5 * flow(fr+1 -> fr)  (:125-128)
+    src = [fr + 1 - (j & 1) for fr in range(num_fr - 1) for j in range(2)]
+    dev = "cuda:%d" % engine.device
+    out = engine.warp_batch(torch.from_numpy(frames).to(dev),
+                            torch.from_numpy(np.ascontiguousarray(flow[:num_fr - 1, :, :h, :w], dtype=np.float32).reshape(-1, h, w, 2)).to(dev),
+                            src, 0.5, 1.0)                                      # ONE launch for the whole clip
+    pred = out.cpu().numpy().reshape(num_fr - 1, 2, h, w, 3)
     for fr in range(num_fr - 1):
-        yuv_1 = np.ascontiguousarray(np.array(Image.open(data_list[fr]))[:h, :w], dtype=np.uint8)
-        yuv_2 = np.ascontiguousarray(np.array(Image.open(data_list[fr + 1]))[:h, :w], dtype=np.uint8)
-        pred[fr, 0] = engine.warp_host(yuv_2, flow[fr, 0], 0.5, 1.0)      # 1 -> 2  (:121-124)
-        pred[fr, 1] = engine.warp_host(yuv_1, flow[fr, 1], 0.5, 1.0)      # 2 -> 1  (:125-128)
         print("Processing for warping imgs [%5d/%5d]" % (fr + 1, num_fr))
     folder = args.frame_folder_path.rstrip('/')
     warp_file_name = folder + '/' + folder.split('/')[-1] + '_ss{}_fr{}_warp.npy'.format(1, num_fr)

@@ -105,6 +105,11 @@ int fisr_window_device_f32(fisr_ctx* ctx, const uint8_t* d_frames, const float* 
  * out f32 [h,w,3] = value * out_scale (the reference stores 0..255, i.e. out_scale 1; 1/255 feeds the network). */
 int fisr_warp_device(fisr_ctx* ctx, const uint8_t* d_yuv, const float* d_flow, float flow_scale, float* d_out, int h,
                      int w, float out_scale, void* stream);
+/* All warps of a clip in ONE launch (the loop of ..warp_img_with_flo.py:112-128): job i writes d_out[i] [h,w,3] = frame
+ * d_frames[d_src_index[i]] (u8 [F,h,w,3]; NULL index = frame i) sampled along d_flow[i] [h,w,2].  For pair k of the reference
+ * loop: job 2k = frame k+1 along flow(k -> k+1), job 2k+1 = frame k along flow(k+1 -> k). */
+int fisr_warp_batch_device(fisr_ctx* ctx, const uint8_t* d_frames, const float* d_flow, const int* d_src_index, int jobs,
+                           float flow_scale, float* d_out, int h, int w, float out_scale, void* stream);
 int fisr_warp_host(fisr_ctx* ctx, const uint8_t* h_yuv, const float* h_flow, float flow_scale, float* h_out, int h,
                    int w, float out_scale);
 
@@ -161,6 +166,21 @@ int fisr_adam_reset(fisr_ctx* ctx, long long step);
 int fisr_get_adam_slot(fisr_ctx* ctx, const char* name, int which, float* h_data, size_t count);
 int fisr_set_adam_slot(fisr_ctx* ctx, const char* name, int which, const float* h_data, size_t count);
 int fisr_adam_set_steps(fisr_ctx* ctx, long long step);
+
+/* ---- multi-GPU: frames exchanged over NVLink peer memory (the reference is single-GPU, main.py:19-20) -------- */
+/* One process per GPU.  Every rank keeps its output frames [B,2h,2w,9] u8 in a buffer from fisr_ipc_alloc, hands the 64-byte
+ * handle (a cudaIpcMemHandle_t) to its peers over any channel (torch.distributed), and maps theirs with fisr_ipc_open.  A rank
+ * computes its (window, tile) units straight into its own frames (fisr_units_device, layout 0) and pushes each finished tile
+ * rectangle into the same place of every peer's frames with fisr_copy2d_async: cudaMemcpy2DAsync on peer-mapped pointers runs on
+ * the copy engines over NVLink 5 / NVSwitch -- an all-gather in frame layout with no SM-resident collective kernel competing with
+ * the persistent conv grids and no re-assembly pass.  (fisr_b200/sharding.py: PeerFrames; NCCL all-gather remains the fallback.) */
+int fisr_ipc_alloc(fisr_ctx* ctx, size_t bytes, void** d_ptr, unsigned char* handle64);
+int fisr_ipc_open(fisr_ctx* ctx, const unsigned char* handle64, void** d_ptr);
+int fisr_ipc_close(fisr_ctx* ctx, void* d_ptr);
+int fisr_ipc_free(fisr_ctx* ctx, void* d_ptr);
+/* dst / src: device pointers (local or peer-mapped), pitches and width in bytes; asynchronous on `stream`. */
+int fisr_copy2d_async(fisr_ctx* ctx, void* d_dst, size_t dst_pitch, const void* d_src, size_t src_pitch, size_t width_bytes,
+                      size_t rows, void* stream);
 
 /* ---- introspection / test hooks ---------------------------------------------------------------------------- */
 /* Single 3x3 SAME conv through the production kernel (ops.py:7-11 plus the fused epilogue):

@@ -107,3 +107,24 @@ def test_pipelined_host_path_equals_sync(engine):
     with pytest.raises(fisr_b200.FisrError):
         engine.window_submit(0, *[np.ascontiguousarray(a) for a in wins[0]], (2, 2))     # slot busy
     engine.window_wait(0)
+
+
+@pytest.mark.parametrize("w", [192, 190])
+def test_warp_batch_matches_cv2(engine, w):
+    """fisr_warp_batch_device: every warp of a clip in one launch (fp32 colour math carried in [0,1], ragged width) against
+    cv2.remap exactly as the reference calls it (..warp_img_with_flo.py:112-128)."""
+    g = np.load(os.path.join(GOLDEN, "scene1_lr_crop.npz"))["frames"][:4, :, :w]
+    g = np.ascontiguousarray(g)
+    n, h = g.shape[0], g.shape[1]
+    rng = np.random.default_rng(7)
+    flow = (rng.standard_normal((n - 1, 2, h, w, 2)) * 6).astype(np.float32)
+    flow[0, 0, :3] -= 40                                             # far outside the frame: BORDER_REPLICATE
+    flow[1, 1, :, -5:] += 25
+    src = [fr + 1 - (j & 1) for fr in range(n - 1) for j in range(2)]
+    out = engine.warp_batch(torch.from_numpy(g).cuda(), torch.from_numpy(flow.reshape(-1, h, w, 2)).cuda(), src, 0.5, 1.0)
+    out = out.cpu().numpy().reshape(n - 1, 2, h, w, 3)
+    for fr in range(n - 1):
+        ref = P.warp_pair_yuv(g[fr], g[fr + 1], flow[fr, 0], flow[fr, 1])
+        assert np.abs(out[fr] - ref).max() < 2e-3                    # 0..255 scale
+    one = engine.warp(torch.from_numpy(g[1]).cuda(), torch.from_numpy(flow[0, 0]).cuda(), 0.5, 1.0).cpu().numpy()
+    assert np.array_equal(one, out[0, 0])

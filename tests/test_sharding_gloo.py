@@ -25,6 +25,18 @@ def test_unit_assignment_is_a_partition():
         sharding.rank_units(0, 3, 1, 4)
 
 
+def test_unit_rect_tiles_the_frame():
+    """PeerFrames pushes a unit's tile to the rectangle this returns: the rectangles of a window's units tile its frame."""
+    grid, sh, sw = (2, 3), 4, 5
+    cover = torch.zeros(2, grid[0] * sh, grid[1] * sw, dtype=torch.int32)
+    for u in range(2 * 6):
+        w, y0, x0 = sharding.unit_rect(u, grid, sh, sw)
+        assert w == u // 6
+        cover[w, y0:y0 + sh, x0:x0 + sw] += 1
+    assert bool((cover == 1).all())
+    assert sharding.unit_rect(5, (2, 2), 1024, 1920) == (1, 0, 1920)
+
+
 def _tile_value(unit, sh, sw):
     t = torch.full((sh, sw, 9), unit % 251, dtype=torch.uint8)
     t[0, 0, 0] = unit // 4

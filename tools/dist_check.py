@@ -22,9 +22,25 @@ gathered = sharding.gather_units(local_out, world)
 got = sharding.assemble_frames(gathered, B, grid)
 ref = eng.units(frames, flow, warp, list(range(B * 4)), grid, layout="frames")
 ok = torch.equal(got, ref)
+# the same all-gather in frame layout over peer memory (copy engines, sharding.PeerFrames)
+oh, ow, _ = eng.canvas_shape(H, W, grid)
+peer = sharding.PeerFrames(eng, rank, world, B, oh, ow)
+for s in (0, 1, 0):                                          # both buffer sets, and a reused one
+    eng.units(frames, flow, warp, units, grid, layout="frames", out=peer.local(s))
+    peer.publish(s, units, grid)
+    peer.drain()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ok = ok and torch.equal(peer.local(s), ref)
+    peer.local(s).zero_()
+    torch.cuda.synchronize()
+    dist.barrier()
+ncopies = peer.copies
+peer.close()
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"DIST_CHECK world={world} units/rank={len(units)} frames={tuple(got.shape)} bit-identical={bool(flag.item())}")
+    print(f"DIST_CHECK world={world} units/rank={len(units)} frames={tuple(got.shape)} nccl-gather and peer-memory exchange "
+          f"({ncopies} 2-D copies from rank 0) bit-identical to one GPU: {bool(flag.item())}")
 dist.barrier(); eng.close(); dist.destroy_process_group()
 sys.exit(0 if flag.item() else 1)

@@ -1,6 +1,11 @@
-"""ms per batched forward of the bench workload (4 tiles of 544x992, CUDA graph replay, inputs in HBM) and of config 2:
-the A/B number for kernel / plan changes (toggle with FISR_NO_PDL / FISR_NO_POOL_FUSION / FISR_NO_HEAD_MERGE)."""
+"""In-process A/B of plan / kernel knobs on the bench workload (4 tiles of 544x992, CUDA graph replay, inputs in HBM) and on
+config 2 (8x192x192).  Variants are environment settings read at plan time; they are measured interleaved, several rounds, in
+ONE process (clock / power state drifts by several percent between processes and boxes), best and median reported.
+
+    python tools/window_time.py f16f8 "" "FISR_CHUNKS=3"
+"""
 import os
+import statistics
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,6 +14,8 @@ import fisr_b200  # noqa: E402
 from fisr_b200.init import xavier_params  # noqa: E402
 
 prec = sys.argv[1] if len(sys.argv) > 1 else "f16f8"
+variants = sys.argv[2:] or [""]
+rounds = int(os.environ.get("AB_ROUNDS", "3"))
 eng = fisr_b200.Engine(0, precision=prec)
 eng.set_params(xavier_params(0, 0.01))
 g = torch.Generator().manual_seed(1)
@@ -16,9 +23,10 @@ frames = torch.randint(0, 256, (1080, 1920, 9), dtype=torch.uint8, generator=g).
 flow = (torch.randn(1080, 1920, 8, generator=g) * 4).cuda()
 warp = torch.rand(1080, 1920, 12, generator=g).cuda()
 out = torch.zeros((2048, 3840, 9), dtype=torch.uint8, device="cuda")
+x = torch.rand(8, 192, 192, 29, generator=g).cuda()
 
 
-def timed(fn, warm=3, reps=20):
+def timed(fn, warm=3, reps=15):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -31,9 +39,25 @@ def timed(fn, warm=3, reps=20):
     return e0.elapsed_time(e1) / reps
 
 
-ms = timed(lambda: eng.window(frames, flow, warp, (2, 2), out=out))
-x = torch.rand(8, 192, 192, 29, generator=g).cuda()
-ms2 = timed(lambda: eng.forward(x))
-flags = " ".join(f"{k}={os.environ[k]}" for k in ("FISR_NO_PDL", "FISR_NO_POOL_FUSION", "FISR_NO_HEAD_MERGE", "FISR_HEAD_F16") if k in os.environ)
-print(f"{prec} [{flags or 'defaults'}]: window (4 x 544x992) {ms:.3f} ms = {2000 / ms:.2f} frames/s; config 2 (8x192x192) {ms2:.3f} ms; "
-      f"checksum {int(out.sum())}")
+res = {v: ([], [], None) for v in variants}
+for r in range(rounds):
+    for v in variants:
+        keys = []
+        for kv in v.split():
+            k, val = kv.split("=")
+            os.environ[k] = val
+            keys.append(k)
+        other = "f16" if prec != "f16" else "f16x3"
+        eng.set_precision(other)
+        eng.set_precision(prec)               # drops the cached plans: geometry is re-planned under this variant's settings
+        w_ms = timed(lambda: eng.window(frames, flow, warp, (2, 2), out=out))
+        c_ms = timed(lambda: eng.forward(x))
+        res[v][0].append(w_ms)
+        res[v][1].append(c_ms)
+        res[v] = (res[v][0], res[v][1], int(out.sum()))
+        for k in keys:
+            del os.environ[k]
+for v in variants:
+    w, c, chk = res[v]
+    print(f"{prec} [{v or 'defaults'}]: window best {min(w):.3f} median {statistics.median(w):.3f} ms ({2000 / min(w):.2f} frames/s); "
+          f"config 2 best {min(c):.3f} median {statistics.median(c):.3f} ms; checksum {chk}")
