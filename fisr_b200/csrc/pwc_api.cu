@@ -1,0 +1,388 @@
+// C ABI of the PWC-Net inference path (include/fisr_b200.h, "PWC-Net"): parameter store under the TensorFlow variable names of
+// philferriere/tfoptflow (scope pwcnet/), one plan (buffers + launch list) per input size, forward of N image pairs.
+// Reference: FISR_tfoptflow/model_pwcnet.py:1012-1593 driven by FISR_for_video_pwcnet_predict_from_img_test.py:96-139.
+#include <cstdarg>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/fisr_b200.h"
+#include "pwc_kernels.h"
+
+using namespace fisr::pwc;
+
+namespace {
+
+constexpr int kLvls = 6, kPredLvl = 2, kCorr = 81, kCorrPad = 84;       // search range 4; corr slot padded to a multiple of 4
+constexpr int kChann[7] = {0, 16, 32, 64, 96, 128, 196};                // model_pwcnet.py:1083
+constexpr int kDense[5] = {128, 128, 96, 64, 32};                       // model_pwcnet.py:1415-1433
+constexpr int kActs = 448;                                              // 128 + 128 + 96 + 64 + 32
+constexpr int kCtxtF[7] = {128, 128, 128, 96, 64, 32, 2};               // model_pwcnet.py:1506-1519
+constexpr int kCtxtD[7] = {1, 2, 4, 8, 16, 1, 1};
+
+struct PDef {
+    std::string name;        // without /kernel, /bias
+    int cin, cout;           // reference channel counts
+    bool transpose;          // conv2d_transpose kernel [4,4,out,in]
+    int gap_at;              // reference input channel index after which 3 zero rows are inserted (-1: none)
+};
+
+// channels of the dense buffer D_l: [act4 | act3 | act2 | act1 | act0 | corr (81 + 3 pad) | c1 | up_flow | up_feat]
+int dense_cs(int lvl) { return kActs + kCorrPad + (lvl == kLvls ? 0 : kChann[lvl] + 4); }
+int dense_off(int k) { int o = kActs; for (int i = 0; i <= k; ++i) o -= kDense[i]; return o; }      // where act_k is written
+int dense_in_off(int k) { return k == 0 ? kActs : dense_off(k - 1); }                               // where conv_k starts reading
+
+std::vector<PDef> build_inventory() {
+    std::vector<PDef> v;
+    for (int l = 1; l <= kLvls; ++l) {
+        const std::string p = "pwcnet/featpyr/conv" + std::to_string(l);
+        v.push_back({p + "a", l == 1 ? 3 : kChann[l - 1], kChann[l], false, -1});
+        v.push_back({p + "aa", kChann[l], kChann[l], false, -1});
+        v.push_back({p + "b", kChann[l], kChann[l], false, -1});
+    }
+    for (int l = kLvls; l >= kPredLvl; --l) {
+        int c = kCorr + (l == kLvls ? 0 : kChann[l] + 4);
+        for (int k = 0; k < 5; ++k) {
+            v.push_back({"pwcnet/predict_flow/conv" + std::to_string(l) + "_" + std::to_string(k), c, kDense[k], false, c - (l == kLvls ? 0 : kChann[l] + 4)});
+            c += kDense[k];
+        }
+        const int gap = c - (l == kLvls ? 0 : kChann[l] + 4);
+        v.push_back({"pwcnet/predict_flow/flow" + std::to_string(l), c, 2, false, gap});
+        int cc = c;
+        for (int k = 0; k < 7; ++k) {
+            v.push_back({"pwcnet/ctxt/dc_conv" + std::to_string(l) + std::to_string(k + 1), cc, kCtxtF[k], false, k == 0 ? gap : -1});
+            cc = kCtxtF[k];
+        }
+        if (l != kPredLvl) {
+            v.push_back({"pwcnet/upsample/up_flow" + std::to_string(l), 2, 2, true, -1});
+            v.push_back({"pwcnet/upsample/up_feat" + std::to_string(l), c, 2, true, gap});
+        }
+    }
+    return v;
+}
+const std::vector<PDef>& inventory() {
+    static const std::vector<PDef> inv = build_inventory();
+    return inv;
+}
+const std::vector<std::string>& names() {
+    static std::vector<std::string> n;
+    if (n.empty())
+        for (const auto& d : inventory()) { n.push_back(d.name + "/kernel"); n.push_back(d.name + "/bias"); }
+    return n;
+}
+
+struct Param {
+    int cin_pad = 0;             // input channels as the kernels see them (reference count + 3 where a gap is inserted)
+    float* d_w = nullptr;        // kernel layout: conv [9][cin_pad][cout]; transpose [16][2][cin_pad]
+    float* d_b = nullptr;
+    std::vector<float> h_w;      // as uploaded (reference layout), for fisr_pwc_get_param
+};
+
+struct Plan {
+    int N = 0, H = 0, W = 0;
+    std::vector<void*> allocs;
+    std::vector<std::function<void(cudaStream_t)>> ops;
+    const float *img1 = nullptr, *img2 = nullptr;     // bound per call
+    float* out = nullptr;
+    float* flow[kLvls + 1] = {nullptr};
+    ~Plan() { for (void* p : allocs) cudaFree(p); }
+};
+
+}  // namespace
+
+struct fisr_pwc {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<Param> params;
+    std::map<std::string, int> index;
+    std::map<std::string, std::unique_ptr<Plan>> plans;
+    Plan* last = nullptr;
+    long long launches = 0;
+    std::string err;
+};
+
+namespace {
+
+std::string g_err;
+int fail(fisr_pwc* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_err = buf;
+    return code;
+}
+#define PWC_TRY(c, expr)                                                                                                       \
+    do {                                                                                                                        \
+        cudaError_t e__ = (expr);                                                                                               \
+        if (e__ != cudaSuccess) return fail(c, FISR_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+struct Guard {
+    int prev = -1;
+    explicit Guard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+struct View { float* p; int cs, coff, C; };      // channels [coff, coff + C) of an NHWC buffer with cs channels per pixel
+
+int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
+    if (N < 1 || H < 64 || W < 64 || H % 64 || W % 64)
+        return fail(c, FISR_E_INVALID, "PWC-Net (6-level pyramid) needs H, W multiples of 64 (got %d x %d x %d): pad like adapt_x", N, H, W);
+    char key[48];
+    snprintf(key, sizeof key, "%d_%d_%d", N, H, W);
+    auto it = c->plans.find(key);
+    if (it != c->plans.end()) { *out = it->second.get(); return FISR_OK; }
+    std::unique_ptr<Plan> plan(new Plan());
+    plan->N = N; plan->H = H; plan->W = W;
+    Plan* pl = plan.get();
+    int rc = FISR_OK;
+    auto alloc = [&](size_t floats) -> float* {
+        void* p = nullptr;
+        if (rc != FISR_OK) return nullptr;
+        if (cudaMalloc(&p, floats * sizeof(float)) != cudaSuccess) { rc = fail(c, FISR_E_NOMEM, "cudaMalloc(%zu floats) failed", floats); return nullptr; }
+        cudaMemsetAsync(p, 0, floats * sizeof(float), c->stream);      // gap / pad channels stay zero for ever
+        plan->allocs.push_back(p);
+        return static_cast<float*>(p);
+    };
+    auto px = [&](int l) { return static_cast<size_t>(N) * (H >> l) * (W >> l); };
+    auto P = [&](const std::string& n) -> const Param& { return c->params[c->index.at(n)]; };
+    auto conv = [&](const std::string& name, View in, View outv, int l_in, int l_out, int stride, int dil, bool leaky, const float* add = nullptr) {
+        const Param& p = P(name);
+        PwcConv a{};
+        a.in = in.p; a.in_cs = in.cs; a.in_coff = in.coff; a.cin = p.cin_pad;
+        a.out = outv.p; a.out_cs = outv.cs; a.out_coff = outv.coff; a.cout = outv.C;
+        a.w = p.d_w; a.b = p.d_b;
+        a.N = N; a.Hin = H >> l_in; a.Win = W >> l_in; a.Hout = H >> l_out; a.Wout = W >> l_out;
+        a.stride = stride; a.dil = dil;
+        // tf 'same': total = (out - 1) s + 2 d + 1 - in, the smaller half first (0 before / 1 after for stride 2 on even sizes)
+        a.pad_y = std::max((a.Hout - 1) * stride + 2 * dil + 1 - a.Hin, 0) / 2;
+        a.pad_x = std::max((a.Wout - 1) * stride + 2 * dil + 1 - a.Win, 0) / 2;
+        a.leaky = leaky ? 1 : 0; a.add = add; a.add_cs = 2;
+        pl->ops.push_back([a](cudaStream_t st) { launch_conv3x3(a, st); });
+    };
+    // ---- buffers
+    float* D[kLvls + 1] = {nullptr};
+    float* c2[kLvls + 1] = {nullptr};
+    for (int l = kPredLvl; l <= kLvls; ++l) D[l] = alloc(px(l) * dense_cs(l));
+    for (int l = 1; l <= kLvls; ++l) c2[l] = alloc(px(l) * kChann[l]);
+    float* c1_1 = alloc(px(1) * kChann[1]);                // level 1 of image 1 feeds conv2a only
+    float* c1_6 = alloc(px(kLvls) * kChann[kLvls]);        // D_6 has no c1 slot (model_pwcnet.py:1549-1551)
+    float* tA = alloc(px(1) * kChann[1]);
+    float* tB = alloc(px(1) * kChann[1]);
+    float* T0 = alloc(px(kPredLvl) * 128);
+    float* T1 = alloc(px(kPredLvl) * 128);
+    float* warpbuf = alloc(px(kPredLvl) * 128);
+    float* flow_raw = alloc(px(kPredLvl) * 2);
+    for (int l = kPredLvl; l <= kLvls; ++l) plan->flow[l] = alloc(px(l) * 2);
+    if (rc != FISR_OK) return rc;
+    auto c1_view = [&](int l) -> View {
+        if (l == 1) return View{c1_1, kChann[1], 0, kChann[1]};
+        if (l == kLvls) return View{c1_6, kChann[l], 0, kChann[l]};
+        return View{D[l], dense_cs(l), kActs + kCorrPad, kChann[l]};
+    };
+    // ---- feature pyramids (model_pwcnet.py:1012-1101): the Siamese extractor on both images
+    for (int img = 0; img < 2; ++img) {
+        View x{nullptr, 3, 0, 3};
+        for (int l = 1; l <= kLvls; ++l) {
+            const std::string p = "pwcnet/featpyr/conv" + std::to_string(l);
+            const int f = kChann[l];
+            View dst = img == 0 ? c1_view(l) : View{c2[l], f, 0, f};
+            View ta{tA, f, 0, f}, tb{tB, f, 0, f};
+            if (l == 1) {        // the image pointer is bound per call
+                const Param& pa = P(p + "a");
+                const int which = img;
+                PwcConv a{};
+                a.in_cs = 3; a.in_coff = 0; a.cin = pa.cin_pad; a.out = tA; a.out_cs = f; a.out_coff = 0; a.cout = f; a.w = pa.d_w; a.b = pa.d_b;
+                a.N = N; a.Hin = H; a.Win = W; a.Hout = H / 2; a.Wout = W / 2; a.stride = 2; a.dil = 1; a.pad_y = 0; a.pad_x = 0; a.leaky = 1;
+                pl->ops.push_back([a, pl, which](cudaStream_t st) { PwcConv b = a; b.in = which ? pl->img2 : pl->img1; launch_conv3x3(b, st); });
+            } else {
+                conv(p + "a", x, ta, l - 1, l, 2, 1, true);
+            }
+            conv(p + "aa", ta, tb, l, l, 1, 1, true);
+            conv(p + "b", tb, dst, l, l, 1, 1, true);
+            x = dst;
+        }
+    }
+    // ---- coarse-to-fine cascade (model_pwcnet.py:1525-1593)
+    for (int l = kLvls; l >= kPredLvl; --l) {
+        const std::string sl = std::to_string(l);
+        const int cs = dense_cs(l), h = H >> l, w = W >> l, C = kChann[l];
+        const View c1v = c1_view(l);
+        float* Dl = D[l];
+        if (l == kLvls) {
+            float* c2l = c2[l];
+            pl->ops.push_back([=](cudaStream_t st) { launch_cost_volume(c1v.p, c1v.cs, c1v.coff, c2l, C, 0, C, Dl, cs, kActs, N, h, w, st); });
+        } else {
+            float* c2l = c2[l];
+            const int uf = kActs + kCorrPad + C;           // up_flow slot
+            const float scaler = 20.f / static_cast<float>(1 << l);
+            pl->ops.push_back([=](cudaStream_t st) {
+                launch_dense_warp(c2l, C, 0, C, Dl, cs, uf, scaler, warpbuf, N, h, w, st);
+                launch_cost_volume(c1v.p, c1v.cs, c1v.coff, warpbuf, C, 0, C, Dl, cs, kActs, N, h, w, st);
+            });
+        }
+        for (int k = 0; k < 5; ++k)
+            conv("pwcnet/predict_flow/conv" + sl + "_" + std::to_string(k), View{Dl, cs, dense_in_off(k), cs - dense_in_off(k)},
+                 View{Dl, cs, dense_off(k), kDense[k]}, l, l, 1, 1, true);
+        conv("pwcnet/predict_flow/flow" + sl, View{Dl, cs, 0, cs}, View{flow_raw, 2, 0, 2}, l, l, 1, 1, false);
+        // context network (model_pwcnet.py:1453-1522): flow + dilated conv chain on upfeat
+        float* bufs[2] = {T0, T1};
+        View cur{Dl, cs, 0, cs};
+        for (int k = 0; k < 7; ++k) {
+            const std::string nm = "pwcnet/ctxt/dc_conv" + sl + std::to_string(k + 1);
+            if (k < 6) {
+                View o{bufs[k & 1], kCtxtF[k], 0, kCtxtF[k]};
+                conv(nm, cur, o, l, l, 1, kCtxtD[k], true);
+                cur = o;
+            } else {
+                conv(nm, cur, View{plan->flow[l], 2, 0, 2}, l, l, 1, 1, false, flow_raw);
+            }
+        }
+        if (l != kPredLvl) {
+            const Param& pf = P("pwcnet/upsample/up_flow" + sl);
+            const Param& pe = P("pwcnet/upsample/up_feat" + sl);
+            float* Dn = D[l - 1];
+            const int csn = dense_cs(l - 1), ufn = kActs + kCorrPad + kChann[l - 1];
+            float* fl = plan->flow[l];
+            const float *wf = pf.d_w, *bf = pf.d_b, *we = pe.d_w, *be = pe.d_b;
+            const int cine = pe.cin_pad;
+            pl->ops.push_back([=](cudaStream_t st) {
+                launch_deconv4x4s2(fl, 2, 0, 2, wf, bf, Dn, csn, ufn, N, h, w, st);
+                launch_deconv4x4s2(Dl, cs, 0, cine, we, be, Dn, csn, ufn + 2, N, h, w, st);
+            });
+        }
+    }
+    {   // flow_pred = resize_bilinear(flow2, x4) * 4 (model_pwcnet.py:1588-1590)
+        float* f2 = plan->flow[kPredLvl];
+        const int h = H >> kPredLvl, w = W >> kPredLvl, S = 1 << kPredLvl;
+        pl->ops.push_back([=](cudaStream_t st) { launch_resize_flow(f2, pl->out, N, h, w, S, static_cast<float>(S), st); });
+    }
+    PWC_TRY(c, cudaStreamSynchronize(c->stream));
+    *out = plan.get();
+    c->plans[key] = std::move(plan);
+    return FISR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fisr_pwc_create(int device, fisr_pwc** out) {
+    if (!out) return FISR_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, FISR_E_CUDA, "no CUDA device (fisr_b200 has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(nullptr, FISR_E_INVALID, "device %d out of range", device);
+    std::unique_ptr<fisr_pwc> c(new fisr_pwc());
+    c->device = device;
+    Guard guard(device);
+    cudaFree(0);
+    PWC_TRY(nullptr, init_kernels());
+    PWC_TRY(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const auto& inv = inventory();
+    c->params.resize(inv.size());
+    for (size_t i = 0; i < inv.size(); ++i) {
+        Param& p = c->params[i];
+        p.cin_pad = inv[i].cin + (inv[i].gap_at >= 0 ? 3 : 0);
+        const size_t wn = static_cast<size_t>(inv[i].transpose ? 16 : 9) * p.cin_pad * inv[i].cout;
+        PWC_TRY(nullptr, cudaMalloc(&p.d_w, wn * sizeof(float)));
+        PWC_TRY(nullptr, cudaMemset(p.d_w, 0, wn * sizeof(float)));
+        PWC_TRY(nullptr, cudaMalloc(&p.d_b, inv[i].cout * sizeof(float)));
+        PWC_TRY(nullptr, cudaMemset(p.d_b, 0, inv[i].cout * sizeof(float)));
+        c->index[inv[i].name] = static_cast<int>(i);
+    }
+    PWC_TRY(nullptr, cudaDeviceSynchronize());
+    *out = c.release();
+    return FISR_OK;
+}
+
+void fisr_pwc_destroy(fisr_pwc* c) {
+    if (!c) return;
+    Guard guard(c->device);
+    cudaDeviceSynchronize();
+    c->plans.clear();
+    for (auto& p : c->params) { cudaFree(p.d_w); cudaFree(p.d_b); }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* fisr_pwc_last_error(const fisr_pwc* c) { return c ? c->err.c_str() : g_err.c_str(); }
+int fisr_pwc_num_params(void) { return static_cast<int>(names().size()); }
+const char* fisr_pwc_param_name(int i) { return (i >= 0 && i < (int)names().size()) ? names()[i].c_str() : nullptr; }
+int fisr_pwc_param_shape(int i, int dims[4]) {
+    const auto& inv = inventory();
+    if (i < 0 || i >= 2 * (int)inv.size() || !dims) return FISR_E_INVALID;
+    const PDef& d = inv[i / 2];
+    if (i % 2) { dims[0] = d.cout; dims[1] = dims[2] = dims[3] = 1; return 1; }
+    if (d.transpose) { dims[0] = 4; dims[1] = 4; dims[2] = d.cout; dims[3] = d.cin; }
+    else { dims[0] = 3; dims[1] = 3; dims[2] = d.cin; dims[3] = d.cout; }
+    return 4;
+}
+
+int fisr_pwc_set_param(fisr_pwc* c, const char* name, const float* h_data, size_t count) {
+    if (!c || !name || !h_data) return FISR_E_INVALID;
+    std::string s(name);
+    const bool is_w = s.size() > 7 && s.substr(s.size() - 7) == "/kernel";
+    const bool is_b = s.size() > 5 && s.substr(s.size() - 5) == "/bias";
+    if (!is_w && !is_b) return fail(c, FISR_E_INVALID, "parameter name must end in /kernel or /bias: %s", name);
+    auto it = c->index.find(s.substr(0, s.size() - (is_w ? 7 : 5)));
+    if (it == c->index.end()) return fail(c, FISR_E_INVALID, "unknown parameter %s", name);
+    const PDef& d = inventory()[it->second];
+    Param& p = c->params[it->second];
+    Guard guard(c->device);
+    PWC_TRY(c, cudaDeviceSynchronize());
+    if (is_b) {
+        if (count != (size_t)d.cout) return fail(c, FISR_E_INVALID, "%s has %d elements, got %zu", name, d.cout, count);
+        PWC_TRY(c, cudaMemcpy(p.d_b, h_data, count * sizeof(float), cudaMemcpyHostToDevice));
+        return FISR_OK;
+    }
+    const size_t taps = d.transpose ? 16 : 9, expect = taps * d.cin * d.cout;
+    if (count != expect) return fail(c, FISR_E_INVALID, "%s has %zu elements, got %zu", name, expect, count);
+    // kernel layout with the 3 zero rows of the padded cost-volume slot: reference input channel i sits at i (+3 past the gap)
+    std::vector<float> packed(taps * p.cin_pad * d.cout, 0.f);
+    auto slot = [&](int ci) { return (d.gap_at >= 0 && ci >= d.gap_at) ? ci + 3 : ci; };
+    for (size_t t = 0; t < taps; ++t)
+        for (int ci = 0; ci < d.cin; ++ci)
+            for (int co = 0; co < d.cout; ++co) {
+                if (d.transpose) packed[(t * d.cout + co) * p.cin_pad + slot(ci)] = h_data[(t * d.cout + co) * d.cin + ci];      // [4,4,out,in]
+                else packed[(t * p.cin_pad + slot(ci)) * d.cout + co] = h_data[(t * d.cin + ci) * d.cout + co];                  // [3,3,in,out]
+            }
+    PWC_TRY(c, cudaMemcpy(p.d_w, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+    p.h_w.assign(h_data, h_data + count);
+    return FISR_OK;
+}
+
+int fisr_pwc_forward(fisr_pwc* c, const float* d_img1, const float* d_img2, int N, int H, int W, float* d_flow, void* stream) {
+    if (!c || !d_img1 || !d_img2 || !d_flow) return FISR_E_INVALID;
+    Guard guard(c->device);
+    Plan* plan = nullptr;
+    const int rc = build_plan(c, N, H, W, &plan);
+    if (rc != FISR_OK) return rc;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    plan->img1 = d_img1; plan->img2 = d_img2; plan->out = d_flow;
+    for (auto& op : plan->ops) op(st);
+    c->launches += static_cast<long long>(plan->ops.size());
+    c->last = plan;
+    PWC_TRY(c, cudaGetLastError());
+    return FISR_OK;
+}
+
+int fisr_pwc_debug_flow(fisr_pwc* c, int lvl, float* h_dst, size_t count) {
+    if (!c || !h_dst || lvl < kPredLvl || lvl > kLvls) return FISR_E_INVALID;
+    if (!c->last) return fail(c, FISR_E_INVALID, "no forward has run yet");
+    Guard guard(c->device);
+    const size_t n = static_cast<size_t>(c->last->N) * (c->last->H >> lvl) * (c->last->W >> lvl) * 2;
+    if (count != n) return fail(c, FISR_E_INVALID, "flow%d has %zu elements, got %zu", lvl, n, count);
+    PWC_TRY(c, cudaDeviceSynchronize());
+    PWC_TRY(c, cudaMemcpy(h_dst, c->last->flow[lvl], n * sizeof(float), cudaMemcpyDeviceToHost));
+    return FISR_OK;
+}
+
+long long fisr_pwc_launch_count(const fisr_pwc* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,317 @@
+// PWC-Net inference kernels: the optical-flow network the reference runs in front of its flow warp
+// (FISR_tfoptflow/model_pwcnet.py:1012-1593, PWC-Net-large, 6-level pyramid, flow predicted at level 2).  fp32 CUDA-core
+// kernels on NHWC tensors addressed as (pointer, channel stride, channel offset), so that the DenseNet-style concatenations of
+// the flow estimator (model_pwcnet.py:1415-1437: x = concat([act, x])) are channel slices of ONE buffer per pyramid level and
+// never copied.  TF semantics restated: 'same' padding puts the odd pad element AFTER the data (stride-2 convs on even sizes pad
+// 0 before, 1 after); conv2d_transpose 4x4 s2 'same' is out[2i + k - 1] += in[i] w[k].
+#include "common.cuh"
+#include "pwc_kernels.h"
+
+namespace fisr {
+namespace pwc {
+
+namespace {
+
+__device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : 0.1f * x; }      // tf.nn.leaky_relu(alpha=0.1)
+
+// ---------------------------------------------------------------- 3x3 conv, wide outputs (Cout a multiple of 4)
+// Implicit GEMM on CUDA cores: a block owns 128 output pixels x 64 output channels, a thread 8 x 8 of them; per (tap, 8 input
+// channels) the block stages the 128 x 8 activation slice (gathered at the tap's stride / dilation offset, zero outside) and the
+// 8 x 64 weight slice in shared memory and every thread does 64 FMAs per 4 shared-memory vector loads.
+constexpr int kPx = 128, kCo = 64, kCi = 8;
+
+template <bool LEAKY>
+__global__ void __launch_bounds__(128) conv3x3_wide_kernel(const PwcConv p) {
+    __shared__ __align__(16) float As[kCi][kPx];
+    __shared__ __align__(16) float Bs[kCi][kCo];
+    const int t = threadIdx.x;
+    const int pg = t & 15, cg = t >> 4;
+    const long long npix = static_cast<long long>(p.N) * p.Hout * p.Wout;
+    const long long P = static_cast<long long>(blockIdx.x) * kPx + t;          // the pixel this thread gathers
+    const int co_base = blockIdx.y * kCo;
+    int n = 0, oy = 0, ox = 0;
+    const bool live = P < npix;
+    if (live) {
+        ox = static_cast<int>(P % p.Wout);
+        const long long r = P / p.Wout;
+        oy = static_cast<int>(r % p.Hout);
+        n = static_cast<int>(r / p.Hout);
+    }
+    const bool vec_in = ((p.in_cs | p.in_coff) & 3) == 0;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const int bci = t >> 4, bco = (t & 15) * 4;                                 // this thread's weight fetch: row bci, 4 columns at bco
+    for (int tap = 0; tap < 9; ++tap) {
+        const int iy = oy * p.stride + (tap / 3) * p.dil - p.pad_y, ix = ox * p.stride + (tap % 3) * p.dil - p.pad_x;
+        const bool inside = live && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+        const float* src = p.in + (static_cast<size_t>(n) * p.Hin + (inside ? iy : 0)) * p.Win * p.in_cs + static_cast<size_t>(inside ? ix : 0) * p.in_cs + p.in_coff;
+        for (int c0 = 0; c0 < p.cin; c0 += kCi) {
+            float a[kCi];
+#pragma unroll
+            for (int j = 0; j < kCi; ++j) a[j] = 0.f;
+            if (inside) {
+                if (vec_in && c0 + kCi <= p.cin) {
+                    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + c0)), v1 = __ldg(reinterpret_cast<const float4*>(src + c0 + 4));
+                    a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w; a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kCi; ++j) if (c0 + j < p.cin) a[j] = __ldg(src + c0 + j);
+                }
+            }
+            float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + bci < p.cin && co_base + bco < p.cout)
+                wv = __ldg(reinterpret_cast<const float4*>(p.w + (static_cast<size_t>(tap) * p.cin + c0 + bci) * p.cout + co_base + bco));
+            __syncthreads();                                                    // previous slice fully consumed
+#pragma unroll
+            for (int j = 0; j < kCi; ++j) As[j][t] = a[j];
+            *reinterpret_cast<float4*>(&Bs[bci][bco]) = wv;
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < kCi; ++c) {
+                const float4 a0 = *reinterpret_cast<const float4*>(&As[c][pg * 8]), a1 = *reinterpret_cast<const float4*>(&As[c][pg * 8 + 4]);
+                const float4 b0 = *reinterpret_cast<const float4*>(&Bs[c][cg * 8]), b1 = *reinterpret_cast<const float4*>(&Bs[c][cg * 8 + 4]);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+        }
+    }
+    const int co0 = co_base + cg * 8;
+    if (co0 >= p.cout) return;
+    float bias[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bias[j] = co0 + j < p.cout ? __ldg(p.b + co0 + j) : 0.f;
+    const bool vec_out = ((p.out_cs | p.out_coff) & 3) == 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long q = static_cast<long long>(blockIdx.x) * kPx + pg * 8 + i;
+        if (q >= npix) break;
+        float* d = p.out + static_cast<size_t>(q) * p.out_cs + p.out_coff + co0;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[j] = acc[i][j] + bias[j]; if (LEAKY) v[j] = lrelu(v[j]); }
+        if (vec_out && co0 + 8 <= p.cout) {
+            *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (co0 + j < p.cout) d[j] = v[j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- 3x3 conv, narrow outputs (Cout <= 4: the flow predictors)
+// A thread owns one output pixel; the 9 x Cin x Cout weights sit in shared memory (broadcast reads).  Optional residual input
+// (refine_flow: flow + dc_conv7, model_pwcnet.py:1522).
+template <int COUT>
+__global__ void __launch_bounds__(128) conv3x3_narrow_kernel(const PwcConv p) {
+    extern __shared__ float wsm[];                              // [9][cin][COUT]
+    for (int i = threadIdx.x; i < 9 * p.cin * COUT; i += blockDim.x) wsm[i] = __ldg(p.w + i);
+    __syncthreads();
+    const long long npix = static_cast<long long>(p.N) * p.Hout * p.Wout;
+    const long long P = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (P >= npix) return;
+    const int ox = static_cast<int>(P % p.Wout);
+    const long long r = P / p.Wout;
+    const int oy = static_cast<int>(r % p.Hout), n = static_cast<int>(r / p.Hout);
+    const bool vec_in = ((p.in_cs | p.in_coff) & 3) == 0;
+    float acc[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) acc[j] = __ldg(p.b + j);
+    for (int tap = 0; tap < 9; ++tap) {
+        const int iy = oy * p.stride + (tap / 3) * p.dil - p.pad_y, ix = ox * p.stride + (tap % 3) * p.dil - p.pad_x;
+        if (iy < 0 || iy >= p.Hin || ix < 0 || ix >= p.Win) continue;
+        const float* src = p.in + (static_cast<size_t>(n) * p.Hin + iy) * p.Win * p.in_cs + static_cast<size_t>(ix) * p.in_cs + p.in_coff;
+        const float* wt = wsm + tap * p.cin * COUT;
+        int c = 0;
+        if (vec_in)
+            for (; c + 4 <= p.cin; c += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
+#pragma unroll
+                for (int j = 0; j < COUT; ++j)
+                    acc[j] = fmaf(v.w, wt[(c + 3) * COUT + j], fmaf(v.z, wt[(c + 2) * COUT + j], fmaf(v.y, wt[(c + 1) * COUT + j], fmaf(v.x, wt[c * COUT + j], acc[j]))));
+            }
+        for (; c < p.cin; ++c) {
+            const float v = __ldg(src + c);
+#pragma unroll
+            for (int j = 0; j < COUT; ++j) acc[j] = fmaf(v, wt[c * COUT + j], acc[j]);
+        }
+    }
+    float* d = p.out + static_cast<size_t>(P) * p.out_cs + p.out_coff;
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) {
+        float v = acc[j];
+        if (p.add) v += __ldg(p.add + static_cast<size_t>(P) * p.add_cs + j);
+        d[j] = p.leaky ? lrelu(v) : v;
+    }
+}
+
+// ---------------------------------------------------------------- conv2d_transpose 4x4, stride 2, 'same', 2 filters (model_pwcnet.py:1180-1224)
+// out[n, oy, ox, co] = b[co] + sum over (ky, kx, ci) with oy = 2 iy + ky - 1, ox = 2 ix + kx - 1 of in[n, iy, ix, ci] w[ky, kx, co, ci]
+__global__ void __launch_bounds__(128) deconv4x4s2_kernel(const float* __restrict__ in, int in_cs, int in_coff, int cin, const float* __restrict__ w,
+                                                          const float* __restrict__ b, float* __restrict__ out, int out_cs, int out_coff, int N, int h, int wd) {
+    const long long npix = static_cast<long long>(N) * 4 * h * wd;
+    const long long P = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (P >= npix) return;
+    const int ox = static_cast<int>(P % (2 * wd));
+    const long long r = P / (2 * wd);
+    const int oy = static_cast<int>(r % (2 * h)), n = static_cast<int>(r / (2 * h));
+    float a0 = __ldg(b), a1 = __ldg(b + 1);
+    const bool vec = ((in_cs | in_coff | cin) & 3) == 0;
+#pragma unroll
+    for (int sy = 0; sy < 2; ++sy) {
+        const int ky = ((oy + 1) & 1) + 2 * sy, iy = (oy + 1 - ky) >> 1;
+        if (iy < 0 || iy >= h) continue;
+#pragma unroll
+        for (int sx = 0; sx < 2; ++sx) {
+            const int kx = ((ox + 1) & 1) + 2 * sx, ix = (ox + 1 - kx) >> 1;
+            if (ix < 0 || ix >= wd) continue;
+            const float* src = in + (static_cast<size_t>(n) * h + iy) * wd * in_cs + static_cast<size_t>(ix) * in_cs + in_coff;
+            const float* w0 = w + static_cast<size_t>((ky * 4 + kx) * 2) * cin;
+            const float* w1 = w0 + cin;
+            int c = 0;
+            if (vec)
+                for (; c + 4 <= cin; c += 4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
+                    const float4 u0 = __ldg(reinterpret_cast<const float4*>(w0 + c)), u1 = __ldg(reinterpret_cast<const float4*>(w1 + c));
+                    a0 = fmaf(v.w, u0.w, fmaf(v.z, u0.z, fmaf(v.y, u0.y, fmaf(v.x, u0.x, a0))));
+                    a1 = fmaf(v.w, u1.w, fmaf(v.z, u1.z, fmaf(v.y, u1.y, fmaf(v.x, u1.x, a1))));
+                }
+            for (; c < cin; ++c) {
+                const float v = __ldg(src + c);
+                a0 = fmaf(v, __ldg(w0 + c), a0);
+                a1 = fmaf(v, __ldg(w1 + c), a1);
+            }
+        }
+    }
+    float* d = out + static_cast<size_t>(P) * out_cs + out_coff;
+    d[0] = a0;
+    d[1] = a1;
+}
+
+// ---------------------------------------------------------------- cost volume, search range 4 (model_pwcnet.py:1226-1277)
+// out[p, (dy+4)*9 + (dx+4)] = leaky_relu(mean_c c1[p, c] * c2[p + (dy, dx), c]), zero outside the image
+__global__ void __launch_bounds__(256) cost_volume_kernel(const float* __restrict__ c1, int c1_cs, int c1_coff, const float* __restrict__ c2, int c2_cs, int c2_coff,
+                                                          int C, float* __restrict__ out, int out_cs, int out_coff, int N, int h, int w) {
+    const long long total = static_cast<long long>(N) * h * w * 81;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int d = static_cast<int>(i % 81);
+    const long long P = i / 81;
+    const int x = static_cast<int>(P % w);
+    const long long r = P / w;
+    const int y = static_cast<int>(r % h), n = static_cast<int>(r / h);
+    const int yy = y + d / 9 - 4, xx = x + d % 9 - 4;
+    float s = 0.f;
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+        const float* a = c1 + static_cast<size_t>(P) * c1_cs + c1_coff;
+        const float* b = c2 + (static_cast<size_t>(n) * h + yy) * w * c2_cs + static_cast<size_t>(xx) * c2_cs + c2_coff;
+        if (((c1_cs | c1_coff | c2_cs | c2_coff | C) & 3) == 0) {
+            for (int c = 0; c < C; c += 4) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(a + c)), v = __ldg(reinterpret_cast<const float4*>(b + c));
+                s = fmaf(u.w, v.w, fmaf(u.z, v.z, fmaf(u.y, v.y, fmaf(u.x, v.x, s))));
+            }
+        } else {
+            for (int c = 0; c < C; ++c) s = fmaf(__ldg(a + c), __ldg(b + c), s);
+        }
+    }
+    out[static_cast<size_t>(P) * out_cs + out_coff + d] = lrelu(s / static_cast<float>(C));
+}
+
+// ---------------------------------------------------------------- dense_image_warp (model_pwcnet.py:1106-1178)
+// out[p, c] = bilinear(img, (x + s u, y + s v)) with TF's _interpolate_bilinear clamping: floor in [0, size - 2], weight in [0, 1]
+__global__ void __launch_bounds__(256) dense_warp_kernel(const float* __restrict__ img, int cs, int coff, int C, const float* __restrict__ flow, int f_cs, int f_coff,
+                                                         float scale, float* __restrict__ out, int N, int h, int w) {
+    const int cv = C / 4;
+    const long long total = static_cast<long long>(N) * h * w * cv;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c4 = static_cast<int>(i % cv) * 4;
+    const long long P = i / cv;
+    const int x = static_cast<int>(P % w);
+    const long long r = P / w;
+    const int y = static_cast<int>(r % h), n = static_cast<int>(r / h);
+    const float qx = static_cast<float>(x) + scale * __ldg(flow + static_cast<size_t>(P) * f_cs + f_coff);
+    const float qy = static_cast<float>(y) + scale * __ldg(flow + static_cast<size_t>(P) * f_cs + f_coff + 1);
+    const float fx0 = fminf(fmaxf(floorf(qx), 0.f), static_cast<float>(w - 2)), fy0 = fminf(fmaxf(floorf(qy), 0.f), static_cast<float>(h - 2));
+    const float ax = fminf(fmaxf(qx - fx0, 0.f), 1.f), ay = fminf(fmaxf(qy - fy0, 0.f), 1.f);
+    const int x0 = static_cast<int>(fx0), y0 = static_cast<int>(fy0);
+    const float* base = img + (static_cast<size_t>(n) * h + y0) * w * cs + static_cast<size_t>(x0) * cs + coff + c4;
+    const float4 tl = __ldg(reinterpret_cast<const float4*>(base)), tr = __ldg(reinterpret_cast<const float4*>(base + cs));
+    const float4 bl = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(w) * cs)), br = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(w) * cs + cs));
+    auto mix = [&](float a, float b, float c, float d) {
+        const float top = a + ax * (b - a), bot = c + ax * (d - c);
+        return top + ay * (bot - top);
+    };
+    *reinterpret_cast<float4*>(out + static_cast<size_t>(P) * C + c4) =
+        make_float4(mix(tl.x, tr.x, bl.x, br.x), mix(tl.y, tr.y, bl.y, br.y), mix(tl.z, tr.z, bl.z, br.z), mix(tl.w, tr.w, bl.w, br.w));
+}
+
+// ---------------------------------------------------------------- tf.image.resize_bilinear x S (legacy: src = dst / S), times `gain`
+__global__ void __launch_bounds__(256) resize_flow_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int h, int w, int S, float gain) {
+    const long long total = static_cast<long long>(N) * h * S * w * S;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ox = static_cast<int>(i % (w * S));
+    const long long r = i / (w * S);
+    const int oy = static_cast<int>(r % (h * S)), n = static_cast<int>(r / (h * S));
+    const float sy = static_cast<float>(oy) / S, sx = static_cast<float>(ox) / S;
+    const int y0 = min(static_cast<int>(sy), h - 1), x0 = min(static_cast<int>(sx), w - 1);
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float fy = sy - y0, fx = sx - x0;
+    const float2* b = reinterpret_cast<const float2*>(in) + static_cast<size_t>(n) * h * w;
+    const float2 tl = __ldg(b + static_cast<size_t>(y0) * w + x0), tr = __ldg(b + static_cast<size_t>(y0) * w + x1);
+    const float2 bl = __ldg(b + static_cast<size_t>(y1) * w + x0), br = __ldg(b + static_cast<size_t>(y1) * w + x1);
+    // the two-pass form of the TF kernel: rows first (top / bottom interpolated along x), then along y
+    const float tx = tl.x * (1.f - fx) + tr.x * fx, bx = bl.x * (1.f - fx) + br.x * fx;
+    const float ty = tl.y * (1.f - fx) + tr.y * fx, by = bl.y * (1.f - fx) + br.y * fx;
+    reinterpret_cast<float2*>(out)[i] = make_float2((tx * (1.f - fy) + bx * fy) * gain, (ty * (1.f - fy) + by * fy) * gain);
+}
+
+inline unsigned blocks_for(long long total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
+
+}  // namespace
+
+cudaError_t init_kernels() {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_narrow_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    return e;
+}
+
+void launch_conv3x3(const PwcConv& p, cudaStream_t st) {
+    const long long npix = static_cast<long long>(p.N) * p.Hout * p.Wout;
+    if (p.cout == 2) {
+        conv3x3_narrow_kernel<2><<<blocks_for(npix, 128), 128, static_cast<size_t>(9) * p.cin * 2 * sizeof(float), st>>>(p);
+        return;
+    }
+    dim3 grid(blocks_for(npix, kPx), (p.cout + kCo - 1) / kCo);
+    if (p.leaky) conv3x3_wide_kernel<true><<<grid, 128, 0, st>>>(p);
+    else conv3x3_wide_kernel<false><<<grid, 128, 0, st>>>(p);
+}
+
+void launch_deconv4x4s2(const float* in, int in_cs, int in_coff, int cin, const float* w, const float* b, float* out, int out_cs, int out_coff,
+                        int N, int h, int wd, cudaStream_t st) {
+    deconv4x4s2_kernel<<<blocks_for(static_cast<long long>(N) * 4 * h * wd, 128), 128, 0, st>>>(in, in_cs, in_coff, cin, w, b, out, out_cs, out_coff, N, h, wd);
+}
+
+void launch_cost_volume(const float* c1, int c1_cs, int c1_coff, const float* c2, int c2_cs, int c2_coff, int C, float* out, int out_cs, int out_coff,
+                        int N, int h, int w, cudaStream_t st) {
+    cost_volume_kernel<<<blocks_for(static_cast<long long>(N) * h * w * 81, 256), 256, 0, st>>>(c1, c1_cs, c1_coff, c2, c2_cs, c2_coff, C, out, out_cs, out_coff, N, h, w);
+}
+
+void launch_dense_warp(const float* img, int cs, int coff, int C, const float* flow, int f_cs, int f_coff, float scale, float* out, int N, int h, int w,
+                       cudaStream_t st) {
+    dense_warp_kernel<<<blocks_for(static_cast<long long>(N) * h * w * (C / 4), 256), 256, 0, st>>>(img, cs, coff, C, flow, f_cs, f_coff, scale, out, N, h, w);
+}
+
+void launch_resize_flow(const float* in, float* out, int N, int h, int w, int S, float gain, cudaStream_t st) {
+    resize_flow_kernel<<<blocks_for(static_cast<long long>(N) * h * S * w * S, 256), 256, 0, st>>>(in, out, N, h, w, S, gain);
+}
+
+}  // namespace pwc
+}  // namespace fisr

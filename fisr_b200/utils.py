@@ -82,21 +82,22 @@ def write_flo_file_5dim(flow, filename):
         flow.tofile(f)
 
 
-def _h5py():
+def _h5_read(fname, key):
+    """``h5py.File(fname, 'r')[key][()]`` (utils.py:31-34,47): h5py when it is installed, else the built-in minimal HDF5 reader
+    (fisr_b200/hdf5_min.py -- superblock v0-v3, contiguous / chunked + deflate / shuffle / fletcher32 datasets)."""
     try:
         import h5py
-        return h5py
-    except ImportError as e:
-        raise ImportError("reading MATLAB v7.3 .mat files needs h5py (not installed here); "
-                          "save the array with np.save and pass the .npy path instead") from e
+    except ImportError:
+        from .hdf5_min import read_dataset
+        return read_dataset(fname, key)
+    with h5py.File(fname, 'r') as f:
+        return f[key][()]
 
 
 def read_mat_file(data_fname, label_fname, data_name, label_name):
     """utils.py:29-42: training data / label [N, N_seq, C, W, H] uint8 -> float32 /255, [N, N_seq, H, W, C]."""
     def load(fname, key):
-        if fname.endswith('.npy'):
-            return np.load(fname)
-        return _h5py().File(fname, 'r')[key][()]
+        return np.load(fname) if fname.endswith('.npy') else _h5_read(fname, key)
     data = np.array(load(data_fname, data_name), dtype=np.float32) / 255.
     label = np.array(load(label_fname, label_name), dtype=np.float32) / 255.
     return np.swapaxes(data, 2, 4), np.swapaxes(label, 2, 4)
@@ -104,12 +105,18 @@ def read_mat_file(data_fname, label_fname, data_name, label_name):
 
 def read_mat_file_warp(data_fname, data_name):
     """utils.py:45-54: warped frames -> float32 /255, [N, N_seq, H, W, C].  A ``.npy`` file holds that layout already
-    (values 0..255, as ``FISR_for_video_Warp_Img`` writes them)."""
+    (values 0..255); a v7.3 ``.mat`` holds the transpose (MATLAB order), like the files ``hdf5storage`` writes."""
     if data_fname.endswith('.npy'):
         return np.array(np.load(data_fname), dtype=np.float32) / 255.
-    data = _h5py().File(data_fname, 'r')[data_name][()]
-    data = np.array(data, dtype=np.float32) / 255.
+    data = np.array(_h5_read(data_fname, data_name), dtype=np.float32) / 255.
     return np.transpose(data, (4, 3, 2, 1, 0))
+
+
+def write_mat_file_warp(data_fname, pred, data_name='pred'):
+    """``hdf5storage.write({u'pred': pred}, '.', name, matlab_compatible=True)`` (..warp_img_with_flo.py:131-137): a MATLAB v7.3
+    file whose dataset is the transpose of ``pred`` [N-1, 2, h, w, 3] float32 (0..255), class 'single'."""
+    from .hdf5_min import write_mat73
+    write_mat73(data_fname, {data_name: np.ascontiguousarray(np.transpose(np.asarray(pred, dtype=np.float32), (4, 3, 2, 1, 0)))})
 
 
 def merge_seq_dim(data):                           # utils.py:78-83

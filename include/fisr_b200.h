@@ -218,6 +218,28 @@ long long fisr_launch_count(const fisr_ctx* ctx);
 int fisr_plan_info(fisr_ctx* ctx, int N, int H, int W, double* flops, double* mma_efficiency, int* num_launches,
                    size_t* workspace_bytes);
 
+/* ---- PWC-Net inference: the flow estimator in front of the warp ------------------------------------- */
+/* `ModelPWCNet(mode='test')` + `predict_from_img_pairs` (FISR_tfoptflow/model_pwcnet.py:204-237,957-1006) configured as
+ * FISR_for_video_pwcnet_predict_from_img_test.py:96-110 sets it: PWC-Net-large, dense + residual connections, 6 pyramid levels,
+ * flow predicted at level 2, search range 4.  Parameters carry the TensorFlow variable names of tfoptflow's checkpoints,
+ * "pwcnet/featpyr/conv1a/kernel" ... "pwcnet/upsample/up_feat3/bias" (182 tensors, 14,079,050 values); conv kernels are HWIO
+ * [3,3,Cin,Cout], conv2d_transpose kernels [4,4,2,Cin].  PARITY UNPINNED: eight modules of the reference's PWC-Net copy and its
+ * checkpoint are not in the tree (model_pwcnet.py:21-28); the CUDA path is checked against oracle/pwcnet_oracle.py. */
+typedef struct fisr_pwc fisr_pwc;
+int fisr_pwc_create(int device, fisr_pwc** out);
+void fisr_pwc_destroy(fisr_pwc* pwc);
+const char* fisr_pwc_last_error(const fisr_pwc* pwc);
+int fisr_pwc_num_params(void);
+const char* fisr_pwc_param_name(int index);
+int fisr_pwc_param_shape(int index, int dims[4]);
+int fisr_pwc_set_param(fisr_pwc* pwc, const char* name, const float* h_data, size_t count);
+/* `nn()` (model_pwcnet.py:1525-1593) on N image pairs: d_img1, d_img2 f32 [N,H,W,3] in 0..1 (adapt_x: /255, zero-padded so that
+ * H, W are multiples of 64) -> d_flow f32 [N,H,W,2] = flow from image 1 to image 2 in pixels, (u, v) per pixel.  Asynchronous. */
+int fisr_pwc_forward(fisr_pwc* pwc, const float* d_img1, const float* d_img2, int N, int H, int W, float* d_flow, void* stream);
+/* refined flow of pyramid level lvl (2..6) of the last forward, [N,H/2^lvl,W/2^lvl,2] (test hook) */
+int fisr_pwc_debug_flow(fisr_pwc* pwc, int lvl, float* h_dst, size_t count);
+long long fisr_pwc_launch_count(const fisr_pwc* pwc);
+
 #ifdef __cplusplus
 }
 #endif
