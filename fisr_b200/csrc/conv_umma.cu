@@ -108,8 +108,10 @@ bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int n
     a.NB = cout_pad / NT;
     a.num_tiles = n_img * a.tiles_x * a.tiles_y * a.NB;
     a.a_plane_bytes = (a.TH + 2) * a.P * 128;
-    // f16f8 (phase-split main loop): one buffer per activation plane (a second one measured no better, even where it fits)
-    a.a_stages = planes == 3 ? 1 : 2;
+    // f16f8 (phase-split main loop): one buffer per activation plane for the wide tiles (a second one measured 10-17 % slower on
+    // the 64-wide layers: it costs weight slots), two for the narrow conv/2 heads, which are HBM bound on their 256-channel input
+    // (4.7 TB/s, 72 % of the measured copy peak) and gain 3-6 % from the deeper patch prefetch (profiles/r02_layers_*.txt)
+    a.a_stages = planes == 3 ? (NT <= 32 ? 2 : 1) : 2;
     if (const char* e = getenv("FISR_ASTAGES")) { if (planes == 3 && NT < 128 && (atoi(e) == 1 || atoi(e) == 2)) a.a_stages = atoi(e); }
     for (int i = 0; i < 8; ++i) a.tapmask[i] = 0x1FFu;
     a.ps_cout = 0;
