@@ -74,3 +74,18 @@ def test_adam_matches_tf1_formula(engine):
     ref = O.model(params, x)[2]
     assert (engine.forward(x.cuda())[2].cpu() - ref).abs().max() < 1e-4
     engine.adam_reset(0)
+
+
+def test_config3_full_batch_forward_and_loss(engine):
+    """BASELINE configs[2] at its full shape -- B = 16, LR 192x192, label 384x384x21, i.e. a 64-image forward of the four
+    weight-shared passes: the 11 scalars of FISRnet.py:651-657 against the fp32 oracle on the same batch (the forward half of
+    the step; gradients at this patch size are checked in test_gpu_backward.py at batch 1, float64 autograd over 16 samples
+    takes ~10 min of host time)."""
+    engine.set_precision("f16x3")
+    params = O.init_params(61)
+    engine.set_params(params)
+    batch = _batch(16, 192, 192, 62)
+    ref, _, _ = L.training_forward(params, *batch)
+    got = engine.train_forward(*[t.cuda() for t in batch])
+    for k in L.SCALAR_NAMES:
+        assert abs(got[k] - float(ref[k])) < 2e-5 * max(1.0, abs(float(ref[k]))), (k, got[k], float(ref[k]))

@@ -77,6 +77,9 @@ def test_window_full_size_geometry(engine):
 
 
 def test_warp_matches_cv2(engine):
+    """cv2.remap is itself the oracle.  The reference pins opencv_python==4.2.0.32 (requirements.txt:9); this image has a newer
+    4.x, whose INTER_LINEAR remap (5 fractional bits, fp32 weight table, border by index clamp) is what the kernel restates --
+    so the warp row is pinned to the cv2 that is installed, not to 4.2.0.32 itself."""
     g = np.load(os.path.join(GOLDEN, "scene1_lr_crop.npz"))["frames"]
     rng = np.random.default_rng(3)
     h, w = g[0].shape[:2]
