@@ -28,3 +28,16 @@ eng.set_precision("f16x3")
 mk = lambda c, s=32: torch.rand(1, s, s, c, generator=g).cuda()
 s = eng.train_backward(mk(15), (mk(16) - 0.5) * 0.1, (mk(8) - 0.5) * 0.1, mk(24), mk(12), mk(21, 64))
 torch.cuda.synchronize(); print("train ok", s["total_loss"], flush=True)
+s = eng.train_step(mk(15), (mk(16) - 0.5) * 0.1, (mk(8) - 0.5) * 0.1, mk(24), mk(12), mk(21, 64), lr=1e-4)      # + multi-tensor Adam / re-pack
+torch.cuda.synchronize(); print("train step ok", s["total_loss"], eng.adam_steps, flush=True)
+st = eng.get_adam_state(); eng.set_adam_state(st["m"], st["v"], st["t"]); eng.adam_reset(0)
+for w in (200, 190):                                                    # word-gather and byte-gather paths of the warp kernel
+    fr = torch.randint(0, 256, (3, 72, w, 3), generator=g, dtype=torch.uint8).cuda()
+    fl = (torch.randn(4, 72, w, 2, generator=g) * 30).cuda()            # far out-of-frame taps: BORDER_REPLICATE
+    out = eng.warp_batch(fr, fl, [1, 0, 2, 1], 0.5, 1.0); torch.cuda.synchronize(); print("warp ok", w, float(out.mean()), flush=True)
+from fisr_b200.pwcnet import PWCNet
+from oracle import pwcnet_oracle as W
+net = PWCNet(0); net.set_params(W.init_params(0))
+f = net.forward(torch.rand(2, 64, 128, 3, generator=g).cuda(), torch.rand(2, 64, 128, 3, generator=g).cuda())
+torch.cuda.synchronize(); print("pwcnet ok", float(f.abs().mean()), flush=True)
+net.close()
