@@ -466,6 +466,26 @@ def measure_extras(eng, dev, peaks, bench_precision):
                              "note": "Engine.warp_batch: 16 warps (9-frame clip) per launch, 10 launches, CUDA events; 23 B/px = u8 source + f32 flow + f32 output"}
     del yuv, flo
 
+    # ---- PWC-Net (the flow step of BASELINE configs[4]): both directions of one 1080p frame pair after the
+    # reference's x2 pre-upscale, padded to multiples of 64 (..pwcnet_predict_from_img_test.py:126-131, model_pwcnet.py:371-409)
+    try:
+        import numpy as np
+        from fisr_b200.pwcnet import PWCNet, param_inventory as pwc_inventory
+        rng = np.random.default_rng(7)
+        net = PWCNet(dev.index)
+        net.set_params({n: ((rng.standard_normal(sh) * (2.0 / max(1, int(np.prod(sh[:3])))) ** 0.5) if len(sh) == 4 else np.zeros(sh)).astype(np.float32)
+                        for n, sh in pwc_inventory().items()})
+        a = torch.rand(2, 2176, 3840, 3, generator=g).to(dev)
+        b = torch.rand(2, 2176, 3840, 3, generator=g).to(dev)
+        n0 = net.launch_count
+        ms = timed(lambda: net.forward(a, b), 1, 3)
+        out["pwcnet_1080p_pair_x2"] = {"ms": ms, "launches_per_forward": (net.launch_count - n0) // 4, "input": "2 x [2176,3840,3] (both directions of one pair)",
+                                       "note": "PWC-Net-large (6 levels, flow at level 2, dense + residual connections), fp32 CUDA-core kernels; random weights"}
+        net.close()
+        del a, b
+    except Exception as e:                       # a next-row component must not take the headline line down with it
+        out["pwcnet_1080p_pair_x2"] = {"error": str(e)[:200]}
+
     # ---- config 2: img [8,192,192,29] forward (FISRnet.py:747-748), both precision modes
     x = torch.rand(8, 192, 192, 29, generator=g).to(dev)
     for prec in ("f16f8", "f16x3"):

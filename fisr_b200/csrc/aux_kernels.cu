@@ -1,6 +1,6 @@
 // HBM-bound helper kernels around the conv stack: weight packing, input packing (with the reference's
-// "bicubic" = strided subsample), legacy bilinear x2 upsample, 2x2 max-pool, tile pack / unpack for the
-// tiled video path, and the flow warp.  All are one-pass, vectorised, coalesced along the channel axis.
+// "bicubic" = strided subsample), legacy bilinear x2 upsample, tile pack / unpack for the tiled video path, and the
+// flow warp.  (The 2x2 max-pool of ops.py:54 rides in the epilogue of the conv that produces its input.)  All are one-pass, vectorised, coalesced along the channel axis.
 #include "common.cuh"
 #include "aux_kernels.h"
 #include "act_io.cuh"
@@ -142,37 +142,6 @@ __global__ void upsample2_kernel(const __half* __restrict__ in, size_t pin, __ha
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = 0.5f * (0.5f * (a[j] + b[j]) + 0.5f * (c[j] + d[j]));
     store8<PLANES>(ob + row + C, pout, o);                                        // (2y+1, 2x+1)
-}
-
-// ---------------------------------------------------------------- 2x2 max pool (ops.py:54)
-// Source may be a channel slice [coff, coff+C) of a wider (virtual-concat) buffer with cs channels.
-template <int PLANES>
-__global__ void maxpool2_kernel(const __half* __restrict__ in, size_t pin, int cs, int coff, __half* __restrict__ out,
-                                size_t pout, int N, int H, int W, int C) {
-    const int cv = C / 8;
-    const int h = H / 2, w = W / 2;
-    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-    const size_t total = static_cast<size_t>(N) * h * w * cv;
-    if (i >= total) return;
-    const int c8 = (i % cv) * 8;
-    size_t r = i / cv;
-    const int x = r % w; r /= w;
-    const int y = r % h;
-    const int n = r / h;
-    float m[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-            float f[8];
-            load8<PLANES>(in + ((static_cast<size_t>(n) * H + 2 * y + dy) * W + 2 * x + dx) * cs + coff + c8, pin, f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
-        }
-    // the maximum is one of the inputs, so re-splitting reproduces its (hi, lo) pair exactly
-    store8<PLANES>(out + ((static_cast<size_t>(n) * h + y) * w + x) * C + c8, pout, m);
 }
 
 // ---------------------------------------------------------------- test / debug converters
@@ -546,16 +515,6 @@ void launch_upsample2(ActBuf in, ActBuf out, int N, int h, int w, int C, int pla
         upsample2_kernel<2><<<blocks_for(total, 256), 256, 0, st>>>(in.p, in.plane, out.p, out.plane, N, h, w, C);
     else
         upsample2_kernel<1><<<blocks_for(total, 256), 256, 0, st>>>(in.p, in.plane, out.p, out.plane, N, h, w, C);
-}
-
-void launch_maxpool2(ActBuf in, int cs, int coff, ActBuf out, int N, int H, int W, int C, int planes, cudaStream_t st) {
-    const size_t total = static_cast<size_t>(N) * (H / 2) * (W / 2) * (C / 8);
-    if (planes == 3)
-        maxpool2_kernel<3><<<blocks_for(total, 256), 256, 0, st>>>(in.p, in.plane, cs, coff, out.p, out.plane, N, H, W, C);
-    else if (planes == 2)
-        maxpool2_kernel<2><<<blocks_for(total, 256), 256, 0, st>>>(in.p, in.plane, cs, coff, out.p, out.plane, N, H, W, C);
-    else
-        maxpool2_kernel<1><<<blocks_for(total, 256), 256, 0, st>>>(in.p, in.plane, cs, coff, out.p, out.plane, N, H, W, C);
 }
 
 void launch_act_from_f32(const float* src, int C, ActBuf dst, int cs, size_t npix, int planes, cudaStream_t st) {

@@ -30,7 +30,6 @@ constexpr int kPredSlot = 32;
 void launch_expand_ps_weights(const float* w, const float* b, float* wps, float* bps, int cout, cudaStream_t st);
 void launch_pack_input(const float* img, int N, int H, int W, int cin, ActBuf l3, ActBuf l2, ActBuf l1, int planes, cudaStream_t st);
 void launch_upsample2(ActBuf in, ActBuf out, int N, int h, int w, int C, int planes, cudaStream_t st);
-void launch_maxpool2(ActBuf in, int cs, int coff, ActBuf out, int N, int H, int W, int C, int planes, cudaStream_t st);
 void launch_act_from_f32(const float* src, int C, ActBuf dst, int cs, size_t npix, int planes, cudaStream_t st);
 void launch_act_to_f32(ActBuf src, int cs, int coff, float* dst, int C, size_t npix, int planes, cudaStream_t st);
 void launch_tile_pack(const uint8_t* frames, const float* flow, const float* warp, int fh, int fw, const TileList& tiles,

@@ -76,10 +76,7 @@ bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int n
     // (round 1) doubled the tile count without shortening a tile (ncu, profiles/r02_ncu_small_layers.md: level-1 bottleneck
     // at 30 % tensor-active with 1 chunk against 57 % for the level-2 one with 2).
     int chunks = W > 8 ? 2 : 1;
-    if (const char* e = getenv("FISR_CHUNKS")) {      // A/B knob (tools/window_time.py): 1 / 2 force, 3 = the round-1 rule
-        if (atoi(e) == 1 || atoi(e) == 2) chunks = atoi(e);
-        if (atoi(e) == 3) chunks = ((long)n_img * ((H * (long)W + 255) / 256) * (cout_pad / NT) < num_sms) ? 1 : 2;
-    }
+    (void)num_sms;
     const int apl = act_planes(planes);
     const bool stack = planes == 2 && NT <= 64;
     // f16f8 layers with wide outputs can run on CTA pairs (cluster of 2, cta_group::2, M = 256): each CTA keeps half of a tap's
@@ -112,7 +109,6 @@ bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int n
     // the 64-wide layers: it costs weight slots), two for the narrow conv/2 heads, which are HBM bound on their 256-channel input
     // (4.7 TB/s, 72 % of the measured copy peak) and gain 3-6 % from the deeper patch prefetch (profiles/r02_layers_*.txt)
     a.a_stages = planes == 3 ? (NT <= 32 ? 2 : 1) : 2;
-    if (const char* e = getenv("FISR_ASTAGES")) { if (planes == 3 && NT < 128 && (atoi(e) == 1 || atoi(e) == 2)) a.a_stages = atoi(e); }
     for (int i = 0; i < 8; ++i) a.tapmask[i] = 0x1FFu;
     a.ps_cout = 0;
     int slots = (kConvMaxSmem - fixed - a.a_stages * apl * a.a_plane_bytes) / slot_bytes;

@@ -129,7 +129,7 @@ struct DebugTensor {
     int N = 0, H = 0, W = 0, C = 0;
 };
 
-enum OpKind { OP_CONV, OP_UPSAMPLE, OP_POOL, OP_PRED2NEXT };
+enum OpKind { OP_CONV, OP_UPSAMPLE, OP_PRED2NEXT };
 struct Op {
     OpKind kind;
     ConvLaunch conv;
@@ -461,7 +461,7 @@ struct Builder {
         a.tma_out = 0;
         memset(&L.tmO_hi, 0, sizeof L.tmO_hi);
         memset(&L.tmO_8, 0, sizeof L.tmO_8);
-        if (plan->planes == 3 && L.epi == 0 && !o.scalar && o.act.p && o.act_cs % 64 == 0 && !getenv("FISR_NO_TMA_OUT")) {
+        if (plan->planes == 3 && L.epi == 0 && !o.scalar && o.act.p && o.act_cs % 64 == 0) {
             if (!encode_out(&L.tmO_hi, &L.tmO_8, o.act, o.act_cs, N, H, W)) return false;
             L.tma_out = true;
             a.tma_out = 1;
@@ -484,14 +484,6 @@ struct Builder {
         snprintf(op.name, sizeof op.name, "upsample2 %dx%dx%d", h, w, C);
         plan->ops.push_back(op);
     }
-    void pool(ActBuf in, int cs, int coff, ActBuf out, int N, int H, int W, int C) {
-        Op op{};
-        op.kind = OP_POOL; op.in = in; op.out = out; op.N = N; op.H = H; op.W = W; op.C = C; op.cs = cs; op.coff = coff;
-        op.bytes = static_cast<double>(N) * H * W * C * 2.0 * act_planes(plan->planes) * 1.25;
-        snprintf(op.name, sizeof op.name, "maxpool2 %dx%dx%d", H, W, C);
-        plan->ops.push_back(op);
-    }
-
     const ConvParam& P(const std::string& name) {
         auto it = ctx->conv_index.find(name);
         if (it == ctx->conv_index.end()) {
@@ -529,9 +521,7 @@ struct Builder {
         ConvOut o; o.raw = n0; o.raw_cs = c; o.act = a0; o.act_cs = c;
         conv(P(p + "/conv/0"), x, x_cs, 0, N, H, W, o, p + "/conv/0");
         ActBuf pooled = act(N, H / 2, W / 2, c);
-        static const bool fuse_pool = !(getenv("FISR_NO_POOL_FUSION") && getenv("FISR_NO_POOL_FUSION")[0] == '1');
-        const ResRec rb = two_res_blocks(p, a0, n0, c, N, H, W, cat, 2 * c, c, fuse_pool ? pooled : ActBuf{});
-        if (!fuse_pool) pool(cat, 2 * c, c, pooled, N, H, W, c);
+        const ResRec rb = two_res_blocks(p, a0, n0, c, N, H, W, cat, 2 * c, c, pooled);      // max_pool(skip) rides in the last epilogue
         *rec = EncRec{p, x, x_cs, c, H, W, a0, cat, pooled, rb};
         return pooled;
     }
@@ -855,7 +845,6 @@ int run_ops(fisr_ctx* ctx, Plan* plan, cudaStream_t st, std::vector<cudaEvent_t>
                 break;
             }
             case OP_UPSAMPLE: launch_upsample2(op.in, op.out, op.N, op.H, op.W, op.C, plan->planes, st); break;
-            case OP_POOL: launch_maxpool2(op.in, op.cs, op.coff, op.out, op.N, op.H, op.W, op.C, plan->planes, st); break;
             case OP_PRED2NEXT: launch_pred_to_next(op.pred, op.out, static_cast<size_t>(op.N) * op.H * op.W, st); break;
         }
     }
@@ -1702,7 +1691,6 @@ int fisr_wgrad3x3(fisr_ctx* ctx, const float* d_x, const float* d_dy, int N, int
     ActBuf xin = b.act(N, H, W, CB * 64), dy = b.act(N, H, W, OB * 64);
     WgradLaunch L{};
     plan_wgrad(N, H, W, CB, OB, ctx->num_sms, ctx->wgrad_exact, &L);
-    if (const char* e = getenv("FISR_WGRAD_VARIANT")) L.args.variant = atoi(e);
     float* partial = static_cast<float*>(b.alloc(L.partial_floats * 4, false));
     const size_t npix = static_cast<size_t>(N) * H * W;
     if (b.rc != FISR_OK) return b.rc;

@@ -44,42 +44,48 @@ __global__ void __launch_bounds__(128) conv3x3_wide_kernel(const PwcConv p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     const int bci = t >> 4, bco = (t & 15) * 4;                                 // this thread's weight fetch: row bci, 4 columns at bco
-    for (int tap = 0; tap < 9; ++tap) {
+    const int nci = (p.cin + kCi - 1) / kCi, steps = 9 * nci;                   // (tap, 8-channel slice) items
+    // software pipeline: the global loads of item s + 1 are in flight while item s is multiplied out of shared memory
+    float a[kCi];
+    float4 wv;
+    auto fetch = [&](int s) {
+        const int tap = s / nci, c0 = (s - tap * nci) * kCi;
         const int iy = oy * p.stride + (tap / 3) * p.dil - p.pad_y, ix = ox * p.stride + (tap % 3) * p.dil - p.pad_x;
         const bool inside = live && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
-        const float* src = p.in + (static_cast<size_t>(n) * p.Hin + (inside ? iy : 0)) * p.Win * p.in_cs + static_cast<size_t>(inside ? ix : 0) * p.in_cs + p.in_coff;
-        for (int c0 = 0; c0 < p.cin; c0 += kCi) {
-            float a[kCi];
 #pragma unroll
-            for (int j = 0; j < kCi; ++j) a[j] = 0.f;
-            if (inside) {
-                if (vec_in && c0 + kCi <= p.cin) {
-                    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + c0)), v1 = __ldg(reinterpret_cast<const float4*>(src + c0 + 4));
-                    a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w; a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
-                } else {
+        for (int j = 0; j < kCi; ++j) a[j] = 0.f;
+        if (inside) {
+            const float* src = p.in + (static_cast<size_t>(n) * p.Hin + iy) * p.Win * p.in_cs + static_cast<size_t>(ix) * p.in_cs + p.in_coff + c0;
+            if (vec_in && c0 + kCi <= p.cin) {
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+                a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w; a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
+            } else {
 #pragma unroll
-                    for (int j = 0; j < kCi; ++j) if (c0 + j < p.cin) a[j] = __ldg(src + c0 + j);
-                }
+                for (int j = 0; j < kCi; ++j) if (c0 + j < p.cin) a[j] = __ldg(src + j);
             }
-            float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c0 + bci < p.cin && co_base + bco < p.cout)
-                wv = __ldg(reinterpret_cast<const float4*>(p.w + (static_cast<size_t>(tap) * p.cin + c0 + bci) * p.cout + co_base + bco));
-            __syncthreads();                                                    // previous slice fully consumed
+        }
+        wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + bci < p.cin && co_base + bco < p.cout)
+            wv = __ldg(reinterpret_cast<const float4*>(p.w + (static_cast<size_t>(tap) * p.cin + c0 + bci) * p.cout + co_base + bco));
+    };
+    fetch(0);
+    for (int s = 0; s < steps; ++s) {
+        __syncthreads();                                                        // previous slice fully consumed
 #pragma unroll
-            for (int j = 0; j < kCi; ++j) As[j][t] = a[j];
-            *reinterpret_cast<float4*>(&Bs[bci][bco]) = wv;
-            __syncthreads();
+        for (int j = 0; j < kCi; ++j) As[j][t] = a[j];
+        *reinterpret_cast<float4*>(&Bs[bci][bco]) = wv;
+        __syncthreads();
+        if (s + 1 < steps) fetch(s + 1);
 #pragma unroll
-            for (int c = 0; c < kCi; ++c) {
-                const float4 a0 = *reinterpret_cast<const float4*>(&As[c][pg * 8]), a1 = *reinterpret_cast<const float4*>(&As[c][pg * 8 + 4]);
-                const float4 b0 = *reinterpret_cast<const float4*>(&Bs[c][cg * 8]), b1 = *reinterpret_cast<const float4*>(&Bs[c][cg * 8 + 4]);
-                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        for (int c = 0; c < kCi; ++c) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[c][pg * 8]), a1 = *reinterpret_cast<const float4*>(&As[c][pg * 8 + 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[c][cg * 8]), b1 = *reinterpret_cast<const float4*>(&Bs[c][cg * 8 + 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-            }
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
     }
     const int co0 = co_base + cg * 8;

@@ -101,10 +101,8 @@ wgrad3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_co
         const bool lead = elect_one();
         uint32_t st = 0, ph = 0, first = 0;
         bool ok = true;
-        // descriptor field roles (probe knob): variant bit 0 swaps which field carries the M-chunk / K-group stride
-        const uint32_t chunk_f = a.lbo_a, kgrp_f = 1024u >> 4;
-        const uint32_t lbo_field = (a.variant & 1) ? kgrp_f : chunk_f;
-        const uint32_t sbo_field = (a.variant & 1) ? chunk_f : kgrp_f;
+        // MN-major SWIZZLE_128B descriptor: LBO carries the stride between 64-element M chunks, SBO the stride between 8-row K groups
+        const uint32_t lbo_field = a.lbo_a, sbo_field = 1024u >> 4;
         const uint32_t desc_hi = sbo_field | (1u << 14) | (2u << 29);
         for (int tile = split; tile < a.num_tiles && ok; tile += a.S) {
             ok = __all_sync(0xffffffffu, mbar_wait(full(st), ph, a.err, WERR_FULL));
@@ -246,7 +244,6 @@ void plan_wgrad(int N, int H, int W, int CB, int OB, int num_sms, bool exact, Wg
     a.S = S;
     a.cin_pad = CB * 64; a.cout_pad = OB * 64;
     a.lbo_a = kWgDPlane >> 4;
-    a.variant = 0;
     // x's lo plane: leaving it out rounds the forward activation to fp16 inside this product only, a zero-mean term of
     // relative size <= 2^-12 per summand (measured: ~1e-4 of a weight-gradient tensor, the level the tensor core's
     // truncating fp32 accumulation already sets, tools/accum_probe.py) for half the MMAs and 30 % less smem traffic.

@@ -15,7 +15,6 @@ struct WgradArgs {
     int tiles_x, tiles_y, num_tiles;
     int cin_pad, cout_pad;
     unsigned lbo_a;           // descriptor field: byte distance >> 4 between the dy hi and lo smem tiles
-    int variant;              // probe knob (0 = production encoding)
 };
 
 struct WgradLaunch {

@@ -535,7 +535,7 @@ class Engine:
         out = []
         for k in range(cnt):
             nm = names.raw[k * 96:(k + 1) * 96].split(b"\0", 1)[0].decode()
-            kind = "conv" if kd[k] < 1000 else ("upsample" if kd[k] < 2000 else ("pool" if kd[k] < 3000 else "pred2next"))
+            kind = "conv" if kd[k] < 1000 else ("upsample" if kd[k] < 2000 else "pred2next")
             out.append({"name": nm, "kind": kind, "nt": kd[k] % 1000, "ms": float(ms[k]), "flops": float(fl[k]),
                         "bytes": float(by[k])})
         return out

@@ -205,7 +205,7 @@ int fisr_debug_conv_output(fisr_ctx* ctx, const char* conv_name, float* h_dst, s
 /* Per-launch device times of the plan for (N,H,W): runs it `reps` times op by op with CUDA events between launches
  * (no graph) and returns the op count; with ms == NULL only returns the count.  flops / bytes are the algorithmic
  * figures of each launch (2*9*Cin*Cout*h*w*N; operands + outputs once), kinds[i] = 0 conv (+ its N tile), 1000
- * upsample, 2000 max-pool; names is max_ops strings of name_stride bytes.  Feeds bench.py's roofline block. */
+ * upsample, 2000 prediction -> next level input; names is max_ops strings of name_stride bytes.  Feeds bench.py's roofline block. */
 int fisr_profile_ops(fisr_ctx* ctx, int N, int H, int W, int reps, int max_ops, float* ms, double* flops, double* bytes,
                      int* kinds, char* names, int name_stride);
 /* Per-op device times of the backward pass for batch B (4B passes) at LR size h x w, like fisr_profile_ops; call

@@ -1,8 +1,9 @@
-"""In-process A/B of plan / kernel knobs on the bench workload (4 tiles of 544x992, CUDA graph replay, inputs in HBM) and on
-config 2 (8x192x192).  Variants are environment settings read at plan time; they are measured interleaved, several rounds, in
-ONE process (clock / power state drifts by several percent between processes and boxes), best and median reported.
+"""In-process A/B of plan-time settings on the bench workload (4 tiles of 544x992, CUDA graph replay, inputs in HBM) and on
+config 2 (8x192x192).  Variants are environment settings the planner reads (getenv at plan time; add one temporarily for the
+experiment at hand -- none is left in the library); they are measured interleaved, several rounds, in ONE process (clock /
+power state drifts by several percent between processes and boxes), best and median reported.
 
-    python tools/window_time.py f16f8 "" "FISR_CHUNKS=3"
+    python tools/window_time.py f16f8 "" "FISR_PAIR=1"
 """
 import os
 import statistics
