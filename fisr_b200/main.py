@@ -70,6 +70,9 @@ def parse_args(argv=None):
                    help='B200 path only: f16x3 = fp32-class split operands (default; training always uses it), f16f8 = fp16 main '
                         'term + fp8 cross terms (inference, ~3e-5 max-abs, 1.2x faster), f16 = single-fp16 fast mode')
     p.add_argument('--device', type=int, default=0, help='B200 path only: CUDA device index')
+    p.add_argument('--pwcnet_ckpt_path', type=str, default=None,
+                   help='FISR_for_video: tfoptflow PWC-Net checkpoint prefix (default: the path hard-wired in the reference, '
+                        'FISR_for_video_pwcnet_predict_from_img_test.py:31); not needed when the .flo file already exists')
     args = p.parse_args(argv)
     for d in (args.checkpoint_dir, args.text_dir, args.log_dir, args.test_img_dir):         # main.py:108-121
         check_folder(d)

@@ -88,3 +88,50 @@ def test_model_method_numpy_and_torch(engine, tmp_path):
         net.model(x.numpy(), 4)
     assert net.model_dir == "FISRnet_exp1"
     assert net.load(str(tmp_path / "nowhere")) == (False, 0)                            # missing ckpt is not an error (:1113)
+
+
+def test_cli_fisr_for_video_whole_pipeline(tmp_path):
+    """``python -m fisr_b200.main --phase FISR_for_video`` on a 4-frame clip, everything from files like the reference's main.py:206-236:
+    PWC-Net weights from a TensorFlow V2 bundle (tfoptflow names), FISRnet weights from a Saver bundle, flow -> ``.flo``, warp ->
+    MATLAB v7.3 ``_warp.mat``, network -> PNGs; checked against the same chain on the oracles (PWC-Net oracle, cv2.remap, FISRnet oracle)."""
+    from fisr_b200 import main as cli
+    from fisr_b200 import tf_checkpoint as T
+    from fisr_b200 import utils
+    from oracle import pwcnet_oracle as W
+    H, Wd, n = 64, 96, 4
+    frames = np.load(os.path.join(GOLDEN, "scene1_lr_crop.npz"))["frames"][:n, :H, :Wd]
+    scene = tmp_path / "scene9"
+    os.makedirs(scene)
+    for i, f in enumerate(frames):
+        Image.fromarray(np.ascontiguousarray(f)).save(str(scene / f"LR_seq_{i}.png"))
+    fisr_params, pwc_params = O.init_params(21), W.init_params(22)
+    ck = tmp_path / "ckpt" / "FISRnet_exp1"
+    T.save_fisrnet_checkpoint(str(ck / "FISRnet-122000"), {k: v.numpy() for k, v in fisr_params.items()}, None, 122000)
+    (ck / "checkpoint").write_text('model_checkpoint_path: "FISRnet-122000"\n')
+    pwc_prefix = str(tmp_path / "pwc" / "pwcnet.ckpt-595000")
+    T.save_checkpoint(pwc_prefix, {k: v.numpy() for k, v in pwc_params.items()})
+    cli.main(["--phase", "FISR_for_video", "--frame_folder_path", str(scene), "--frame_num", str(n), "--FISR_input_size", f"{H},{Wd}",
+              "--FISR_test_patch", "1,1", "--checkpoint_dir", str(tmp_path / "ckpt"), "--test_img_dir", str(tmp_path / "img"),
+              "--text_dir", str(tmp_path / "txt"), "--log_dir", str(tmp_path / "log"), "--pwcnet_ckpt_path", pwc_prefix])
+    # ---- the same chain on the oracles
+    rgb = [utils.YUV2RGB_matlab(f.astype(np.float32)) for f in frames]
+    flow_ref = np.zeros((n - 1, 2, H, Wd, 2), np.float32)
+    for fr in range(n - 1):
+        a, b, hw0 = W.prepare_pair(rgb[fr], rgb[fr + 1])
+        ff = W.forward(pwc_params, torch.from_numpy(np.stack([a, b])), torch.from_numpy(np.stack([b, a]))).numpy()
+        flow_ref[fr] = np.stack([W.finish_flow(ff[k], hw0, (H, Wd)) for k in range(2)])
+    flow = utils.read_flo_file_5dim(str(scene / "scene9_test_ss1_fr4.flo"))
+    assert np.abs(flow - flow_ref).max() < 2e-4 * max(1.0, np.abs(flow_ref).max())
+    warp_ref = np.stack([P.warp_pair_yuv(frames[k], frames[k + 1], flow[k, 0], flow[k, 1]) for k in range(n - 1)])
+    warp = utils.read_mat_file_warp(str(scene / "scene9_ss1_fr4_warp.mat"), 'pred')
+    assert np.abs(warp * np.float32(255.) - warp_ref).max() < 2e-3
+    fl = utils.merge_seq_dim(np.concatenate((flow[0:n - 2], flow[1:n - 1]), axis=1))
+    wp = utils.merge_seq_dim(np.concatenate((warp[0:n - 2], warp[1:n - 1]), axis=1))
+    out_dir = scene / "FISR_frames"
+    assert len(os.listdir(out_dir)) == 2 * (2 * n - 3)
+    for fr in range(n - 2):
+        img = np.concatenate([frames[fr + s] for s in range(3)], axis=2)
+        ref = P.window_forward_u8(fisr_params, img, fl[fr], wp[fr].astype(np.float32), (1, 1))
+        got = np.array(Image.open(str(out_dir / f"pred_YUV_{fr * 2}.png")))
+        d = np.abs(got.astype(int) - ref[:, :, 0:3].astype(int))
+        assert d.max() <= 1 and (d == 0).mean() > 0.999
