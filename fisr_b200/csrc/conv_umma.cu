@@ -69,6 +69,14 @@ bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int n
     // depends on the per-image geometry only (never on the batch), so results are bit-identical however a
     // window's tiles are sharded over batches / GPUs (NT decides the fp32 summation order, see STACK).
     if (cout_pad >= 128 && (long)H * W >= 64L * 64) NT = 128;
+    if (planes == 3 && cout_pad >= 128) {
+        // f16f8: every accumulator column sees the same MMAs in the same order whatever NT, so the choice may look at the batch: take
+        // the N tile with the cheaper schedule, waves x (time of one work item).  An N = 64 item covers half the channels of an
+        // N = 128 one but runs at the shared-memory operand roof (48 instead of 32 cycles per MMA): 0.67 of its time, not 0.5.
+        const long tiles = (long)n_img * ((H + 15) / 16) * ((W + 15) / 16);
+        const long w128 = (tiles * (cout_pad / 128) + num_sms - 1) / num_sms, w64 = (tiles * (cout_pad / 64) + num_sms - 1) / num_sms;
+        NT = (3 * w128 <= 2 * w64) ? 128 : 64;
+    }
     (void)kb;
     // Two chunks (16 x 16 tiles) unless the image is a single chunk wide.  Every chunk has its own MMA issuer warp and one
     // thread issues a tcgen05.mma only every ~70-150 cycles (tests/cuda/umma_rate_probe.cu), so a one-chunk CTA is ISSUE
