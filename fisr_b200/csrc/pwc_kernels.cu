@@ -13,12 +13,15 @@ namespace pwc {
 namespace {
 
 __device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : 0.1f * x; }      // tf.nn.leaky_relu(alpha=0.1)
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    return static_cast<unsigned long long>(__float_as_uint(lo)) | (static_cast<unsigned long long>(__float_as_uint(hi)) << 32);
+}
 
 // ---------------------------------------------------------------- 3x3 conv, wide outputs (Cout a multiple of 4)
-// Implicit GEMM on CUDA cores: a block owns 128 output pixels x 64 output channels, a thread 8 x 8 of them; per (tap, 8 input
-// channels) the block stages the 128 x 8 activation slice (gathered at the tap's stride / dilation offset, zero outside) and the
-// 8 x 64 weight slice in shared memory and every thread does 64 FMAs per 4 shared-memory vector loads.
-constexpr int kPx = 128, kCo = 64, kCi = 8;
+// Implicit GEMM on CUDA cores: a block owns 128 output pixels x 64 output channels, a thread 8 x 8 of them; per (tap, 16 input
+// channels) the block stages the 128 x 16 activation slice (gathered at the tap's stride / dilation offset, zero outside) and the
+// 16 x 64 weight slice in shared memory and every thread does 64 FMAs per 4 shared-memory vector loads.
+constexpr int kPx = 128, kCo = 64, kCi = 16;
 
 template <bool LEAKY>
 __global__ void __launch_bounds__(128) conv3x3_wide_kernel(const PwcConv p) {
@@ -38,16 +41,18 @@ __global__ void __launch_bounds__(128) conv3x3_wide_kernel(const PwcConv p) {
         n = static_cast<int>(r / p.Hout);
     }
     const bool vec_in = ((p.in_cs | p.in_coff) & 3) == 0;
-    float acc[8][8];
+    // accumulators as packed fp32 pairs: fma.rn.f32x2 (FFMA2, sm_100) does two FMAs per issued instruction, which matters in a
+    // kernel that is issue bound (512 scalar FFMAs per 8-channel slice next to ~100 other instructions)
+    unsigned long long acc2[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc2[i][j] = 0ull;
     const int bci = t >> 4, bco = (t & 15) * 4;                                 // this thread's weight fetch: row bci, 4 columns at bco
     const int nci = (p.cin + kCi - 1) / kCi, steps = 9 * nci;                   // (tap, 8-channel slice) items
     // software pipeline: the global loads of item s + 1 are in flight while item s is multiplied out of shared memory
     float a[kCi];
-    float4 wv;
+    float4 wv[kCi / 8];
     auto fetch = [&](int s) {
         const int tap = s / nci, c0 = (s - tap * nci) * kCi;
         const int iy = oy * p.stride + (tap / 3) * p.dil - p.pad_y, ix = ox * p.stride + (tap % 3) * p.dil - p.pad_x;
@@ -57,23 +62,30 @@ __global__ void __launch_bounds__(128) conv3x3_wide_kernel(const PwcConv p) {
         if (inside) {
             const float* src = p.in + (static_cast<size_t>(n) * p.Hin + iy) * p.Win * p.in_cs + static_cast<size_t>(ix) * p.in_cs + p.in_coff + c0;
             if (vec_in && c0 + kCi <= p.cin) {
-                const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
-                a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w; a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
+#pragma unroll
+                for (int q = 0; q < kCi / 4; ++q) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + 4 * q));
+                    a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < kCi; ++j) if (c0 + j < p.cin) a[j] = __ldg(src + j);
             }
         }
-        wv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c0 + bci < p.cin && co_base + bco < p.cout)
-            wv = __ldg(reinterpret_cast<const float4*>(p.w + (static_cast<size_t>(tap) * p.cin + c0 + bci) * p.cout + co_base + bco));
+#pragma unroll
+        for (int q = 0; q < kCi / 8; ++q) {
+            wv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + bci + 8 * q < p.cin && co_base + bco < p.cout)
+                wv[q] = __ldg(reinterpret_cast<const float4*>(p.w + (static_cast<size_t>(tap) * p.cin + c0 + bci + 8 * q) * p.cout + co_base + bco));
+        }
     };
     fetch(0);
     for (int s = 0; s < steps; ++s) {
         __syncthreads();                                                        // previous slice fully consumed
 #pragma unroll
         for (int j = 0; j < kCi; ++j) As[j][t] = a[j];
-        *reinterpret_cast<float4*>(&Bs[bci][bco]) = wv;
+#pragma unroll
+        for (int q = 0; q < kCi / 8; ++q) *reinterpret_cast<float4*>(&Bs[bci + 8 * q][bco]) = wv[q];
         __syncthreads();
         if (s + 1 < steps) fetch(s + 1);
 #pragma unroll
@@ -81,11 +93,13 @@ __global__ void __launch_bounds__(128) conv3x3_wide_kernel(const PwcConv p) {
             const float4 a0 = *reinterpret_cast<const float4*>(&As[c][pg * 8]), a1 = *reinterpret_cast<const float4*>(&As[c][pg * 8 + 4]);
             const float4 b0 = *reinterpret_cast<const float4*>(&Bs[c][cg * 8]), b1 = *reinterpret_cast<const float4*>(&Bs[c][cg * 8 + 4]);
             const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const unsigned long long bp[4] = {pack2(b0.x, b0.y), pack2(b0.z, b0.w), pack2(b1.x, b1.y), pack2(b1.z, b1.w)};
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 8; ++i) {
+                const unsigned long long ap = pack2(av[i], av[i]);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][j]) : "l"(ap), "l"(bp[j]));
+            }
         }
     }
     const int co0 = co_base + cg * 8;
@@ -101,7 +115,10 @@ __global__ void __launch_bounds__(128) conv3x3_wide_kernel(const PwcConv p) {
         float* d = p.out + static_cast<size_t>(q) * p.out_cs + p.out_coff + co0;
         float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { v[j] = acc[i][j] + bias[j]; if (LEAKY) v[j] = lrelu(v[j]); }
+        for (int j = 0; j < 8; ++j) {
+            v[j] = __uint_as_float(static_cast<unsigned>(acc2[i][j >> 1] >> ((j & 1) * 32))) + bias[j];
+            if (LEAKY) v[j] = lrelu(v[j]);
+        }
         if (vec_out && co0 + 8 <= p.cout) {
             *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
             *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);

@@ -1,0 +1,11 @@
+"""ncu / timing target: one PWC-Net forward on both directions of a 1080p pair after the x2 pre-upscale (2 x 2176 x 3840)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from fisr_b200.pwcnet import PWCNet
+from oracle import pwcnet_oracle as W
+net = PWCNet(0); net.set_params(W.init_params(0))
+a = torch.rand(2, 2176, 3840, 3).cuda(); b = torch.rand(2, 2176, 3840, 3).cuda()
+for _ in range(2): f = net.forward(a, b)
+torch.cuda.synchronize()
+print(float(f.abs().mean()))
