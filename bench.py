@@ -495,7 +495,7 @@ def measure_extras(eng, dev, peaks, bench_precision):
         tf = info["flops"] / ms / 1e9
         out[f"config2_forward_{prec}"] = {"ms": ms, "gflop": info["flops"] / 1e9, "tflops": tf, "frac": tf / peak_tf,
                                           "workspace_gb": info["workspace_bytes"] / 1e9,
-                                          "note": "Engine.forward on a device tensor: pack + 158 launches (CUDA graph) + 3 output copies; 3.4 GB activation workspace > L2"}
+                                          "note": f"Engine.forward on a device tensor: pack + {info['launches']} launches (CUDA graph) + 3 output copies; activation workspace > L2"}
 
     # ---- config 3: one training step B = 16, LR 192x192 (4 weight-shared passes = 64 images), forward + loss + backward + Adam
     eng.set_precision("f16x3")

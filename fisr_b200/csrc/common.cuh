@@ -114,6 +114,12 @@ struct ConvArgs {
     int pool_cs;
     const __half* mask;       // dgrad: hi plane of the forward activation whose ReLU gradient gates this output, or nullptr
     int mask_cs, mask_off;
+    // Output pixel (n, y, x) of the launch has pixel index n * opix_n + y * opix_y + x * opix_x in every output / residual / mask
+    // buffer (H * W, W, 1 for a plain NHWC image).  Other values let a launch write a strided sub-lattice of a larger image: the
+    // PWC-Net context network runs a dilation-d conv as d*d undilated convs on the polyphase sub-images (pwc_api.cu).
+    int opix_n, opix_y, opix_x;
+    float act_slope;          // > 0: leaky ReLU with this negative slope on the activation output (act_relu must be 0); split mode only
+    int store_cout;           // > 0: the wide epilogue stores only channels < store_cout (outputs that sit inside a wider buffer)
 };
 
 }  // namespace fisr

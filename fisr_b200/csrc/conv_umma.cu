@@ -1,6 +1,8 @@
 // Host side of the tcgen05 3x3 conv: kernel-family dispatch and tile geometry / shared-memory planning.
 // The device code lives in conv_umma_kernel.cuh and is instantiated in conv_inst_p{1,2}_n{16,64,128}.cu.
 #include <cstdlib>
+#include <cstring>
+#include <string>
 #include "common.cuh"
 #include "conv_umma.h"
 #include "sm100_ptx.cuh"
@@ -119,6 +121,8 @@ bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int n
     a.a_stages = planes == 3 ? (NT <= 32 ? 2 : 1) : 2;
     for (int i = 0; i < 8; ++i) a.tapmask[i] = 0x1FFu;
     a.ps_cout = 0;
+    a.opix_n = H * W; a.opix_y = W; a.opix_x = 1;
+    a.act_slope = 0.f; a.store_cout = 0;
     int slots = (kConvMaxSmem - fixed - a.a_stages * apl * a.a_plane_bytes) / slot_bytes;
     if (slots > convk::kMaxBSlots) slots = convk::kMaxBSlots;
     if (slots < 2) return false;
@@ -126,6 +130,51 @@ bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int n
     L->NT = NT; L->chunks = chunks; L->planes = planes; L->pair = pair;
     L->smem_bytes = fixed + a.a_stages * apl * a.a_plane_bytes + slots * slot_bytes;
     L->efficiency = best_eff;
+    return true;
+}
+
+
+bool build_split_conv(EncodeTiledFn encode, const SplitConvDesc& d, int num_sms, int* d_err, ConvLaunch* L, std::string* why) {
+    auto bad = [&](const std::string& m) { if (why) *why = m; return false; };
+    memset(static_cast<void*>(L), 0, sizeof *L);
+    if (d.cout_pad != split_conv_cout_pad(d.cout)) return bad("cout_pad does not match split_conv_cout_pad(cout)");
+    if ((d.in_cs | d.cin_off | d.out_cs) % 8 || d.out_off % 4 || d.in_sx % 8 || d.in_sy % 8 || d.in_sn % 8 || d.in_plane % 8 || d.out_plane % 4)
+        return bad("channel strides / offsets must keep 16-byte (input) and 8-byte (output) alignment");
+    if (static_cast<double>(d.out_pixels) * d.out_cs >= 4294967296.0) return bad("output exceeds 32-bit element offsets");
+    if (!plan_conv_geometry(d.H, d.W, d.N, d.cout_pad, 2, num_sms, L)) return bad("no tile geometry");
+    ConvArgs& a = L->args;
+    a.bias = d.bias;
+    a.out_act = d.out; a.act_plane = d.out_plane;
+    a.act_cs = d.out_cs; a.act_off0 = a.act_off1 = d.out_off; a.act_split = 0;
+    a.act_relu = d.relu ? 1 : 0; a.act_slope = d.relu ? 0.f : d.slope;
+    a.scalar_out = d.cout_pad <= 16;
+    a.err = d_err;
+    a.N = d.N; a.H = d.H; a.W = d.W;
+    a.opix_n = static_cast<int>(d.opix_n); a.opix_y = static_cast<int>(d.opix_y); a.opix_x = static_cast<int>(d.opix_x);
+    a.cin_off = d.cin_off; a.KB = (d.cin + 63) / 64; a.cout = d.cout;
+    a.ksteps_last = (d.cin - (a.KB - 1) * 64 + 15) / 16;
+    a.store_cout = (d.cout_pad > 16 && d.cout < d.cout_pad) ? d.cout : 0;
+    L->epi = 0;
+    L->tma_out = false;
+    for (int pl = 0; pl < 2; ++pl) {
+        cuuint64_t dims[4] = {(cuuint64_t)d.in_cs, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.N};
+        cuuint64_t strides[3] = {(cuuint64_t)d.in_sx * 2, (cuuint64_t)d.in_sy * 2, (cuuint64_t)d.in_sn * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)a.P, (cuuint32_t)(a.TH + 2), 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        const CUresult r = encode(pl ? &L->tmA_lo : &L->tmA_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(d.in + (pl ? d.in_plane : 0)), dims,
+                                  strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return bad("cuTensorMapEncodeTiled(input view) failed: " + std::to_string((int)r));
+    }
+    {
+        cuuint64_t dims[2] = {64, (cuuint64_t)2 * a.KB * 9 * d.cout_pad};
+        cuuint64_t strides[1] = {128};
+        cuuint32_t box[2] = {64, (cuuint32_t)L->NT};
+        cuuint32_t es[2] = {1, 1};
+        const CUresult r = encode(&L->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(d.wp), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return bad("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
+    }
     return true;
 }
 

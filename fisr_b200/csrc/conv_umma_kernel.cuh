@@ -97,7 +97,7 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // 9-channel pred tensor and into channels 29.. of the next level's input (FISRnet.py:107-108,113,144).
 template <int PLANES, int NCOL>
 __device__ __forceinline__ void epilogue_scalar(const ConvArgs& a, const uint32_t (&v)[NCOL], int n, int y, int x) {
-    const int pix = (n * a.H + y) * a.W + x;
+    const int pix = n * a.opix_n + y * a.opix_y + x * a.opix_x;
 #pragma unroll
     for (int ch = 0; ch < NCOL; ++ch) {
         if (ch < a.cout) {
@@ -107,7 +107,8 @@ __device__ __forceinline__ void epilogue_scalar(const ConvArgs& a, const uint32_
             const int co = ch, opix = pix;
             if (a.out_raw) a.out_raw[static_cast<size_t>(opix) * a.raw_cs + co + (co < a.raw_split ? a.raw_off0 : a.raw_off1)] = f;
             if (a.out_act) {
-                const float g = a.act_relu ? fmaxf(f, 0.f) : f;
+                float g = a.act_relu ? fmaxf(f, 0.f) : f;
+                if (PLANES == 2 && a.act_slope > 0.f) g = fmaxf(g, g * a.act_slope);
                 const SplitHalf s = split_f32(g);
                 const int c = co + (co < a.act_split ? a.act_off0 : a.act_off1);
                 __half* d = a.out_act + static_cast<size_t>(opix) * a.act_cs + c;
@@ -518,6 +519,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const bool idle = NARROW && CHUNKS == 1 && grp == 1;
         const uint32_t stg = sStage32 + ew * kStageBytesPerWarp;
         const float relu_floor = a.act_relu ? 0.f : -INFINITY;
+        [[maybe_unused]] const bool leaky = a.act_slope > 0.f;
         // Transpose staging: element (row r, 16-B group j) lives at group r*4 + (j ^ ((r >> 1) & 3)).
         //   write: lane = row, group j      -> the 8 lanes of a phase hit 8 different bank groups
         //   read : lane -> row (lane >> 2) + 8*i, group lane & 3 -> 2 rows x 4 groups per phase, again all different
@@ -619,7 +621,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                     const int y = t.y0 + ty, x = t.x0 + tx;
                     const bool valid = (y < a.H) && (x < a.W);
                     vmask |= (valid ? 1u : 0u) << i;
-                    const uint32_t pix = valid ? static_cast<uint32_t>((t.n * a.H + y) * a.W + x) : 0u;
+                    const uint32_t pix = valid ? static_cast<uint32_t>(t.n * a.opix_n + y * a.opix_y + x * a.opix_x) : 0u;
                     if (EPI & EPI_RES) o_res[i] = pix * a.res_cs + cg_lane;
                     if (EPI & EPI_RAW) o_raw[i] = pix * a.raw_cs + a.raw_off1 + cg_lane;
                     if (EPI & EPI_MASK) o_msk[i] = pix * a.mask_cs + a.mask_off + cg_lane;
@@ -692,11 +694,13 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                     // fused 2x2 max-pool (closing conv of an encoder level, ops.py:52-54): post-ReLU values of this lane's 4 rows
                     [[maybe_unused]] float pf[4][4];
                     const bool pooling = (EPI == EPI_RES) && a.pool_out != nullptr;
+                    // outputs inside a wider buffer (split mode): columns past the true channel count are not stored
+                    const uint32_t smask = (PLANES == 2 && a.store_cout > 0 && cg_lane + c0 >= a.store_cout) ? 0u : vmask;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float4 val = vals[i];
                         if (EPI == EPI_RES) { pf[i][0] = pf[i][1] = pf[i][2] = pf[i][3] = 0.f; }
-                        if ((vmask >> i) & 1) {
+                        if ((smask >> i) & 1) {
                             float f0, f1, f2, f3;
                             if (F8) {
                                 f0 = fmaf(val.x, kF8AccScale, b4.x); f1 = fmaf(val.y, kF8AccScale, b4.y);
@@ -714,6 +718,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                             if (EPI & EPI_RAW) *reinterpret_cast<float4*>(a.out_raw + o_raw[i] + c0) = make_float4(f0, f1, f2, f3);
                             f0 = fmaxf(f0, relu_floor); f1 = fmaxf(f1, relu_floor);
                             f2 = fmaxf(f2, relu_floor); f3 = fmaxf(f3, relu_floor);
+                            if (PLANES == 2 && leaky) {
+                                f0 = fmaxf(f0, f0 * a.act_slope); f1 = fmaxf(f1, f1 * a.act_slope);
+                                f2 = fmaxf(f2, f2 * a.act_slope); f3 = fmaxf(f3, f3 * a.act_slope);
+                            }
                             if (EPI == EPI_RES) { pf[i][0] = f0; pf[i][1] = f1; pf[i][2] = f2; pf[i][3] = f3; }
                             uint32_t h01, l01, h23, l23;
                             split2_f32(f0, f1, h01, l01);

@@ -23,9 +23,6 @@ using namespace fisr;
 
 namespace {
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 constexpr int CH = 64;       // FISRnet.py:74
 constexpr int IN_CH = 29;    // FISRnet.py:287

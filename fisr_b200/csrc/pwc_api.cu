@@ -1,7 +1,9 @@
 // C ABI of the PWC-Net inference path (include/fisr_b200.h, "PWC-Net"): parameter store under the TensorFlow variable names of
 // philferriere/tfoptflow (scope pwcnet/), one plan (buffers + launch list) per input size, forward of N image pairs.
 // Reference: FISR_tfoptflow/model_pwcnet.py:1012-1593 driven by FISR_for_video_pwcnet_predict_from_img_test.py:96-139.
+#include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -10,13 +12,17 @@
 #include <vector>
 
 #include "../../include/fisr_b200.h"
+#include "aux_kernels.h"
+#include "conv_umma.h"
 #include "pwc_kernels.h"
 
 using namespace fisr::pwc;
+using fisr::ConvLaunch;
 
 namespace {
 
-constexpr int kLvls = 6, kPredLvl = 2, kCorr = 81, kCorrPad = 84;       // search range 4; corr slot padded to a multiple of 4
+constexpr int kLvls = 6, kPredLvl = 2, kCorr = 81, kCorrPad = 88, kGap = kCorrPad - kCorr;   // search range 4; corr slot padded to a multiple of 8
+constexpr int kTail = 8;                                                // up_flow (2) + up_feat (2) + 4 zero channels: 16-byte pixel rows for TMA
 constexpr int kChann[7] = {0, 16, 32, 64, 96, 128, 196};                // model_pwcnet.py:1083
 constexpr int kDense[5] = {128, 128, 96, 64, 32};                       // model_pwcnet.py:1415-1433
 constexpr int kActs = 448;                                              // 128 + 128 + 96 + 64 + 32
@@ -27,11 +33,12 @@ struct PDef {
     std::string name;        // without /kernel, /bias
     int cin, cout;           // reference channel counts
     bool transpose;          // conv2d_transpose kernel [4,4,out,in]
-    int gap_at;              // reference input channel index after which 3 zero rows are inserted (-1: none)
+    int gap_at;              // reference input channel index after which kGap zero rows are inserted (-1: none)
 };
 
-// channels of the dense buffer D_l: [act4 | act3 | act2 | act1 | act0 | corr (81 + 3 pad) | c1 | up_flow | up_feat]
-int dense_cs(int lvl) { return kActs + kCorrPad + (lvl == kLvls ? 0 : kChann[lvl] + 4); }
+// channels of the dense buffer D_l: [act4 | act3 | act2 | act1 | act0 | corr (81 + 7 pad) | c1 | up_flow | up_feat | 4 pad]
+int dense_cs(int lvl) { return kActs + kCorrPad + (lvl == kLvls ? 0 : kChann[lvl] + kTail); }
+int pad8(int c) { return (c + 7) / 8 * 8; }
 int dense_off(int k) { int o = kActs; for (int i = 0; i <= k; ++i) o -= kDense[i]; return o; }      // where act_k is written
 int dense_in_off(int k) { return k == 0 ? kActs : dense_off(k - 1); }                               // where conv_k starts reading
 
@@ -75,16 +82,29 @@ const std::vector<std::string>& names() {
 }
 
 struct Param {
-    int cin_pad = 0;             // input channels as the kernels see them (reference count + 3 where a gap is inserted)
+    int cin_pad = 0;             // input channels as the kernels see them (reference count + kGap where a gap is inserted)
+    int cout = 0;
     float* d_w = nullptr;        // kernel layout: conv [9][cin_pad][cout]; transpose [16][2][cin_pad]
     float* d_b = nullptr;
+    // tensor-core path (stride-1 3x3 convs with >= 16 outputs): fp16 (hi, lo) operand planes and the bias padded to cout_pad
+    int KB = 0, cout_pad = 0;
+    __half* d_wp = nullptr;
+    float* d_bp = nullptr;
+    bool packed = false;
     std::vector<float> h_w;      // as uploaded (reference layout), for fisr_pwc_get_param
+};
+
+struct Op {
+    bool umma = false;
+    ConvLaunch conv;                                   // umma: one tcgen05 conv launch (tensor maps encoded at plan build)
+    std::function<void(cudaStream_t)> fn;              // otherwise
 };
 
 struct Plan {
     int N = 0, H = 0, W = 0;
     std::vector<void*> allocs;
-    std::vector<std::function<void(cudaStream_t)>> ops;
+    std::vector<Op> ops;
+    int umma_ops = 0;
     const float *img1 = nullptr, *img2 = nullptr;     // bound per call
     float* out = nullptr;
     float* flow[kLvls + 1] = {nullptr};
@@ -94,8 +114,12 @@ struct Plan {
 }  // namespace
 
 struct fisr_pwc {
-    int device = 0;
+    int device = 0, num_sms = 0;
     cudaStream_t stream = nullptr;
+    fisr::EncodeTiledFn encode = nullptr;
+    int* d_err = nullptr;        // barrier-timeout flag of the conv kernel
+    int* h_err = nullptr;        // pinned copy, refreshed at the end of every forward
+    int use_umma = 2;            // FISR_PWC_UMMA=0: every conv on the CUDA-core kernel; 1: tensor cores except the dilated layers (A/B measurements)
     std::vector<Param> params;
     std::map<std::string, int> index;
     std::map<std::string, std::unique_ptr<Plan>> plans;
@@ -128,7 +152,23 @@ struct Guard {
     ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-struct View { float* p; int cs, coff, C; };      // channels [coff, coff + C) of an NHWC buffer with cs channels per pixel
+struct View { Planes b; int coff, C; };      // channels [coff, coff + C) of a plane buffer
+
+int ensure_packed(fisr_pwc* c, Param& p) {
+    if (p.packed) return FISR_OK;
+    p.KB = (p.cin_pad + 63) / 64;
+    p.cout_pad = fisr::split_conv_cout_pad(p.cout);
+    if (!p.d_wp) {
+        PWC_TRY(c, cudaMalloc(&p.d_wp, static_cast<size_t>(2) * p.KB * 9 * p.cout_pad * 64 * sizeof(__half)));
+        PWC_TRY(c, cudaMalloc(&p.d_bp, p.cout_pad * sizeof(float)));
+    }
+    PWC_TRY(c, cudaMemsetAsync(p.d_bp, 0, p.cout_pad * sizeof(float), c->stream));
+    PWC_TRY(c, cudaMemcpyAsync(p.d_bp, p.d_b, p.cout * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    fisr::launch_prep_weights(p.d_w, p.d_wp, p.cin_pad, p.cout, p.KB, p.cout_pad, 2, c->stream);
+    PWC_TRY(c, cudaGetLastError());
+    p.packed = true;
+    return FISR_OK;
+}
 
 int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
     if (N < 1 || H < 64 || W < 64 || H % 64 || W % 64)
@@ -141,68 +181,119 @@ int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
     plan->N = N; plan->H = H; plan->W = W;
     Plan* pl = plan.get();
     int rc = FISR_OK;
-    auto alloc = [&](size_t floats) -> float* {
+    auto alloc_bytes = [&](size_t bytes) -> void* {
         void* p = nullptr;
         if (rc != FISR_OK) return nullptr;
-        if (cudaMalloc(&p, floats * sizeof(float)) != cudaSuccess) { rc = fail(c, FISR_E_NOMEM, "cudaMalloc(%zu floats) failed", floats); return nullptr; }
-        cudaMemsetAsync(p, 0, floats * sizeof(float), c->stream);      // gap / pad channels stay zero for ever
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { rc = fail(c, FISR_E_NOMEM, "cudaMalloc(%zu bytes) failed", bytes); return nullptr; }
+        cudaMemsetAsync(p, 0, bytes, c->stream);      // gap / pad channels stay zero for ever
         plan->allocs.push_back(p);
-        return static_cast<float*>(p);
+        return p;
     };
     auto px = [&](int l) { return static_cast<size_t>(N) * (H >> l) * (W >> l); };
-    auto P = [&](const std::string& n) -> const Param& { return c->params[c->index.at(n)]; };
-    auto conv = [&](const std::string& name, View in, View outv, int l_in, int l_out, int stride, int dil, bool leaky, const float* add = nullptr) {
-        const Param& p = P(name);
+    auto planes = [&](size_t npix, int cs) -> Planes {
+        Planes b{};
+        b.cs = cs;
+        b.plane = (npix * cs + 511) / 512 * 512;
+        b.p = static_cast<__half*>(alloc_bytes(2 * b.plane * sizeof(__half)));
+        return b;
+    };
+    auto f32 = [&](size_t n) { return static_cast<float*>(alloc_bytes(n * sizeof(float))); };
+    auto P = [&](const std::string& n) -> Param& { return c->params[c->index.at(n)]; };
+    auto push = [&](std::function<void(cudaStream_t)> fn) { Op op; op.fn = std::move(fn); pl->ops.push_back(std::move(op)); };
+    // One conv layer: on the tensor cores when it is a stride-1 conv with >= 16 outputs on an image of at least 4 x 4 pixels --
+    // dilation d as d (column phase) x d (row phase) undilated convs on the polyphase sub-images, each launch covering the d
+    // column phases of one row phase of one image as a batch -- else on the CUDA-core kernel.
+    auto conv = [&](const std::string& name, View in, View outv, int l_in, int l_out, int stride, int dil, bool leaky, float* out_f32 = nullptr,
+                    const float* add = nullptr) {
+        if (rc != FISR_OK) return;
+        Param& p = P(name);
+        const int Hin = H >> l_in, Win = W >> l_in, Hout = H >> l_out, Wout = W >> l_out;
+        const bool divisible = Hout % dil == 0 && Wout % dil == 0;
+        if (c->use_umma >= (dil == 1 ? 1 : 2) && stride == 1 && !out_f32 && p.cout >= 16 && divisible && Hout / dil >= 4 && Wout / dil >= 4) {
+            if ((rc = ensure_packed(c, p)) != FISR_OK) return;
+            const int hs = Hout / dil, ws = Wout / dil;
+            const long long pixrow = static_cast<long long>(Wout), piximg = static_cast<long long>(Hout) * Wout;
+            for (int n = 0; n < (dil == 1 ? 1 : N); ++n)
+                for (int py = 0; py < dil; ++py) {
+                    fisr::SplitConvDesc d{};
+                    const long long pix0 = dil == 1 ? 0 : n * piximg + py * pixrow;          // first pixel of this launch's lattice
+                    d.in = in.b.p + pix0 * in.b.cs; d.in_plane = in.b.plane; d.in_cs = in.b.cs;
+                    d.cin_off = in.coff; d.cin = p.cin_pad;
+                    d.out = outv.b.p + pix0 * outv.b.cs; d.out_plane = outv.b.plane; d.out_cs = outv.b.cs; d.out_off = outv.coff;
+                    if (dil == 1) {
+                        d.N = N; d.in_sx = in.b.cs; d.in_sy = pixrow * in.b.cs; d.in_sn = piximg * in.b.cs;
+                        d.opix_x = 1; d.opix_y = pixrow; d.opix_n = piximg;
+                    } else {          // image index = column phase
+                        d.N = dil; d.in_sx = static_cast<long long>(dil) * in.b.cs; d.in_sy = dil * pixrow * in.b.cs; d.in_sn = in.b.cs;
+                        d.opix_x = dil; d.opix_y = dil * pixrow; d.opix_n = 1;
+                    }
+                    d.H = hs; d.W = ws;
+                    d.out_pixels = static_cast<long long>(N) * piximg;
+                    d.wp = p.d_wp; d.bias = p.d_bp; d.cout = p.cout; d.cout_pad = p.cout_pad;
+                    d.relu = 0; d.slope = leaky ? 0.1f : 0.f;
+                    Op op;
+                    op.umma = true;
+                    std::string why;
+                    if (!fisr::build_split_conv(c->encode, d, c->num_sms, c->d_err, &op.conv, &why)) {
+                        rc = fail(c, FISR_E_CUDA, "conv %s (%d x %d, dilation %d): %s", name.c_str(), Hout, Wout, dil, why.c_str());
+                        return;
+                    }
+                    pl->ops.push_back(std::move(op));
+                    pl->umma_ops++;
+                }
+            return;
+        }
         PwcConv a{};
-        a.in = in.p; a.in_cs = in.cs; a.in_coff = in.coff; a.cin = p.cin_pad;
-        a.out = outv.p; a.out_cs = outv.cs; a.out_coff = outv.coff; a.cout = outv.C;
+        a.in = in.b; a.in_coff = in.coff; a.cin = p.cin_pad;
+        a.out = outv.b; a.out_coff = outv.coff; a.cout = p.cout; a.out_f32 = out_f32;
         a.w = p.d_w; a.b = p.d_b;
-        a.N = N; a.Hin = H >> l_in; a.Win = W >> l_in; a.Hout = H >> l_out; a.Wout = W >> l_out;
+        a.N = N; a.Hin = Hin; a.Win = Win; a.Hout = Hout; a.Wout = Wout;
         a.stride = stride; a.dil = dil;
         // tf 'same': total = (out - 1) s + 2 d + 1 - in, the smaller half first (0 before / 1 after for stride 2 on even sizes)
         a.pad_y = std::max((a.Hout - 1) * stride + 2 * dil + 1 - a.Hin, 0) / 2;
         a.pad_x = std::max((a.Wout - 1) * stride + 2 * dil + 1 - a.Win, 0) / 2;
         a.leaky = leaky ? 1 : 0; a.add = add; a.add_cs = 2;
-        pl->ops.push_back([a](cudaStream_t st) { launch_conv3x3(a, st); });
+        push([a](cudaStream_t st) { launch_conv3x3(a, st); });
     };
     // ---- buffers
-    float* D[kLvls + 1] = {nullptr};
-    float* c2[kLvls + 1] = {nullptr};
-    for (int l = kPredLvl; l <= kLvls; ++l) D[l] = alloc(px(l) * dense_cs(l));
-    for (int l = 1; l <= kLvls; ++l) c2[l] = alloc(px(l) * kChann[l]);
-    float* c1_1 = alloc(px(1) * kChann[1]);                // level 1 of image 1 feeds conv2a only
-    float* c1_6 = alloc(px(kLvls) * kChann[kLvls]);        // D_6 has no c1 slot (model_pwcnet.py:1549-1551)
-    float* tA = alloc(px(1) * kChann[1]);
-    float* tB = alloc(px(1) * kChann[1]);
-    float* T0 = alloc(px(kPredLvl) * 128);
-    float* T1 = alloc(px(kPredLvl) * 128);
-    float* warpbuf = alloc(px(kPredLvl) * 128);
-    float* flow_raw = alloc(px(kPredLvl) * 2);
-    for (int l = kPredLvl; l <= kLvls; ++l) plan->flow[l] = alloc(px(l) * 2);
+    Planes D[kLvls + 1] = {}, c2[kLvls + 1] = {}, tA[kLvls + 1] = {}, tB[kLvls + 1] = {};
+    for (int l = kPredLvl; l <= kLvls; ++l) D[l] = planes(px(l), dense_cs(l));
+    for (int l = 1; l <= kLvls; ++l) c2[l] = planes(px(l), pad8(kChann[l]));
+    Planes c1_1 = planes(px(1), pad8(kChann[1]));                // level 1 of image 1 feeds conv2a only
+    Planes c1_6 = planes(px(kLvls), pad8(kChann[kLvls]));        // D_6 has no c1 slot (model_pwcnet.py:1549-1551)
+    Planes img_p = planes(static_cast<size_t>(N) * H * W, 8);    // the input image in plane format, 3 of 8 channels used
+    {   // scratch of the pyramid: levels whose channel count is a multiple of 8 share two buffers, the others get their own
+        // (their pad channels must stay zero: they are read by the TMA boxes of the next conv)
+        Planes sA = planes(px(1), kChann[1]), sB = planes(px(1), kChann[1]);
+        for (int l = 1; l <= kLvls; ++l) {
+            if (kChann[l] % 8 == 0) { tA[l] = sA; tB[l] = sB; tA[l].cs = tB[l].cs = kChann[l]; }
+            else { tA[l] = planes(px(l), pad8(kChann[l])); tB[l] = planes(px(l), pad8(kChann[l])); }
+        }
+    }
+    Planes T0 = planes(px(kPredLvl), 128), T1 = planes(px(kPredLvl), 128);
+    Planes warpbuf = planes(px(kPredLvl), 128);
+    float* flow_raw = f32(px(kPredLvl) * 2);
+    for (int l = kPredLvl; l <= kLvls; ++l) plan->flow[l] = f32(px(l) * 2);
     if (rc != FISR_OK) return rc;
     auto c1_view = [&](int l) -> View {
-        if (l == 1) return View{c1_1, kChann[1], 0, kChann[1]};
-        if (l == kLvls) return View{c1_6, kChann[l], 0, kChann[l]};
-        return View{D[l], dense_cs(l), kActs + kCorrPad, kChann[l]};
+        if (l == 1) return View{c1_1, 0, kChann[1]};
+        if (l == kLvls) return View{c1_6, 0, kChann[l]};
+        return View{D[l], kActs + kCorrPad, kChann[l]};
     };
     // ---- feature pyramids (model_pwcnet.py:1012-1101): the Siamese extractor on both images
     for (int img = 0; img < 2; ++img) {
-        View x{nullptr, 3, 0, 3};
+        {   // the image pointer is bound per call
+            const int which = img;
+            const size_t npix = static_cast<size_t>(N) * H * W;
+            push([=](cudaStream_t st) { fisr::launch_act_from_f32(which ? pl->img2 : pl->img1, 3, fisr::ActBuf{img_p.p, img_p.plane}, 8, npix, 2, st); });
+        }
+        View x{img_p, 0, 3};
         for (int l = 1; l <= kLvls; ++l) {
             const std::string p = "pwcnet/featpyr/conv" + std::to_string(l);
             const int f = kChann[l];
-            View dst = img == 0 ? c1_view(l) : View{c2[l], f, 0, f};
-            View ta{tA, f, 0, f}, tb{tB, f, 0, f};
-            if (l == 1) {        // the image pointer is bound per call
-                const Param& pa = P(p + "a");
-                const int which = img;
-                PwcConv a{};
-                a.in_cs = 3; a.in_coff = 0; a.cin = pa.cin_pad; a.out = tA; a.out_cs = f; a.out_coff = 0; a.cout = f; a.w = pa.d_w; a.b = pa.d_b;
-                a.N = N; a.Hin = H; a.Win = W; a.Hout = H / 2; a.Wout = W / 2; a.stride = 2; a.dil = 1; a.pad_y = 0; a.pad_x = 0; a.leaky = 1;
-                pl->ops.push_back([a, pl, which](cudaStream_t st) { PwcConv b = a; b.in = which ? pl->img2 : pl->img1; launch_conv3x3(b, st); });
-            } else {
-                conv(p + "a", x, ta, l - 1, l, 2, 1, true);
-            }
+            View dst = img == 0 ? c1_view(l) : View{c2[l], 0, f};
+            View ta{tA[l], 0, f}, tb{tB[l], 0, f};
+            conv(p + "a", x, ta, l - 1, l, 2, 1, true);
             conv(p + "aa", ta, tb, l, l, 1, 1, true);
             conv(p + "b", tb, dst, l, l, 1, 1, true);
             x = dst;
@@ -213,55 +304,53 @@ int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
         const std::string sl = std::to_string(l);
         const int cs = dense_cs(l), h = H >> l, w = W >> l, C = kChann[l];
         const View c1v = c1_view(l);
-        float* Dl = D[l];
+        const Planes Dl = D[l], c2l = c2[l];
         if (l == kLvls) {
-            float* c2l = c2[l];
-            pl->ops.push_back([=](cudaStream_t st) { launch_cost_volume(c1v.p, c1v.cs, c1v.coff, c2l, C, 0, C, Dl, cs, kActs, N, h, w, st); });
+            push([=](cudaStream_t st) { launch_cost_volume(c1v.b, c1v.coff, c2l, 0, C, Dl, kActs, N, h, w, st); });
         } else {
-            float* c2l = c2[l];
             const int uf = kActs + kCorrPad + C;           // up_flow slot
             const float scaler = 20.f / static_cast<float>(1 << l);
-            pl->ops.push_back([=](cudaStream_t st) {
-                launch_dense_warp(c2l, C, 0, C, Dl, cs, uf, scaler, warpbuf, N, h, w, st);
-                launch_cost_volume(c1v.p, c1v.cs, c1v.coff, warpbuf, C, 0, C, Dl, cs, kActs, N, h, w, st);
-            });
+            Planes wb = warpbuf;
+            wb.cs = pad8(C);
+            push([=](cudaStream_t st) { launch_dense_warp(c2l, 0, C, Dl, uf, scaler, wb, N, h, w, st); });
+            push([=](cudaStream_t st) { launch_cost_volume(c1v.b, c1v.coff, wb, 0, C, Dl, kActs, N, h, w, st); });
         }
         for (int k = 0; k < 5; ++k)
-            conv("pwcnet/predict_flow/conv" + sl + "_" + std::to_string(k), View{Dl, cs, dense_in_off(k), cs - dense_in_off(k)},
-                 View{Dl, cs, dense_off(k), kDense[k]}, l, l, 1, 1, true);
-        conv("pwcnet/predict_flow/flow" + sl, View{Dl, cs, 0, cs}, View{flow_raw, 2, 0, 2}, l, l, 1, 1, false);
+            conv("pwcnet/predict_flow/conv" + sl + "_" + std::to_string(k), View{Dl, dense_in_off(k), cs - dense_in_off(k)},
+                 View{Dl, dense_off(k), kDense[k]}, l, l, 1, 1, true);
+        conv("pwcnet/predict_flow/flow" + sl, View{Dl, 0, cs}, View{}, l, l, 1, 1, false, flow_raw);
         // context network (model_pwcnet.py:1453-1522): flow + dilated conv chain on upfeat
-        float* bufs[2] = {T0, T1};
-        View cur{Dl, cs, 0, cs};
+        View cur{Dl, 0, cs};
         for (int k = 0; k < 7; ++k) {
             const std::string nm = "pwcnet/ctxt/dc_conv" + sl + std::to_string(k + 1);
             if (k < 6) {
-                View o{bufs[k & 1], kCtxtF[k], 0, kCtxtF[k]};
+                Planes t = (k & 1) ? T1 : T0;
+                t.cs = kCtxtF[k];
+                View o{t, 0, kCtxtF[k]};
                 conv(nm, cur, o, l, l, 1, kCtxtD[k], true);
                 cur = o;
             } else {
-                conv(nm, cur, View{plan->flow[l], 2, 0, 2}, l, l, 1, 1, false, flow_raw);
+                conv(nm, cur, View{}, l, l, 1, 1, false, plan->flow[l], flow_raw);
             }
         }
         if (l != kPredLvl) {
             const Param& pf = P("pwcnet/upsample/up_flow" + sl);
             const Param& pe = P("pwcnet/upsample/up_feat" + sl);
-            float* Dn = D[l - 1];
-            const int csn = dense_cs(l - 1), ufn = kActs + kCorrPad + kChann[l - 1];
-            float* fl = plan->flow[l];
+            const Planes Dn = D[l - 1];
+            const int ufn = kActs + kCorrPad + kChann[l - 1];
+            const float* fl = plan->flow[l];
             const float *wf = pf.d_w, *bf = pf.d_b, *we = pe.d_w, *be = pe.d_b;
             const int cine = pe.cin_pad;
-            pl->ops.push_back([=](cudaStream_t st) {
-                launch_deconv4x4s2(fl, 2, 0, 2, wf, bf, Dn, csn, ufn, N, h, w, st);
-                launch_deconv4x4s2(Dl, cs, 0, cine, we, be, Dn, csn, ufn + 2, N, h, w, st);
-            });
+            push([=](cudaStream_t st) { launch_deconv4x4s2(Planes{}, 0, fl, 2, 2, wf, bf, Dn, ufn, N, h, w, st); });
+            push([=](cudaStream_t st) { launch_deconv4x4s2(Dl, 0, nullptr, 0, cine, we, be, Dn, ufn + 2, N, h, w, st); });
         }
     }
     {   // flow_pred = resize_bilinear(flow2, x4) * 4 (model_pwcnet.py:1588-1590)
         float* f2 = plan->flow[kPredLvl];
         const int h = H >> kPredLvl, w = W >> kPredLvl, S = 1 << kPredLvl;
-        pl->ops.push_back([=](cudaStream_t st) { launch_resize_flow(f2, pl->out, N, h, w, S, static_cast<float>(S), st); });
+        push([=](cudaStream_t st) { launch_resize_flow(f2, pl->out, N, h, w, S, static_cast<float>(S), st); });
     }
+    if (rc != FISR_OK) return rc;
     PWC_TRY(c, cudaStreamSynchronize(c->stream));
     *out = plan.get();
     c->plans[key] = std::move(plan);
@@ -282,13 +371,31 @@ int fisr_pwc_create(int device, fisr_pwc** out) {
     c->device = device;
     Guard guard(device);
     cudaFree(0);
+    cudaDeviceProp prop;
+    PWC_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(nullptr, FISR_E_CUDA, "fisr_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    c->num_sms = prop.multiProcessorCount;
+    {
+        cudaDriverEntryPointQueryResult q;
+        void* fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+            return fail(nullptr, FISR_E_CUDA, "cuTensorMapEncodeTiled unavailable");
+        c->encode = reinterpret_cast<fisr::EncodeTiledFn>(fn);
+    }
+    if (const char* e = getenv("FISR_PWC_UMMA")) c->use_umma = atoi(e);
+    PWC_TRY(nullptr, fisr::conv3x3_init());
     PWC_TRY(nullptr, init_kernels());
     PWC_TRY(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PWC_TRY(nullptr, cudaMalloc(&c->d_err, sizeof(int)));
+    PWC_TRY(nullptr, cudaMemset(c->d_err, 0, sizeof(int)));
+    PWC_TRY(nullptr, cudaMallocHost(&c->h_err, sizeof(int)));
+    *c->h_err = 0;
     const auto& inv = inventory();
     c->params.resize(inv.size());
     for (size_t i = 0; i < inv.size(); ++i) {
         Param& p = c->params[i];
-        p.cin_pad = inv[i].cin + (inv[i].gap_at >= 0 ? 3 : 0);
+        p.cin_pad = inv[i].cin + (inv[i].gap_at >= 0 ? kGap : 0);
+        p.cout = inv[i].cout;
         const size_t wn = static_cast<size_t>(inv[i].transpose ? 16 : 9) * p.cin_pad * inv[i].cout;
         PWC_TRY(nullptr, cudaMalloc(&p.d_w, wn * sizeof(float)));
         PWC_TRY(nullptr, cudaMemset(p.d_w, 0, wn * sizeof(float)));
@@ -306,7 +413,9 @@ void fisr_pwc_destroy(fisr_pwc* c) {
     Guard guard(c->device);
     cudaDeviceSynchronize();
     c->plans.clear();
-    for (auto& p : c->params) { cudaFree(p.d_w); cudaFree(p.d_b); }
+    for (auto& p : c->params) { cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); cudaFree(p.d_bp); }
+    cudaFree(c->d_err);
+    if (c->h_err) cudaFreeHost(c->h_err);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -339,13 +448,14 @@ int fisr_pwc_set_param(fisr_pwc* c, const char* name, const float* h_data, size_
     if (is_b) {
         if (count != (size_t)d.cout) return fail(c, FISR_E_INVALID, "%s has %d elements, got %zu", name, d.cout, count);
         PWC_TRY(c, cudaMemcpy(p.d_b, h_data, count * sizeof(float), cudaMemcpyHostToDevice));
+        p.packed = false;
         return FISR_OK;
     }
     const size_t taps = d.transpose ? 16 : 9, expect = taps * d.cin * d.cout;
     if (count != expect) return fail(c, FISR_E_INVALID, "%s has %zu elements, got %zu", name, expect, count);
-    // kernel layout with the 3 zero rows of the padded cost-volume slot: reference input channel i sits at i (+3 past the gap)
+    // kernel layout with the kGap zero rows of the padded cost-volume slot: reference input channel i sits at i (+kGap past the gap)
     std::vector<float> packed(taps * p.cin_pad * d.cout, 0.f);
-    auto slot = [&](int ci) { return (d.gap_at >= 0 && ci >= d.gap_at) ? ci + 3 : ci; };
+    auto slot = [&](int ci) { return (d.gap_at >= 0 && ci >= d.gap_at) ? ci + kGap : ci; };
     for (size_t t = 0; t < taps; ++t)
         for (int ci = 0; ci < d.cin; ++ci)
             for (int co = 0; co < d.cout; ++co) {
@@ -354,6 +464,7 @@ int fisr_pwc_set_param(fisr_pwc* c, const char* name, const float* h_data, size_
             }
     PWC_TRY(c, cudaMemcpy(p.d_w, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
     p.h_w.assign(h_data, h_data + count);
+    p.packed = false;
     return FISR_OK;
 }
 
@@ -361,11 +472,19 @@ int fisr_pwc_forward(fisr_pwc* c, const float* d_img1, const float* d_img2, int 
     if (!c || !d_img1 || !d_img2 || !d_flow) return FISR_E_INVALID;
     Guard guard(c->device);
     Plan* plan = nullptr;
-    const int rc = build_plan(c, N, H, W, &plan);
+    if (*c->h_err) return fail(c, FISR_E_CUDA, "a conv kernel of an earlier forward timed out on a barrier (code %d)", *c->h_err);
+    for (auto& p : c->params)            // parameters changed since the plan was built: re-pack the operand planes in place
+        if (p.d_wp && !p.packed) { const int rp = ensure_packed(c, p); if (rp != FISR_OK) return rp; }
+    int rc = build_plan(c, N, H, W, &plan);
     if (rc != FISR_OK) return rc;
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    if (st != c->stream) PWC_TRY(c, cudaStreamSynchronize(c->stream));      // operand packing / buffer clears ran on the context stream
     plan->img1 = d_img1; plan->img2 = d_img2; plan->out = d_flow;
-    for (auto& op : plan->ops) op(st);
+    for (auto& op : plan->ops) {
+        if (op.umma) PWC_TRY(c, fisr::launch_conv3x3(op.conv, c->num_sms, st));
+        else op.fn(st);
+    }
+    PWC_TRY(c, cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     c->launches += static_cast<long long>(plan->ops.size());
     c->last = plan;
     PWC_TRY(c, cudaGetLastError());
@@ -379,6 +498,7 @@ int fisr_pwc_debug_flow(fisr_pwc* c, int lvl, float* h_dst, size_t count) {
     const size_t n = static_cast<size_t>(c->last->N) * (c->last->H >> lvl) * (c->last->W >> lvl) * 2;
     if (count != n) return fail(c, FISR_E_INVALID, "flow%d has %zu elements, got %zu", lvl, n, count);
     PWC_TRY(c, cudaDeviceSynchronize());
+    if (*c->h_err) return fail(c, FISR_E_CUDA, "a conv kernel timed out on a barrier (code %d)", *c->h_err);
     PWC_TRY(c, cudaMemcpy(h_dst, c->last->flow[lvl], n * sizeof(float), cudaMemcpyDeviceToHost));
     return FISR_OK;
 }

@@ -1,8 +1,9 @@
 // PWC-Net inference kernels: the optical-flow network the reference runs in front of its flow warp
-// (FISR_tfoptflow/model_pwcnet.py:1012-1593, PWC-Net-large, 6-level pyramid, flow predicted at level 2).  fp32 CUDA-core
-// kernels on NHWC tensors addressed as (pointer, channel stride, channel offset), so that the DenseNet-style concatenations of
-// the flow estimator (model_pwcnet.py:1415-1437: x = concat([act, x])) are channel slices of ONE buffer per pyramid level and
-// never copied.  TF semantics restated: 'same' padding puts the odd pad element AFTER the data (stride-2 convs on even sizes pad
+// (FISR_tfoptflow/model_pwcnet.py:1012-1593, PWC-Net-large, 6-level pyramid, flow predicted at level 2).  Everything that is
+// not a stride-1 3x3 conv on the tensor cores (conv_umma_kernel.cuh, launched from pwc_api.cu): CUDA-core kernels on NHWC
+// tensors in the split fp16 (hi, lo) plane format of the conv kernels, addressed as (planes, channel offset), so that the
+// DenseNet-style concatenations of the flow estimator (model_pwcnet.py:1415-1437: x = concat([act, x])) are channel slices of ONE
+// buffer per pyramid level and never copied.  Arithmetic is fp32; the planes hold 22 mantissa bits of each value.  TF semantics restated: 'same' padding puts the odd pad element AFTER the data (stride-2 convs on even sizes pad
 // 0 before, 1 after); conv2d_transpose 4x4 s2 'same' is out[2i + k - 1] += in[i] w[k].
 #include "common.cuh"
 #include "pwc_kernels.h"
@@ -15,6 +16,41 @@ namespace {
 __device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : 0.1f * x; }      // tf.nn.leaky_relu(alpha=0.1)
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
     return static_cast<unsigned long long>(__float_as_uint(lo)) | (static_cast<unsigned long long>(__float_as_uint(hi)) << 32);
+}
+
+// ---- split-plane accessors: element i of a buffer is hi[i] + lo[i] with lo = hi + plane
+__device__ __forceinline__ float ld1(const __half* p, size_t plane, size_t i) { return __half2float(__ldg(p + i)) + __half2float(__ldg(p + plane + i)); }
+__device__ __forceinline__ float2 join2(uint32_t h, uint32_t l) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h)), b = __half22float2(*reinterpret_cast<const __half2*>(&l));
+    return make_float2(a.x + b.x, a.y + b.y);
+}
+__device__ __forceinline__ float4 ld4(const __half* p, size_t plane, size_t i) {          // i % 4 == 0
+    const uint2 h = __ldg(reinterpret_cast<const uint2*>(p + i)), l = __ldg(reinterpret_cast<const uint2*>(p + plane + i));
+    const float2 a = join2(h.x, l.x), b = join2(h.y, l.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void ld8(const __half* p, size_t plane, size_t i, float* v) {   // i % 8 == 0
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(p + i)), l = __ldg(reinterpret_cast<const uint4*>(p + plane + i));
+    const float2 a = join2(h.x, l.x), b = join2(h.y, l.y), c = join2(h.z, l.z), d = join2(h.w, l.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void st1(__half* p, size_t plane, size_t i, float v) {
+    const SplitHalf s = split_f32(v);
+    p[i] = s.hi;
+    p[plane + i] = s.lo;
+}
+__device__ __forceinline__ void st2(__half* p, size_t plane, size_t i, float v0, float v1) {          // i % 2 == 0
+    uint32_t h, l;
+    split2_f32(v0, v1, h, l);
+    *reinterpret_cast<uint32_t*>(p + i) = h;
+    *reinterpret_cast<uint32_t*>(p + plane + i) = l;
+}
+__device__ __forceinline__ void st4(__half* p, size_t plane, size_t i, float4 v) {          // i % 4 == 0
+    uint32_t h01, l01, h23, l23;
+    split2_f32(v.x, v.y, h01, l01);
+    split2_f32(v.z, v.w, h23, l23);
+    *reinterpret_cast<uint2*>(p + i) = make_uint2(h01, h23);
+    *reinterpret_cast<uint2*>(p + plane + i) = make_uint2(l01, l23);
 }
 
 // ---------------------------------------------------------------- 3x3 conv, wide outputs (Cout a multiple of 4)
@@ -40,7 +76,7 @@ __global__ void __launch_bounds__(128) conv3x3_wide_kernel(const PwcConv p) {
         oy = static_cast<int>(r % p.Hout);
         n = static_cast<int>(r / p.Hout);
     }
-    const bool vec_in = ((p.in_cs | p.in_coff) & 3) == 0;
+    const bool vec_in = ((p.in.cs | p.in_coff) & 7) == 0;
     // accumulators as packed fp32 pairs: fma.rn.f32x2 (FFMA2, sm_100) does two FMAs per issued instruction, which matters in a
     // kernel that is issue bound (512 scalar FFMAs per 8-channel slice next to ~100 other instructions)
     unsigned long long acc2[8][4];
@@ -60,16 +96,13 @@ __global__ void __launch_bounds__(128) conv3x3_wide_kernel(const PwcConv p) {
 #pragma unroll
         for (int j = 0; j < kCi; ++j) a[j] = 0.f;
         if (inside) {
-            const float* src = p.in + (static_cast<size_t>(n) * p.Hin + iy) * p.Win * p.in_cs + static_cast<size_t>(ix) * p.in_cs + p.in_coff + c0;
+            const size_t src = (static_cast<size_t>(n) * p.Hin + iy) * p.Win * p.in.cs + static_cast<size_t>(ix) * p.in.cs + p.in_coff + c0;
             if (vec_in && c0 + kCi <= p.cin) {
 #pragma unroll
-                for (int q = 0; q < kCi / 4; ++q) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + 4 * q));
-                    a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
-                }
+                for (int q = 0; q < kCi / 8; ++q) ld8(p.in.p, p.in.plane, src + 8 * q, a + 8 * q);
             } else {
 #pragma unroll
-                for (int j = 0; j < kCi; ++j) if (c0 + j < p.cin) a[j] = __ldg(src + j);
+                for (int j = 0; j < kCi; ++j) if (c0 + j < p.cin) a[j] = ld1(p.in.p, p.in.plane, src + j);
             }
         }
 #pragma unroll
@@ -107,12 +140,12 @@ __global__ void __launch_bounds__(128) conv3x3_wide_kernel(const PwcConv p) {
     float bias[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) bias[j] = co0 + j < p.cout ? __ldg(p.b + co0 + j) : 0.f;
-    const bool vec_out = ((p.out_cs | p.out_coff) & 3) == 0;
+    const bool vec_out = ((p.out.cs | p.out_coff) & 3) == 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const long long q = static_cast<long long>(blockIdx.x) * kPx + pg * 8 + i;
         if (q >= npix) break;
-        float* d = p.out + static_cast<size_t>(q) * p.out_cs + p.out_coff + co0;
+        const size_t d = static_cast<size_t>(q) * p.out.cs + p.out_coff + co0;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -120,11 +153,11 @@ __global__ void __launch_bounds__(128) conv3x3_wide_kernel(const PwcConv p) {
             if (LEAKY) v[j] = lrelu(v[j]);
         }
         if (vec_out && co0 + 8 <= p.cout) {
-            *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            st4(p.out.p, p.out.plane, d, make_float4(v[0], v[1], v[2], v[3]));
+            st4(p.out.p, p.out.plane, d + 4, make_float4(v[4], v[5], v[6], v[7]));
         } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) if (co0 + j < p.cout) d[j] = v[j];
+            for (int j = 0; j < 8; ++j) if (co0 + j < p.cout) st1(p.out.p, p.out.plane, d + j, v[j]);
         }
     }
 }
@@ -143,30 +176,30 @@ __global__ void __launch_bounds__(128) conv3x3_narrow_kernel(const PwcConv p) {
     const int ox = static_cast<int>(P % p.Wout);
     const long long r = P / p.Wout;
     const int oy = static_cast<int>(r % p.Hout), n = static_cast<int>(r / p.Hout);
-    const bool vec_in = ((p.in_cs | p.in_coff) & 3) == 0;
+    const bool vec_in = ((p.in.cs | p.in_coff) & 3) == 0;
     float acc[COUT];
 #pragma unroll
     for (int j = 0; j < COUT; ++j) acc[j] = __ldg(p.b + j);
     for (int tap = 0; tap < 9; ++tap) {
         const int iy = oy * p.stride + (tap / 3) * p.dil - p.pad_y, ix = ox * p.stride + (tap % 3) * p.dil - p.pad_x;
         if (iy < 0 || iy >= p.Hin || ix < 0 || ix >= p.Win) continue;
-        const float* src = p.in + (static_cast<size_t>(n) * p.Hin + iy) * p.Win * p.in_cs + static_cast<size_t>(ix) * p.in_cs + p.in_coff;
+        const size_t src = (static_cast<size_t>(n) * p.Hin + iy) * p.Win * p.in.cs + static_cast<size_t>(ix) * p.in.cs + p.in_coff;
         const float* wt = wsm + tap * p.cin * COUT;
         int c = 0;
         if (vec_in)
             for (; c + 4 <= p.cin; c += 4) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
+                const float4 v = ld4(p.in.p, p.in.plane, src + c);
 #pragma unroll
                 for (int j = 0; j < COUT; ++j)
                     acc[j] = fmaf(v.w, wt[(c + 3) * COUT + j], fmaf(v.z, wt[(c + 2) * COUT + j], fmaf(v.y, wt[(c + 1) * COUT + j], fmaf(v.x, wt[c * COUT + j], acc[j]))));
             }
         for (; c < p.cin; ++c) {
-            const float v = __ldg(src + c);
+            const float v = ld1(p.in.p, p.in.plane, src + c);
 #pragma unroll
             for (int j = 0; j < COUT; ++j) acc[j] = fmaf(v, wt[c * COUT + j], acc[j]);
         }
     }
-    float* d = p.out + static_cast<size_t>(P) * p.out_cs + p.out_coff;
+    float* d = p.out_f32 + static_cast<size_t>(P) * COUT;
 #pragma unroll
     for (int j = 0; j < COUT; ++j) {
         float v = acc[j];
@@ -177,8 +210,10 @@ __global__ void __launch_bounds__(128) conv3x3_narrow_kernel(const PwcConv p) {
 
 // ---------------------------------------------------------------- conv2d_transpose 4x4, stride 2, 'same', 2 filters (model_pwcnet.py:1180-1224)
 // out[n, oy, ox, co] = b[co] + sum over (ky, kx, ci) with oy = 2 iy + ky - 1, ox = 2 ix + kx - 1 of in[n, iy, ix, ci] w[ky, kx, co, ci]
-__global__ void __launch_bounds__(128) deconv4x4s2_kernel(const float* __restrict__ in, int in_cs, int in_coff, int cin, const float* __restrict__ w,
-                                                          const float* __restrict__ b, float* __restrict__ out, int out_cs, int out_coff, int N, int h, int wd) {
+// The input is either a plane buffer or a plain fp32 [.., 2] flow (up_flow reads the fp32 flow of the level above).
+template <bool IN_F32>
+__global__ void __launch_bounds__(128) deconv4x4s2_kernel(Planes in, int in_coff, const float* __restrict__ in_f32, int in_f32_cs, int cin,
+                                                          const float* __restrict__ w, const float* __restrict__ b, Planes out, int out_coff, int N, int h, int wd) {
     const long long npix = static_cast<long long>(N) * 4 * h * wd;
     const long long P = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (P >= npix) return;
@@ -186,7 +221,8 @@ __global__ void __launch_bounds__(128) deconv4x4s2_kernel(const float* __restric
     const long long r = P / (2 * wd);
     const int oy = static_cast<int>(r % (2 * h)), n = static_cast<int>(r / (2 * h));
     float a0 = __ldg(b), a1 = __ldg(b + 1);
-    const bool vec = ((in_cs | in_coff | cin) & 3) == 0;
+    const int ics = IN_F32 ? in_f32_cs : in.cs;
+    const bool vec = !IN_F32 && ((in.cs | in_coff | cin) & 3) == 0;
 #pragma unroll
     for (int sy = 0; sy < 2; ++sy) {
         const int ky = ((oy + 1) & 1) + 2 * sy, iy = (oy + 1 - ky) >> 1;
@@ -195,33 +231,30 @@ __global__ void __launch_bounds__(128) deconv4x4s2_kernel(const float* __restric
         for (int sx = 0; sx < 2; ++sx) {
             const int kx = ((ox + 1) & 1) + 2 * sx, ix = (ox + 1 - kx) >> 1;
             if (ix < 0 || ix >= wd) continue;
-            const float* src = in + (static_cast<size_t>(n) * h + iy) * wd * in_cs + static_cast<size_t>(ix) * in_cs + in_coff;
+            const size_t src = (static_cast<size_t>(n) * h + iy) * wd * ics + static_cast<size_t>(ix) * ics + (IN_F32 ? 0 : in_coff);
             const float* w0 = w + static_cast<size_t>((ky * 4 + kx) * 2) * cin;
             const float* w1 = w0 + cin;
             int c = 0;
             if (vec)
                 for (; c + 4 <= cin; c += 4) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
+                    const float4 v = ld4(in.p, in.plane, src + c);
                     const float4 u0 = __ldg(reinterpret_cast<const float4*>(w0 + c)), u1 = __ldg(reinterpret_cast<const float4*>(w1 + c));
                     a0 = fmaf(v.w, u0.w, fmaf(v.z, u0.z, fmaf(v.y, u0.y, fmaf(v.x, u0.x, a0))));
                     a1 = fmaf(v.w, u1.w, fmaf(v.z, u1.z, fmaf(v.y, u1.y, fmaf(v.x, u1.x, a1))));
                 }
             for (; c < cin; ++c) {
-                const float v = __ldg(src + c);
+                const float v = IN_F32 ? __ldg(in_f32 + src + c) : ld1(in.p, in.plane, src + c);
                 a0 = fmaf(v, __ldg(w0 + c), a0);
                 a1 = fmaf(v, __ldg(w1 + c), a1);
             }
         }
     }
-    float* d = out + static_cast<size_t>(P) * out_cs + out_coff;
-    d[0] = a0;
-    d[1] = a1;
+    st2(out.p, out.plane, static_cast<size_t>(P) * out.cs + out_coff, a0, a1);
 }
 
 // ---------------------------------------------------------------- cost volume, search range 4 (model_pwcnet.py:1226-1277)
 // out[p, (dy+4)*9 + (dx+4)] = leaky_relu(mean_c c1[p, c] * c2[p + (dy, dx), c]), zero outside the image
-__global__ void __launch_bounds__(256) cost_volume_kernel(const float* __restrict__ c1, int c1_cs, int c1_coff, const float* __restrict__ c2, int c2_cs, int c2_coff,
-                                                          int C, float* __restrict__ out, int out_cs, int out_coff, int N, int h, int w) {
+__global__ void __launch_bounds__(256) cost_volume_kernel(Planes c1, int c1_coff, Planes c2, int c2_coff, int C, Planes out, int out_coff, int N, int h, int w) {
     const long long total = static_cast<long long>(N) * h * w * 81;
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -233,24 +266,23 @@ __global__ void __launch_bounds__(256) cost_volume_kernel(const float* __restric
     const int yy = y + d / 9 - 4, xx = x + d % 9 - 4;
     float s = 0.f;
     if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
-        const float* a = c1 + static_cast<size_t>(P) * c1_cs + c1_coff;
-        const float* b = c2 + (static_cast<size_t>(n) * h + yy) * w * c2_cs + static_cast<size_t>(xx) * c2_cs + c2_coff;
-        if (((c1_cs | c1_coff | c2_cs | c2_coff | C) & 3) == 0) {
+        const size_t a = static_cast<size_t>(P) * c1.cs + c1_coff;
+        const size_t b = (static_cast<size_t>(n) * h + yy) * w * c2.cs + static_cast<size_t>(xx) * c2.cs + c2_coff;
+        if (((c1.cs | c1_coff | c2.cs | c2_coff | C) & 3) == 0) {
             for (int c = 0; c < C; c += 4) {
-                const float4 u = __ldg(reinterpret_cast<const float4*>(a + c)), v = __ldg(reinterpret_cast<const float4*>(b + c));
+                const float4 u = ld4(c1.p, c1.plane, a + c), v = ld4(c2.p, c2.plane, b + c);
                 s = fmaf(u.w, v.w, fmaf(u.z, v.z, fmaf(u.y, v.y, fmaf(u.x, v.x, s))));
             }
         } else {
-            for (int c = 0; c < C; ++c) s = fmaf(__ldg(a + c), __ldg(b + c), s);
+            for (int c = 0; c < C; ++c) s = fmaf(ld1(c1.p, c1.plane, a + c), ld1(c2.p, c2.plane, b + c), s);
         }
     }
-    out[static_cast<size_t>(P) * out_cs + out_coff + d] = lrelu(s / static_cast<float>(C));
+    st1(out.p, out.plane, static_cast<size_t>(P) * out.cs + out_coff + d, lrelu(s / static_cast<float>(C)));
 }
 
 // ---------------------------------------------------------------- dense_image_warp (model_pwcnet.py:1106-1178)
 // out[p, c] = bilinear(img, (x + s u, y + s v)) with TF's _interpolate_bilinear clamping: floor in [0, size - 2], weight in [0, 1]
-__global__ void __launch_bounds__(256) dense_warp_kernel(const float* __restrict__ img, int cs, int coff, int C, const float* __restrict__ flow, int f_cs, int f_coff,
-                                                         float scale, float* __restrict__ out, int N, int h, int w) {
+__global__ void __launch_bounds__(256) dense_warp_kernel(Planes img, int coff, int C, Planes flow, int f_coff, float scale, Planes out, int N, int h, int w) {
     const int cv = C / 4;
     const long long total = static_cast<long long>(N) * h * w * cv;
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -260,20 +292,21 @@ __global__ void __launch_bounds__(256) dense_warp_kernel(const float* __restrict
     const int x = static_cast<int>(P % w);
     const long long r = P / w;
     const int y = static_cast<int>(r % h), n = static_cast<int>(r / h);
-    const float qx = static_cast<float>(x) + scale * __ldg(flow + static_cast<size_t>(P) * f_cs + f_coff);
-    const float qy = static_cast<float>(y) + scale * __ldg(flow + static_cast<size_t>(P) * f_cs + f_coff + 1);
+    const size_t fi = static_cast<size_t>(P) * flow.cs + f_coff;
+    const float qx = static_cast<float>(x) + scale * ld1(flow.p, flow.plane, fi);
+    const float qy = static_cast<float>(y) + scale * ld1(flow.p, flow.plane, fi + 1);
     const float fx0 = fminf(fmaxf(floorf(qx), 0.f), static_cast<float>(w - 2)), fy0 = fminf(fmaxf(floorf(qy), 0.f), static_cast<float>(h - 2));
     const float ax = fminf(fmaxf(qx - fx0, 0.f), 1.f), ay = fminf(fmaxf(qy - fy0, 0.f), 1.f);
     const int x0 = static_cast<int>(fx0), y0 = static_cast<int>(fy0);
-    const float* base = img + (static_cast<size_t>(n) * h + y0) * w * cs + static_cast<size_t>(x0) * cs + coff + c4;
-    const float4 tl = __ldg(reinterpret_cast<const float4*>(base)), tr = __ldg(reinterpret_cast<const float4*>(base + cs));
-    const float4 bl = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(w) * cs)), br = __ldg(reinterpret_cast<const float4*>(base + static_cast<size_t>(w) * cs + cs));
+    const size_t base = (static_cast<size_t>(n) * h + y0) * w * img.cs + static_cast<size_t>(x0) * img.cs + coff + c4;
+    const float4 tl = ld4(img.p, img.plane, base), tr = ld4(img.p, img.plane, base + img.cs);
+    const float4 bl = ld4(img.p, img.plane, base + static_cast<size_t>(w) * img.cs), br = ld4(img.p, img.plane, base + static_cast<size_t>(w) * img.cs + img.cs);
     auto mix = [&](float a, float b, float c, float d) {
         const float top = a + ax * (b - a), bot = c + ax * (d - c);
         return top + ay * (bot - top);
     };
-    *reinterpret_cast<float4*>(out + static_cast<size_t>(P) * C + c4) =
-        make_float4(mix(tl.x, tr.x, bl.x, br.x), mix(tl.y, tr.y, bl.y, br.y), mix(tl.z, tr.z, bl.z, br.z), mix(tl.w, tr.w, bl.w, br.w));
+    st4(out.p, out.plane, static_cast<size_t>(P) * out.cs + c4,
+        make_float4(mix(tl.x, tr.x, bl.x, br.x), mix(tl.y, tr.y, bl.y, br.y), mix(tl.z, tr.z, bl.z, br.z), mix(tl.w, tr.w, bl.w, br.w)));
 }
 
 // ---------------------------------------------------------------- tf.image.resize_bilinear x S (legacy: src = dst / S), times `gain`
@@ -317,19 +350,19 @@ void launch_conv3x3(const PwcConv& p, cudaStream_t st) {
     else conv3x3_wide_kernel<false><<<grid, 128, 0, st>>>(p);
 }
 
-void launch_deconv4x4s2(const float* in, int in_cs, int in_coff, int cin, const float* w, const float* b, float* out, int out_cs, int out_coff,
+void launch_deconv4x4s2(Planes in, int in_coff, const float* in_f32, int in_f32_cs, int cin, const float* w, const float* b, Planes out, int out_coff,
                         int N, int h, int wd, cudaStream_t st) {
-    deconv4x4s2_kernel<<<blocks_for(static_cast<long long>(N) * 4 * h * wd, 128), 128, 0, st>>>(in, in_cs, in_coff, cin, w, b, out, out_cs, out_coff, N, h, wd);
+    const unsigned blocks = blocks_for(static_cast<long long>(N) * 4 * h * wd, 128);
+    if (in_f32) deconv4x4s2_kernel<true><<<blocks, 128, 0, st>>>(in, in_coff, in_f32, in_f32_cs, cin, w, b, out, out_coff, N, h, wd);
+    else deconv4x4s2_kernel<false><<<blocks, 128, 0, st>>>(in, in_coff, in_f32, in_f32_cs, cin, w, b, out, out_coff, N, h, wd);
 }
 
-void launch_cost_volume(const float* c1, int c1_cs, int c1_coff, const float* c2, int c2_cs, int c2_coff, int C, float* out, int out_cs, int out_coff,
-                        int N, int h, int w, cudaStream_t st) {
-    cost_volume_kernel<<<blocks_for(static_cast<long long>(N) * h * w * 81, 256), 256, 0, st>>>(c1, c1_cs, c1_coff, c2, c2_cs, c2_coff, C, out, out_cs, out_coff, N, h, w);
+void launch_cost_volume(Planes c1, int c1_coff, Planes c2, int c2_coff, int C, Planes out, int out_coff, int N, int h, int w, cudaStream_t st) {
+    cost_volume_kernel<<<blocks_for(static_cast<long long>(N) * h * w * 81, 256), 256, 0, st>>>(c1, c1_coff, c2, c2_coff, C, out, out_coff, N, h, w);
 }
 
-void launch_dense_warp(const float* img, int cs, int coff, int C, const float* flow, int f_cs, int f_coff, float scale, float* out, int N, int h, int w,
-                       cudaStream_t st) {
-    dense_warp_kernel<<<blocks_for(static_cast<long long>(N) * h * w * (C / 4), 256), 256, 0, st>>>(img, cs, coff, C, flow, f_cs, f_coff, scale, out, N, h, w);
+void launch_dense_warp(Planes img, int coff, int C, Planes flow, int f_coff, float scale, Planes out, int N, int h, int w, cudaStream_t st) {
+    dense_warp_kernel<<<blocks_for(static_cast<long long>(N) * h * w * (C / 4), 256), 256, 0, st>>>(img, coff, C, flow, f_coff, scale, out, N, h, w);
 }
 
 void launch_resize_flow(const float* in, float* out, int N, int h, int w, int S, float gain, cudaStream_t st) {

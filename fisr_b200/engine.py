@@ -297,9 +297,10 @@ class Engine:
         frames = self._dev(frames, torch.uint8)
         flow = self._dev(flow, torch.float32)
         J, h, w, _ = flow.shape
-        idx = torch.as_tensor(list(src_index), dtype=torch.int32, device=frames.device)
-        if idx.numel() != J or int(idx.min()) < 0 or int(idx.max()) >= frames.shape[0] or tuple(frames.shape[1:]) != (h, w, 3):
-            raise FisrError(f"warp_batch: {J} flows, {idx.numel()} source indices, frames {tuple(frames.shape)}")
+        src = [int(i) for i in src_index]                 # checked on the host: no device round trip before the launch
+        if len(src) != J or min(src, default=0) < 0 or max(src, default=0) >= frames.shape[0] or tuple(frames.shape[1:]) != (h, w, 3):
+            raise FisrError(f"warp_batch: {J} flows, {len(src)} source indices, frames {tuple(frames.shape)}")
+        idx = torch.tensor(src, dtype=torch.int32).pin_memory().to(frames.device, non_blocking=True)
         out = torch.empty((J, h, w, 3), dtype=torch.float32, device=frames.device)
         self._enter(frames, flow, idx, out)
         self._check(self.lib.fisr_warp_batch_device(self.h, frames.data_ptr(), flow.data_ptr(), idx.data_ptr(), J, flow_scale,

@@ -34,7 +34,8 @@ def _pair(n, h, w, seed):
     return a, b
 
 
-@pytest.mark.parametrize("n,h,w", [(1, 64, 64), (2, 128, 192), (1, 192, 320)])
+# 256 x 320 and larger: the dilation-16 layer of the context network runs on the tensor cores too (polyphase images of >= 4 x 4)
+@pytest.mark.parametrize("n,h,w", [(1, 64, 64), (2, 128, 192), (1, 192, 320), (1, 256, 320), (2, 320, 512)])
 def test_forward_matches_oracle(pwc, n, h, w):
     params = W.init_params(5)
     pwc.set_params(params)
@@ -52,6 +53,36 @@ def test_forward_matches_oracle(pwc, n, h, w):
         assert err < 2e-4 * max(1.0, np.abs(r).max()), (lvl, err)
     scale = max(1.0, float(ref.abs().max()))
     assert float((got.double() - ref).abs().max()) < 2e-4 * scale
+
+
+def test_tensor_core_path_matches_cuda_core_path():
+    """The same forward with every conv on the CUDA-core kernel (FISR_PWC_UMMA=0), with the undilated stride-1 convs on the tcgen05
+    kernel (1) and with the dilated ones as polyphase launches too (2, the default), at a size where every dilation qualifies."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device in this container (GPU tests run under gpurun)")
+    from fisr_b200.pwcnet import PWCNet
+    params = W.init_params(11)
+    a, b = _pair(1, 512, 768, seed=3)
+    a, b = a.cuda(), b.cuda()
+    flows = {}
+    old = os.environ.get("FISR_PWC_UMMA")
+    try:
+        for mode in ("0", "1", "2"):
+            os.environ["FISR_PWC_UMMA"] = mode
+            net = PWCNet(0)
+            net.set_params(params)
+            out = net.forward(a, b).cpu().numpy()
+            flows[mode] = [net.debug_flow(lvl, 1, 512, 768) for lvl in range(6, 1, -1)] + [out]
+            net.close()
+    finally:
+        if old is None:
+            os.environ.pop("FISR_PWC_UMMA", None)
+        else:
+            os.environ["FISR_PWC_UMMA"] = old
+    for mode in ("1", "2"):
+        for i, (x, y) in enumerate(zip(flows[mode], flows["0"])):
+            err = float(np.abs(x - y).max())
+            assert err < 2e-4 * max(1.0, float(np.abs(y).max())), (mode, i, err)
 
 
 def test_each_building_block(pwc):
