@@ -98,6 +98,26 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 template <int PLANES, int NCOL>
 __device__ __forceinline__ void epilogue_scalar(const ConvArgs& a, const uint32_t (&v)[NCOL], int n, int y, int x) {
     const int pix = n * a.opix_n + y * a.opix_y + x * a.opix_x;
+    if constexpr (PLANES == 2 && NCOL == 16) {
+        // all 16 columns are real channels of an 8-channel-aligned slot: 2 x 16-byte stores per plane instead of 32 scalar ones
+        if (a.cout == 16 && !a.out_raw && a.out_act && ((a.act_cs | a.act_off1) & 7) == 0 && a.act_split == 0) {
+            uint32_t h[8], l[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float2 b2 = __ldg(reinterpret_cast<const float2*>(a.bias) + j);
+                float g0 = __uint_as_float(v[2 * j]) + b2.x, g1 = __uint_as_float(v[2 * j + 1]) + b2.y;
+                if (a.act_relu) { g0 = fmaxf(g0, 0.f); g1 = fmaxf(g1, 0.f); }
+                if (a.act_slope > 0.f) { g0 = fmaxf(g0, g0 * a.act_slope); g1 = fmaxf(g1, g1 * a.act_slope); }
+                split2_f32(g0, g1, h[j], l[j]);
+            }
+            __half* d = a.out_act + static_cast<size_t>(pix) * a.act_cs + a.act_off1;
+            *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(d + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+            *reinterpret_cast<uint4*>(d + a.act_plane) = make_uint4(l[0], l[1], l[2], l[3]);
+            *reinterpret_cast<uint4*>(d + a.act_plane + 8) = make_uint4(l[4], l[5], l[6], l[7]);
+            return;
+        }
+    }
 #pragma unroll
     for (int ch = 0; ch < NCOL; ++ch) {
         if (ch < a.cout) {

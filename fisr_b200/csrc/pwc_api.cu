@@ -91,7 +91,7 @@ struct Param {
     __half* d_wp = nullptr;
     float* d_bp = nullptr;
     bool packed = false;
-    std::vector<float> h_w;      // as uploaded (reference layout), for fisr_pwc_get_param
+    std::vector<float> h_w, h_b; // as uploaded (reference layout)
 };
 
 struct Op {
@@ -121,6 +121,7 @@ struct fisr_pwc {
     int* h_err = nullptr;        // pinned copy, refreshed at the end of every forward
     int use_umma = 2;            // FISR_PWC_UMMA=0: every conv on the CUDA-core kernel; 1: tensor cores except the dilated layers (A/B measurements)
     std::vector<Param> params;
+    Param fused[kLvls + 1];      // predict_flow/flow<l> and upsample/up_feat<l> as ONE 3x3 conv with 16 output columns (build_fused)
     std::map<std::string, int> index;
     std::map<std::string, std::unique_ptr<Plan>> plans;
     Plan* last = nullptr;
@@ -170,6 +171,53 @@ int ensure_packed(fisr_pwc* c, Param& p) {
     return FISR_OK;
 }
 
+// The flow predictor (3x3, 2 outputs) and the up_feat transposed conv (4x4, stride 2, 2 outputs) both read the whole dense buffer
+// of a level.  out[2i + a] of the transposed conv gathers in[i + dy] w[ky] with (a, dy) -> ky: (0, 0) -> 1, (0, -1) -> 3,
+// (1, 0) -> 2, (1, +1) -> 0 (same in x), i.e. it is a 3x3 conv at input resolution with one output column per (sub-pixel, filter):
+// both layers run as ONE tensor-core conv with 16 columns, [flow 0..1 | (2a + b) * 2 + co of up_feat | 6 zeros].
+int build_fused(fisr_pwc* c, int l) {
+    Param& f = c->fused[l];
+    if (f.packed) return FISR_OK;
+    const std::string sl = std::to_string(l);
+    const Param& pf = c->params[c->index.at("pwcnet/predict_flow/flow" + sl)];
+    const PDef& df = inventory()[c->index.at("pwcnet/predict_flow/flow" + sl)];
+    f.cin_pad = pf.cin_pad;
+    f.cout = 16;
+    std::vector<float> w(static_cast<size_t>(9) * f.cin_pad * 16, 0.f), b(16, 0.f);
+    auto slot = [&](int ci) { return (df.gap_at >= 0 && ci >= df.gap_at) ? ci + kGap : ci; };
+    if (!pf.h_w.empty())
+        for (int t = 0; t < 9; ++t)
+            for (int ci = 0; ci < df.cin; ++ci)
+                for (int co = 0; co < 2; ++co) w[(static_cast<size_t>(t) * f.cin_pad + slot(ci)) * 16 + co] = pf.h_w[(static_cast<size_t>(t) * df.cin + ci) * 2 + co];
+    if (!pf.h_b.empty()) { b[0] = pf.h_b[0]; b[1] = pf.h_b[1]; }
+    if (l != kPredLvl) {
+        const Param& pe = c->params[c->index.at("pwcnet/upsample/up_feat" + sl)];
+        const PDef& de = inventory()[c->index.at("pwcnet/upsample/up_feat" + sl)];
+        static const int kTap[2][3] = {{3, 1, -1}, {-1, 2, 0}};          // [sub-pixel parity][dy + 1] -> transposed-conv tap, -1: none
+        if (!pe.h_w.empty())
+            for (int sa = 0; sa < 2; ++sa)
+                for (int sb = 0; sb < 2; ++sb)
+                    for (int dy = 0; dy < 3; ++dy)
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const int ky = kTap[sa][dy], kx = kTap[sb][dx];
+                            if (ky < 0 || kx < 0) continue;
+                            for (int co = 0; co < 2; ++co)
+                                for (int ci = 0; ci < de.cin; ++ci)           // reference layout [4,4,out,in]
+                                    w[(static_cast<size_t>(dy * 3 + dx) * f.cin_pad + slot(ci)) * 16 + 2 + (2 * sa + sb) * 2 + co] =
+                                        pe.h_w[(static_cast<size_t>(ky * 4 + kx) * 2 + co) * de.cin + ci];
+                        }
+        if (!pe.h_b.empty())
+            for (int s4 = 0; s4 < 4; ++s4) { b[2 + 2 * s4] = pe.h_b[0]; b[3 + 2 * s4] = pe.h_b[1]; }
+    }
+    if (!f.d_w) {
+        PWC_TRY(c, cudaMalloc(&f.d_w, w.size() * sizeof(float)));
+        PWC_TRY(c, cudaMalloc(&f.d_b, 16 * sizeof(float)));
+    }
+    PWC_TRY(c, cudaMemcpy(f.d_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    PWC_TRY(c, cudaMemcpy(f.d_b, b.data(), 16 * sizeof(float), cudaMemcpyHostToDevice));
+    return ensure_packed(c, f);
+}
+
 int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
     if (N < 1 || H < 64 || W < 64 || H % 64 || W % 64)
         return fail(c, FISR_E_INVALID, "PWC-Net (6-level pyramid) needs H, W multiples of 64 (got %d x %d x %d): pad like adapt_x", N, H, W);
@@ -203,10 +251,9 @@ int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
     // One conv layer: on the tensor cores when it is a stride-1 conv with >= 16 outputs on an image of at least 4 x 4 pixels --
     // dilation d as d (column phase) x d (row phase) undilated convs on the polyphase sub-images, each launch covering the d
     // column phases of one row phase of one image as a batch -- else on the CUDA-core kernel.
-    auto conv = [&](const std::string& name, View in, View outv, int l_in, int l_out, int stride, int dil, bool leaky, float* out_f32 = nullptr,
-                    const float* add = nullptr) {
+    auto conv_p = [&](Param& p, const std::string& name, View in, View outv, int l_in, int l_out, int stride, int dil, bool leaky, float* out_f32 = nullptr,
+                      const float* add = nullptr) {
         if (rc != FISR_OK) return;
-        Param& p = P(name);
         const int Hin = H >> l_in, Win = W >> l_in, Hout = H >> l_out, Wout = W >> l_out;
         const bool divisible = Hout % dil == 0 && Wout % dil == 0;
         if (c->use_umma >= (dil == 1 ? 1 : 2) && stride == 1 && !out_f32 && p.cout >= 16 && divisible && Hout / dil >= 4 && Wout / dil >= 4) {
@@ -255,13 +302,18 @@ int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
         a.leaky = leaky ? 1 : 0; a.add = add; a.add_cs = 2;
         push([a](cudaStream_t st) { launch_conv3x3(a, st); });
     };
+    auto conv = [&](const std::string& name, View in, View outv, int l_in, int l_out, int stride, int dil, bool leaky, float* out_f32 = nullptr,
+                    const float* add = nullptr) {
+        if (rc != FISR_OK) return;
+        conv_p(P(name), name, in, outv, l_in, l_out, stride, dil, leaky, out_f32, add);
+    };
     // ---- buffers
     Planes D[kLvls + 1] = {}, c2[kLvls + 1] = {}, tA[kLvls + 1] = {}, tB[kLvls + 1] = {};
     for (int l = kPredLvl; l <= kLvls; ++l) D[l] = planes(px(l), dense_cs(l));
     for (int l = 1; l <= kLvls; ++l) c2[l] = planes(px(l), pad8(kChann[l]));
     Planes c1_1 = planes(px(1), pad8(kChann[1]));                // level 1 of image 1 feeds conv2a only
     Planes c1_6 = planes(px(kLvls), pad8(kChann[kLvls]));        // D_6 has no c1 slot (model_pwcnet.py:1549-1551)
-    Planes img_p = planes(static_cast<size_t>(N) * H * W, 8);    // the input image in plane format, 3 of 8 channels used
+    Planes F16 = planes(px(kPredLvl), 16);                       // output columns of the fused predict_flow / up_feat conv
     {   // scratch of the pyramid: levels whose channel count is a multiple of 8 share two buffers, the others get their own
         // (their pad channels must stay zero: they are read by the TMA boxes of the next conv)
         Planes sA = planes(px(1), kChann[1]), sB = planes(px(1), kChann[1]);
@@ -282,18 +334,21 @@ int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
     };
     // ---- feature pyramids (model_pwcnet.py:1012-1101): the Siamese extractor on both images
     for (int img = 0; img < 2; ++img) {
-        {   // the image pointer is bound per call
-            const int which = img;
-            const size_t npix = static_cast<size_t>(N) * H * W;
-            push([=](cudaStream_t st) { fisr::launch_act_from_f32(which ? pl->img2 : pl->img1, 3, fisr::ActBuf{img_p.p, img_p.plane}, 8, npix, 2, st); });
-        }
-        View x{img_p, 0, 3};
+        View x{};
         for (int l = 1; l <= kLvls; ++l) {
             const std::string p = "pwcnet/featpyr/conv" + std::to_string(l);
             const int f = kChann[l];
             View dst = img == 0 ? c1_view(l) : View{c2[l], 0, f};
             View ta{tA[l], 0, f}, tb{tB[l], 0, f};
-            conv(p + "a", x, ta, l - 1, l, 2, 1, true);
+            if (l == 1) {        // straight from the fp32 image, whose pointer is bound per call
+                const Param& pa = P(p + "a");
+                const int which = img;
+                const float *w1 = pa.d_w, *b1 = pa.d_b;
+                const Planes o1 = tA[1];
+                push([=](cudaStream_t st) { launch_first_conv(which ? pl->img2 : pl->img1, w1, b1, o1, N, H, W, st); });
+            } else {
+                conv(p + "a", x, ta, l - 1, l, 2, 1, true);
+            }
             conv(p + "aa", ta, tb, l, l, 1, 1, true);
             conv(p + "b", tb, dst, l, l, 1, 1, true);
             x = dst;
@@ -305,6 +360,7 @@ int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
         const int cs = dense_cs(l), h = H >> l, w = W >> l, C = kChann[l];
         const View c1v = c1_view(l);
         const Planes Dl = D[l], c2l = c2[l];
+        bool fused_up = false;
         if (l == kLvls) {
             push([=](cudaStream_t st) { launch_cost_volume(c1v.b, c1v.coff, c2l, 0, C, Dl, kActs, N, h, w, st); });
         } else {
@@ -318,7 +374,17 @@ int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
         for (int k = 0; k < 5; ++k)
             conv("pwcnet/predict_flow/conv" + sl + "_" + std::to_string(k), View{Dl, dense_in_off(k), cs - dense_in_off(k)},
                  View{Dl, dense_off(k), kDense[k]}, l, l, 1, 1, true);
-        conv("pwcnet/predict_flow/flow" + sl, View{Dl, 0, cs}, View{}, l, l, 1, 1, false, flow_raw);
+        if (c->use_umma && h >= 4 && w >= 4) {       // flow predictor + up_feat of the next level: one 16-column conv, then split
+            if ((rc = build_fused(c, l)) != FISR_OK) return rc;
+            Planes Fl = F16;
+            conv_p(c->fused[l], "fused flow" + sl, View{Dl, 0, cs}, View{Fl, 0, 16}, l, l, 1, 1, false);
+            const Planes Dn = l != kPredLvl ? D[l - 1] : Planes{};
+            const int upf = l != kPredLvl ? kActs + kCorrPad + kChann[l - 1] + 2 : 0;
+            push([=](cudaStream_t st) { launch_flow_upfeat_scatter(Fl, flow_raw, Dn, upf, N, h, w, st); });
+            fused_up = true;
+        } else {
+            conv("pwcnet/predict_flow/flow" + sl, View{Dl, 0, cs}, View{}, l, l, 1, 1, false, flow_raw);
+        }
         // context network (model_pwcnet.py:1453-1522): flow + dilated conv chain on upfeat
         View cur{Dl, 0, cs};
         for (int k = 0; k < 7; ++k) {
@@ -342,7 +408,7 @@ int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
             const float *wf = pf.d_w, *bf = pf.d_b, *we = pe.d_w, *be = pe.d_b;
             const int cine = pe.cin_pad;
             push([=](cudaStream_t st) { launch_deconv4x4s2(Planes{}, 0, fl, 2, 2, wf, bf, Dn, ufn, N, h, w, st); });
-            push([=](cudaStream_t st) { launch_deconv4x4s2(Dl, 0, nullptr, 0, cine, we, be, Dn, ufn + 2, N, h, w, st); });
+            if (!fused_up) push([=](cudaStream_t st) { launch_deconv4x4s2(Dl, 0, nullptr, 0, cine, we, be, Dn, ufn + 2, N, h, w, st); });
         }
     }
     {   // flow_pred = resize_bilinear(flow2, x4) * 4 (model_pwcnet.py:1588-1590)
@@ -414,6 +480,7 @@ void fisr_pwc_destroy(fisr_pwc* c) {
     cudaDeviceSynchronize();
     c->plans.clear();
     for (auto& p : c->params) { cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); cudaFree(p.d_bp); }
+    for (auto& p : c->fused) { cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); cudaFree(p.d_bp); }
     cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -448,7 +515,9 @@ int fisr_pwc_set_param(fisr_pwc* c, const char* name, const float* h_data, size_
     if (is_b) {
         if (count != (size_t)d.cout) return fail(c, FISR_E_INVALID, "%s has %d elements, got %zu", name, d.cout, count);
         PWC_TRY(c, cudaMemcpy(p.d_b, h_data, count * sizeof(float), cudaMemcpyHostToDevice));
+        p.h_b.assign(h_data, h_data + count);
         p.packed = false;
+        for (auto& f : c->fused) f.packed = false;
         return FISR_OK;
     }
     const size_t taps = d.transpose ? 16 : 9, expect = taps * d.cin * d.cout;
@@ -465,6 +534,7 @@ int fisr_pwc_set_param(fisr_pwc* c, const char* name, const float* h_data, size_
     PWC_TRY(c, cudaMemcpy(p.d_w, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
     p.h_w.assign(h_data, h_data + count);
     p.packed = false;
+    for (auto& f : c->fused) f.packed = false;
     return FISR_OK;
 }
 
@@ -475,6 +545,8 @@ int fisr_pwc_forward(fisr_pwc* c, const float* d_img1, const float* d_img2, int 
     if (*c->h_err) return fail(c, FISR_E_CUDA, "a conv kernel of an earlier forward timed out on a barrier (code %d)", *c->h_err);
     for (auto& p : c->params)            // parameters changed since the plan was built: re-pack the operand planes in place
         if (p.d_wp && !p.packed) { const int rp = ensure_packed(c, p); if (rp != FISR_OK) return rp; }
+    for (int l = kPredLvl; l <= kLvls; ++l)
+        if (c->fused[l].d_wp && !c->fused[l].packed) { const int rp = build_fused(c, l); if (rp != FISR_OK) return rp; }
     int rc = build_plan(c, N, H, W, &plan);
     if (rc != FISR_OK) return rc;
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;

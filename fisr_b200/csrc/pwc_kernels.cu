@@ -254,30 +254,72 @@ __global__ void __launch_bounds__(128) deconv4x4s2_kernel(Planes in, int in_coff
 
 // ---------------------------------------------------------------- cost volume, search range 4 (model_pwcnet.py:1226-1277)
 // out[p, (dy+4)*9 + (dx+4)] = leaky_relu(mean_c c1[p, c] * c2[p + (dy, dx), c]), zero outside the image
+// A block owns 4 rows x 32 columns of pixels; per 16-channel slice it stages its c1 tile and the (4 + 8) x (32 + 8) c2 region in
+// shared memory (channel-major, so a warp = one pixel row reads consecutive words) and a thread accumulates 36 or 45 of the 81
+// displacements of one pixel: rows dy < 0 (thread half 0) or dy >= 0 (half 1).
+constexpr int kCvTy = 4, kCvTx = 32, kCvC = 16, kCvRy = kCvTy + 8, kCvRx = kCvTx + 8;
+
 __global__ void __launch_bounds__(256) cost_volume_kernel(Planes c1, int c1_coff, Planes c2, int c2_coff, int C, Planes out, int out_coff, int N, int h, int w) {
-    const long long total = static_cast<long long>(N) * h * w * 81;
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int d = static_cast<int>(i % 81);
-    const long long P = i / 81;
-    const int x = static_cast<int>(P % w);
-    const long long r = P / w;
-    const int y = static_cast<int>(r % h), n = static_cast<int>(r / h);
-    const int yy = y + d / 9 - 4, xx = x + d % 9 - 4;
-    float s = 0.f;
-    if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
-        const size_t a = static_cast<size_t>(P) * c1.cs + c1_coff;
-        const size_t b = (static_cast<size_t>(n) * h + yy) * w * c2.cs + static_cast<size_t>(xx) * c2.cs + c2_coff;
-        if (((c1.cs | c1_coff | c2.cs | c2_coff | C) & 3) == 0) {
-            for (int c = 0; c < C; c += 4) {
-                const float4 u = ld4(c1.p, c1.plane, a + c), v = ld4(c2.p, c2.plane, b + c);
-                s = fmaf(u.w, v.w, fmaf(u.z, v.z, fmaf(u.y, v.y, fmaf(u.x, v.x, s))));
+    __shared__ float s1[kCvC][kCvTy * kCvTx];
+    __shared__ float s2[kCvC][kCvRy * kCvRx];
+    const int t = threadIdx.x;
+    const int x0 = blockIdx.x * kCvTx, y0 = blockIdx.y * kCvTy, n = blockIdx.z;
+    const int pix = t & 127, half = t >> 7;
+    const int tx = pix & 31, ty = pix >> 5;
+    const int dy0 = half ? 4 : 0, ndy = half ? 5 : 4;          // rows of the 9 x 9 window this thread owns
+    float acc[45];
+#pragma unroll
+    for (int i = 0; i < 45; ++i) acc[i] = 0.f;
+    for (int cb = 0; cb < C; cb += kCvC) {
+        __syncthreads();
+        // (pixel, 8-channel group) units: consecutive threads take consecutive pixels of one group
+        for (int u = t; u < 2 * kCvTy * kCvTx; u += 256) {
+            const int p = u % (kCvTy * kCvTx), g = u / (kCvTy * kCvTx);
+            const int y = y0 + (p >> 5), x = x0 + (p & 31);
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (y < h && x < w) {
+                const size_t base = (static_cast<size_t>(n) * h + y) * w * c1.cs + static_cast<size_t>(x) * c1.cs + c1_coff + cb + 8 * g;
+                if (cb + 8 * g + 8 <= C) { const float4 a = ld4(c1.p, c1.plane, base), b = ld4(c1.p, c1.plane, base + 4); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+                else if (cb + 8 * g + 4 <= C) { const float4 a = ld4(c1.p, c1.plane, base); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
             }
-        } else {
-            for (int c = 0; c < C; ++c) s = fmaf(ld1(c1.p, c1.plane, a + c), ld1(c2.p, c2.plane, b + c), s);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s1[8 * g + j][p] = v[j];
+        }
+        for (int u = t; u < 2 * kCvRy * kCvRx; u += 256) {
+            const int p = u % (kCvRy * kCvRx), g = u / (kCvRy * kCvRx);
+            const int y = y0 - 4 + p / kCvRx, x = x0 - 4 + p % kCvRx;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (y >= 0 && y < h && x >= 0 && x < w) {
+                const size_t base = (static_cast<size_t>(n) * h + y) * w * c2.cs + static_cast<size_t>(x) * c2.cs + c2_coff + cb + 8 * g;
+                if (cb + 8 * g + 8 <= C) { const float4 a = ld4(c2.p, c2.plane, base), b = ld4(c2.p, c2.plane, base + 4); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+                else if (cb + 8 * g + 4 <= C) { const float4 a = ld4(c2.p, c2.plane, base); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s2[8 * g + j][p] = v[j];
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int c = 0; c < kCvC; ++c) {
+            const float a = s1[c][pix];
+            const float* row = &s2[c][(ty + dy0) * kCvRx + tx];
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                if (r < ndy) {
+#pragma unroll
+                    for (int dx = 0; dx < 9; ++dx) acc[r * 9 + dx] = fmaf(a, row[r * kCvRx + dx], acc[r * 9 + dx]);
+                }
+            }
         }
     }
-    st1(out.p, out.plane, static_cast<size_t>(P) * out.cs + out_coff + d, lrelu(s / static_cast<float>(C)));
+    const int y = y0 + ty, x = x0 + tx;
+    if (y >= h || x >= w) return;
+    const float inv = 1.f / static_cast<float>(C);
+    const size_t o = ((static_cast<size_t>(n) * h + y) * w + x) * out.cs + out_coff + dy0 * 9;     // dy0 * 9 = 0 or 36: even
+    const int cnt = ndy * 9;
+#pragma unroll
+    for (int i = 0; i + 1 < 45; i += 2)
+        if (i + 1 < cnt) st2(out.p, out.plane, o + i, lrelu(acc[i] * inv), lrelu(acc[i + 1] * inv));
+    if (half) st1(out.p, out.plane, o + 44, lrelu(acc[44] * inv));
 }
 
 // ---------------------------------------------------------------- dense_image_warp (model_pwcnet.py:1106-1178)
@@ -307,6 +349,66 @@ __global__ void __launch_bounds__(256) dense_warp_kernel(Planes img, int coff, i
     };
     st4(out.p, out.plane, static_cast<size_t>(P) * out.cs + c4,
         make_float4(mix(tl.x, tr.x, bl.x, br.x), mix(tl.y, tr.y, bl.y, br.y), mix(tl.z, tr.z, bl.z, br.z), mix(tl.w, tr.w, bl.w, br.w)));
+}
+
+// ---------------------------------------------------------------- conv1a: 3 -> 16, stride 2, leaky ReLU, straight from the fp32 image
+// (model_pwcnet.py:1083-1096).  'same' on an even size with stride 2 pads only after the data: taps (2oy + ky, 2ox + kx), ky, kx in 0..2.
+__global__ void __launch_bounds__(128) first_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ b, Planes out,
+                                                         int N, int H, int W) {
+    __shared__ float ws[27 * 16 + 16];
+    for (int i = threadIdx.x; i < 27 * 16 + 16; i += blockDim.x) ws[i] = i < 27 * 16 ? __ldg(w + i) : __ldg(b + i - 27 * 16);
+    __syncthreads();
+    const int ho = H / 2, wo = W / 2;
+    const long long npix = static_cast<long long>(N) * ho * wo;
+    const long long P = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (P >= npix) return;
+    const int ox = static_cast<int>(P % wo);
+    const long long r = P / wo;
+    const int oy = static_cast<int>(r % ho), n = static_cast<int>(r / ho);
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = ws[27 * 16 + j];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = 2 * oy + ky;
+        if (iy >= H) continue;
+        const float* row = img + ((static_cast<size_t>(n) * H + iy) * W + 2 * ox) * 3;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            if (2 * ox + kx >= W) continue;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                const float v = __ldg(row + kx * 3 + ci);
+                const float* wt = ws + ((ky * 3 + kx) * 3 + ci) * 16;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = fmaf(v, wt[j], acc[j]);
+            }
+        }
+    }
+    const size_t o = static_cast<size_t>(P) * out.cs;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) st4(out.p, out.plane, o + j, make_float4(lrelu(acc[j]), lrelu(acc[j + 1]), lrelu(acc[j + 2]), lrelu(acc[j + 3])));
+}
+
+// ---------------------------------------------------------------- outputs of the fused flow-predictor / up_feat conv (pwc_api.cu)
+// F [N,h,w,16]: columns 0..1 = predict_flow (fp32 out), columns 2 + (2a + b) * 2 + co = up_feat output pixel (2y + a, 2x + b), channel co
+__global__ void __launch_bounds__(256) flow_upfeat_scatter_kernel(Planes F, float* __restrict__ flow, Planes Dn, int up_off, int N, int h, int w) {
+    const long long npix = static_cast<long long>(N) * h * w;
+    const long long P = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (P >= npix) return;
+    float v[16];
+    ld8(F.p, F.plane, static_cast<size_t>(P) * F.cs, v);
+    ld8(F.p, F.plane, static_cast<size_t>(P) * F.cs + 8, v + 8);
+    reinterpret_cast<float2*>(flow)[P] = make_float2(v[0], v[1]);
+    if (!Dn.p) return;
+    const int x = static_cast<int>(P % w);
+    const long long r = P / w;
+    const int y = static_cast<int>(r % h), n = static_cast<int>(r / h);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const size_t op = (static_cast<size_t>(n) * 2 * h + 2 * y + (s >> 1)) * (2 * w) + 2 * x + (s & 1);
+        st2(Dn.p, Dn.plane, op * Dn.cs + up_off, v[2 + 2 * s], v[3 + 2 * s]);
+    }
 }
 
 // ---------------------------------------------------------------- tf.image.resize_bilinear x S (legacy: src = dst / S), times `gain`
@@ -358,7 +460,17 @@ void launch_deconv4x4s2(Planes in, int in_coff, const float* in_f32, int in_f32_
 }
 
 void launch_cost_volume(Planes c1, int c1_coff, Planes c2, int c2_coff, int C, Planes out, int out_coff, int N, int h, int w, cudaStream_t st) {
-    cost_volume_kernel<<<blocks_for(static_cast<long long>(N) * h * w * 81, 256), 256, 0, st>>>(c1, c1_coff, c2, c2_coff, C, out, out_coff, N, h, w);
+    dim3 grid((w + kCvTx - 1) / kCvTx, (h + kCvTy - 1) / kCvTy, N);
+    cost_volume_kernel<<<grid, 256, 0, st>>>(c1, c1_coff, c2, c2_coff, C, out, out_coff, N, h, w);
+}
+
+// ---------------------------------------------------------------- first pyramid conv: fp32 image [N,H,W,3] -> 16 channels at half resolution
+void launch_first_conv(const float* img, const float* w, const float* b, Planes out, int N, int H, int W, cudaStream_t st) {
+    first_conv_kernel<<<blocks_for(static_cast<long long>(N) * (H / 2) * (W / 2), 128), 128, 0, st>>>(img, w, b, out, N, H, W);
+}
+
+void launch_flow_upfeat_scatter(Planes F, float* flow, Planes Dn, int up_off, int N, int h, int w, cudaStream_t st) {
+    flow_upfeat_scatter_kernel<<<blocks_for(static_cast<long long>(N) * h * w, 256), 256, 0, st>>>(F, flow, Dn, up_off, N, h, w);
 }
 
 void launch_dense_warp(Planes img, int coff, int C, Planes flow, int f_coff, float scale, Planes out, int N, int h, int w, cudaStream_t st) {

@@ -31,6 +31,10 @@ void launch_deconv4x4s2(Planes in, int in_coff, const float* in_f32, int in_f32_
                         int N, int h, int wd, cudaStream_t st);
 void launch_cost_volume(Planes c1, int c1_coff, Planes c2, int c2_coff, int C, Planes out, int out_coff, int N, int h, int w, cudaStream_t st);
 void launch_dense_warp(Planes img, int coff, int C, Planes flow, int f_coff, float scale, Planes out, int N, int h, int w, cudaStream_t st);
+// conv1a of the feature pyramid on the fp32 input image: w [9][3][16], b [16] -> out [N, H/2, W/2, 16]
+void launch_first_conv(const float* img, const float* w, const float* b, Planes out, int N, int H, int W, cudaStream_t st);
+// splits the 16 columns of the fused predict_flow / up_feat conv: fp32 flow [N,h,w,2] and (Dn.p != nullptr) the 2 up_feat channels of level l - 1
+void launch_flow_upfeat_scatter(Planes F, float* flow, Planes Dn, int up_off, int N, int h, int w, cudaStream_t st);
 void launch_resize_flow(const float* in, float* out, int N, int h, int w, int S, float gain, cudaStream_t st);
 
 }  // namespace pwc
