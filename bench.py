@@ -480,7 +480,17 @@ def measure_extras(eng, dev, peaks, bench_precision):
         n0 = net.launch_count
         ms = timed(lambda: net.forward(a, b), 1, 3)
         out["pwcnet_1080p_pair_x2"] = {"ms": ms, "launches_per_forward": (net.launch_count - n0) // 4, "input": "2 x [2176,3840,3] (both directions of one pair)",
-                                       "note": "PWC-Net-large (6 levels, flow at level 2, dense + residual connections), fp32 CUDA-core kernels; random weights"}
+                                       "note": "PWC-Net-large (6 levels, flow at level 2, dense + residual connections): stride-1 3x3 convs on the tcgen05 split-mode (fp16 hi/lo, fp32-class) kernel, the rest on CUDA cores; random weights"}
+        # the whole per-pair job of FISR_for_video_Compute_Flow from host frames: upload of two uint8 YUV frames, pre-processing, network,
+        # post-processing (all on the device), download of the [2,1080,1920,2] flow
+        y1 = rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+        y2 = rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+        net.flow_pair_yuv(y1, y2)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            net.flow_pair_yuv(y1, y2)
+        out["pwcnet_1080p_pair_x2"]["flow_pair_host_to_host_ms"] = (time.perf_counter() - t0) / 3 * 1e3
         net.close()
         del a, b
     except Exception as e:                       # a next-row component must not take the headline line down with it

@@ -95,6 +95,8 @@ def load() -> C.CDLL:
         "fisr_pwc_param_shape": (i, [i, C.POINTER(i)]),
         "fisr_pwc_set_param": (i, [vp, C.c_char_p, vp, sz]),
         "fisr_pwc_forward": (i, [vp, vp, vp, i, i, i, vp, vp]),
+        "fisr_pwc_prepare_pair": (i, [vp, vp, vp, i, vp, i, i, i, vp, vp, vp]),
+        "fisr_pwc_finish_flow": (i, [vp, vp, i, i, i, i, i, i, i, vp, i, vp, i, C.c_double, vp, vp]),
         "fisr_pwc_debug_flow": (i, [vp, i, vp, sz]),
         "fisr_pwc_launch_count": (C.c_longlong, [vp]),
         "fisr_launch_count": (C.c_longlong, [vp]),
@@ -116,6 +118,6 @@ EXPORTS = [
     "fisr_train_backward", "fisr_get_grad", "fisr_adam_apply", "fisr_train_step", "fisr_set_loss_scale", "fisr_get_loss_scale", "fisr_set_wgrad_exact",
     "fisr_dgrad3x3", "fisr_profile_train", "fisr_conv3x3", "fisr_wgrad3x3", "fisr_debug_conv_output", "fisr_profile_ops", "fisr_launch_count", "fisr_plan_info",
     "fisr_pwc_create", "fisr_pwc_destroy", "fisr_pwc_last_error", "fisr_pwc_num_params", "fisr_pwc_param_name", "fisr_pwc_param_shape",
-    "fisr_pwc_set_param", "fisr_pwc_forward", "fisr_pwc_debug_flow", "fisr_pwc_launch_count",
+    "fisr_pwc_set_param", "fisr_pwc_forward", "fisr_pwc_prepare_pair", "fisr_pwc_finish_flow", "fisr_pwc_debug_flow", "fisr_pwc_launch_count",
     "fisr_ipc_alloc", "fisr_ipc_open", "fisr_ipc_close", "fisr_ipc_free", "fisr_copy2d_async",
 ]

@@ -563,6 +563,47 @@ int fisr_pwc_forward(fisr_pwc* c, const float* d_img1, const float* d_img2, int 
     return FISR_OK;
 }
 
+int fisr_pwc_prepare_pair(fisr_pwc* c, const void* d_frame0, const void* d_frame1, int src_kind, const double* h_yuv2rgb, int h, int w, int scale,
+                          float* d_img1, float* d_img2, void* stream) {
+    if (!c || !d_frame0 || !d_frame1 || !d_img1 || !d_img2) return FISR_E_INVALID;
+    if (h < 2 || w < 2 || scale < 1 || (src_kind != 0 && src_kind != 1) || (src_kind == 0 && !h_yuv2rgb))
+        return fail(c, FISR_E_INVALID, "fisr_pwc_prepare_pair: %d x %d, scale %d, source kind %d", h, w, scale, src_kind);
+    Guard guard(c->device);
+    PrepConst k{};
+    if (src_kind == 0) { memcpy(k.T, h_yuv2rgb, 9 * sizeof(double)); memcpy(k.off, h_yuv2rgb + 9, 3 * sizeof(double)); }
+    const int oh = h * scale, ow = w * scale;
+    k.ry = static_cast<double>(h) / static_cast<double>(oh);
+    k.rx = static_cast<double>(w) / static_cast<double>(ow);
+    const int Hp = (oh + 63) / 64 * 64, Wp = (ow + 63) / 64 * 64;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    launch_prepare_pair(d_frame0, d_frame1, src_kind == 0, d_img1, d_img2, h, w, oh, ow, Hp, Wp, k, st);
+    c->launches++;
+    PWC_TRY(c, cudaGetLastError());
+    return FISR_OK;
+}
+
+int fisr_pwc_finish_flow(fisr_pwc* c, const float* d_flow, int N, int Hp, int Wp, int h0, int w0, int h_out, int w_out, const double* h_wy, int ry,
+                         const double* h_wx, int rx, double scale, float* d_out, void* stream) {
+    if (!c || !d_flow || !d_out) return FISR_E_INVALID;
+    if (N < 1 || h0 < 1 || w0 < 1 || h0 > Hp || w0 > Wp || h_out < 1 || w_out < 1 || ry < 0 || rx < 0 || ry > kMaxGaussRadius || rx > kMaxGaussRadius ||
+        (ry > 0 && !h_wy) || (rx > 0 && !h_wx) || ry >= h0 || rx >= w0 || !(scale > 0))
+        return fail(c, FISR_E_INVALID, "fisr_pwc_finish_flow: crop %d x %d of %d x %d -> %d x %d, radii %d / %d", h0, w0, Hp, Wp, h_out, w_out, ry, rx);
+    Guard guard(c->device);
+    FinishConst k{};
+    k.wy[0] = k.wx[0] = 1.0;
+    k.ry = ry; k.rx = rx;
+    if (ry > 0) memcpy(k.wy, h_wy, (ry + 1) * sizeof(double));
+    if (rx > 0) memcpy(k.wx, h_wx, (rx + 1) * sizeof(double));
+    k.ratio_y = static_cast<double>(h0) / static_cast<double>(h_out);
+    k.ratio_x = static_cast<double>(w0) / static_cast<double>(w_out);
+    k.scale = scale;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    launch_finish_flow(d_flow, N, Hp, Wp, h0, w0, h_out, w_out, d_out, k, st);
+    c->launches++;
+    PWC_TRY(c, cudaGetLastError());
+    return FISR_OK;
+}
+
 int fisr_pwc_debug_flow(fisr_pwc* c, int lvl, float* h_dst, size_t count) {
     if (!c || !h_dst || lvl < kPredLvl || lvl > kLvls) return FISR_E_INVALID;
     if (!c->last) return fail(c, FISR_E_INVALID, "no forward has run yet");

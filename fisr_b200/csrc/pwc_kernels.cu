@@ -411,6 +411,132 @@ __global__ void __launch_bounds__(256) flow_upfeat_scatter_kernel(Planes F, floa
     }
 }
 
+// ---------------------------------------------------------------- the reference driver around the network, on the device
+// FISR_for_video_pwcnet_predict_from_img_test.py:113-131 + adapt_x (model_pwcnet.py:371-409): YUV -> RGB (float64, clipped to
+// 0..255), x`scale` skimage.transform.resize (order 1, mode 'reflect', pixel-centre coordinates, float64; rows first, then
+// columns), truncation to uint8, /255 in float32, zero pad to multiples of 64.  Every float64 step is a separately rounded
+// multiply / add in the order numpy evaluates it, so the uint8 truncation sees the same value as the host pipeline.
+__device__ __forceinline__ int mirror_index(long long i, int n) {          // scipy 'mirror' / skimage 'reflect': -1 -> 1, n -> n - 2
+    if (n == 1) return 0;
+    const long long period = 2LL * (n - 1);
+    long long m = i % period;
+    if (m < 0) m += period;
+    return static_cast<int>(m >= n ? period - m : m);
+}
+struct LerpTap { int i0, i1; double f0, f1; };                               // value = a[i0] * f0 + a[i1] * f1
+__device__ __forceinline__ LerpTap lerp_tap(int o, double ratio, int n) {    // coords = (o + 0.5) * (n_in / n_out) - 0.5
+    const double c = __dadd_rn(__dmul_rn(static_cast<double>(o) + 0.5, ratio), -0.5);
+    const double fl = floor(c);
+    const double fr = __dadd_rn(c, -fl);
+    LerpTap t;
+    t.i0 = mirror_index(static_cast<long long>(fl), n);
+    t.i1 = mirror_index(static_cast<long long>(fl) + 1, n);
+    t.f0 = __dadd_rn(1.0, -fr);
+    t.f1 = fr;
+    return t;
+}
+
+template <bool YUV>
+__device__ __forceinline__ void load_rgb(const void* src, int w, int y, int x, const PrepConst& k, double (&rgb)[3]) {
+    if constexpr (YUV) {
+        const uint8_t* p = static_cast<const uint8_t*>(src) + (static_cast<size_t>(y) * w + x) * 3;
+        const double Y = static_cast<double>(__ldg(p)), U = static_cast<double>(__ldg(p + 1)), V = static_cast<double>(__ldg(p + 2));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {        // utils.py:106-115: T[p,0] * y + T[p,1] * u + T[p,2] * v - offset[p], then clip
+            double v = __dadd_rn(__dadd_rn(__dmul_rn(k.T[3 * c], Y), __dmul_rn(k.T[3 * c + 1], U)), __dmul_rn(k.T[3 * c + 2], V));
+            v = __dadd_rn(v, -k.off[c]);
+            rgb[c] = fmin(fmax(v, 0.0), 255.0);
+        }
+    } else {
+        const double* p = static_cast<const double*>(src) + (static_cast<size_t>(y) * w + x) * 3;
+        rgb[0] = __ldg(p); rgb[1] = __ldg(p + 1); rgb[2] = __ldg(p + 2);
+    }
+}
+
+// grid.y = which frame of the pair; frame 0 lands in img1[0] and img2[1], frame 1 in img1[1] and img2[0] (both directions as one batch)
+template <bool YUV>
+__global__ void __launch_bounds__(256) prepare_pair_kernel(const void* __restrict__ src0, const void* __restrict__ src1, float* __restrict__ img1,
+                                                           float* __restrict__ img2, int h, int w, int oh, int ow, int Hp, int Wp, PrepConst k) {
+    const long long P = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (P >= static_cast<long long>(Hp) * Wp) return;
+    const int X = static_cast<int>(P % Wp), Y = static_cast<int>(P / Wp);
+    const int which = blockIdx.y;
+    float o[3] = {0.f, 0.f, 0.f};
+    if (Y < oh && X < ow) {
+        const void* src = which ? src1 : src0;
+        const LerpTap ty = lerp_tap(Y, k.ry, h), tx = lerp_tap(X, k.rx, w);
+        double p00[3], p10[3], p01[3], p11[3];
+        load_rgb<YUV>(src, w, ty.i0, tx.i0, k, p00);
+        load_rgb<YUV>(src, w, ty.i1, tx.i0, k, p10);
+        load_rgb<YUV>(src, w, ty.i0, tx.i1, k, p01);
+        load_rgb<YUV>(src, w, ty.i1, tx.i1, k, p11);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double r0 = __dadd_rn(__dmul_rn(p00[c], ty.f0), __dmul_rn(p10[c], ty.f1));
+            const double r1 = __dadd_rn(__dmul_rn(p01[c], ty.f0), __dmul_rn(p11[c], ty.f1));
+            const double v = __dadd_rn(__dmul_rn(r0, tx.f0), __dmul_rn(r1, tx.f1));
+            o[c] = __fdiv_rn(static_cast<float>(static_cast<int>(v) & 255), 255.f);      // np.array(.., dtype=np.uint8), then / np.float32(255)
+        }
+    }
+    const size_t img = static_cast<size_t>(Hp) * Wp * 3, at = static_cast<size_t>(P) * 3;
+    float* d1 = img1 + (which ? img : 0) + at;
+    float* d2 = img2 + (which ? 0 : img) + at;
+    d1[0] = o[0]; d1[1] = o[1]; d1[2] = o[2];
+    d2[0] = o[0]; d2[1] = o[1]; d2[2] = o[2];
+}
+
+// postproc_y_hat_test crop (model_pwcnet.py:449-470) + ..predict_from_img_test.py:137: skimage resize of the cropped flow with
+// anti_aliasing (scipy.ndimage.gaussian_filter, mode 'mirror': rows then columns, symmetric-kernel summation order of
+// NI_Correlate1D), order-1 interpolation (rows, then columns), / scale, float32.
+struct FlowSrc { const float2* f; int Wp, h0, w0; };
+__device__ __forceinline__ void gauss_rows(const FlowSrc& s, int y, int x, const FinishConst& k, double (&g)[2]) {      // filter along y at column x
+    const float2 c = __ldg(s.f + static_cast<size_t>(y) * s.Wp + x);
+    g[0] = __dmul_rn(static_cast<double>(c.x), k.wy[0]);
+    g[1] = __dmul_rn(static_cast<double>(c.y), k.wy[0]);
+    for (int j = k.ry; j >= 1; --j) {
+        const float2 a = __ldg(s.f + static_cast<size_t>(mirror_index(y - j, s.h0)) * s.Wp + x);
+        const float2 b = __ldg(s.f + static_cast<size_t>(mirror_index(y + j, s.h0)) * s.Wp + x);
+        g[0] = __dadd_rn(g[0], __dmul_rn(__dadd_rn(static_cast<double>(a.x), static_cast<double>(b.x)), k.wy[j]));
+        g[1] = __dadd_rn(g[1], __dmul_rn(__dadd_rn(static_cast<double>(a.y), static_cast<double>(b.y)), k.wy[j]));
+    }
+}
+__device__ __forceinline__ void gauss_both(const FlowSrc& s, int y, int x, const FinishConst& k, double (&g)[2]) {      // rows, then columns
+    double c[2];
+    gauss_rows(s, y, x, k, c);
+    g[0] = __dmul_rn(c[0], k.wx[0]);
+    g[1] = __dmul_rn(c[1], k.wx[0]);
+    for (int j = k.rx; j >= 1; --j) {
+        double a[2], b[2];
+        gauss_rows(s, y, mirror_index(x - j, s.w0), k, a);
+        gauss_rows(s, y, mirror_index(x + j, s.w0), k, b);
+        g[0] = __dadd_rn(g[0], __dmul_rn(__dadd_rn(a[0], b[0]), k.wx[j]));
+        g[1] = __dadd_rn(g[1], __dmul_rn(__dadd_rn(a[1], b[1]), k.wx[j]));
+    }
+}
+__global__ void __launch_bounds__(128) finish_flow_kernel(const float* __restrict__ flow, int N, int Hp, int Wp, int h0, int w0, int oh, int ow,
+                                                          float* __restrict__ out, FinishConst k) {
+    const long long P = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (P >= static_cast<long long>(N) * oh * ow) return;
+    const int X = static_cast<int>(P % ow);
+    const long long r = P / ow;
+    const int Y = static_cast<int>(r % oh), n = static_cast<int>(r / oh);
+    const FlowSrc s{reinterpret_cast<const float2*>(flow) + static_cast<size_t>(n) * Hp * Wp, Wp, h0, w0};
+    const LerpTap ty = lerp_tap(Y, k.ratio_y, h0), tx = lerp_tap(X, k.ratio_x, w0);
+    double g00[2], g10[2], g01[2], g11[2];
+    gauss_both(s, ty.i0, tx.i0, k, g00);
+    gauss_both(s, ty.i1, tx.i0, k, g10);
+    gauss_both(s, ty.i0, tx.i1, k, g01);
+    gauss_both(s, ty.i1, tx.i1, k, g11);
+    float o[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const double r0 = __dadd_rn(__dmul_rn(g00[c], ty.f0), __dmul_rn(g10[c], ty.f1));
+        const double r1 = __dadd_rn(__dmul_rn(g01[c], ty.f0), __dmul_rn(g11[c], ty.f1));
+        o[c] = __double2float_rn(__ddiv_rn(__dadd_rn(__dmul_rn(r0, tx.f0), __dmul_rn(r1, tx.f1)), k.scale));
+    }
+    reinterpret_cast<float2*>(out)[P] = make_float2(o[0], o[1]);
+}
+
 // ---------------------------------------------------------------- tf.image.resize_bilinear x S (legacy: src = dst / S), times `gain`
 __global__ void __launch_bounds__(256) resize_flow_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int h, int w, int S, float gain) {
     const long long total = static_cast<long long>(N) * h * S * w * S;
@@ -467,6 +593,17 @@ void launch_cost_volume(Planes c1, int c1_coff, Planes c2, int c2_coff, int C, P
 // ---------------------------------------------------------------- first pyramid conv: fp32 image [N,H,W,3] -> 16 channels at half resolution
 void launch_first_conv(const float* img, const float* w, const float* b, Planes out, int N, int H, int W, cudaStream_t st) {
     first_conv_kernel<<<blocks_for(static_cast<long long>(N) * (H / 2) * (W / 2), 128), 128, 0, st>>>(img, w, b, out, N, H, W);
+}
+
+void launch_prepare_pair(const void* src0, const void* src1, bool yuv, float* img1, float* img2, int h, int w, int oh, int ow, int Hp, int Wp,
+                         const PrepConst& k, cudaStream_t st) {
+    dim3 grid(blocks_for(static_cast<long long>(Hp) * Wp, 256), 2);
+    if (yuv) prepare_pair_kernel<true><<<grid, 256, 0, st>>>(src0, src1, img1, img2, h, w, oh, ow, Hp, Wp, k);
+    else prepare_pair_kernel<false><<<grid, 256, 0, st>>>(src0, src1, img1, img2, h, w, oh, ow, Hp, Wp, k);
+}
+
+void launch_finish_flow(const float* flow, int N, int Hp, int Wp, int h0, int w0, int oh, int ow, float* out, const FinishConst& k, cudaStream_t st) {
+    finish_flow_kernel<<<blocks_for(static_cast<long long>(N) * oh * ow, 128), 128, 0, st>>>(flow, N, Hp, Wp, h0, w0, oh, ow, out, k);
 }
 
 void launch_flow_upfeat_scatter(Planes F, float* flow, Planes Dn, int up_off, int N, int h, int w, cudaStream_t st) {

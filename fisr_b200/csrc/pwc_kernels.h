@@ -35,6 +35,13 @@ void launch_dense_warp(Planes img, int coff, int C, Planes flow, int f_coff, flo
 void launch_first_conv(const float* img, const float* w, const float* b, Planes out, int N, int H, int W, cudaStream_t st);
 // splits the 16 columns of the fused predict_flow / up_feat conv: fp32 flow [N,h,w,2] and (Dn.p != nullptr) the 2 up_feat channels of level l - 1
 void launch_flow_upfeat_scatter(Planes F, float* flow, Planes Dn, int up_off, int N, int h, int w, cudaStream_t st);
+// pre / post-processing of the reference's driver (float64 arithmetic in numpy's evaluation order)
+struct PrepConst { double T[9], off[3]; double ry, rx; };          // YUV -> RGB matrix / offset (utils.py:106-115), n_in / n_out per axis
+constexpr int kMaxGaussRadius = 8;
+struct FinishConst { double wy[kMaxGaussRadius + 1], wx[kMaxGaussRadius + 1]; int ry, rx; double ratio_y, ratio_x, scale; };   // w[j] = weight at distance j
+void launch_prepare_pair(const void* src0, const void* src1, bool yuv, float* img1, float* img2, int h, int w, int oh, int ow, int Hp, int Wp,
+                         const PrepConst& k, cudaStream_t st);
+void launch_finish_flow(const float* flow, int N, int Hp, int Wp, int h0, int w0, int oh, int ow, float* out, const FinishConst& k, cudaStream_t st);
 void launch_resize_flow(const float* in, float* out, int N, int h, int w, int S, float gain, cudaStream_t st);
 
 }  // namespace pwc

@@ -1,9 +1,9 @@
 """PWC-Net inference on the B200 path: the flow estimator the reference runs in front of its warp
 (FISR_tfoptflow/model_pwcnet.py, driven by FISR_for_video_pwcnet_predict_from_img_test.py:84-147).
 
-``PWCNet`` owns one ``fisr_pwc`` context (C ABI); every kernel is in libfisr_b200.so.  The host side mirrors the reference's
-driver: YUV -> RGB, x2 ``skimage.transform.resize``, uint8, /255, zero pad to multiples of 64, crop, anti-aliased x1/2 resize, /2
-(skimage is restated with numpy / scipy, it is not installable here).  PARITY UNPINNED: see include/fisr_b200.h.
+``PWCNet`` owns one ``fisr_pwc`` context (C ABI); every kernel is in libfisr_b200.so, including the reference driver's pre- and
+post-processing (YUV -> RGB, x2 ``skimage.transform.resize``, uint8, /255, zero pad to multiples of 64; crop, anti-aliased x1/2
+resize, /2), which runs in float64 on the device in numpy's evaluation order.  PARITY UNPINNED: see include/fisr_b200.h.
 """
 from __future__ import annotations
 
@@ -102,65 +102,80 @@ class PWCNet:
         return a
 
     # ------------------------------------------------------------------ the reference's driver around the network
+    def _run(self, tensors, call, what):
+        """One library call on the side stream, ordered against torch's current stream on entry and exit."""
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        for t in tensors:
+            t.record_stream(self.stream)
+        self._check(call(self.stream.cuda_stream), what)
+        cur.wait_stream(self.stream)
+
+    def prepare_pair(self, f1: torch.Tensor, f2: torch.Tensor, scale: int = 2):
+        """..predict_from_img_test.py:113-131 + adapt_x on the device: two frames [h,w,3] (uint8 YUV, or float64 RGB in 0..255) ->
+        (img1, img2) f32 [2,Hp,Wp,3] = the batch of both directions, ready for ``forward``."""
+        from .utils import yuv2rgb_constants
+        h, w = int(f1.shape[0]), int(f1.shape[1])
+        kind = {torch.uint8: 0, torch.float64: 1}.get(f1.dtype)
+        if kind is None or f2.dtype != f1.dtype or tuple(f1.shape) != (h, w, 3) or tuple(f2.shape) != (h, w, 3) or scale < 1 \
+                or not (f1.is_cuda and f2.is_cuda and f1.is_contiguous() and f2.is_contiguous()):
+            raise FisrError(f"prepare_pair: frames {tuple(f1.shape)} {f1.dtype} / {tuple(f2.shape)} {f2.dtype}, scale {scale}")
+        Hp, Wp = -(-h * scale // 64) * 64, -(-w * scale // 64) * 64
+        img1 = torch.empty((2, Hp, Wp, 3), dtype=torch.float32, device=f1.device)
+        img2 = torch.empty_like(img1)
+        k = np.ascontiguousarray(yuv2rgb_constants(), dtype=np.float64)
+        self._run((f1, f2, img1, img2), lambda st: self.lib.fisr_pwc_prepare_pair(
+            self.h, f1.data_ptr(), f2.data_ptr(), kind, k.ctypes.data, h, w, scale, img1.data_ptr(), img2.data_ptr(), st), "fisr_pwc_prepare_pair")
+        return img1, img2
+
+    def finish_flow(self, flow: torch.Tensor, hw0: Tuple[int, int], out_hw: Tuple[int, int], scale: int = 2) -> torch.Tensor:
+        """postproc_y_hat_test crop + anti-aliased resize + / scale (..predict_from_img_test.py:137) on the device:
+        flow f32 [N,Hp,Wp,2] -> [N,h,w,2]."""
+        n, Hp, Wp, _ = flow.shape
+        (h0, w0), (h, w) = hw0, out_hw
+        if not (flow.is_cuda and flow.dtype == torch.float32 and flow.is_contiguous() and flow.shape[3] == 2):
+            raise FisrError("finish_flow takes a contiguous float32 CUDA tensor [N,Hp,Wp,2]")
+        wy, wx = _gauss_weights(max(0.0, (h0 / h - 1) / 2)), _gauss_weights(max(0.0, (w0 / w - 1) / 2))
+        out = torch.empty((n, h, w, 2), dtype=torch.float32, device=flow.device)
+        self._run((flow, out), lambda st: self.lib.fisr_pwc_finish_flow(
+            self.h, flow.data_ptr(), n, Hp, Wp, h0, w0, h, w, wy.ctypes.data, len(wy) - 1, wx.ctypes.data, len(wx) - 1, float(scale),
+            out.data_ptr(), st), "fisr_pwc_finish_flow")
+        return out
+
+    def _flow_pair(self, f1: torch.Tensor, f2: torch.Tensor, scale: int) -> np.ndarray:
+        """Pre-processing, network and post-processing of one frame pair on the device: only the two frames go up and the
+        [2,h,w,2] flow comes down."""
+        h, w = int(f1.shape[0]), int(f1.shape[1])
+        img1, img2 = self.prepare_pair(f1, f2, scale)
+        flow = self.forward(img1, img2)
+        return self.finish_flow(flow, (h * scale, w * scale), (h, w), scale).cpu().numpy()
+
     def flow_pair(self, rgb1: np.ndarray, rgb2: np.ndarray, scale: int = 2) -> np.ndarray:
         """Bidirectional flow of one frame pair as ..predict_from_img_test.py:126-138 computes it: rgb float [h,w,3] in 0..255 ->
         float32 [2,h,w,2] (1 -> 2, 2 -> 1) at the input resolution."""
-        h, w = rgb1.shape[:2]
-        a, b, hw0 = prepare_pair(rgb1, rgb2, scale)
         dev = torch.device("cuda", self.device)
-        ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
-        flow = self.forward(torch.stack([ta, tb]), torch.stack([tb, ta])).cpu().numpy()       # both directions as one batch
-        return np.stack([finish_flow(flow[k], hw0, (h, w), scale) for k in range(2)])
+        f1 = torch.from_numpy(np.ascontiguousarray(rgb1, dtype=np.float64)).to(dev)
+        f2 = torch.from_numpy(np.ascontiguousarray(rgb2, dtype=np.float64)).to(dev)
+        return self._flow_pair(f1, f2, scale)
+
+    def flow_pair_yuv(self, yuv1: np.ndarray, yuv2: np.ndarray, scale: int = 2) -> np.ndarray:
+        """The same from the uint8 YUV frames the reference's driver reads (..predict_from_img_test.py:113-120): the YUV -> RGB
+        conversion of utils.YUV2RGB_matlab runs on the device too."""
+        if yuv1.dtype != np.uint8 or yuv2.dtype != np.uint8:
+            raise FisrError("flow_pair_yuv takes uint8 frames")
+        dev = torch.device("cuda", self.device)
+        f1 = torch.from_numpy(np.ascontiguousarray(yuv1)).to(dev)
+        f2 = torch.from_numpy(np.ascontiguousarray(yuv2)).to(dev)
+        return self._flow_pair(f1, f2, scale)
 
 
-# ---------------------------------------------------------------------------------------- skimage.transform.resize, restated
-def skimage_resize(img: np.ndarray, out_hw: Tuple[int, int], anti_aliasing: bool = False) -> np.ndarray:
-    """``skimage.transform.resize`` along axes (-3, -2): order 1, mode 'reflect' (scipy 'mirror'), pixel-centre-aligned
-    coordinates, Gaussian pre-filter of sigma (factor - 1) / 2 per down-scaled axis when ``anti_aliasing``."""
-    from scipy import ndimage as ndi
-    img = np.asarray(img, dtype=np.float64)
-    h, w = img.shape[-3], img.shape[-2]
-    oh, ow = out_hw
-    if anti_aliasing:
-        sig = [0.0] * img.ndim
-        sig[-3], sig[-2] = max(0.0, (h / oh - 1) / 2), max(0.0, (w / ow - 1) / 2)
-        if any(sig):
-            img = ndi.gaussian_filter(img, sig, mode="mirror")
-
-    def lerp_axis(a, coords, axis):
-        n = a.shape[axis]
-        period = 2 * (n - 1) if n > 1 else 1
-        i0 = np.floor(coords).astype(np.int64)
-        fr = coords - i0
-
-        def mirror(i):
-            if n == 1:
-                return np.zeros_like(i)
-            i = np.mod(i, period)
-            return np.where(i >= n, period - i, i)
-
-        shape = [1] * a.ndim
-        shape[axis] = -1
-        fr = fr.reshape(shape)
-        return np.take(a, mirror(i0), axis=axis) * (1 - fr) + np.take(a, mirror(i0 + 1), axis=axis) * fr
-
-    ys = (np.arange(oh) + 0.5) * (h / oh) - 0.5
-    xs = (np.arange(ow) + 0.5) * (w / ow) - 0.5
-    return lerp_axis(lerp_axis(img, ys, img.ndim - 3), xs, img.ndim - 2)
-
-
-def prepare_pair(rgb1: np.ndarray, rgb2: np.ndarray, scale: int = 2):
-    """..predict_from_img_test.py:126-131 + adapt_x (model_pwcnet.py:371-409): x`scale` resize, uint8 truncation, /255, zero pad
-    to multiples of 64.  Returns (img1, img2) float32 [H,W,3] and the unpadded size."""
-    h, w = rgb1.shape[:2]
-    outs = []
-    for a in (rgb1, rgb2):
-        u8 = np.array(skimage_resize(a, (h * scale, w * scale)), dtype=np.uint8)
-        x = u8.astype(np.float32) / np.float32(255.)
-        outs.append(np.ascontiguousarray(np.pad(x, [(0, (-x.shape[0]) % 64), (0, (-x.shape[1]) % 64), (0, 0)], mode="constant")))
-    return outs[0], outs[1], (h * scale, w * scale)
-
-
-def finish_flow(flow: np.ndarray, hw0: Tuple[int, int], out_hw: Tuple[int, int], scale: int = 2) -> np.ndarray:
-    """postproc_y_hat_test crop (model_pwcnet.py:449-470) + ..predict_from_img_test.py:137: anti-aliased resize, / scale."""
-    return (skimage_resize(flow[:hw0[0], :hw0[1]], out_hw, anti_aliasing=True) / scale).astype(np.float32)
+def _gauss_weights(sigma: float) -> np.ndarray:
+    """Weights at distance 0..radius of the kernel ``scipy.ndimage.gaussian_filter`` builds for ``sigma`` (truncate = 4,
+    _gaussian_kernel1d); a single 1 when there is nothing to filter."""
+    if sigma <= 1e-15:
+        return np.ones(1, dtype=np.float64)
+    radius = int(4.0 * float(sigma) + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    phi = phi / phi.sum()
+    return np.ascontiguousarray(phi[radius:], dtype=np.float64)

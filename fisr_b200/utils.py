@@ -129,11 +129,18 @@ def split_seq_dim(data):                           # utils.py:86-91
     return np.transpose(np.reshape(data, (sz[0], sz[1], sz[2], sz[3] // 3, 3)), axes=(0, 3, 1, 2, 4))
 
 
-def YUV2RGB_matlab(yuv):                           # utils.py:106-115
+def yuv2rgb_constants():
+    """The 3x3 matrix T and the offset of ``YUV2RGB_matlab`` (utils.py:106-110) as 12 float64 values (T row-major, then offset)."""
     Tinv = np.array([[0.00456621, 0., 0.00625893], [0.00456621, -0.00153632, -0.00318811], [0.00456621, 0.00791071, 0.]])
     offset = [[16], [128], [128]]
     T = 255 * Tinv
     offset = 255 * Tinv @ offset
+    return np.concatenate([T.ravel(), np.asarray(offset).ravel()])
+
+
+def YUV2RGB_matlab(yuv):                           # utils.py:106-115
+    k = yuv2rgb_constants()
+    T, offset = k[:9].reshape(3, 3), k[9:].reshape(3, 1)
     rgb = np.zeros(yuv.shape)
     for p in range(3):
         rgb[:, :, p] = T[p, 0] * yuv[:, :, 0] + T[p, 1] * yuv[:, :, 1] + T[p, 2] * yuv[:, :, 2] - offset[p]

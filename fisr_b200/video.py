@@ -51,7 +51,7 @@ def FISR_for_video_Compute_Flow(args, pwcnet=None):
     reference's default path), read without TensorFlow.  Neither the checkpoint nor eight modules of the reference's PWC-Net copy
     are in the reference tree, so this row is parity-unpinned; an existing flow file is used as is."""
     from .pwcnet import PWCNet
-    from .utils import YUV2RGB_matlab, write_flo_file_5dim
+    from .utils import write_flo_file_5dim
     folder = args.frame_folder_path.rstrip('/')
     path = folder + '/' + folder.split('/')[-1] + '_test_ss{}_fr{}.flo'.format(1, args.frame_num)
     if os.path.exists(path) and pwcnet is None:
@@ -69,10 +69,10 @@ def FISR_for_video_Compute_Flow(args, pwcnet=None):
     num_fr = args.frame_num
     pred = np.zeros((num_fr - 1, 2, h, w, 2), dtype=np.float32)
     for fr in range(num_fr - 1):
-        # PWC-Net works on RGB: the YUV frames are converted first (:113-120; same matrix as utils.YUV2RGB_matlab)
-        rgb_1 = YUV2RGB_matlab(np.array(Image.open(data_list[fr]), dtype=np.float32)[:h, :w])
-        rgb_2 = YUV2RGB_matlab(np.array(Image.open(data_list[fr + 1]), dtype=np.float32)[:h, :w])
-        pred[fr] = pwcnet.flow_pair(rgb_1, rgb_2, scale=2)
+        # PWC-Net works on RGB: the YUV frames are converted first (:113-120; utils.YUV2RGB_matlab's arithmetic, on the device)
+        yuv_1 = np.array(Image.open(data_list[fr]), dtype=np.uint8)[:h, :w]
+        yuv_2 = np.array(Image.open(data_list[fr + 1]), dtype=np.uint8)[:h, :w]
+        pred[fr] = pwcnet.flow_pair_yuv(yuv_1, yuv_2, scale=2)
         print("Processing for computing flows [%5d/%5d]" % (fr + 1, num_fr))
     write_flo_file_5dim(pred, path)
     print('[*] Flow file saved!')

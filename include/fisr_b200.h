@@ -236,6 +236,19 @@ int fisr_pwc_set_param(fisr_pwc* pwc, const char* name, const float* h_data, siz
 /* `nn()` (model_pwcnet.py:1525-1593) on N image pairs: d_img1, d_img2 f32 [N,H,W,3] in 0..1 (adapt_x: /255, zero-padded so that
  * H, W are multiples of 64) -> d_flow f32 [N,H,W,2] = flow from image 1 to image 2 in pixels, (u, v) per pixel.  Asynchronous. */
 int fisr_pwc_forward(fisr_pwc* pwc, const float* d_img1, const float* d_img2, int N, int H, int W, float* d_flow, void* stream);
+/* The driver around the network for ONE frame pair (FISR_for_video_pwcnet_predict_from_img_test.py:113-131, adapt_x
+ * model_pwcnet.py:371-409), on the device: [YUV -> RGB,] x`scale` skimage.transform.resize (order 1, 'reflect'), uint8 truncation,
+ * /255, zero pad to multiples of 64, written as the batch of both directions: d_img1 = [frame 0, frame 1], d_img2 = [frame 1,
+ * frame 0], each f32 [2,Hp,Wp,3] with Hp, Wp = h * scale, w * scale rounded up to 64.  src_kind 0: uint8 YUV frames [h,w,3]
+ * (h_yuv2rgb = 12 doubles, the 3x3 matrix T then the offset of utils.py:106-115, as the host computes them); src_kind 1: float64
+ * RGB frames [h,w,3] in 0..255 (h_yuv2rgb ignored).  Arithmetic is float64 in numpy's evaluation order.  Asynchronous. */
+int fisr_pwc_prepare_pair(fisr_pwc* pwc, const void* d_frame0, const void* d_frame1, int src_kind, const double* h_yuv2rgb, int h, int w,
+                          int scale, float* d_img1, float* d_img2, void* stream);
+/* postproc_y_hat_test (model_pwcnet.py:449-470) + ..predict_from_img_test.py:137: d_flow f32 [N,Hp,Wp,2] cropped to h0 x w0,
+ * Gaussian pre-filter (scipy.ndimage.gaussian_filter, mode 'mirror'; h_wy / h_wx = the ry + 1 / rx + 1 kernel weights at distance
+ * 0, 1, .. as scipy computes them; radius 0 = no filter), order-1 resize to h_out x w_out, / scale -> d_out f32 [N,h_out,w_out,2]. */
+int fisr_pwc_finish_flow(fisr_pwc* pwc, const float* d_flow, int N, int Hp, int Wp, int h0, int w0, int h_out, int w_out, const double* h_wy,
+                         int ry, const double* h_wx, int rx, double scale, float* d_out, void* stream);
 /* refined flow of pyramid level lvl (2..6) of the last forward, [N,H/2^lvl,W/2^lvl,2] (test hook) */
 int fisr_pwc_debug_flow(fisr_pwc* pwc, int lvl, float* h_dst, size_t count);
 long long fisr_pwc_launch_count(const fisr_pwc* pwc);

@@ -85,6 +85,30 @@ def test_tensor_core_path_matches_cuda_core_path():
             assert err < 2e-4 * max(1.0, float(np.abs(y).max())), (mode, i, err)
 
 
+@pytest.mark.parametrize("h,w", [(72, 104), (75, 101), (64, 64)])
+def test_driver_pre_and_post_processing_on_the_device(pwc, h, w):
+    """fisr_pwc_prepare_pair / fisr_pwc_finish_flow against the host restatement of the reference's driver (skimage resize, uint8
+    truncation, padding; crop, scipy Gaussian, resize): the float64 arithmetic is evaluated in numpy's order, so the network input
+    is bit-identical and the finished flow agrees to float32 rounding."""
+    from fisr_b200 import utils
+    rng = np.random.default_rng(h * w)
+    yuv = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+    rgb = [utils.YUV2RGB_matlab(f.astype(np.float32)) for f in yuv]
+    a, b, hw0 = W.prepare_pair(rgb[0], rgb[1])
+    for frames in ([torch.from_numpy(f).cuda() for f in yuv], [torch.from_numpy(np.ascontiguousarray(f, dtype=np.float64)).cuda() for f in rgb]):
+        img1, img2 = pwc.prepare_pair(frames[0], frames[1], 2)
+        assert tuple(img1.shape) == (2,) + a.shape
+        assert np.array_equal(img1[0].cpu().numpy(), a) and np.array_equal(img1[1].cpu().numpy(), b)
+        assert np.array_equal(img2[0].cpu().numpy(), b) and np.array_equal(img2[1].cpu().numpy(), a)
+    flow = (rng.standard_normal((2,) + a.shape[:2] + (2,)) * 5).astype(np.float32)
+    got = pwc.finish_flow(torch.from_numpy(flow).cuda(), hw0, (h, w), 2).cpu().numpy()
+    for k in range(2):
+        want = W.finish_flow(flow[k], hw0, (h, w))
+        assert got[k].shape == want.shape
+        assert np.abs(got[k] - want).max() <= 1e-6, np.abs(got[k] - want).max()
+        assert np.mean(got[k] == want) > 0.999
+
+
 def test_each_building_block(pwc):
     """The TF-specific semantics one by one, on the oracle side against plain formulas (runs without the GPU too)."""
     g = torch.Generator().manual_seed(0)
