@@ -40,4 +40,9 @@ from oracle import pwcnet_oracle as W
 net = PWCNet(0); net.set_params(W.init_params(0))
 f = net.forward(torch.rand(2, 64, 128, 3, generator=g).cuda(), torch.rand(2, 64, 128, 3, generator=g).cuda())
 torch.cuda.synchronize(); print("pwcnet ok", float(f.abs().mean()), flush=True)
+f = net.forward(torch.rand(1, 256, 320, 3, generator=g).cuda(), torch.rand(1, 256, 320, 3, generator=g).cuda())      # every dilation as polyphase launches
+torch.cuda.synchronize(); print("pwcnet polyphase ok", float(f.abs().mean()), flush=True)
+import numpy as np
+yuv = np.random.default_rng(0).integers(0, 256, (2, 43, 61, 3), dtype=np.uint8)                                     # driver pre / post-processing kernels
+f = net.flow_pair_yuv(yuv[0], yuv[1]); print("flow_pair ok", f.shape, float(np.abs(f).mean()), flush=True)
 net.close()
