@@ -34,6 +34,39 @@ from .init import xavier_params
 from .utils import check_folder, merge_seq_dim, read_flo_file_5dim, read_mat_file_warp
 
 
+
+class _FrameWriter:
+    """PNG output off the critical path: colour conversion + PNG compression of a 4K frame take ~1 s on one core against 25 ms of GPU
+    work per window, so they run on a thread pool (PIL and numpy release the GIL) while the next windows are computed.  The files
+    are the ones the sequential loop of the reference writes (FISRnet.py:888-904, 1066-1077); at most ``max_pending`` frames wait."""
+
+    def __init__(self, workers=None, max_pending=12):
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        self.pool = ThreadPoolExecutor(max_workers=workers or min(8, os.cpu_count() or 1))
+        self.slots = threading.Semaphore(max_pending)
+        self.futures = []
+
+    def _job(self, yuv, rgb_path, yuv_path):
+        try:
+            Image.fromarray(utils.YUV2RGB_matlab(yuv).astype('uint8')).save(rgb_path)
+            if yuv_path:
+                Image.fromarray(yuv.astype('uint8')).save(yuv_path)
+        finally:
+            self.slots.release()
+
+    def save(self, yuv, rgb_path, yuv_path=None):
+        """``yuv``: uint8 [H,W,3]; writes its RGB conversion to ``rgb_path`` and, if given, the YUV frame itself to ``yuv_path``."""
+        self.slots.acquire()
+        self.futures.append(self.pool.submit(self._job, yuv, rgb_path, yuv_path))
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+        for f in self.futures:
+            f.result()                      # re-raise the first failure
+        self.futures = []
+
+
 class FISRnet(object):
     model_name = "FISRnet"
 
@@ -225,6 +258,7 @@ class FISRnet(object):
         n_in_seq, n_test_in_seq = 3, 5
         n_GT_seq, n_test_label_seq = n_in_seq * 2 - 3, 2 * n_test_in_seq - 3
         psnr_fisr, psnr_sr, ssim_fisr, ssim_sr, inf_time = [], [], [], [], []
+        writer = _FrameWriter()
         start_time = time.time()
         H, W = self.test_input_size
         h = H - np.remainder(H, 32 * num_patch[0])
@@ -260,9 +294,10 @@ class FISRnet(object):
                 print(" --------------------------------------------------------------- test_SSIM: fr1 (FI-SR) %.8f, "
                       "fr2 (SR) %.8f, fr3 (FI-SR) %.8f  " % (test_SSIM[0], test_SSIM[1], test_SSIM[2]))
                 for s in range(n_GT_seq):
+                    if s == 2 and sample_i < n_test_in_seq - n_in_seq:
+                        continue            # the next sample's frame 0 has the same file name and is written later (FISRnet.py:901-904)
                     fr_name = os.path.basename(test_label_path[scene_i * n_test_label_seq + sample_i * 2 + s])[3:]
-                    rgb_img = utils.YUV2RGB_matlab(pred[:, :, s * 3:(s + 1) * 3])
-                    Image.fromarray(rgb_img.astype('uint8')).save(os.path.join(test_img_dir, 'pred_{}'.format(fr_name)))
+                    writer.save(pred[:, :, s * 3:(s + 1) * 3], os.path.join(test_img_dir, 'pred_{}'.format(fr_name)))
                 psnr_fisr.append(test_PSNR[0])
                 psnr_sr.append(test_PSNR[1])
                 ssim_fisr.append(test_SSIM[0])
@@ -273,6 +308,7 @@ class FISRnet(object):
         print("######### Test (average) test_PSNR: FISR %.8f[dB], SR %.8f[dB]  #########"
               % (np.mean(psnr_fisr), np.mean(psnr_sr)))
         print("######### Test (average) test_SSIM: FISR %.8f, SR %.8f #########" % (np.mean(ssim_fisr), np.mean(ssim_sr)))
+        writer.close()
         print("######### Estimated Inference Time (per window = three 4K frames): %.8f[s]  #########" % np.mean(inf_time))
 
     # ------------------------------------------------------------------ FISR_for_video (FISRnet.py:937-1084)
@@ -302,17 +338,20 @@ class FISRnet(object):
                 yield img[:h, :w], flow[fr, :h, :w], warp[fr, :h, :w]      # FISRnet.py:1008-1021
 
         # two windows in flight: the copies of window k+1 overlap the kernels of window k (fisr_window_submit / _wait)
+        writer = _FrameWriter()
         t_prev = time.time()
         for fr, pred in enumerate(self.engine.video_windows(windows(), tuple(int(v) for v in num_patch))):   # YUV uint8 [2h,2w,9]
             inf_time.append(time.time() - t_prev)
             t_prev = time.time()
             for seq_i in range(3):                                                              # FISRnet.py:1066-1077
-                yuv = pred[:, :, seq_i * 3:(seq_i + 1) * 3]
+                if seq_i == 2 and fr + 1 < num_fr - 2:
+                    continue                # the next window's frame 0 has the same file name and is written later
                 name = str(fr * 2 + seq_i).zfill(digits)
-                Image.fromarray(utils.YUV2RGB_matlab(yuv).astype('uint8')).save(FISR_img_dir + '/pred_{}.png'.format(name))
-                Image.fromarray(yuv.astype('uint8')).save(FISR_img_dir + '/pred_YUV_{}.png'.format(name))
+                writer.save(pred[:, :, seq_i * 3:(seq_i + 1) * 3], FISR_img_dir + '/pred_{}.png'.format(name),
+                            FISR_img_dir + '/pred_YUV_{}.png'.format(name))
             print(" <FISR processing> [%4d/%4d]-th input multiple data sample (stride1), time: %4.4f(minutes)  "
                   % (fr + 1, num_fr - 2, (time.time() - start_time) / 60))
+        writer.close()
         print("######### Estimated Inference Time (per window = three 4K frames): %.8f[s]  #########" % np.mean(inf_time))
 
     # ------------------------------------------------------------------ checkpoints (FISRnet.py:1086-1115)

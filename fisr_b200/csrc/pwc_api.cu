@@ -96,6 +96,7 @@ struct Param {
 
 struct Op {
     bool umma = false;
+    int group = 0;                                     // > 0: launches with the same id are independent (the polyphase launches of one dilated layer)
     ConvLaunch conv;                                   // umma: one tcgen05 conv launch (tensor maps encoded at plan build)
     std::function<void(cudaStream_t)> fn;              // otherwise
 };
@@ -104,7 +105,7 @@ struct Plan {
     int N = 0, H = 0, W = 0;
     std::vector<void*> allocs;
     std::vector<Op> ops;
-    int umma_ops = 0;
+    int umma_ops = 0, groups = 0;
     const float *img1 = nullptr, *img2 = nullptr;     // bound per call
     float* out = nullptr;
     float* flow[kLvls + 1] = {nullptr};
@@ -117,9 +118,15 @@ struct fisr_pwc {
     int device = 0, num_sms = 0;
     cudaStream_t stream = nullptr;
     fisr::EncodeTiledFn encode = nullptr;
+    // independent launches of one layer are spread over the caller's stream and these, so that the partial last wave of one
+    // persistent conv kernel overlaps the first wave of the next (each launch fills the GPU for only 1.3 - 3.6 waves)
+    static constexpr int kSide = 3;
+    cudaStream_t side[kSide] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {nullptr, nullptr, nullptr};
     int* d_err = nullptr;        // barrier-timeout flag of the conv kernel
     int* h_err = nullptr;        // pinned copy, refreshed at the end of every forward
-    int use_umma = 2;            // FISR_PWC_UMMA=0: every conv on the CUDA-core kernel; 1: tensor cores except the dilated layers (A/B measurements)
+    int use_umma = 3;            // FISR_PWC_UMMA=0: every conv on the CUDA-core kernel; 1: tensor cores except the dilated layers; 2: + dilated
+                                 // layers as polyphase launches; 3 (default): + those launches spread over 4 streams (A/B measurements)
     std::vector<Param> params;
     Param fused[kLvls + 1];      // predict_flow/flow<l> and upsample/up_feat<l> as ONE 3x3 conv with 16 output columns (build_fused)
     std::map<std::string, int> index;
@@ -260,6 +267,7 @@ int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
             if ((rc = ensure_packed(c, p)) != FISR_OK) return;
             const int hs = Hout / dil, ws = Wout / dil;
             const long long pixrow = static_cast<long long>(Wout), piximg = static_cast<long long>(Hout) * Wout;
+            const int group = dil == 1 ? 0 : ++pl->groups;
             for (int n = 0; n < (dil == 1 ? 1 : N); ++n)
                 for (int py = 0; py < dil; ++py) {
                     fisr::SplitConvDesc d{};
@@ -280,6 +288,7 @@ int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
                     d.relu = 0; d.slope = leaky ? 0.1f : 0.f;
                     Op op;
                     op.umma = true;
+                    op.group = group;
                     std::string why;
                     if (!fisr::build_split_conv(c->encode, d, c->num_sms, c->d_err, &op.conv, &why)) {
                         rc = fail(c, FISR_E_CUDA, "conv %s (%d x %d, dilation %d): %s", name.c_str(), Hout, Wout, dil, why.c_str());
@@ -452,6 +461,11 @@ int fisr_pwc_create(int device, fisr_pwc** out) {
     PWC_TRY(nullptr, fisr::conv3x3_init());
     PWC_TRY(nullptr, init_kernels());
     PWC_TRY(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < fisr_pwc::kSide; ++i) {
+        PWC_TRY(nullptr, cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+        PWC_TRY(nullptr, cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    }
+    PWC_TRY(nullptr, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     PWC_TRY(nullptr, cudaMalloc(&c->d_err, sizeof(int)));
     PWC_TRY(nullptr, cudaMemset(c->d_err, 0, sizeof(int)));
     PWC_TRY(nullptr, cudaMallocHost(&c->h_err, sizeof(int)));
@@ -481,6 +495,11 @@ void fisr_pwc_destroy(fisr_pwc* c) {
     c->plans.clear();
     for (auto& p : c->params) { cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); cudaFree(p.d_bp); }
     for (auto& p : c->fused) { cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); cudaFree(p.d_bp); }
+    for (int i = 0; i < fisr_pwc::kSide; ++i) {
+        if (c->side[i]) cudaStreamDestroy(c->side[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -552,9 +571,25 @@ int fisr_pwc_forward(fisr_pwc* c, const float* d_img1, const float* d_img2, int 
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
     if (st != c->stream) PWC_TRY(c, cudaStreamSynchronize(c->stream));      // operand packing / buffer clears ran on the context stream
     plan->img1 = d_img1; plan->img2 = d_img2; plan->out = d_flow;
-    for (auto& op : plan->ops) {
-        if (op.umma) PWC_TRY(c, fisr::launch_conv3x3(op.conv, c->num_sms, st));
-        else op.fn(st);
+    const bool fan_out = c->use_umma >= 3;
+    for (size_t i = 0; i < plan->ops.size(); ++i) {
+        Op& op = plan->ops[i];
+        if (!op.umma) { op.fn(st); continue; }
+        if (op.group == 0 || !fan_out) { PWC_TRY(c, fisr::launch_conv3x3(op.conv, c->num_sms, st)); continue; }
+        // a group of independent launches: fork to the side streams, round robin, join
+        size_t end = i;
+        while (end < plan->ops.size() && plan->ops[end].umma && plan->ops[end].group == op.group) ++end;
+        PWC_TRY(c, cudaEventRecord(c->ev_fork, st));
+        for (int k = 0; k < fisr_pwc::kSide; ++k) PWC_TRY(c, cudaStreamWaitEvent(c->side[k], c->ev_fork, 0));
+        for (size_t j = i; j < end; ++j) {
+            const int lane = static_cast<int>((j - i) % (fisr_pwc::kSide + 1));
+            PWC_TRY(c, fisr::launch_conv3x3(plan->ops[j].conv, c->num_sms, lane == 0 ? st : c->side[lane - 1]));
+        }
+        for (int k = 0; k < fisr_pwc::kSide; ++k) {
+            PWC_TRY(c, cudaEventRecord(c->ev_join[k], c->side[k]));
+            PWC_TRY(c, cudaStreamWaitEvent(st, c->ev_join[k], 0));
+        }
+        i = end - 1;
     }
     PWC_TRY(c, cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     c->launches += static_cast<long long>(plan->ops.size());
