@@ -155,6 +155,13 @@ bool build_split_conv(EncodeTiledFn encode, const SplitConvDesc& d, int num_sms,
     a.ksteps_last = (d.cin - (a.KB - 1) * 64 + 15) / 16;
     a.store_cout = (d.cout_pad > 16 && d.cout < d.cout_pad) ? d.cout : 0;
     L->epi = 0;
+    if (d.raw || d.res) {
+        if (d.cout_pad <= 16 || d.cout % 4) return bad("fp32 side tensors need a wide output with a multiple of 4 channels");
+        a.out_raw = d.raw; a.raw_cs = d.cout; a.raw_off0 = a.raw_off1 = 0; a.raw_split = 0;
+        a.res = d.res; a.res_cs = d.cout;
+        L->epi = (d.res ? 1 : 0) | (d.raw ? 2 : 0);
+        if (static_cast<double>(d.out_pixels) * d.cout >= 4294967296.0) return bad("fp32 side tensor exceeds 32-bit element offsets");
+    }
     L->tma_out = false;
     for (int pl = 0; pl < 2; ++pl) {
         cuuint64_t dims[4] = {(cuuint64_t)d.in_cs, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.N};

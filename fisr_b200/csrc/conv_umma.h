@@ -41,6 +41,9 @@ struct SplitConvDesc {
     const __half* wp; const float* bias; int cout, cout_pad;
     int N, H, W;
     int relu; float slope;       // relu = 1: ReLU; slope > 0: leaky ReLU; neither: linear
+    // optional fp32 side tensors, both indexed with the output pixel index and `cout` floats per pixel (+ cout_pad of slack at the end):
+    float* raw;                  // pre-activation result (incl. bias and residual) is also written here
+    const float* res;            // added before the activation -- a conv split over two launches accumulates through raw -> res
 };
 // cout_pad a layer's weights must be packed for (independent of the image size)
 inline int split_conv_cout_pad(int cout) { return cout <= 16 ? 16 : cout <= 64 ? 64 : (cout + 127) / 128 * 128; }

@@ -97,6 +97,7 @@ struct Param {
 struct Op {
     bool umma = false;
     int group = 0;                                     // > 0: launches with the same id are independent (the polyphase launches of one dilated layer)
+    int lane = 0;                                      // 1: the feature pyramid of image 2, which runs beside image 1's on a side stream
     ConvLaunch conv;                                   // umma: one tcgen05 conv launch (tensor maps encoded at plan build)
     std::function<void(cudaStream_t)> fn;              // otherwise
 };
@@ -129,6 +130,7 @@ struct fisr_pwc {
                                  // layers as polyphase launches; 3 (default): + those launches spread over 4 streams (A/B measurements)
     std::vector<Param> params;
     Param fused[kLvls + 1];      // predict_flow/flow<l> and upsample/up_feat<l> as ONE 3x3 conv with 16 output columns (build_fused)
+    Param s2[kLvls + 1][2];      // featpyr/conv<l>a (stride 2) as two stride-1 convs on the row phases of the input (build_stride2)
     std::map<std::string, int> index;
     std::map<std::string, std::unique_ptr<Plan>> plans;
     Plan* last = nullptr;
@@ -225,6 +227,44 @@ int build_fused(fisr_pwc* c, int l) {
     return ensure_packed(c, f);
 }
 
+// A stride-2 3x3 conv ('same' on an even size: taps x[2o + k], k = 0..2) on the tensor cores.  View the input as super-pixels:
+// pixel X of row phase py holds the 2C channels of input pixels (2Y + py, 2X) and (2Y + py, 2X + 1), which are contiguous in a compact
+// NHWC buffer.  Then  out[Y, X] = sum over py of a stride-1 3x3 conv on that view whose only non-zero taps are
+//   rows:  py = 0: dy' = 0 (ky = 0), dy' = +1 (ky = 2);   py = 1: dy' = 0 (ky = 1)
+//   cols:  channel half 0: dx' = 0 (kx = 0), dx' = +1 (kx = 2);   channel half 1: dx' = 0 (kx = 1)
+// Two launches: phase 0 writes bias + partial sum to an fp32 scratch, phase 1 adds it as its residual and applies the activation.
+int build_stride2(fisr_pwc* c, int l) {
+    const std::string name = "pwcnet/featpyr/conv" + std::to_string(l) + "a";
+    const Param& src = c->params[c->index.at(name)];
+    const PDef& d = inventory()[c->index.at(name)];
+    const int C = d.cin, co = d.cout;
+    for (int py = 0; py < 2; ++py) {
+        Param& f = c->s2[l][py];
+        if (f.packed) continue;
+        f.cin_pad = 2 * C;
+        f.cout = co;
+        std::vector<float> w(static_cast<size_t>(9) * 2 * C * co, 0.f), b(co, 0.f);
+        if (!src.h_w.empty())
+            for (int ky = py; ky < 3; ky += 2)                  // py = 0: ky 0, 2;  py = 1: ky 1
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ty = ky / 2 + 1, tx = kx / 2 + 1, half = kx & 1;
+                    for (int ci = 0; ci < C; ++ci)
+                        for (int o = 0; o < co; ++o)
+                            w[(static_cast<size_t>(ty * 3 + tx) * 2 * C + half * C + ci) * co + o] = src.h_w[(static_cast<size_t>(ky * 3 + kx) * C + ci) * co + o];
+                }
+        if (py == 0 && !src.h_b.empty()) b = src.h_b;
+        if (!f.d_w) {
+            PWC_TRY(c, cudaMalloc(&f.d_w, w.size() * sizeof(float)));
+            PWC_TRY(c, cudaMalloc(&f.d_b, co * sizeof(float)));
+        }
+        PWC_TRY(c, cudaMemcpy(f.d_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+        PWC_TRY(c, cudaMemcpy(f.d_b, b.data(), co * sizeof(float), cudaMemcpyHostToDevice));
+        const int rc = ensure_packed(c, f);
+        if (rc != FISR_OK) return rc;
+    }
+    return FISR_OK;
+}
+
 int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
     if (N < 1 || H < 64 || W < 64 || H % 64 || W % 64)
         return fail(c, FISR_E_INVALID, "PWC-Net (6-level pyramid) needs H, W multiples of 64 (got %d x %d x %d): pad like adapt_x", N, H, W);
@@ -254,7 +294,9 @@ int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
     };
     auto f32 = [&](size_t n) { return static_cast<float*>(alloc_bytes(n * sizeof(float))); };
     auto P = [&](const std::string& n) -> Param& { return c->params[c->index.at(n)]; };
-    auto push = [&](std::function<void(cudaStream_t)> fn) { Op op; op.fn = std::move(fn); pl->ops.push_back(std::move(op)); };
+    int lane = 0;
+    float* s2tmp[2] = {nullptr, nullptr};      // fp32 partial sums of the two-launch stride-2 convs, one per pyramid lane
+    auto push = [&](std::function<void(cudaStream_t)> fn) { Op op; op.fn = std::move(fn); op.lane = lane; pl->ops.push_back(std::move(op)); };
     // One conv layer: on the tensor cores when it is a stride-1 conv with >= 16 outputs on an image of at least 4 x 4 pixels --
     // dilation d as d (column phase) x d (row phase) undilated convs on the polyphase sub-images, each launch covering the d
     // column phases of one row phase of one image as a batch -- else on the CUDA-core kernel.
@@ -289,6 +331,7 @@ int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
                     Op op;
                     op.umma = true;
                     op.group = group;
+                    op.lane = lane;
                     std::string why;
                     if (!fisr::build_split_conv(c->encode, d, c->num_sms, c->d_err, &op.conv, &why)) {
                         rc = fail(c, FISR_E_CUDA, "conv %s (%d x %d, dilation %d): %s", name.c_str(), Hout, Wout, dil, why.c_str());
@@ -297,6 +340,39 @@ int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
                     pl->ops.push_back(std::move(op));
                     pl->umma_ops++;
                 }
+            return;
+        }
+        if (c->use_umma >= 1 && stride == 2 && l_in >= 1 && !out_f32 && Hout >= 4 && Wout >= 4 && in.coff == 0 && in.b.cs == in.C &&
+            in.C % 8 == 0 && p.cout % 4 == 0 && p.cout > 16 && name.find("featpyr/conv") != std::string::npos) {
+            const int l = l_out;
+            if ((rc = build_stride2(c, l)) != FISR_OK) return;
+            const long long pixrow = static_cast<long long>(Wout), piximg = static_cast<long long>(Hout) * Wout;
+            float* tmp = s2tmp[lane];
+            for (int py = 0; py < 2; ++py) {
+                Param& q = c->s2[l][py];
+                fisr::SplitConvDesc d{};
+                d.in = in.b.p + static_cast<long long>(py) * Win * in.b.cs; d.in_plane = in.b.plane; d.in_cs = 2 * in.b.cs;
+                d.in_sx = 2LL * in.b.cs; d.in_sy = 2LL * Win * in.b.cs; d.in_sn = static_cast<long long>(Hin) * Win * in.b.cs;
+                d.cin_off = 0; d.cin = q.cin_pad;
+                d.out = outv.b.p; d.out_plane = outv.b.plane; d.out_cs = outv.b.cs; d.out_off = outv.coff;
+                d.opix_x = 1; d.opix_y = pixrow; d.opix_n = piximg;
+                d.N = N; d.H = Hout; d.W = Wout;
+                d.out_pixels = static_cast<long long>(N) * piximg;
+                d.wp = q.d_wp; d.bias = q.d_bp; d.cout = q.cout; d.cout_pad = q.cout_pad;
+                d.relu = 0; d.slope = (py == 1 && leaky) ? 0.1f : 0.f;
+                d.raw = py == 0 ? tmp : nullptr;
+                d.res = py == 1 ? tmp : nullptr;
+                Op op;
+                op.umma = true;
+                op.lane = lane;
+                std::string why;
+                if (!fisr::build_split_conv(c->encode, d, c->num_sms, c->d_err, &op.conv, &why)) {
+                    rc = fail(c, FISR_E_CUDA, "conv %s (stride 2, row phase %d): %s", name.c_str(), py, why.c_str());
+                    return;
+                }
+                pl->ops.push_back(std::move(op));
+                pl->umma_ops++;
+            }
             return;
         }
         PwcConv a{};
@@ -317,18 +393,22 @@ int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
         conv_p(P(name), name, in, outv, l_in, l_out, stride, dil, leaky, out_f32, add);
     };
     // ---- buffers
-    Planes D[kLvls + 1] = {}, c2[kLvls + 1] = {}, tA[kLvls + 1] = {}, tB[kLvls + 1] = {};
+    Planes D[kLvls + 1] = {}, c2[kLvls + 1] = {}, tA[2][kLvls + 1] = {}, tB[2][kLvls + 1] = {};
     for (int l = kPredLvl; l <= kLvls; ++l) D[l] = planes(px(l), dense_cs(l));
     for (int l = 1; l <= kLvls; ++l) c2[l] = planes(px(l), pad8(kChann[l]));
+    Planes c1c[kLvls + 1] = {};                                  // image 1's pyramid levels 2..5, compact (input of the next stride-2 conv);
+    for (int l = 2; l < kLvls; ++l) c1c[l] = planes(px(l), kChann[l]);      // copied into their slot of D_l for the cascade
+    for (int i = 0; i < 2; ++i) s2tmp[i] = f32(px(2) * kChann[2] + 512);
     Planes c1_1 = planes(px(1), pad8(kChann[1]));                // level 1 of image 1 feeds conv2a only
     Planes c1_6 = planes(px(kLvls), pad8(kChann[kLvls]));        // D_6 has no c1 slot (model_pwcnet.py:1549-1551)
     Planes F16 = planes(px(kPredLvl), 16);                       // output columns of the fused predict_flow / up_feat conv
-    {   // scratch of the pyramid: levels whose channel count is a multiple of 8 share two buffers, the others get their own
-        // (their pad channels must stay zero: they are read by the TMA boxes of the next conv)
+    for (int img = 0; img < 2; ++img) {
+        // scratch of one image's pyramid (the two pyramids run side by side): levels whose channel count is a multiple of 8 share two
+        // buffers, the others get their own (their pad channels must stay zero: they are read by the TMA boxes of the next conv)
         Planes sA = planes(px(1), kChann[1]), sB = planes(px(1), kChann[1]);
         for (int l = 1; l <= kLvls; ++l) {
-            if (kChann[l] % 8 == 0) { tA[l] = sA; tB[l] = sB; tA[l].cs = tB[l].cs = kChann[l]; }
-            else { tA[l] = planes(px(l), pad8(kChann[l])); tB[l] = planes(px(l), pad8(kChann[l])); }
+            if (kChann[l] % 8 == 0) { tA[img][l] = sA; tB[img][l] = sB; tA[img][l].cs = tB[img][l].cs = kChann[l]; }
+            else { tA[img][l] = planes(px(l), pad8(kChann[l])); tB[img][l] = planes(px(l), pad8(kChann[l])); }
         }
     }
     Planes T0 = planes(px(kPredLvl), 128), T1 = planes(px(kPredLvl), 128);
@@ -344,25 +424,33 @@ int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
     // ---- feature pyramids (model_pwcnet.py:1012-1101): the Siamese extractor on both images
     for (int img = 0; img < 2; ++img) {
         View x{};
+        lane = c->use_umma >= 3 ? img : 0;
         for (int l = 1; l <= kLvls; ++l) {
             const std::string p = "pwcnet/featpyr/conv" + std::to_string(l);
             const int f = kChann[l];
-            View dst = img == 0 ? c1_view(l) : View{c2[l], 0, f};
-            View ta{tA[l], 0, f}, tb{tB[l], 0, f};
+            const bool via_compact = img == 0 && l >= 2 && l < kLvls;
+            View dst = via_compact ? View{c1c[l], 0, f} : (img == 0 ? c1_view(l) : View{c2[l], 0, f});
+            View ta{tA[img][l], 0, f}, tb{tB[img][l], 0, f};
             if (l == 1) {        // straight from the fp32 image, whose pointer is bound per call
                 const Param& pa = P(p + "a");
                 const int which = img;
                 const float *w1 = pa.d_w, *b1 = pa.d_b;
-                const Planes o1 = tA[1];
+                const Planes o1 = tA[img][1];
                 push([=](cudaStream_t st) { launch_first_conv(which ? pl->img2 : pl->img1, w1, b1, o1, N, H, W, st); });
             } else {
                 conv(p + "a", x, ta, l - 1, l, 2, 1, true);
             }
             conv(p + "aa", ta, tb, l, l, 1, 1, true);
             conv(p + "b", tb, dst, l, l, 1, 1, true);
+            if (via_compact) {
+                const Planes srcp = c1c[l], dstp = D[l];
+                const long long np = static_cast<long long>(px(l));
+                push([=](cudaStream_t st) { launch_copy_channels(srcp, 0, dstp, kActs + kCorrPad, f, np, st); });
+            }
             x = dst;
         }
     }
+    lane = 0;
     // ---- coarse-to-fine cascade (model_pwcnet.py:1525-1593)
     for (int l = kLvls; l >= kPredLvl; --l) {
         const std::string sl = std::to_string(l);
@@ -495,6 +583,7 @@ void fisr_pwc_destroy(fisr_pwc* c) {
     c->plans.clear();
     for (auto& p : c->params) { cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); cudaFree(p.d_bp); }
     for (auto& p : c->fused) { cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); cudaFree(p.d_bp); }
+    for (auto& q : c->s2) for (auto& p : q) { cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); cudaFree(p.d_bp); }
     for (int i = 0; i < fisr_pwc::kSide; ++i) {
         if (c->side[i]) cudaStreamDestroy(c->side[i]);
         if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
@@ -537,6 +626,7 @@ int fisr_pwc_set_param(fisr_pwc* c, const char* name, const float* h_data, size_
         p.h_b.assign(h_data, h_data + count);
         p.packed = false;
         for (auto& f : c->fused) f.packed = false;
+        for (auto& f : c->s2) f[0].packed = f[1].packed = false;
         return FISR_OK;
     }
     const size_t taps = d.transpose ? 16 : 9, expect = taps * d.cin * d.cout;
@@ -554,6 +644,7 @@ int fisr_pwc_set_param(fisr_pwc* c, const char* name, const float* h_data, size_
     p.h_w.assign(h_data, h_data + count);
     p.packed = false;
     for (auto& f : c->fused) f.packed = false;
+    for (auto& f : c->s2) f[0].packed = f[1].packed = false;
     return FISR_OK;
 }
 
@@ -564,16 +655,30 @@ int fisr_pwc_forward(fisr_pwc* c, const float* d_img1, const float* d_img2, int 
     if (*c->h_err) return fail(c, FISR_E_CUDA, "a conv kernel of an earlier forward timed out on a barrier (code %d)", *c->h_err);
     for (auto& p : c->params)            // parameters changed since the plan was built: re-pack the operand planes in place
         if (p.d_wp && !p.packed) { const int rp = ensure_packed(c, p); if (rp != FISR_OK) return rp; }
-    for (int l = kPredLvl; l <= kLvls; ++l)
+    for (int l = kPredLvl; l <= kLvls; ++l) {
         if (c->fused[l].d_wp && !c->fused[l].packed) { const int rp = build_fused(c, l); if (rp != FISR_OK) return rp; }
+        if (c->s2[l][0].d_wp && !(c->s2[l][0].packed && c->s2[l][1].packed)) { const int rp = build_stride2(c, l); if (rp != FISR_OK) return rp; }
+    }
     int rc = build_plan(c, N, H, W, &plan);
     if (rc != FISR_OK) return rc;
-    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
-    if (st != c->stream) PWC_TRY(c, cudaStreamSynchronize(c->stream));      // operand packing / buffer clears ran on the context stream
+    cudaStream_t st0 = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    if (st0 != c->stream) PWC_TRY(c, cudaStreamSynchronize(c->stream));      // operand packing / buffer clears ran on the context stream
     plan->img1 = d_img1; plan->img2 = d_img2; plan->out = d_flow;
     const bool fan_out = c->use_umma >= 3;
+    bool forked = false;
     for (size_t i = 0; i < plan->ops.size(); ++i) {
         Op& op = plan->ops[i];
+        if (op.lane == 1 && !forked) {          // first op of image 2's pyramid: it depends on nothing before it in this forward
+            PWC_TRY(c, cudaEventRecord(c->ev_fork, st0));
+            PWC_TRY(c, cudaStreamWaitEvent(c->side[0], c->ev_fork, 0));
+            forked = true;
+        }
+        if (op.lane == 0 && forked) {           // first op of the cascade: needs both pyramids
+            PWC_TRY(c, cudaEventRecord(c->ev_join[0], c->side[0]));
+            PWC_TRY(c, cudaStreamWaitEvent(st0, c->ev_join[0], 0));
+            forked = false;
+        }
+        cudaStream_t st = op.lane == 1 ? c->side[0] : st0;
         if (!op.umma) { op.fn(st); continue; }
         if (op.group == 0 || !fan_out) { PWC_TRY(c, fisr::launch_conv3x3(op.conv, c->num_sms, st)); continue; }
         // a group of independent launches: fork to the side streams, round robin, join
@@ -591,7 +696,7 @@ int fisr_pwc_forward(fisr_pwc* c, const float* d_img1, const float* d_img2, int 
         }
         i = end - 1;
     }
-    PWC_TRY(c, cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PWC_TRY(c, cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, st0));
     c->launches += static_cast<long long>(plan->ops.size());
     c->last = plan;
     PWC_TRY(c, cudaGetLastError());

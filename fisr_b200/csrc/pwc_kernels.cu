@@ -537,6 +537,18 @@ __global__ void __launch_bounds__(128) finish_flow_kernel(const float* __restric
     reinterpret_cast<float2*>(out)[P] = make_float2(o[0], o[1]);
 }
 
+// ---------------------------------------------------------------- channel-slice copy between plane buffers (C % 8 == 0, 16-byte rows)
+__global__ void __launch_bounds__(256) copy_channels_kernel(Planes src, int src_off, Planes dst, int dst_off, int C, long long npix) {
+    const int g = C / 8;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= npix * g) return;
+    const long long P = i / g;
+    const int c = static_cast<int>(i % g) * 8;
+    const size_t a = static_cast<size_t>(P) * src.cs + src_off + c, b = static_cast<size_t>(P) * dst.cs + dst_off + c;
+    *reinterpret_cast<uint4*>(dst.p + b) = __ldg(reinterpret_cast<const uint4*>(src.p + a));
+    *reinterpret_cast<uint4*>(dst.p + dst.plane + b) = __ldg(reinterpret_cast<const uint4*>(src.p + src.plane + a));
+}
+
 // ---------------------------------------------------------------- tf.image.resize_bilinear x S (legacy: src = dst / S), times `gain`
 __global__ void __launch_bounds__(256) resize_flow_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int h, int w, int S, float gain) {
     const long long total = static_cast<long long>(N) * h * S * w * S;
@@ -604,6 +616,10 @@ void launch_prepare_pair(const void* src0, const void* src1, bool yuv, float* im
 
 void launch_finish_flow(const float* flow, int N, int Hp, int Wp, int h0, int w0, int oh, int ow, float* out, const FinishConst& k, cudaStream_t st) {
     finish_flow_kernel<<<blocks_for(static_cast<long long>(N) * oh * ow, 128), 128, 0, st>>>(flow, N, Hp, Wp, h0, w0, oh, ow, out, k);
+}
+
+void launch_copy_channels(Planes src, int src_off, Planes dst, int dst_off, int C, long long npix, cudaStream_t st) {
+    copy_channels_kernel<<<blocks_for(npix * (C / 8), 256), 256, 0, st>>>(src, src_off, dst, dst_off, C, npix);
 }
 
 void launch_flow_upfeat_scatter(Planes F, float* flow, Planes Dn, int up_off, int N, int h, int w, cudaStream_t st) {

@@ -42,6 +42,8 @@ struct FinishConst { double wy[kMaxGaussRadius + 1], wx[kMaxGaussRadius + 1]; in
 void launch_prepare_pair(const void* src0, const void* src1, bool yuv, float* img1, float* img2, int h, int w, int oh, int ow, int Hp, int Wp,
                          const PrepConst& k, cudaStream_t st);
 void launch_finish_flow(const float* flow, int N, int Hp, int Wp, int h0, int w0, int oh, int ow, float* out, const FinishConst& k, cudaStream_t st);
+// dst[.., dst_off + c] = src[.., src_off + c] for c < C (C, offsets and channel strides multiples of 8)
+void launch_copy_channels(Planes src, int src_off, Planes dst, int dst_off, int C, long long npix, cudaStream_t st);
 void launch_resize_flow(const float* in, float* out, int N, int h, int w, int S, float gain, cudaStream_t st);
 
 }  // namespace pwc
