@@ -491,6 +491,15 @@ def measure_extras(eng, dev, peaks, bench_precision):
         for _ in range(3):
             net.flow_pair_yuv(y1, y2)
         out["pwcnet_1080p_pair_x2"]["flow_pair_host_to_host_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+        # the same as a pipeline over a 7-frame clip: every frame uploaded once, the download of pair k under the kernels of pair k + 1
+        clip = [y1, y2, y1, y2, y1, y2, y1]
+        for _ in net.flow_sequence_yuv(iter(clip[:3])):
+            pass
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in net.flow_sequence_yuv(iter(clip)):
+            pass
+        out["pwcnet_1080p_pair_x2"]["flow_sequence_ms_per_pair"] = (time.perf_counter() - t0) / 6 * 1e3
         net.close()
         del a, b
     except Exception as e:                       # a next-row component must not take the headline line down with it

@@ -150,6 +150,36 @@ class PWCNet:
         flow = self.forward(img1, img2)
         return self.finish_flow(flow, (h * scale, w * scale), (h, w), scale).cpu().numpy()
 
+    def flow_sequence_yuv(self, frames, scale: int = 2):
+        """Bidirectional flow of every adjacent pair of a frame sequence (the loop of ..predict_from_img_test.py:111-139): ``frames``
+        yields uint8 YUV frames [h,w,3]; yields float32 [2,h,w,2] per pair (valid until the next item is requested).  Every frame
+        is uploaded once, and the download of pair k overlaps the kernels of pair k + 1 (pinned buffers, one pair in flight)."""
+        dev = torch.device("cuda", self.device)
+        prev, pending, k = None, None, 0
+        hosts = [None, None]
+        for f in frames:
+            if f.dtype != np.uint8:
+                raise FisrError("flow_sequence_yuv takes uint8 frames")
+            cur = torch.from_numpy(np.ascontiguousarray(f)).pin_memory().to(dev, non_blocking=True)
+            if prev is not None:
+                h, w = int(cur.shape[0]), int(cur.shape[1])
+                img1, img2 = self.prepare_pair(prev, cur, scale)
+                out = self.finish_flow(self.forward(img1, img2), (h * scale, w * scale), (h, w), scale)
+                if hosts[k] is None or hosts[k].shape != out.shape:
+                    hosts[k] = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+                hosts[k].copy_(out, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                if pending is not None:
+                    pending[1].synchronize()
+                    yield pending[0].numpy()
+                pending = (hosts[k], ev)
+                k ^= 1
+            prev = cur
+        if pending is not None:
+            pending[1].synchronize()
+            yield pending[0].numpy()
+
     def flow_pair(self, rgb1: np.ndarray, rgb2: np.ndarray, scale: int = 2) -> np.ndarray:
         """Bidirectional flow of one frame pair as ..predict_from_img_test.py:126-138 computes it: rgb float [h,w,3] in 0..255 ->
         float32 [2,h,w,2] (1 -> 2, 2 -> 1) at the input resolution."""

@@ -68,11 +68,21 @@ def FISR_for_video_Compute_Flow(args, pwcnet=None):
     h, w = args.FISR_input_size[0], args.FISR_input_size[1]
     num_fr = args.frame_num
     pred = np.zeros((num_fr - 1, 2, h, w, 2), dtype=np.float32)
-    for fr in range(num_fr - 1):
-        # PWC-Net works on RGB: the YUV frames are converted first (:113-120; utils.YUV2RGB_matlab's arithmetic, on the device)
-        yuv_1 = np.array(Image.open(data_list[fr]), dtype=np.uint8)[:h, :w]
-        yuv_2 = np.array(Image.open(data_list[fr + 1]), dtype=np.uint8)[:h, :w]
-        pred[fr] = pwcnet.flow_pair_yuv(yuv_1, yuv_2, scale=2)
+
+    def frames():
+        # PWC-Net works on RGB: the YUV frames are converted first (:113-120; utils.YUV2RGB_matlab's arithmetic, on the device).
+        # Every PNG is decoded once, a few frames ahead of the GPU, on worker threads (PIL releases the GIL while decoding).
+        from concurrent.futures import ThreadPoolExecutor
+        load = lambda p: np.array(Image.open(p), dtype=np.uint8)[:h, :w]
+        with ThreadPoolExecutor(max_workers=2) as ex:
+            ahead = [ex.submit(load, p) for p in data_list[:min(4, num_fr)]]
+            for i in range(num_fr):
+                if i + 4 < num_fr:
+                    ahead.append(ex.submit(load, data_list[i + 4]))
+                yield ahead.pop(0).result()
+
+    for fr, flow in enumerate(pwcnet.flow_sequence_yuv(frames(), scale=2)):
+        pred[fr] = flow
         print("Processing for computing flows [%5d/%5d]" % (fr + 1, num_fr))
     write_flo_file_5dim(pred, path)
     print('[*] Flow file saved!')

@@ -109,6 +109,16 @@ def test_driver_pre_and_post_processing_on_the_device(pwc, h, w):
         assert np.mean(got[k] == want) > 0.999
 
 
+def test_flow_sequence_is_the_pairwise_loop(pwc):
+    """The pipelined sequence API (frames uploaded once, downloads overlapped) returns exactly what the one-pair call returns."""
+    pwc.set_params(W.init_params(4))
+    yuv = np.random.default_rng(8).integers(0, 256, (4, 40, 72, 3), dtype=np.uint8)
+    seq = [f.copy() for f in pwc.flow_sequence_yuv(iter(yuv))]
+    assert len(seq) == 3
+    for k in range(3):
+        assert np.array_equal(seq[k], pwc.flow_pair_yuv(yuv[k], yuv[k + 1]))
+
+
 def test_each_building_block(pwc):
     """The TF-specific semantics one by one, on the oracle side against plain formulas (runs without the GPU too)."""
     g = torch.Generator().manual_seed(0)

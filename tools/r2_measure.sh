@@ -19,3 +19,7 @@ timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_d
 tools/gpu_ncu.sh f16f8 conv64 93 2 pool64 96 1 conv128 98 2 head 131 2
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:warp_yuv -s 3 -c 1 -o gpurun_out/prof_warp -f python tools/warp_target.py 4 > gpurun_out/ncu_warp.log 2>&1
 python tools/warp_target.py 4 2>&1 | grep -v Warn
+# PWC-Net: launch list of 5 forwards on both directions of a 1080p pair, full capture of the level-2 estimator convs
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/r02_pwc_launches.csv python tools/pwc_target.py > gpurun_out/ncu_pwc.log 2>&1
+python tools/summarize_launches.py gpurun_out/r02_pwc_launches.csv > gpurun_out/r02_pwc_launches.txt; head -6 gpurun_out/r02_pwc_launches.txt
+for m in 0 1 2 3; do FISR_PWC_UMMA=$m timeout 300 python tools/pwc_target.py 2>&1 | tail -1; done
