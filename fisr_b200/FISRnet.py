@@ -333,9 +333,21 @@ class FISRnet(object):
         start_time = time.time()
         digits = math.ceil(math.log10(2 * (num_fr - 1)))
         def windows():
-            for fr in range(num_fr - 2):
-                img = np.concatenate([np.array(Image.open(test_data_path[fr + s])) for s in range(3)], axis=2)
-                yield img[:h, :w], flow[fr, :h, :w], warp[fr, :h, :w]      # FISRnet.py:1008-1021
+            # every PNG is decoded once (consecutive windows share two of their three frames), a few frames ahead, on worker threads
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=2) as ex:
+                decoded = {}
+                def frame(i):
+                    if i not in decoded:
+                        decoded[i] = ex.submit(lambda p: np.array(Image.open(p)), test_data_path[i])
+                    return decoded[i]
+                for fr in range(num_fr - 2):
+                    for ahead in range(5):
+                        if fr + ahead < num_fr:
+                            frame(fr + ahead)
+                    img = np.concatenate([frame(fr + s).result() for s in range(3)], axis=2)
+                    decoded.pop(fr - 1, None)
+                    yield img[:h, :w], flow[fr, :h, :w], warp[fr, :h, :w]      # FISRnet.py:1008-1021
 
         # two windows in flight: the copies of window k+1 overlap the kernels of window k (fisr_window_submit / _wait)
         writer = _FrameWriter()

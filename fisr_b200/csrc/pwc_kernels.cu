@@ -255,71 +255,90 @@ __global__ void __launch_bounds__(128) deconv4x4s2_kernel(Planes in, int in_coff
 // ---------------------------------------------------------------- cost volume, search range 4 (model_pwcnet.py:1226-1277)
 // out[p, (dy+4)*9 + (dx+4)] = leaky_relu(mean_c c1[p, c] * c2[p + (dy, dx), c]), zero outside the image
 // A block owns 4 rows x 32 columns of pixels; per 16-channel slice it stages its c1 tile and the (4 + 8) x (32 + 8) c2 region in
-// shared memory (channel-major, so a warp = one pixel row reads consecutive words) and a thread accumulates 36 or 45 of the 81
-// displacements of one pixel: rows dy < 0 (thread half 0) or dy >= 0 (half 1).
-constexpr int kCvTy = 4, kCvTx = 32, kCvC = 16, kCvRy = kCvTy + 8, kCvRx = kCvTx + 8;
+// shared memory, channel-major.  A thread owns 4 consecutive pixels of a row and ONE row dy of the 9 x 9 window: per channel it
+// reads its 4 c1 values and the 12 c2 values they see (4 x 128-bit shared loads) for 36 FMAs; a warp = the 32 pixel groups of the
+// tile for one dy, so a quarter-warp always reads 128 contiguous bytes.
+constexpr int kCvTy = 4, kCvTx = 32, kCvC = 16, kCvRy = kCvTy + 8, kCvRx = kCvTx + 8, kCvThreads = 9 * 32;
 
-__global__ void __launch_bounds__(256) cost_volume_kernel(Planes c1, int c1_coff, Planes c2, int c2_coff, int C, Planes out, int out_coff, int N, int h, int w) {
-    __shared__ float s1[kCvC][kCvTy * kCvTx];
-    __shared__ float s2[kCvC][kCvRy * kCvRx];
+__global__ void __launch_bounds__(kCvThreads) cost_volume_kernel(Planes c1, int c1_coff, Planes c2, int c2_coff, int C, Planes out, int out_coff, int N, int h, int w) {
+    __shared__ __align__(16) float s1[kCvC][kCvTy * kCvTx];
+    __shared__ __align__(16) float s2[kCvC][kCvRy * kCvRx];
     const int t = threadIdx.x;
     const int x0 = blockIdx.x * kCvTx, y0 = blockIdx.y * kCvTy, n = blockIdx.z;
-    const int pix = t & 127, half = t >> 7;
-    const int tx = pix & 31, ty = pix >> 5;
-    const int dy0 = half ? 4 : 0, ndy = half ? 5 : 4;          // rows of the 9 x 9 window this thread owns
-    float acc[45];
+    const int g = t & 31, dyi = t >> 5;                // pixel group, row of the search window (dy = dyi - 4)
+    const int gy = g >> 3, gx = (g & 7) * 4;
+    float acc[4][9];
 #pragma unroll
-    for (int i = 0; i < 45; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) acc[i][j] = 0.f;
     for (int cb = 0; cb < C; cb += kCvC) {
         __syncthreads();
         // (pixel, 8-channel group) units: consecutive threads take consecutive pixels of one group
-        for (int u = t; u < 2 * kCvTy * kCvTx; u += 256) {
-            const int p = u % (kCvTy * kCvTx), g = u / (kCvTy * kCvTx);
+        for (int u = t; u < 2 * kCvTy * kCvTx; u += kCvThreads) {
+            const int p = u % (kCvTy * kCvTx), grp = u / (kCvTy * kCvTx);
             const int y = y0 + (p >> 5), x = x0 + (p & 31);
             float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (y < h && x < w) {
-                const size_t base = (static_cast<size_t>(n) * h + y) * w * c1.cs + static_cast<size_t>(x) * c1.cs + c1_coff + cb + 8 * g;
-                if (cb + 8 * g + 8 <= C) { const float4 a = ld4(c1.p, c1.plane, base), b = ld4(c1.p, c1.plane, base + 4); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
-                else if (cb + 8 * g + 4 <= C) { const float4 a = ld4(c1.p, c1.plane, base); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
+                const size_t base = (static_cast<size_t>(n) * h + y) * w * c1.cs + static_cast<size_t>(x) * c1.cs + c1_coff + cb + 8 * grp;
+                if (cb + 8 * grp + 8 <= C) { const float4 a = ld4(c1.p, c1.plane, base), b = ld4(c1.p, c1.plane, base + 4); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+                else if (cb + 8 * grp + 4 <= C) { const float4 a = ld4(c1.p, c1.plane, base); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s1[8 * g + j][p] = v[j];
+            for (int j = 0; j < 8; ++j) s1[8 * grp + j][p] = v[j];
         }
-        for (int u = t; u < 2 * kCvRy * kCvRx; u += 256) {
-            const int p = u % (kCvRy * kCvRx), g = u / (kCvRy * kCvRx);
+        for (int u = t; u < 2 * kCvRy * kCvRx; u += kCvThreads) {
+            const int p = u % (kCvRy * kCvRx), grp = u / (kCvRy * kCvRx);
             const int y = y0 - 4 + p / kCvRx, x = x0 - 4 + p % kCvRx;
             float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (y >= 0 && y < h && x >= 0 && x < w) {
-                const size_t base = (static_cast<size_t>(n) * h + y) * w * c2.cs + static_cast<size_t>(x) * c2.cs + c2_coff + cb + 8 * g;
-                if (cb + 8 * g + 8 <= C) { const float4 a = ld4(c2.p, c2.plane, base), b = ld4(c2.p, c2.plane, base + 4); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
-                else if (cb + 8 * g + 4 <= C) { const float4 a = ld4(c2.p, c2.plane, base); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
+                const size_t base = (static_cast<size_t>(n) * h + y) * w * c2.cs + static_cast<size_t>(x) * c2.cs + c2_coff + cb + 8 * grp;
+                if (cb + 8 * grp + 8 <= C) { const float4 a = ld4(c2.p, c2.plane, base), b = ld4(c2.p, c2.plane, base + 4); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+                else if (cb + 8 * grp + 4 <= C) { const float4 a = ld4(c2.p, c2.plane, base); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s2[8 * g + j][p] = v[j];
+            for (int j = 0; j < 8; ++j) s2[8 * grp + j][p] = v[j];
         }
         __syncthreads();
 #pragma unroll 4
         for (int c = 0; c < kCvC; ++c) {
-            const float a = s1[c][pix];
-            const float* row = &s2[c][(ty + dy0) * kCvRx + tx];
+            const float4 a4 = *reinterpret_cast<const float4*>(&s1[c][gy * kCvTx + gx]);
+            const float* row = &s2[c][(gy + dyi) * kCvRx + gx];
+            const float4 b0 = *reinterpret_cast<const float4*>(row), b1 = *reinterpret_cast<const float4*>(row + 4), b2 = *reinterpret_cast<const float4*>(row + 8);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float b[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
 #pragma unroll
-            for (int r = 0; r < 5; ++r) {
-                if (r < ndy) {
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int dx = 0; dx < 9; ++dx) acc[r * 9 + dx] = fmaf(a, row[r * kCvRx + dx], acc[r * 9 + dx]);
-                }
-            }
+                for (int dx = 0; dx < 9; ++dx) acc[i][dx] = fmaf(a[i], b[i + dx], acc[i][dx]);
         }
     }
-    const int y = y0 + ty, x = x0 + tx;
-    if (y >= h || x >= w) return;
+    // Output through shared memory: a pixel's 81 values are contiguous in the dense buffer, but a thread holds 9 of them for 4
+    // pixels -- stored directly, every warp store touches 32 different 32-byte sectors with 4 bytes each (measured: the kernel ran
+    // at the L2's partial-sector write rate, 3 GB of sector traffic for 340 MB).  Two rows of the tile at a time are transposed
+    // through the c2 staging buffer and written by whole warps, 64 + 17 channels of one pixel per pass.
     const float inv = 1.f / static_cast<float>(C);
-    const size_t o = ((static_cast<size_t>(n) * h + y) * w + x) * out.cs + out_coff + dy0 * 9;     // dy0 * 9 = 0 or 36: even
-    const int cnt = ndy * 9;
+    float* so = &s2[0][0];                                     // [64 pixels][81]
+    const int warp = t >> 5, lane = t & 31;
+    for (int half = 0; half < 2; ++half) {
+        __syncthreads();                                       // c2 tile (or the previous half) fully consumed
+        if ((gy >> 1) == half) {
 #pragma unroll
-    for (int i = 0; i + 1 < 45; i += 2)
-        if (i + 1 < cnt) st2(out.p, out.plane, o + i, lrelu(acc[i] * inv), lrelu(acc[i + 1] * inv));
-    if (half) st1(out.p, out.plane, o + 44, lrelu(acc[44] * inv));
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int dx = 0; dx < 9; ++dx) so[((gy & 1) * kCvTx + gx + i) * 81 + dyi * 9 + dx] = lrelu(acc[i][dx] * inv);
+        }
+        __syncthreads();
+        for (int p = warp; p < 2 * kCvTx; p += kCvThreads / 32) {
+            const int y = y0 + 2 * half + (p >> 5), x = x0 + (p & 31);
+            if (y >= h || x >= w) continue;
+            const size_t o = ((static_cast<size_t>(n) * h + y) * w + x) * out.cs + out_coff;       // even: channel pairs are 4-byte aligned
+            const float* v = so + p * 81;
+            st2(out.p, out.plane, o + 2 * lane, v[2 * lane], v[2 * lane + 1]);
+            if (lane < 8) st2(out.p, out.plane, o + 64 + 2 * lane, v[64 + 2 * lane], v[65 + 2 * lane]);
+            else if (lane == 8) st1(out.p, out.plane, o + 80, v[80]);
+        }
+    }
 }
 
 // ---------------------------------------------------------------- dense_image_warp (model_pwcnet.py:1106-1178)
@@ -599,7 +618,7 @@ void launch_deconv4x4s2(Planes in, int in_coff, const float* in_f32, int in_f32_
 
 void launch_cost_volume(Planes c1, int c1_coff, Planes c2, int c2_coff, int C, Planes out, int out_coff, int N, int h, int w, cudaStream_t st) {
     dim3 grid((w + kCvTx - 1) / kCvTx, (h + kCvTy - 1) / kCvTy, N);
-    cost_volume_kernel<<<grid, 256, 0, st>>>(c1, c1_coff, c2, c2_coff, C, out, out_coff, N, h, w);
+    cost_volume_kernel<<<grid, kCvThreads, 0, st>>>(c1, c1_coff, c2, c2_coff, C, out, out_coff, N, h, w);
 }
 
 // ---------------------------------------------------------------- first pyramid conv: fp32 image [N,H,W,3] -> 16 channels at half resolution
