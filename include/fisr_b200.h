@@ -224,7 +224,11 @@ int fisr_plan_info(fisr_ctx* ctx, int N, int H, int W, double* flops, double* mm
  * flow predicted at level 2, search range 4.  Parameters carry the TensorFlow variable names of tfoptflow's checkpoints,
  * "pwcnet/featpyr/conv1a/kernel" ... "pwcnet/upsample/up_feat3/bias" (182 tensors, 14,079,050 values); conv kernels are HWIO
  * [3,3,Cin,Cout], conv2d_transpose kernels [4,4,2,Cin].  PARITY UNPINNED: eight modules of the reference's PWC-Net copy and its
- * checkpoint are not in the tree (model_pwcnet.py:21-28); the CUDA path is checked against oracle/pwcnet_oracle.py. */
+ * checkpoint are not in the tree (model_pwcnet.py:21-28); the CUDA path is checked against oracle/pwcnet_oracle.py.
+ * Every 3x3 conv with >= 16 outputs on an image of >= 4 x 4 pixels runs on the tcgen05 kernel in split mode (fp16 hi / lo planes,
+ * fp32-class): dilated layers as polyphase launches, stride-2 layers as two row-phase launches, the flow predictor fused with the
+ * next level's up_feat transposed conv.  FISR_PWC_UMMA=0..3 in the environment of fisr_pwc_create selects how much of that is
+ * used (0: CUDA-core kernels only ... 3: everything, default) for A/B measurements. */
 typedef struct fisr_pwc fisr_pwc;
 int fisr_pwc_create(int device, fisr_pwc** out);
 void fisr_pwc_destroy(fisr_pwc* pwc);
