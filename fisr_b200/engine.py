@@ -291,7 +291,7 @@ class Engine:
         return out
 
     def warp_batch(self, frames: torch.Tensor, flow: torch.Tensor, src_index, flow_scale: float = 0.5,
-                   out_scale: float = 1.0) -> torch.Tensor:
+                   out_scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """All warps of a clip in one launch: frames u8 [F,h,w,3], flow f32 [J,h,w,2], ``src_index[j]`` = the frame job j
         samples -> f32 [J,h,w,3] (the loop of ..warp_img_with_flo.py:112-128)."""
         frames = self._dev(frames, torch.uint8)
@@ -300,8 +300,14 @@ class Engine:
         src = [int(i) for i in src_index]                 # checked on the host: no device round trip before the launch
         if len(src) != J or min(src, default=0) < 0 or max(src, default=0) >= frames.shape[0] or tuple(frames.shape[1:]) != (h, w, 3):
             raise FisrError(f"warp_batch: {J} flows, {len(src)} source indices, frames {tuple(frames.shape)}")
-        idx = torch.tensor(src, dtype=torch.int32).pin_memory().to(frames.device, non_blocking=True)
-        out = torch.empty((J, h, w, 3), dtype=torch.float32, device=frames.device)
+        key = (tuple(src), frames.device)
+        if getattr(self, "_warp_idx_key", None) != key:      # the index table of a clip is uploaded once and kept
+            self._warp_idx, self._warp_idx_key = torch.tensor(src, dtype=torch.int32, device=frames.device), key
+        idx = self._warp_idx
+        if out is None:
+            out = torch.empty((J, h, w, 3), dtype=torch.float32, device=frames.device)
+        elif tuple(self._dev(out, torch.float32).shape) != (J, h, w, 3):
+            raise FisrError(f"warp_batch: out has shape {tuple(out.shape)}, expected {(J, h, w, 3)}")
         self._enter(frames, flow, idx, out)
         self._check(self.lib.fisr_warp_batch_device(self.h, frames.data_ptr(), flow.data_ptr(), idx.data_ptr(), J, flow_scale,
                                                     out.data_ptr(), h, w, out_scale, self._stream()), "fisr_warp_batch_device")

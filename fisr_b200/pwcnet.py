@@ -157,10 +157,19 @@ class PWCNet:
         dev = torch.device("cuda", self.device)
         prev, pending, k = None, None, 0
         hosts = [None, None]
+        stage, staged, j = [None, None], [None, None], 0          # pinned upload buffers, reused every other frame
         for f in frames:
             if f.dtype != np.uint8:
                 raise FisrError("flow_sequence_yuv takes uint8 frames")
-            cur = torch.from_numpy(np.ascontiguousarray(f)).pin_memory().to(dev, non_blocking=True)
+            if stage[j] is None or tuple(stage[j].shape) != tuple(f.shape):
+                stage[j] = torch.empty(tuple(f.shape), dtype=torch.uint8, pin_memory=True)
+            if staged[j] is not None:
+                staged[j].synchronize()                             # the upload that last used this buffer (two frames ago)
+            stage[j].numpy()[...] = f
+            cur = stage[j].to(dev, non_blocking=True)
+            staged[j] = torch.cuda.Event()
+            staged[j].record()
+            j ^= 1
             if prev is not None:
                 h, w = int(cur.shape[0]), int(cur.shape[1])
                 img1, img2 = self.prepare_pair(prev, cur, scale)

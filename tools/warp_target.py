@@ -14,13 +14,14 @@ sigma = float(sys.argv[1]) if len(sys.argv) > 1 else 4.0
 yuv = torch.randint(0, 256, (nfr, H, W, 3), dtype=torch.uint8, generator=g).cuda()
 flo = (torch.randn(jobs, H, W, 2, generator=g) * sigma).cuda()
 src = [fr + 1 - (j & 1) for fr in range(nfr - 1) for j in range(2)]
+out = torch.empty((jobs, H, W, 3), dtype=torch.float32, device='cuda')
 for _ in range(3):
-    eng.warp_batch(yuv, flo, src, 0.5, 1 / 255.)
+    eng.warp_batch(yuv, flo, src, 0.5, 1 / 255., out=out)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(10):
-    eng.warp_batch(yuv, flo, src, 0.5, 1 / 255.)
+    eng.warp_batch(yuv, flo, src, 0.5, 1 / 255., out=out)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
