@@ -80,13 +80,14 @@ class PWCNet:
         got = load_checkpoint(prefix, names, verify_crc=True)
         self.set_params({n: got[n] for n in names})
 
-    def forward(self, img1: torch.Tensor, img2: torch.Tensor) -> torch.Tensor:
+    def forward(self, img1: torch.Tensor, img2: torch.Tensor, out: "torch.Tensor | None" = None) -> torch.Tensor:
         """``nn()`` (model_pwcnet.py:1525-1593): img1, img2 f32 [N,H,W,3] in 0..1 on the GPU, H, W multiples of 64 -> flow [N,H,W,2]."""
         for t in (img1, img2):
             if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 4 and t.shape[3] == 3):
                 raise FisrError("PWCNet.forward takes contiguous float32 CUDA tensors [N,H,W,3]")
         n, h, w, _ = img1.shape
-        out = torch.empty((n, h, w, 2), dtype=torch.float32, device=img1.device)
+        if out is None:
+            out = torch.empty((n, h, w, 2), dtype=torch.float32, device=img1.device)
         cur = torch.cuda.current_stream(self.device)
         self.stream.wait_stream(cur)
         for t in (img1, img2, out):
@@ -111,7 +112,7 @@ class PWCNet:
         self._check(call(self.stream.cuda_stream), what)
         cur.wait_stream(self.stream)
 
-    def prepare_pair(self, f1: torch.Tensor, f2: torch.Tensor, scale: int = 2):
+    def prepare_pair(self, f1: torch.Tensor, f2: torch.Tensor, scale: int = 2, out=None):
         """..predict_from_img_test.py:113-131 + adapt_x on the device: two frames [h,w,3] (uint8 YUV, or float64 RGB in 0..255) ->
         (img1, img2) f32 [2,Hp,Wp,3] = the batch of both directions, ready for ``forward``."""
         from .utils import yuv2rgb_constants
@@ -121,14 +122,18 @@ class PWCNet:
                 or not (f1.is_cuda and f2.is_cuda and f1.is_contiguous() and f2.is_contiguous()):
             raise FisrError(f"prepare_pair: frames {tuple(f1.shape)} {f1.dtype} / {tuple(f2.shape)} {f2.dtype}, scale {scale}")
         Hp, Wp = -(-h * scale // 64) * 64, -(-w * scale // 64) * 64
-        img1 = torch.empty((2, Hp, Wp, 3), dtype=torch.float32, device=f1.device)
-        img2 = torch.empty_like(img1)
+        if out is None:
+            img1 = torch.empty((2, Hp, Wp, 3), dtype=torch.float32, device=f1.device)
+            img2 = torch.empty_like(img1)
+        else:
+            img1, img2 = out
         k = np.ascontiguousarray(yuv2rgb_constants(), dtype=np.float64)
         self._run((f1, f2, img1, img2), lambda st: self.lib.fisr_pwc_prepare_pair(
             self.h, f1.data_ptr(), f2.data_ptr(), kind, k.ctypes.data, h, w, scale, img1.data_ptr(), img2.data_ptr(), st), "fisr_pwc_prepare_pair")
         return img1, img2
 
-    def finish_flow(self, flow: torch.Tensor, hw0: Tuple[int, int], out_hw: Tuple[int, int], scale: int = 2) -> torch.Tensor:
+    def finish_flow(self, flow: torch.Tensor, hw0: Tuple[int, int], out_hw: Tuple[int, int], scale: int = 2,
+                    out: "torch.Tensor | None" = None) -> torch.Tensor:
         """postproc_y_hat_test crop + anti-aliased resize + / scale (..predict_from_img_test.py:137) on the device:
         flow f32 [N,Hp,Wp,2] -> [N,h,w,2]."""
         n, Hp, Wp, _ = flow.shape
@@ -136,7 +141,8 @@ class PWCNet:
         if not (flow.is_cuda and flow.dtype == torch.float32 and flow.is_contiguous() and flow.shape[3] == 2):
             raise FisrError("finish_flow takes a contiguous float32 CUDA tensor [N,Hp,Wp,2]")
         wy, wx = _gauss_weights(max(0.0, (h0 / h - 1) / 2)), _gauss_weights(max(0.0, (w0 / w - 1) / 2))
-        out = torch.empty((n, h, w, 2), dtype=torch.float32, device=flow.device)
+        if out is None:
+            out = torch.empty((n, h, w, 2), dtype=torch.float32, device=flow.device)
         self._run((flow, out), lambda st: self.lib.fisr_pwc_finish_flow(
             self.h, flow.data_ptr(), n, Hp, Wp, h0, w0, h, w, wy.ctypes.data, len(wy) - 1, wx.ctypes.data, len(wx) - 1, float(scale),
             out.data_ptr(), st), "fisr_pwc_finish_flow")
@@ -155,7 +161,7 @@ class PWCNet:
         yields uint8 YUV frames [h,w,3]; yields float32 [2,h,w,2] per pair (valid until the next item is requested).  Every frame
         is uploaded once, and the download of pair k overlaps the kernels of pair k + 1 (pinned buffers, one pair in flight)."""
         dev = torch.device("cuda", self.device)
-        prev, pending, k = None, None, 0
+        prev, pending, k, work = None, None, 0, None
         hosts = [None, None]
         stage, staged, j = [None, None], [None, None], 0          # pinned upload buffers, reused every other frame
         for f in frames:
@@ -172,8 +178,12 @@ class PWCNet:
             j ^= 1
             if prev is not None:
                 h, w = int(cur.shape[0]), int(cur.shape[1])
-                img1, img2 = self.prepare_pair(prev, cur, scale)
-                out = self.finish_flow(self.forward(img1, img2), (h * scale, w * scale), (h, w), scale)
+                if work is None or work[3].shape[1:3] != (h, w):      # device buffers of the whole sequence (every call is stream ordered)
+                    Hp, Wp = -(-h * scale // 64) * 64, -(-w * scale // 64) * 64
+                    work = [torch.empty((2, Hp, Wp, 3), dtype=torch.float32, device=dev), torch.empty((2, Hp, Wp, 3), dtype=torch.float32, device=dev),
+                            torch.empty((2, Hp, Wp, 2), dtype=torch.float32, device=dev), torch.empty((2, h, w, 2), dtype=torch.float32, device=dev)]
+                img1, img2 = self.prepare_pair(prev, cur, scale, out=(work[0], work[1]))
+                out = self.finish_flow(self.forward(img1, img2, out=work[2]), (h * scale, w * scale), (h, w), scale, out=work[3])
                 if hosts[k] is None or hosts[k].shape != out.shape:
                     hosts[k] = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
                 hosts[k].copy_(out, non_blocking=True)
