@@ -19,7 +19,7 @@ cudaError_t launch_family(const ConvLaunch& L, int num_sms, cudaStream_t stream)
 #define FISR_DECL(NT_, PL_)                                     \
     template <> cudaError_t init_family<NT_, PL_>();            \
     template <> cudaError_t launch_family<NT_, PL_>(const ConvLaunch&, int, cudaStream_t);
-FISR_DECL(16, 1) FISR_DECL(64, 1) FISR_DECL(128, 1) FISR_DECL(16, 2) FISR_DECL(64, 2) FISR_DECL(128, 2)
+FISR_DECL(16, 1) FISR_DECL(64, 1) FISR_DECL(128, 1) FISR_DECL(16, 2) FISR_DECL(64, 2) FISR_DECL(96, 2) FISR_DECL(128, 2)
 FISR_DECL(16, 3) FISR_DECL(32, 3) FISR_DECL(64, 3) FISR_DECL(128, 3) FISR_DECL(64, 4) FISR_DECL(128, 4)
 #undef FISR_DECL
 }  // namespace convk
@@ -32,6 +32,7 @@ cudaError_t conv3x3_init() {
     if (e == cudaSuccess) e = init_family<128, 1>();
     if (e == cudaSuccess) e = init_family<16, 2>();
     if (e == cudaSuccess) e = init_family<64, 2>();
+    if (e == cudaSuccess) e = init_family<96, 2>();
     if (e == cudaSuccess) e = init_family<128, 2>();
     if (e == cudaSuccess) e = init_family<16, 3>();
     if (e == cudaSuccess) e = init_family<32, 3>();
@@ -55,6 +56,7 @@ cudaError_t launch_conv3x3(const ConvLaunch& L, int num_sms, cudaStream_t stream
     } else if (L.planes == 2) {
         if (L.NT == 16) return launch_family<16, 2>(L, num_sms, stream);
         if (L.NT == 64) return launch_family<64, 2>(L, num_sms, stream);
+        if (L.NT == 96) return launch_family<96, 2>(L, num_sms, stream);
         if (L.NT == 128) return launch_family<128, 2>(L, num_sms, stream);
     } else {
         if (L.NT == 16) return launch_family<16, 1>(L, num_sms, stream);
@@ -79,6 +81,7 @@ bool plan_conv_geometry(int H, int W, int n_img, int cout_pad, int planes, int n
         const long w128 = (tiles * (cout_pad / 128) + num_sms - 1) / num_sms, w64 = (tiles * (cout_pad / 64) + num_sms - 1) / num_sms;
         NT = (3 * w128 <= 2 * w64) ? 128 : 64;
     }
+    if (planes == 2 && cout_pad == 96) NT = 96;          // PWC-Net's 96-channel layers (split mode): no padding to 128
     (void)kb;
     // Two chunks (16 x 16 tiles) unless the image is a single chunk wide.  Every chunk has its own MMA issuer warp and one
     // thread issues a tcgen05.mma only every ~70-150 cycles (tests/cuda/umma_rate_probe.cu), so a one-chunk CTA is ISSUE

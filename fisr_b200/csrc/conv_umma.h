@@ -46,7 +46,7 @@ struct SplitConvDesc {
     const float* res;            // added before the activation -- a conv split over two launches accumulates through raw -> res
 };
 // cout_pad a layer's weights must be packed for (independent of the image size)
-inline int split_conv_cout_pad(int cout) { return cout <= 16 ? 16 : cout <= 64 ? 64 : (cout + 127) / 128 * 128; }
+inline int split_conv_cout_pad(int cout) { return cout <= 16 ? 16 : cout <= 64 ? 64 : cout <= 96 ? 96 : (cout + 127) / 128 * 128; }
 bool build_split_conv(EncodeTiledFn encode, const SplitConvDesc& d, int num_sms, int* d_err, ConvLaunch* L, std::string* why);
 
 cudaError_t conv3x3_init();

@@ -200,8 +200,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     constexpr int APL = PLANES == 1 ? 1 : 2;                    // activation planes staged in shared memory
     constexpr int DCOLS = STACK ? 2 * NT : NT;                  // accumulator columns per 128-row chunk
     constexpr int ACC_COLS = CHUNKS * DCOLS;                    // fp32 columns of one accumulator stage
-    constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
-    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns must be a power of two <= 512");
+    constexpr int TMEM_NEED = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;      // two accumulator stages
+    constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;   // allocations are powers of two (N = 96 tiles need 384)
+    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_NEED <= 512, "TMEM columns must be a power of two <= 512");
     constexpr int PLANE_BYTES = (PAIR ? NT / 2 : NT) * 128;     // one weight plane of one tap (a CTA of a pair holds half the rows)
     constexpr int B_SLOT_BYTES = STACK ? 2 * PLANE_BYTES : PLANE_BYTES;
     constexpr int SLOTS_PER_TAP = STACK ? 1 : APL;
@@ -873,6 +874,9 @@ cudaError_t launch_family(const ConvLaunch& L, int num_sms, cudaStream_t stream)
     M(NT_, PL_, 1, EPI_RES) M(NT_, PL_, 2, EPI_RES) M(NT_, PL_, 1, EPI_RES | EPI_RAW) M(NT_, PL_, 2, EPI_RES | EPI_RAW) \
     M(NT_, PL_, 1, EPI_D2S) M(NT_, PL_, 2, EPI_D2S)
 #define FISR_FOR_EPI_NARROW(M, NT_, PL_) M(NT_, PL_, 1, 0) M(NT_, PL_, 2, 0)      // NT = 16 / 32: scalar epilogue
+// N = 96 tiles (PWC-Net): act | act+raw | act+res (the two-launch stride-2 convs accumulate through raw -> res)
+#define FISR_FOR_EPI_PWC(M, NT_, PL_)                                                                       \
+    M(NT_, PL_, 1, 0) M(NT_, PL_, 2, 0) M(NT_, PL_, 1, EPI_RAW) M(NT_, PL_, 2, EPI_RAW) M(NT_, PL_, 1, EPI_RES) M(NT_, PL_, 2, EPI_RES)
 // dgrad variants (training, split mode only): mask | mask+res | mask+res+raw | mask+raw (| mask+s2d for the 64-wide tile)
 #define FISR_FOR_EPI_BWD(M, NT_, PL_)                                                                       \
     M(NT_, PL_, 1, EPI_MASK) M(NT_, PL_, 2, EPI_MASK) M(NT_, PL_, 1, EPI_MASK | EPI_RES) M(NT_, PL_, 2, EPI_MASK | EPI_RES) \
