@@ -23,3 +23,5 @@ python tools/warp_target.py 4 2>&1 | grep -v Warn
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/r02_pwc_launches.csv python tools/pwc_target.py > gpurun_out/ncu_pwc.log 2>&1
 python tools/summarize_launches.py gpurun_out/r02_pwc_launches.csv > gpurun_out/r02_pwc_launches.txt; head -6 gpurun_out/r02_pwc_launches.txt
 for m in 0 1 2 3; do FISR_PWC_UMMA=$m timeout 300 python tools/pwc_target.py 2>&1 | tail -1; done
+# level-2 estimator convs + fused flow conv + dc_conv1 of the fourth forward (3 warm-up forwards of 248 tcgen05 launches each)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv3x3_umma -s $((3 * 248 + 180)) -c 7 -o gpurun_out/prof_pwc_level2 -f python tools/pwc_target.py > gpurun_out/ncu_pwc_level2.log 2>&1; tail -1 gpurun_out/ncu_pwc_level2.log

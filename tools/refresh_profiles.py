@@ -62,6 +62,13 @@ if all(os.path.exists(r) for r in reps):
             out += parts[i] + parts[i + 1]
     open(dst, "w").write(out)
 
+rep = os.path.join(G, "prof_pwc_level2.ncu-rep")
+dst = os.path.join(P, "r02_ncu_pwc.md")
+if os.path.exists(rep):
+    old = open(dst).read()
+    i0, i1 = old.index("| metric | unit |"), old.index("\n## Reading")
+    open(dst, "w").write(old[:i0] + summary(rep) + "\n" + old[i1:])
+
 rep = os.path.join(G, "prof_warp.ncu-rep")
 dst = os.path.join(P, "r02_ncu_warp.md")
 if os.path.exists(rep):
