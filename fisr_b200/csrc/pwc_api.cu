@@ -131,6 +131,7 @@ struct fisr_pwc {
     std::vector<Param> params;
     Param fused[kLvls + 1];      // predict_flow/flow<l> and upsample/up_feat<l> as ONE 3x3 conv with 16 output columns (build_fused)
     Param s2[kLvls + 1][2];      // featpyr/conv<l>a (stride 2) as two stride-1 convs on the row phases of the input (build_stride2)
+    Param pk4[2];                // featpyr/conv1aa, conv1b (16 -> 16) on 4-pixel super-pixels: 64 -> 64 (build_packed4)
     std::map<std::string, int> index;
     std::map<std::string, std::unique_ptr<Plan>> plans;
     Plan* last = nullptr;
@@ -265,6 +266,39 @@ int build_stride2(fisr_pwc* c, int l) {
     return FISR_OK;
 }
 
+// A 16 -> 16 conv on a compact [H, W, 16] tensor read as [H, W/4, 64]: super-pixel X' holds pixels 4X' .. 4X' + 3.  Output sub-pixel q,
+// tap kx reads input pixel 4X' + q + kx - 1 = sub-pixel (q + kx - 1) mod 4 of super-pixel X' + floor((q + kx - 1) / 4): a 3x3 conv with
+// 64 input and 64 output channels whose weights are a block-sparse copy of the 16 x 16 ones.  4x the MMA work (trivial at K = 144), but
+// the TMA boxes are all real data: on the 16-channel view a 64-channel box fetched 128 B per pixel for 32 B of tensor (ncu: 1.96 GB of
+// L2 -> SM traffic for 267 MB of input) and the level-1 convs ran at the L2 rate.
+int build_packed4(fisr_pwc* c, int which, const std::string& name) {
+    Param& f = c->pk4[which];
+    if (f.packed) return FISR_OK;
+    const Param& src = c->params[c->index.at(name)];
+    f.cin_pad = 64;
+    f.cout = 64;
+    std::vector<float> w(static_cast<size_t>(9) * 64 * 64, 0.f), b(64, 0.f);
+    if (!src.h_w.empty())
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx)
+                for (int q = 0; q < 4; ++q) {
+                    const int s = q + kx - 1, dx = s < 0 ? -1 : (s > 3 ? 1 : 0), qi = s - 4 * dx;
+                    for (int ci = 0; ci < 16; ++ci)
+                        for (int co = 0; co < 16; ++co)
+                            w[(static_cast<size_t>(ky * 3 + dx + 1) * 64 + qi * 16 + ci) * 64 + q * 16 + co] = src.h_w[(static_cast<size_t>(ky * 3 + kx) * 16 + ci) * 16 + co];
+                }
+    if (!src.h_b.empty())
+        for (int q = 0; q < 4; ++q)
+            for (int co = 0; co < 16; ++co) b[q * 16 + co] = src.h_b[co];
+    if (!f.d_w) {
+        PWC_TRY(c, cudaMalloc(&f.d_w, w.size() * sizeof(float)));
+        PWC_TRY(c, cudaMalloc(&f.d_b, 64 * sizeof(float)));
+    }
+    PWC_TRY(c, cudaMemcpy(f.d_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    PWC_TRY(c, cudaMemcpy(f.d_b, b.data(), 64 * sizeof(float), cudaMemcpyHostToDevice));
+    return ensure_packed(c, f);
+}
+
 int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
     if (N < 1 || H < 64 || W < 64 || H % 64 || W % 64)
         return fail(c, FISR_E_INVALID, "PWC-Net (6-level pyramid) needs H, W multiples of 64 (got %d x %d x %d): pad like adapt_x", N, H, W);
@@ -305,6 +339,34 @@ int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
         if (rc != FISR_OK) return;
         const int Hin = H >> l_in, Win = W >> l_in, Hout = H >> l_out, Wout = W >> l_out;
         const bool divisible = Hout % dil == 0 && Wout % dil == 0;
+        if (c->use_umma >= 1 && stride == 1 && dil == 1 && !out_f32 && p.cin_pad == 16 && p.cout == 16 && in.coff == 0 && in.b.cs == 16 && outv.coff == 0 &&
+            outv.b.cs == 16 && Wout % 4 == 0 && Wout / 4 >= 4 && Hout >= 4 && (name == "pwcnet/featpyr/conv1aa" || name == "pwcnet/featpyr/conv1b")) {
+            const int which = name == "pwcnet/featpyr/conv1b";
+            if ((rc = build_packed4(c, which, name)) != FISR_OK) return;
+            Param& q = c->pk4[which];
+            const int wp = Wout / 4;
+            fisr::SplitConvDesc d{};
+            d.in = in.b.p; d.in_plane = in.b.plane; d.in_cs = 64;
+            d.in_sx = 64; d.in_sy = static_cast<long long>(Wout) * 16; d.in_sn = static_cast<long long>(Hout) * Wout * 16;
+            d.cin_off = 0; d.cin = 64;
+            d.out = outv.b.p; d.out_plane = outv.b.plane; d.out_cs = 64; d.out_off = 0;
+            d.opix_x = 1; d.opix_y = wp; d.opix_n = static_cast<long long>(Hout) * wp;
+            d.N = N; d.H = Hout; d.W = wp;
+            d.out_pixels = static_cast<long long>(N) * Hout * wp;
+            d.wp = q.d_wp; d.bias = q.d_bp; d.cout = 64; d.cout_pad = q.cout_pad;
+            d.relu = 0; d.slope = leaky ? 0.1f : 0.f;
+            Op op;
+            op.umma = true;
+            op.lane = lane;
+            std::string why;
+            if (!fisr::build_split_conv(c->encode, d, c->num_sms, c->d_err, &op.conv, &why)) {
+                rc = fail(c, FISR_E_CUDA, "conv %s (4-pixel packing): %s", name.c_str(), why.c_str());
+                return;
+            }
+            pl->ops.push_back(std::move(op));
+            pl->umma_ops++;
+            return;
+        }
         if (c->use_umma >= (dil == 1 ? 1 : 2) && stride == 1 && !out_f32 && p.cout >= 16 && divisible && Hout / dil >= 4 && Wout / dil >= 4) {
             if ((rc = ensure_packed(c, p)) != FISR_OK) return;
             const int hs = Hout / dil, ws = Wout / dil;
@@ -584,6 +646,7 @@ void fisr_pwc_destroy(fisr_pwc* c) {
     for (auto& p : c->params) { cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); cudaFree(p.d_bp); }
     for (auto& p : c->fused) { cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); cudaFree(p.d_bp); }
     for (auto& q : c->s2) for (auto& p : q) { cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); cudaFree(p.d_bp); }
+    for (auto& p : c->pk4) { cudaFree(p.d_w); cudaFree(p.d_b); cudaFree(p.d_wp); cudaFree(p.d_bp); }
     for (int i = 0; i < fisr_pwc::kSide; ++i) {
         if (c->side[i]) cudaStreamDestroy(c->side[i]);
         if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
@@ -627,6 +690,7 @@ int fisr_pwc_set_param(fisr_pwc* c, const char* name, const float* h_data, size_
         p.packed = false;
         for (auto& f : c->fused) f.packed = false;
         for (auto& f : c->s2) f[0].packed = f[1].packed = false;
+        c->pk4[0].packed = c->pk4[1].packed = false;
         return FISR_OK;
     }
     const size_t taps = d.transpose ? 16 : 9, expect = taps * d.cin * d.cout;
@@ -645,6 +709,7 @@ int fisr_pwc_set_param(fisr_pwc* c, const char* name, const float* h_data, size_
     p.packed = false;
     for (auto& f : c->fused) f.packed = false;
     for (auto& f : c->s2) f[0].packed = f[1].packed = false;
+    c->pk4[0].packed = c->pk4[1].packed = false;
     return FISR_OK;
 }
 
@@ -659,6 +724,8 @@ int fisr_pwc_forward(fisr_pwc* c, const float* d_img1, const float* d_img2, int 
         if (c->fused[l].d_wp && !c->fused[l].packed) { const int rp = build_fused(c, l); if (rp != FISR_OK) return rp; }
         if (c->s2[l][0].d_wp && !(c->s2[l][0].packed && c->s2[l][1].packed)) { const int rp = build_stride2(c, l); if (rp != FISR_OK) return rp; }
     }
+    for (int k = 0; k < 2; ++k)
+        if (c->pk4[k].d_wp && !c->pk4[k].packed) { const int rp = build_packed4(c, k, k ? "pwcnet/featpyr/conv1b" : "pwcnet/featpyr/conv1aa"); if (rp != FISR_OK) return rp; }
     int rc = build_plan(c, N, H, W, &plan);
     if (rc != FISR_OK) return rc;
     cudaStream_t st0 = stream ? static_cast<cudaStream_t>(stream) : c->stream;
