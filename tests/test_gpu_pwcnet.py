@@ -57,7 +57,8 @@ def test_forward_matches_oracle(pwc, n, h, w):
 
 def test_tensor_core_path_matches_cuda_core_path():
     """The same forward with every conv on the CUDA-core kernel (FISR_PWC_UMMA=0), with the undilated stride-1 convs on the tcgen05
-    kernel (1) and with the dilated ones as polyphase launches too (2, the default), at a size where every dilation qualifies."""
+    kernel (1), with the dilated ones as polyphase launches too (2) and with those launches / the two pyramids spread over streams (3, the
+    default), at a size where every dilation qualifies.  Modes 2 and 3 run the same kernels on the same data: bit-identical."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device in this container (GPU tests run under gpurun)")
     from fisr_b200.pwcnet import PWCNet
@@ -67,7 +68,7 @@ def test_tensor_core_path_matches_cuda_core_path():
     flows = {}
     old = os.environ.get("FISR_PWC_UMMA")
     try:
-        for mode in ("0", "1", "2"):
+        for mode in ("0", "1", "2", "3"):
             os.environ["FISR_PWC_UMMA"] = mode
             net = PWCNet(0)
             net.set_params(params)
@@ -79,10 +80,12 @@ def test_tensor_core_path_matches_cuda_core_path():
             os.environ.pop("FISR_PWC_UMMA", None)
         else:
             os.environ["FISR_PWC_UMMA"] = old
-    for mode in ("1", "2"):
+    for mode in ("1", "2", "3"):
         for i, (x, y) in enumerate(zip(flows[mode], flows["0"])):
             err = float(np.abs(x - y).max())
             assert err < 2e-4 * max(1.0, float(np.abs(y).max())), (mode, i, err)
+    for x, y in zip(flows["3"], flows["2"]):
+        assert np.array_equal(x, y)
 
 
 @pytest.mark.parametrize("h,w", [(72, 104), (75, 101), (64, 64)])
