@@ -1,6 +1,11 @@
 // C ABI of the PWC-Net inference path (include/fisr_b200.h, "PWC-Net"): parameter store under the TensorFlow variable names of
 // philferriere/tfoptflow (scope pwcnet/), one plan (buffers + launch list) per input size, forward of N image pairs.
 // Reference: FISR_tfoptflow/model_pwcnet.py:1012-1593 driven by FISR_for_video_pwcnet_predict_from_img_test.py:96-139.
+// Routing of the 3x3 convs (build_plan): everything with >= 16 outputs on an image of >= 4 x 4 pixels goes to the tcgen05 conv kernel in
+// split mode through build_split_conv (conv_umma.cu) -- dense-block channel slices as TMA boxes that start at a channel offset, dilated
+// layers as polyphase launches, stride-2 layers as two row-phase launches (build_stride2), the flow predictor fused with the next
+// level's up_feat transposed conv (build_fused), the 16-channel level-1 layers on 4-pixel super-pixels (build_packed4); the rest runs on
+// the CUDA-core kernels of pwc_kernels.cu.  Activations are fp16 (hi, lo) planes throughout.
 #include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
