@@ -582,6 +582,11 @@ int build_plan(fisr_pwc* c, int N, int H, int W, Plan** out) {
     }
     if (rc != FISR_OK) return rc;
     PWC_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->plans.size() >= 4) {          // a 1080p plan holds ~7 GB: keep at most four input sizes resident
+        PWC_TRY(c, cudaDeviceSynchronize());
+        c->plans.clear();
+        c->last = nullptr;
+    }
     *out = plan.get();
     c->plans[key] = std::move(plan);
     return FISR_OK;
